@@ -1,0 +1,409 @@
+"""Generate tests/golden/*.npz by EXECUTING the unmodified reference.
+
+Run in the build container only (needs /root/reference):
+
+    python oracle/make_golden.py
+
+The vectors are small on purpose (a few thousand samples per case): they pin
+the oracle (oracle/jmc_oracle.py) bit for bit and serve as fixed-sample replay
+inputs for the CUDA parity tests on the GPU box, where the reference is absent.
+Seed convention: ``random.seed(20260101 + case)`` right before each sampler run.
+"""
+import os
+import random
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+from oracle import ref_shim  # noqa: E402
+
+ref_shim.install()
+
+from jetmontecarlo.analytics import qcd_utils as Q  # noqa: E402
+from jetmontecarlo.analytics.radiators import fixedcoupling as FC  # noqa: E402
+from jetmontecarlo.analytics.radiators import running_coupling as RC  # noqa: E402
+from jetmontecarlo.analytics.sudakov_factors.fixedcoupling import critSudakov_fc_LL  # noqa: E402
+from jetmontecarlo.montecarlo.integrator import integrator, integrate_1d  # noqa: E402
+from jetmontecarlo.montecarlo.sampler import simpleSampler  # noqa: E402
+from jetmontecarlo.numerics import observables as OBS  # noqa: E402
+from jetmontecarlo.numerics import weights as W  # noqa: E402
+from jetmontecarlo.numerics.radiators.samplers import (  # noqa: E402
+    criticalSampler, precriticalSampler, ungroomedSampler)
+from jetmontecarlo.utils import partonshower_utils as PS  # noqa: E402
+from jetmontecarlo.utils.interpolation import lin_log_mixed_list  # noqa: E402
+from jetmontecarlo.utils.hist_utils import vals_to_pdf  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+SEED = 20260101
+np.seterr(all='ignore')
+
+
+def save(name, **arrays):
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **arrays)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
+def integ_arrays(it):
+    return dict(edges=np.asarray(it.bins), density=np.asarray(it.density),
+                density_err=np.asarray(it.densityErr),
+                integral=np.asarray(it.integral, dtype=float),
+                integral_err=np.asarray(it.integralErr))
+
+
+# ---------------------------------------------------------------- KATs ----
+def kats():
+    k = {}
+    k['alpha_fixed'] = Q.alpha_fixed
+    k['beta_0'] = Q.beta_0
+    k['MU_NP'] = Q.MU_NP
+    k['alpha_s(.2,.3)'] = Q.alpha_s(.2, .3)
+    k['alpha_s(1e-3,1e-3)'] = Q.alpha_s(1e-3, 1e-3)
+    for jet in ('quark', 'gluon'):
+        j = jet[0]
+        k[j + ':splittingFn(.2,LL)'] = Q.splittingFn(.2, jet, 'LL')
+        k[j + ':splittingFn(.2,LL_nonsing)'] = Q.splittingFn(.2, jet, 'LL_nonsing')
+        k[j + ':splittingFn(.2,MLL)'] = Q.splittingFn(.2, jet, 'MLL')
+        k[j + ':radiatorWeight(.2,.3,fc,LL)'] = W.radiatorWeight(.2, .3, jet, True, 'LL')
+        k[j + ':radiatorWeight(.2,.3,rc,MLL)'] = W.radiatorWeight(.2, .3, jet, False, 'MLL')
+        k[j + ':critPDFAnalytic_fc_LL(.2,.3,.1)'] = FC.critPDFAnalytic_fc_LL(.2, .3, z_c=.1, jet_type=jet)
+        k[j + ':critRadAnalytic(.3,.1)'] = RC.critRadAnalytic(.3, .1, jet)
+        k[j + ':critRadAnalytic(2e-3,.1)'] = RC.critRadAnalytic(2e-3, .1, jet)
+        k[j + ':critRadAnalytic(1e-4,.1)'] = RC.critRadAnalytic(1e-4, .1, jet)
+        k[j + ':critPDFAnalytic(.2,.3,.1)'] = RC.critPDFAnalytic(.2, .3, .1, jet)
+        k[j + ':critRadPrimeAnalytic(.3,.1)'] = RC.critRadPrimeAnalytic(.3, .1, jet)
+        k[j + ':subRadAnalytic_fc_LL(.01,2)'] = FC.subRadAnalytic_fc_LL(.01, 2, jet)
+        k[j + ':subPDFAnalytic_fc_LL(.01,2)'] = FC.subPDFAnalytic_fc_LL(.01, 2, jet)
+        k[j + ':subPDFAnalytic_fc_LL(.01,2,R=.3)'] = FC.subPDFAnalytic_fc_LL(.01, 2, jet, maxRadius=.3)
+        k[j + ':subRadAnalytic(.01,2)'] = RC.subRadAnalytic(.01, 2, jet)
+        k[j + ':subRadAnalytic(1e-5,2)'] = RC.subRadAnalytic(1e-5, 2, jet)
+        k[j + ':subRadPrimeAnalytic(.01,2)'] = RC.subRadPrimeAnalytic(.01, 2, jet)
+        k[j + ':subPDFAnalytic(.01,2,R=.3)'] = RC.subPDFAnalytic(.01, 2, jet, maxRadius=.3)
+        k[j + ':critSudakov_fc_LL(.01,.1,2)'] = float(critSudakov_fc_LL(.01, .1, 2, jet))
+        k[j + ':precriticalEmissionWeight(.03,.3,.1)'] = W.precriticalEmissionWeight(.03, .3, .1, jet)
+        c = np.array([[.2, .3]])
+        s = np.array([[.05, .4]])
+        k[j + ':twoEmissionWeight(fc)'] = W.twoEmissionWeight(c, s, .1, 2., jet, True)[0]
+        k[j + ':twoEmissionWeight(rc)'] = W.twoEmissionWeight(c, s, .1, 2., jet, False)[0]
+    k['C_groomed(.2,.3,.1,2)'] = OBS.C_groomed(.2, .3, .1, 2)
+    k['C_groomed(.2,.3,.1,2,zpre=.03,f=1,MLL)'] = OBS.C_groomed(.2, .3, .1, 2, z_pre=.03, f=1, acc='MLL')
+    k['C_groomed(.2,.3,.1,2,zpre=.1,f=0,MLL)'] = OBS.C_groomed(.2, .3, .1, 2, z_pre=.1, f=0, acc='MLL')
+    k['C_ungroomed(.2,.3,2,MLL)'] = OBS.C_ungroomed(.2, .3, 2, 'MLL')
+    k['landau'] = float(np.exp(-1 / (2 * Q.alpha_fixed * Q.beta_0)))
+    names = np.array(sorted(k))
+    vals = np.array([float(k[n]) for n in names])
+    save("kats", names=names, values=vals)
+
+
+# ------------------------------------------------- function-level vectors --
+def function_vectors():
+    """Every analytic function on broad log-uniform inputs that reach all
+    regions, including the NaN (Landau) ones."""
+    rng = np.random.RandomState(SEED)
+    n = 1200
+    z = np.exp(rng.uniform(np.log(1e-12), np.log(.5), n))
+    th = np.exp(rng.uniform(np.log(1e-12), 0., n))
+    C = np.exp(rng.uniform(np.log(1e-14), np.log(.7), n))
+    zpre = np.exp(rng.uniform(np.log(1e-12), np.log(.12), n))
+    maxr = np.exp(rng.uniform(np.log(1e-6), 0., n))
+    # put a few values exactly on thresholds / edges
+    z[:4] = [.1, .5, .25, 1e-300]
+    th[:4] = [1., 2 * Q.MU_NP, Q.MU_NP / .1, 1e-300]
+    C[:4] = [.5, Q.MU_NP, Q.MU_NP ** 2 * 2, 0.]
+    out = dict(z=z, theta=th, C=C, z_pre=zpre, max_radius=maxr)
+    out['alpha_s'] = Q.alpha_s(z, th)
+    for jet in ('quark', 'gluon'):
+        j = jet[0]
+        for acc in ('LL', 'LL_nonsing', 'MLL'):
+            out[f'{j}:splittingFn:{acc}'] = Q.splittingFn(z, jet, acc)
+            for fc in (True, False):
+                out[f'{j}:radiatorWeight:{acc}:{int(fc)}'] = W.radiatorWeight(z, th, jet, fc, acc)
+        for zc in (.05, .1, .2):
+            out[f'{j}:critPDF_fc:{zc}'] = FC.critPDFAnalytic_fc_LL(z, th, zc, jet)
+            out[f'{j}:critPDF_rc:{zc}'] = RC.critPDFAnalytic(z, th, zc, jet)
+            out[f'{j}:critRad_rc:{zc}'] = RC.critRadAnalytic(th, zc, jet)
+            out[f'{j}:critRadPrime_rc:{zc}'] = RC.critRadPrimeAnalytic(th, zc, jet)
+            out[f'{j}:critRad_fc:{zc}'] = FC.critRadAnalytic_fc_LL(th, zc, jet)
+            out[f'{j}:preWeight:{zc}'] = W.precriticalEmissionWeight(zpre, th, zc, jet)
+            out[f'{j}:preRad_fc:{zc}'] = FC.preRadAnalytic_fc_LL(zpre, th, zc, jet)
+        for beta in (2., 3., 1.5, 4.):
+            out[f'{j}:subRad_fc:{beta}'] = FC.subRadAnalytic_fc_LL(C, beta, jet)
+            out[f'{j}:subRadPrime_fc:{beta}'] = FC.subRadPrimeAnalytic_fc_LL(C, beta, jet)
+            out[f'{j}:subPDF_fc:{beta}'] = FC.subPDFAnalytic_fc_LL(C, beta, jet)
+            out[f'{j}:subPDF_fc_R:{beta}'] = FC.subPDFAnalytic_fc_LL(C, beta, jet, maxRadius=maxr)
+            out[f'{j}:subRad_rc:{beta}'] = RC.subRadAnalytic(C, beta, jet)
+            out[f'{j}:subRadPrime_rc:{beta}'] = RC.subRadPrimeAnalytic(C, beta, jet)
+            out[f'{j}:subPDF_rc:{beta}'] = RC.subPDFAnalytic(C, beta, jet)
+            out[f'{j}:subPDF_rc_R:{beta}'] = RC.subPDFAnalytic(C, beta, jet, maxRadius=maxr)
+            out[f'{j}:subRad_rc_R:{beta}'] = RC.subRadAnalytic(C, beta, jet, maxRadius=maxr)
+    for beta in (2., 3., 1.5):
+        for acc in ('LL', 'MLL'):
+            out[f'C_ungroomed:{beta}:{acc}'] = OBS.C_ungroomed(z, th, beta, acc)
+            zz = np.maximum(z, .1)
+            out[f'C_groomed:{beta}:{acc}'] = OBS.C_groomed(zz, th, .1, beta, acc=acc)
+            out[f'C_groomed_pre_f1:{beta}:{acc}'] = OBS.C_groomed(zz, th, .1, beta, z_pre=np.minimum(zpre, .1), f=1., acc=acc)
+            out[f'C_groomed_pre_f.3:{beta}:{acc}'] = OBS.C_groomed(zz, th, .1, beta, z_pre=np.minimum(zpre, .1), f=.3, acc=acc)
+            out[f'C_groomed_mmdt:{beta}:{acc}'] = OBS.C_groomed(zz, th, .1, beta, z_pre=.1, f=0., acc=acc)
+    save("functions", **out)
+
+
+# ------------------------------------------------------ config replays ----
+def run_sampler(s, n, case):
+    random.seed(SEED + case)
+    s.generateSamples(n)
+    return np.asarray(s.samples), np.asarray(s.jacobians, dtype=float), float(s.area)
+
+
+def config_c1():
+    """C1: ungroomed quark LL fixed coupling, log sampling, e_2^(2)."""
+    n = 2500
+    for case, (method, eps) in enumerate([('log', 1e-10), ('lin', 0.), ('log', 1e-3)]):
+        s = ungroomedSampler(method, epsilon=eps)
+        samples, jac, area = run_sampler(s, n, case)
+        z, th = samples[:, 0], samples[:, 1]
+        out = dict(seed=SEED + case, samples=samples, jac=jac, area=area, epsilon=eps)
+        for jet in ('quark', 'gluon'):
+            for fc, acc in ((True, 'LL'), (False, 'MLL')):
+                obs = OBS.C_ungroomed(z, th, 2., acc)
+                w = W.radiatorWeight(z, th, jet, fixedcoupling=fc, acc=acc)
+                it = integrator()
+                it.setLastBinBndCondition([0., 'plus'])
+                it.setBins(100, obs, 'log' if method == 'log' else 'lin')
+                it.setDensity(obs, w * jac, area)
+                it.integrate()
+                tag = f"{jet}_{'fc' if fc else 'rc'}_{acc}:"
+                out[tag + 'obs'] = obs
+                out[tag + 'weights'] = w
+                out[tag + 'midpoints'] = it.bin_midpoints
+                for k, v in integ_arrays(it).items():
+                    out[tag + k] = v
+        save(f"c1_{method}{case}", **out)
+
+
+def config_crit():
+    """Critical emission Sudakov (test_fixedcoupcritsudakov / running variant)."""
+    n = 2500
+    case = 10
+    for method, eps in (('log', 1e-10), ('lin', 0.)):
+        for zc in (.1, .05):
+            s = criticalSampler(method, zc=zc, epsilon=eps)
+            samples, jac, area = run_sampler(s, n, case)
+            z, th = samples[:, 0], samples[:, 1]
+            out = dict(seed=SEED + case, samples=samples, jac=jac, area=area,
+                       z_cut=zc, epsilon=eps)
+            for jet in ('quark', 'gluon'):
+                for fc in (True, False):
+                    for beta in (2., 3.):
+                        obs = OBS.C_groomed(z, th, zc, beta)
+                        w = W.criticalEmissionWeight(z, th, zc, jet, fixedcoupling=fc)
+                        wj = w * jac
+                        if not fc:
+                            wj = np.nan_to_num(wj)
+                        it = integrator()
+                        it.setLastBinBndCondition([1., 'minus'])
+                        it.setBins(100, obs, method)
+                        it.setDensity(obs, wj, area)
+                        it.integrate()
+                        tag = f"{jet}_{'fc' if fc else 'rc'}_b{beta:g}:"
+                        out[tag + 'obs'] = obs
+                        out[tag + 'weights'] = w
+                        for k, v in integ_arrays(it).items():
+                            out[tag + k] = v
+            save(f"crit_{method}_{zc}", **out)
+            case += 1
+
+
+def config_c3_c4():
+    """C3: Soft Drop (mMDT form) crit+sub, verbatim twoEmissionWeight; C4 adds
+    the pre-critical emission with the zero-bin logic."""
+    n = 4000
+    zc, beta, eps = .1, 2., 1e-10
+    case = 30
+    random.seed(SEED + case)
+    cs = criticalSampler('log', zc=zc, epsilon=eps)
+    cs.generateSamples(n)
+    ss = ungroomedSampler('log', epsilon=eps)
+    ss.generateSamples(n)
+    ps = precriticalSampler('log', zc=zc, epsilon=eps)
+    ps.generateSamples(n)
+    zero_bin_u = np.array([random.random() for _ in range(n)])
+    crit, sub, zpre = np.asarray(cs.samples), np.asarray(ss.samples), np.asarray(ps.samples)
+    jc, js, jp = (np.asarray(x.jacobians, dtype=float) for x in (cs, ss, ps))
+    edges = np.logspace(np.log10(eps) - 1, np.log10(.5), 100)
+    base = dict(seed=SEED + case, crit=crit, sub=sub, z_pre=zpre, jac_crit=jc,
+                jac_sub=js, jac_pre=jp, area_crit=cs.area, area_sub=ss.area,
+                area_pre=ps.area, zero_bin_u=zero_bin_u, edges_fixed=edges)
+    out3 = dict(base)
+    for jet in ('quark', 'gluon'):
+        for fc in (True, False):
+            tag = f"{jet}_{'fc' if fc else 'rc'}"
+            w = W.twoEmissionWeight(crit, sub, zc, beta, jet, fixedcoupling=fc)
+            csub = sub[:, 0] * sub[:, 1] ** beta * sub[:, 1] ** beta
+            for acc in ('LL', 'MLL'):
+                ccrit = OBS.C_groomed(crit[:, 0], crit[:, 1], zc, beta,
+                                      z_pre=zc, f=0., acc=acc)
+                obs = np.maximum(ccrit, csub)
+                wj = np.nan_to_num(w) * jc * js
+                it = integrator()
+                it.setLastBinBndCondition([1., 'minus'])
+                it.bins = edges
+                it.hasBins = True
+                it.setDensity(obs, wj, cs.area * ss.area)
+                it.integrate()
+                t = f"{tag}_{acc}:"
+                out3[t + 'obs'] = obs
+                out3[t + 'weights'] = w
+                out3['csub'] = csub
+                out3[f'c_crit:{acc}'] = ccrit
+                for k, v in integ_arrays(it).items():
+                    out3[t + k] = v
+    save("c3", **out3)
+    # C4 (fixed coupling only in the reference), all-emission integrand of
+    # examples/tests/comparison_tests/comparison_utils_probabilistic.py:384-474
+    for jet in ('quark', 'gluon'):
+        CRj = Q.CR(jet)
+        th_c = crit[:, 1]
+        zp = zpre.copy()
+        cdf_eps = np.exp(-2. * CRj * Q.alpha_fixed / np.pi * np.log(Q.R0 / th_c)
+                         * np.log(zc / eps))
+        zp[zero_bin_u < cdf_eps] = 0.
+        c_sub = sub[:, 0] * th_c ** beta
+        obs = np.maximum(OBS.C_groomed(crit[:, 0], th_c, zc, beta, z_pre=zp, f=1., acc='LL'), c_sub)
+        zero_w = np.exp(-2. * CRj * Q.alpha_fixed / np.pi * np.log(Q.R0 / th_c)
+                        * np.log(zc / eps)) * (zp == 0)
+        pw = np.nan_to_num(W.precriticalEmissionWeight(zp, th_c, zc, jet, True) * (zp > 0))
+        w = (W.criticalEmissionWeight(crit[:, 0], th_c, zc, jet, fixedcoupling=True)
+             * FC.subPDFAnalytic_fc_LL(c_sub / th_c ** beta, beta, jet_type=jet)
+             * (zero_w + pw))
+        jacs = np.where(zp == 0, jc * js, jc * jp * js)
+        area = cs.area * ps.area * ss.area
+        it = integrator()
+        it.setLastBinBndCondition([1., 'minus'])
+        it.setBins(100, obs, 'log')
+        it.setDensity(obs, w * jacs, area)
+        it.integrate()
+        save(f"c4_{jet}_fc", seed=SEED + case, z_pre_zb=zp, obs=obs, weights=w, jacs=jacs,
+             area=area, **integ_arrays(it))
+
+
+def config_c5():
+    """C5: sub radiator on a theta_crit grid (gen_crit_sub_num_rad loop body)."""
+    n = 3000
+    eps = 1e-10
+    case = 50
+    s = ungroomedSampler('log', epsilon=eps)
+    samples, jac, area = run_sampler(s, n, case)
+    grid = lin_log_mixed_list(eps, 1., 12)
+    for beta in (2., 3.):
+        for jet, fc, oacc, sacc in (('quark', True, 'LL', 'LL'), ('gluon', False, 'MLL', 'MLL')):
+            E, D, DE, I, IE = [], [], [], [], []
+            for thc in grid:
+                th_em = samples[:, 1] * thc
+                obs = OBS.C_ungroomed(samples[:, 0], th_em, beta, acc=oacc)
+                it = integrator()
+                it.setLastBinBndCondition([0., 'plus'])
+                it.setBins(40, obs, 'log', min_log_bin=thc ** beta * 1e-15)
+                w = W.radiatorWeight(samples[:, 0], th_em, jet, fixedcoupling=fc, acc=sacc)
+                it.setDensity(obs, w * (jac * thc), area)
+                it.integrate()
+                a = integ_arrays(it)
+                E.append(a['edges']); D.append(a['density']); DE.append(a['density_err'])
+                I.append(a['integral']); IE.append(a['integral_err'])
+            save(f"c5_{jet}_{'fc' if fc else 'rc'}_b{beta:g}", seed=SEED + case,
+                 samples=samples, jac=jac, area=area, grid=grid, epsilon=eps,
+                 edges=np.array(E), density=np.array(D), density_err=np.array(DE),
+                 integral=np.array(I), integral_err=np.array(IE))
+
+
+def simple_integrals():
+    """simpleSampler + integrate_1d known answers (test_simpleIntegrator.py)."""
+    case = 60
+    for method, eps in (('lin', 0.), ('log', 1e-8)):
+        s = simpleSampler(method, bounds=[0, 1], epsilon=eps)
+        samples, jac, area = run_sampler(s, 4000, case)
+        it = integrator()
+        it.setFirstBinBndCondition(0.)
+        it.setBins(50, samples, method)
+        w = 3. * samples ** 2.
+        it.setDensity(samples, w * jac, area)
+        it.integrate()
+        save(f"simple_{method}", seed=SEED + case, samples=samples, jac=jac, area=area,
+             weights=w, epsilon=eps, **integ_arrays(it))
+        case += 1
+    random.seed(SEED + case)
+    val, err, x = integrate_1d(lambda x: 2. * x, [.1, .5], bin_space='lin', num_samples=2000)
+    save("integrate_1d_lin", seed=SEED + case, value=val, error=err, x=x)
+    random.seed(SEED + case + 1)
+    integ, err, xs = integrate_1d(lambda x: 1. / x, [.1, .5], bin_space='log', epsilon=1e-6,
+                                  num_samples=2000, num_bins=20, bnd_cond=0, bnd_cond_bin='first')
+    save("integrate_1d_log", seed=SEED + case + 1, integral=np.asarray(integ, float),
+         error=np.asarray(err), xs=np.asarray(xs))
+
+
+def shower():
+    """Veto-algorithm shower chains (z, theta) and their ECFs."""
+    case = 70
+    for jet in ('quark', 'gluon'):
+        for acc in ('LL', 'MLL'):
+            random.seed(SEED + case)
+            njets = 400
+            jets = PS.gen_jets(njets, beta=2., jet_type=jet, radius=1., acc=acc,
+                               cutoff=Q.MU_NP, verbose=0)
+            n_uniform = None
+            chains_z, chains_t, lens = [], [], []
+            for jt in jets:
+                zs, ts = [], []
+                for m in jt.partons:
+                    if m.daughter1 is None or m.daughter2 is None:
+                        continue
+                    d1, d2 = m.daughter1, m.daughter2
+                    ts.append(PS.angle(d1.momentum, d2.momentum))
+                    zs.append(min(d1.momentum.mag() / m.momentum.mag(),
+                                  d2.momentum.mag() / m.momentum.mag()))
+                chains_z += zs
+                chains_t += ts
+                lens.append(len(zs))
+            out = dict(seed=SEED + case, lens=np.array(lens), z=np.array(chains_z),
+                       theta=np.array(chains_t))
+            for oacc in ('LL', 'MLL'):
+                for nem in (1, 2, 'all'):
+                    out[f'ungroomed:{oacc}:{nem}'] = np.array(
+                        PS.getECFs_ungroomed(jets, beta=2., obs_acc=oacc, n_emissions=nem))
+                for nem in (1, 'all'):
+                    out[f'softdrop:{oacc}:{nem}'] = np.array(
+                        PS.getECFs_softdrop(jets, .1, beta=2., beta_sd=0., obs_acc=oacc,
+                                            n_emissions=nem))
+                # n_emissions=2 evaluated one jet at a time so the in-place
+                # decrement at partonshower_utils.py:765 cannot leak across jets
+                out[f'softdrop:{oacc}:2'] = np.array(
+                    [PS.getECFs_softdrop([jt] * 5, .1, beta=2., beta_sd=0., obs_acc=oacc,
+                                         n_emissions=2)[0] for jt in jets])
+                out[f'softdrop_bsd1:{oacc}:1'] = np.array(
+                    PS.getECFs_softdrop(jets, .1, beta=2., beta_sd=1., obs_acc=oacc,
+                                        n_emissions=1))
+            save(f"shower_{jet}_{acc}", **out)
+            case += 1
+
+
+def misc():
+    save("lin_log_mixed", a=lin_log_mixed_list(1e-10, 1., 12), b=lin_log_mixed_list(1e-15, 1., 501))
+    rng = np.random.RandomState(7)
+    vals = np.exp(rng.uniform(np.log(1e-14), 0, 3000))
+    wts = rng.uniform(0, 2, 3000)
+    xs, pdf = vals_to_pdf(vals, 50, weights=wts, log_cutoff=1e-10)
+    save("vals_to_pdf", vals=vals, weights=wts, xs=xs, pdf=pdf)
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    kats()
+    function_vectors()
+    config_c1()
+    config_crit()
+    config_c3_c4()
+    config_c5()
+    simple_integrals()
+    shower()
+    misc()
