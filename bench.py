@@ -1,0 +1,382 @@
+#!/usr/bin/env python
+"""bench.py -- weighted phase-space samples/s of the fused hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--samples S] [--precision f32|f64]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...      # the reference's CPU algorithm on the host cores
+
+Workload (BASELINE.json configs[2], the one the metric is quoted on; it fits one
+GPU because samples are never stored): Soft Drop (z_cut=0.1, beta_SD=0 i.e. the
+mMDT form of C_groomed) critical x subsequent emission MLL ECF e_2^(2)
+distribution of quark jets, log sampling with epsilon=1e-10, the reference's
+verbatim running-coupling twoEmissionWeight with np.nan_to_num, 100 fixed
+logspace edges (sudakov_utils.py:533), boundary condition [1,'minus'].
+One step = one whole job: S samples per GPU -> (sum w, sum w^2, count) ->
+density +- error -> cdf +- error.  Weak scaling: S per GPU is fixed.
+
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "weighted phase-space samples/sec"
+UNIT = "samples/s"
+EPS, Z_CUT, BETA = 1e-10, .1, 2.
+N_EDGES = 100
+# SURVEY.md 8(d) contract figures, flop-equivalents and SFU ops per weighted sample
+FLOP_EQ = {"c3_rc": 390., "c3_fc": 230.}
+SFU_OPS = {"c3_rc": 28., "c3_fc": 14.}
+# work of a sample whose reference weight is NaN -> 0 (99.7 % of C3-rc samples): Philox
+# (100 int), 4 exp, observable, Landau predicate, log-bin, count  ("algorithmic work")
+FLOP_EQ_ZERO_WEIGHT, SFU_ZERO_WEIGHT = 150., 6.
+
+
+def edges_c3():
+    return np.logspace(np.log10(EPS) - 1, np.log10(.5), N_EDGES)
+
+
+def workload_config(args, world):
+    return {
+        "workload": "C3: Soft Drop (z_cut=0.1, beta_sd=0, mMDT C_groomed) critical x subsequent MLL ECF e2^(2), "
+                    "quark, running coupling verbatim twoEmissionWeight + nan_to_num, log sampling eps=1e-10",
+        "samples_per_gpu_per_step": int(args.samples), "global_samples_per_step": int(args.samples) * world,
+        "bins": N_EDGES - 1, "edges": "np.logspace(-11, log10(.5), 100)", "boundary_condition": "[1,'minus']",
+        "rng": "philox4x32-10, counter = global sample index", "sharding": "sample index ranges per rank, "
+        "one all-reduce of [sum w, sum w^2, count]" if world > 1 else "single GPU",
+        "l2": "256 MiB memset between timed steps; the path reads no per-sample HBM data "
+              "(inputs: 800 B of bin edges)",
+        "e2e_path": "jmc_integrate_host (C ABI, host buffers)" if world == 1 else
+                    "jetmontecarlo_b200.fused.integrate (host edges -> device, jmc_run, NCCL all-reduce, "
+                    "jmc_finalize/jmc_cumulative, results -> host)",
+    }
+
+
+# ---------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(gpu_index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 <= t <= t1 and len(r) >= 9] or [r for _, r in self.rows if len(r) >= 9]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = [float(r[1]) for r in rows]
+        reasons = set()
+        for r in rows:
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": float(rows[0][2]), "reasons": sorted(reasons),
+                "samples": len(rows), "power_w_max": max(float(r[3]) for r in rows)}
+
+
+# ---------------------------------------------------------------------------
+# CPU baseline: the reference's algorithm restated by the oracle
+# ---------------------------------------------------------------------------
+def _cpu_chunk(args):
+    """One process: the reference's path on `n` samples -- Python-loop sampling
+    (sampler.py:30-34), NumPy weights and np.histogram (oracle restatement)."""
+    n, seed, loop = args
+    from oracle import jmc_oracle as O
+    np.seterr(all='ignore')
+    t0 = time.perf_counter()
+    if loop:
+        crit, jc = O.sample_loop_critical('log', n, Z_CUT, EPS, seed)
+        sub, js = O.sample_loop_ungroomed('log', n, EPS, seed + 1)
+    else:
+        u = O.mt_uniforms(seed, 4 * n)
+        crit, jc, _ = O.sample_critical('log', u[:2 * n].reshape(n, 2), Z_CUT, EPS)
+        sub, js, _ = O.sample_ungroomed('log', u[2 * n:].reshape(n, 2), EPS)
+    csub = sub[:, 0] * sub[:, 1] ** BETA * sub[:, 1] ** BETA
+    obs = np.maximum(O.ecf_groomed(crit[:, 0], crit[:, 1], Z_CUT, BETA, z_pre=Z_CUT, f=0., acc='MLL'), csub)
+    w = np.nan_to_num(O.weight_two_emission(crit, sub, Z_CUT, BETA, 'quark', False)) * jc * js
+    h, h2, c = O.histograms(obs, w, edges_c3())
+    return h, h2, c, time.perf_counter() - t0
+
+
+def cpu_reference_step(n_per_proc, procs, seed, loop, pool):
+    t0 = time.perf_counter()
+    parts = pool.map(_cpu_chunk, [(n_per_proc, seed + 7919 * i, loop) for i in range(procs)])
+    from oracle import jmc_oracle as O
+    h = sum(p[0] for p in parts)
+    h2 = sum(p[1] for p in parts)
+    c = sum(p[2] for p in parts)
+    area = np.log(1. / EPS) ** 4.
+    dens, err = O.density_from_hist(h, h2, c, edges_c3(), area, n_per_proc * procs)
+    O.cumulative(dens, err, edges_c3(), last_bc=[1., 'minus'])
+    return time.perf_counter() - t0
+
+
+def run_reference_arm(args):
+    """bench.py --impl reference: the reference's own CPU algorithm (oracle port;
+    the Python reference itself cannot travel to the GPU box) on all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    n_per_proc = int(args.cpu_samples) if args.cpu_samples else 12000
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        for w in range(args.warmup):
+            cpu_reference_step(n_per_proc, cores, 100 + w, True, pool)
+        times = [cpu_reference_step(n_per_proc, cores, 1000 + k, True, pool) for k in range(args.steps)]
+        vec_n = n_per_proc * 20
+        vec_t = cpu_reference_step(vec_n, cores, 5000, False, pool)
+    total = n_per_proc * cores
+    value = total * args.steps / sum(times)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": dict(workload_config(args, 1), samples_per_step=total),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "%d samples per step (%d per process x %d processes); Python-loop sampling as "
+                                   "sampler.py:30-34 + NumPy weights + np.histogram, fanned over all cores "
+                                   "(the reference itself is single-threaded)" % (total, n_per_proc, cores),
+                         "vectorised_port_value": vec_n * cores / vec_t,
+                         "vectorised_port_note": "same path with NumPy-vectorised sampling (not what the reference "
+                                                 "does; an upper bound for a NumPy implementation), all cores"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def cpu_baseline_quick():
+    """single-thread port of the reference path on a bounded sample (~10-20 s)"""
+    n = 150000
+    _, _, _, t_loop = _cpu_chunk((n, 42, True))
+    nv = 2000000
+    _, _, _, t_vec = _cpu_chunk((nv, 43, False))
+    return {"value": n / t_loop, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": "%d C3 samples, single thread: Python-loop sampling (sampler.py:30-34 restated) + NumPy "
+                      "weights + np.histogram; host has %d cores" % (n, os.cpu_count() or 1),
+            "vectorised_port_value": nv / t_vec,
+            "vectorised_port_note": "%d samples with NumPy-vectorised sampling instead of the reference's loop, "
+                                    "1 thread" % nv}
+
+
+# ---------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--samples", type=float, default=1e9, help="samples per GPU per step")
+    ap.add_argument("--precision", default="f32", choices=["f32", "f64"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-samples", type=float, default=0, help="reference arm: samples per process per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--variant", default="c3_rc", choices=["c3_rc", "c3_fc"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    from jetmontecarlo_b200 import _device as D
+    from jetmontecarlo_b200 import _lib, fused
+    from jetmontecarlo_b200.fused import Integrand
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node = --gpus"
+
+    n = int(args.samples)
+    ig = Integrand.crit_sub('log', Z_CUT, EPS, beta=BETA, jet_type='quark', fixedcoupling=(args.variant == "c3_fc"),
+                            obs_acc='MLL')
+    s = ig.c_struct()
+    h_edges = edges_c3()
+    edges = D.to_device(h_edges)
+    nb = N_EDGES - 1
+    prec = fused.PRECISIONS[args.precision]
+    sum_w, sum_w2 = D.zeros((nb,)), D.zeros((nb,))
+    count = D.zeros((nb,), dtype=torch.int64)
+    dens, derr, integ, ierr = D.empty((nb,)), D.empty((nb,)), D.empty((nb + 1,)), D.empty((nb,))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    packed = torch.empty((3, nb), dtype=torch.float64, device="cuda")
+
+    def step(k):
+        """one whole job on this rank's shard; returns nothing, all on torch's current stream"""
+        sum_w.zero_(); sum_w2.zero_(); count.zero_()
+        first = (k * world + rank) * n        # every step and rank draws fresh sample indices
+        _lib.check(_lib.lib.jmc_run(C.byref(s), n, 20260101, first, prec, D.ptr(edges), N_EDGES, D.ptr(sum_w),
+                                    D.ptr(sum_w2), D.ptr(count), None, D.stream()))
+        if world > 1:
+            torch.stack([sum_w, sum_w2, count.to(torch.float64)], out=packed)
+            dist.all_reduce(packed)
+            sum_w.copy_(packed[0]); sum_w2.copy_(packed[1]); count.copy_(packed[2].to(torch.int64))
+        _lib.check(_lib.lib.jmc_finalize(D.ptr(sum_w), D.ptr(sum_w2), D.ptr(count), D.ptr(edges), N_EDGES,
+                                         float(ig.area), n * world, _lib.BC_LAST_MINUS, 1., D.ptr(dens), D.ptr(derr),
+                                         D.ptr(integ), D.ptr(ierr), D.stream()))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for k in range(args.warmup):
+        step(k)
+    barrier()
+
+    # ---- device-timed region: K steps, CUDA events per step, L2 flushed in between
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = _lib.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+          for _ in range(args.steps)]
+    barrier()
+    t_wall0 = time.perf_counter()
+    for k in range(args.steps):
+        flush.zero_()
+        ev[k][0].record()
+        sum_w.zero_(); sum_w2.zero_(); count.zero_()
+        first = ((args.warmup + k) * world + rank) * n
+        _lib.check(_lib.lib.jmc_run(C.byref(s), n, 20260101, first, prec, D.ptr(edges), N_EDGES, D.ptr(sum_w),
+                                    D.ptr(sum_w2), D.ptr(count), None, D.stream()))
+        ev[k][1].record()
+        if world > 1:
+            torch.stack([sum_w, sum_w2, count.to(torch.float64)], out=packed)
+            dist.all_reduce(packed)
+            sum_w.copy_(packed[0]); sum_w2.copy_(packed[1]); count.copy_(packed[2].to(torch.int64))
+        _lib.check(_lib.lib.jmc_finalize(D.ptr(sum_w), D.ptr(sum_w2), D.ptr(count), D.ptr(edges), N_EDGES,
+                                         float(ig.area), n * world, _lib.BC_LAST_MINUS, 1., D.ptr(dens), D.ptr(derr),
+                                         D.ptr(integ), D.ptr(ierr), D.stream()))
+        ev[k][2].record()
+    barrier()
+    t_wall1 = time.perf_counter()
+    launches = _lib.launch_count() - launches0
+    step_ms = [a.elapsed_time(c) for a, _, c in ev]
+    kern_ms = [a.elapsed_time(b) for a, b, _ in ev]
+    t_rank = torch.tensor([sum(step_ms), sum(kern_ms)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_rank, op=dist.ReduceOp.MAX)
+    total_ms, total_kern_ms = t_rank.tolist()
+    clock_info = clocks.stop(t_wall0, t_wall1) if clocks else None
+    value = n * world * args.steps / (total_ms * 1e-3)
+    cdf0 = float(integ[0].item())
+
+    # ---- end to end through the public API with host buffers
+    barrier()
+    e2e_steps = args.steps
+    nbytes_in = h_edges.nbytes
+    nbytes_out = 8 * (4 * nb + 1) + 8 * 3 * nb
+    if world == 1:
+        hd, hde, hi, hie = (np.empty(nb), np.empty(nb), np.empty(nb + 1), np.empty(nb))
+        hsw, hsw2, hc = np.empty(nb), np.empty(nb), np.empty(nb, dtype=np.uint64)
+        P = lambda a: a.ctypes.data_as(C.c_void_p)
+
+        def e2e_step(k):
+            _lib.check(_lib.lib.jmc_integrate_host(C.byref(s), n, 20260101, (1000 + k) * n, prec, P(h_edges), N_EDGES,
+                                                   _lib.BC_LAST_MINUS, 1., P(hd), P(hde), P(hi), P(hie), P(hsw),
+                                                   P(hsw2), P(hc)))
+            return hi[0]
+    else:
+        pinned = torch.from_numpy(h_edges).pin_memory()
+
+        def e2e_step(k):
+            it = fused.integrate(ig, n * world, edges=pinned.numpy(), seed=20260101 + 1000 + k,
+                                 precision=args.precision, last_bc=[1., 'minus'])
+            return it.integral[0]
+        nbytes_out = 8 * (2 * nb) + 8 * (2 * nb + 1)
+        nbytes_in = h_edges.nbytes * 2 + 8 * 2 * nb
+    e2e_step(-1)
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(e2e_steps):
+        e2e_step(k)
+    torch.cuda.synchronize()
+    t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e_value = n * world * e2e_steps / t_e2e.item()
+
+    if rank == 0:
+        kern_s = total_kern_ms * 1e-3 / args.steps
+        per_gpu_rate = n / kern_s
+        sm_mhz = (clock_info or {}).get("sm_mhz") or 1965.
+        sm_count = _lib.lib.jmc_sm_count()
+        fp32_peak = 2 * 128 * sm_count * sm_mhz * 1e6 / 1e12       # TFLOP/s at the clock this kernel sustained
+        sfu_peak = 16 * sm_count * sm_mhz * 1e6                     # ops/s
+        if args.variant == "c3_rc":
+            active = 0.003       # measured share of non-NaN weights (SURVEY 8d caveat; tests check it)
+            flop_eq = active * FLOP_EQ["c3_rc"] + (1 - active) * FLOP_EQ_ZERO_WEIGHT
+            sfu = active * SFU_OPS["c3_rc"] + (1 - active) * SFU_ZERO_WEIGHT
+        else:
+            flop_eq, sfu = FLOP_EQ["c3_fc"], SFU_OPS["c3_fc"]
+        achieved = per_gpu_rate * flop_eq / 1e12
+        roofline = {
+            "bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
+            "traffic": None,
+            "kernel": "run_fast_kernel" if args.precision == "f32" else "run_exact_kernel",
+            "kernel_ms_per_launch": kern_s * 1e3, "flop_eq_per_sample": flop_eq, "sfu_per_sample": sfu,
+            "sfu_frac": per_gpu_rate * sfu / sfu_peak,
+            "achieved_contract_figure": per_gpu_rate * FLOP_EQ[args.variant] / 1e12,
+            "peak_source": "2 x 128 FP32 lanes x %d SMs x %.0f MHz (clock sampled during the timed region); "
+                           "MEASURED_PEAKS.json has no FP32/SFU figure, its HBM peak does not bound a kernel "
+                           "with ~0 B/sample of DRAM traffic" % (sm_count, sm_mhz),
+        }
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+            "config": dict(workload_config(args, world), variant=args.variant, cdf_first_bin=cdf0),
+            "clocks": clock_info,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(nbytes_in),
+                    "d2h_bytes_per_step": int(nbytes_out)},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_quick()
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,289 @@
+/* jmc_b200.h -- C ABI of libjmc_b200.so: the B200 (sm_100a) implementation of the
+ * JetMonteCarlo Monte Carlo integration hot path
+ *
+ *     sample emission phase space -> jacobian x weight -> weighted histogram
+ *     -> density +- error -> cumulative integral +- error.
+ *
+ * The reference (samcaf/JetMonteCarlo) is pure Python/NumPy and has NO FFI or
+ * plugin layer on this path; every entry point below therefore cites the Python
+ * interface it replaces (paths relative to the reference's jetmontecarlo/
+ * package) and INTEGRATION.md shows the ctypes binding a maintainer would add.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no C++/torch types cross this boundary;
+ *  - pointers named d_* are DEVICE pointers owned by the caller, h_* are HOST
+ *    pointers; `stream` is a cudaStream_t passed as void* (NULL = legacy
+ *    default stream).  Device entry points are asynchronous on `stream`;
+ *    host entry points (suffix _host) synchronise before returning;
+ *  - every function returns 0 on success or a negative JMC_E* code; the
+ *    message of the last failure on the calling thread is jmc_last_error();
+ *  - histogram outputs ACCUMULATE (+=) into the caller's buffers so that a job
+ *    can be split over several launches; the caller zeroes them first.
+ *  - all arithmetic of the replay path is IEEE FP64 in NumPy operation order.
+ */
+#ifndef JMC_B200_H
+#define JMC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JMC_ABI_VERSION 1
+
+/* error codes */
+#define JMC_OK 0
+#define JMC_EINVAL (-1)   /* bad argument (message says which)            */
+#define JMC_ECUDA (-2)    /* CUDA runtime error (message has the string)  */
+#define JMC_ENODEV (-3)   /* no usable sm_100 device                      */
+#define JMC_ELIMIT (-4)   /* size beyond a documented limit               */
+#define JMC_EDOMAIN (-5)  /* reference would raise (e.g. veto prob > 1)   */
+
+/* enums (kept as int32 in the structs) */
+enum { JMC_LIN = 0, JMC_LOG = 1 };                         /* sampleMethod 'lin' / 'log'        */
+enum { JMC_QUARK = 0, JMC_GLUON = 1 };                     /* jet_type                          */
+enum { JMC_ACC_LL = 0, JMC_ACC_LL_NONSING = 1, JMC_ACC_MLL = 2 };
+enum { JMC_BC_FIRST = 0, JMC_BC_LAST_PLUS = 1, JMC_BC_LAST_MINUS = 2 };
+enum { JMC_F64 = 0, JMC_F32 = 1 };                         /* arithmetic of the fused path      */
+
+/* Samplers.  ref: montecarlo/sampler.py:114-140 (simple),
+ * numerics/radiators/samplers.py:23-119 (critical), :125-180 (precritical),
+ * :189-302 (ungroomed). */
+enum { JMC_SAMPLER_SIMPLE = 0, JMC_SAMPLER_CRITICAL = 1,
+       JMC_SAMPLER_PRECRITICAL = 2, JMC_SAMPLER_UNGROOMED = 3 };
+
+typedef struct jmc_sampler {
+    int32_t kind;        /* JMC_SAMPLER_*                                  */
+    int32_t method;      /* JMC_LIN / JMC_LOG                              */
+    double  epsilon;     /* log-sampling cutoff                            */
+    double  zc;          /* critical / precritical: z_cut                  */
+    double  radius;      /* critical / ungroomed: jet radius               */
+    double  lo, hi;      /* simple: bounds                                 */
+} jmc_sampler;
+
+/* Array functions of the replay path (jmc_eval_fn).  Arguments a0..a3 are
+ * per-sample arrays (stride in doubles) or NULL = use the scalar in
+ * jmc_fn_params.  ref lines are in the table of DESIGN.md and next to each
+ * device function in csrc/jmc_physics.cuh. */
+enum {
+    JMC_FN_ALPHA_S = 0,          /* a0=z a1=theta            qcd_utils.py:115-119              */
+    JMC_FN_SPLITTING = 1,        /* a0=z                     qcd_utils.py:160-190              */
+    JMC_FN_RADIATOR_WEIGHT = 2,  /* a0=z a1=theta            numerics/weights.py:15-26         */
+    JMC_FN_CRIT_PDF_FC = 3,      /* a0=z a1=theta            radiators/fixedcoupling.py:59-72  */
+    JMC_FN_CRIT_RAD_FC = 4,      /* a0=theta                 radiators/fixedcoupling.py:7-19   */
+    JMC_FN_SUB_RAD_FC = 5,       /* a0=C [a1=maxRadius]      radiators/fixedcoupling.py:77-90  */
+    JMC_FN_SUB_RADPRIME_FC = 6,  /* a0=C [a1=maxRadius]      radiators/fixedcoupling.py:92-108 */
+    JMC_FN_SUB_PDF_FC = 7,       /* a0=C [a1=maxRadius]      radiators/fixedcoupling.py:162-176*/
+    JMC_FN_PRE_RAD_FC = 8,       /* a0=z_pre a1=theta_crit a2=maxRadius  radiators/fixedcoupling.py:181-192*/
+    JMC_FN_CRIT_RAD_RC = 9,      /* a0=theta                 radiators/running_coupling.py:263-289 */
+    JMC_FN_CRIT_RADPRIME_RC = 10,/* a0=theta                 radiators/running_coupling.py:326-347 */
+    JMC_FN_CRIT_PDF_RC = 11,     /* a0=z a1=theta            radiators/running_coupling.py:386-404 */
+    JMC_FN_SUB_RAD_RC = 12,      /* a0=C [a1=maxRadius]      radiators/running_coupling.py:119-148 */
+    JMC_FN_SUB_RADPRIME_RC = 13, /* a0=C [a1=maxRadius]      radiators/running_coupling.py:350-380 */
+    JMC_FN_SUB_PDF_RC = 14,      /* a0=C [a1=maxRadius]      radiators/running_coupling.py:409-422 */
+    JMC_FN_PRE_WEIGHT = 15,      /* a0=z_pre a1=theta_crit   numerics/weights.py:43-58         */
+    JMC_FN_C_GROOMED = 16,       /* a0=z a1=theta [a2=z_pre] [a3=f]  numerics/observables.py:15-79 */
+    JMC_FN_C_UNGROOMED = 17,     /* a0=z a1=theta            numerics/observables.py:82-109    */
+    JMC_FN_TWO_EMISSION = 18,    /* a0=z_c a1=th_c a2=z_s a3=th_s    numerics/weights.py:63-99 */
+    JMC_FN_PRE_WEIGHT_ZEROBIN = 19, /* a0=z_pre a1=theta_crit  examples/tests/comparison_tests/
+                                       comparison_utils_probabilistic.py:82-98 */
+    JMC_FN_COUNT = 20
+};
+
+typedef struct jmc_fn_params {
+    int32_t jet;             /* JMC_QUARK / JMC_GLUON                          */
+    int32_t acc;             /* JMC_ACC_* (splitting / observable accuracy)    */
+    int32_t fixed_coupling;  /* 1 = alpha_fixed, 0 = running                   */
+    int32_t reserved;
+    double  z_cut;           /* z_c / z_cut                                    */
+    double  beta;            /* angular exponent                               */
+    double  max_radius;      /* maxRadius scalar (when a1 == NULL)             */
+    double  z_pre;           /* C_groomed: scalar z_pre (when a2 == NULL)      */
+    double  f_soft;          /* C_groomed: scalar f (when a3 == NULL)          */
+    double  epsilon;         /* zero-bin weight cutoff                         */
+    double  s0, s1, s2, s3;  /* scalar stand-ins for NULL a0..a3               */
+} jmc_fn_params;
+
+/* Integrands = (samplers, observable, weight) combinations of the hot path. */
+enum {
+    /* ungroomedSampler; obs C_ungroomed(z, theta*theta_scale, beta, obs_acc);
+     * w = radiatorWeight(z, theta*theta_scale, jet, fc, split_acc) * jac
+     *     [* theta_scale for log sampling].
+     * ref: examples/tests/radiator_tests/test_runningcoupsubradiators.py:125-201,
+     *      numerics/radiators/generation.py:303-335 (theta_scale = theta_crit). */
+    JMC_KIND_RADIATOR = 0,
+    /* criticalSampler; obs C_groomed(z, theta, z_cut, beta, z_pre, f, obs_acc);
+     * w = criticalEmissionWeight * jac.
+     * ref: examples/tests/oneEmission_tests/test_fixedcoupcritsudakov.py:124-220. */
+    JMC_KIND_CRIT = 1,
+    /* criticalSampler x ungroomedSampler; csub = z_s th_s^b th_s^b;
+     * obs = max(C_groomed(z_c, th_c, z_cut, beta, z_pre, f, obs_acc), csub);
+     * w = twoEmissionWeight * jac_c * jac_s.
+     * ref: numerics/weights.py:63-99,
+     *      examples/sudakov_comparisons/sudakov_utils.py:481-486,525-538. */
+    JMC_KIND_CRIT_SUB = 2,
+    /* critical x ungroomed x precritical with the zero-bin draw (fc only).
+     * ref: examples/tests/comparison_tests/comparison_utils_probabilistic.py:384-474. */
+    JMC_KIND_PRE_CRIT_SUB = 3,
+    /* simpleSampler; obs = sample; w = jac (the caller's weight function runs
+     * on the host).  ref: montecarlo/integrator.py:390-457. */
+    JMC_KIND_SIMPLE = 4,
+    /* Angularity shower with the MLL veto algorithm; one "sample" = one jet,
+     * weight 1.  obs = ungroomed or Soft Drop ECF of the emission chain.
+     * ref: utils/partonshower_utils.py:130-328, 445-499, 676-790. */
+    JMC_KIND_SHOWER = 5,
+    JMC_KIND_COUNT = 6
+};
+
+typedef struct jmc_integrand {
+    int32_t kind;            /* JMC_KIND_*                                     */
+    int32_t method;          /* JMC_LIN / JMC_LOG (all samplers of the kind)   */
+    int32_t jet;             /* JMC_QUARK / JMC_GLUON                          */
+    int32_t fixed_coupling;  /* 1 / 0                                          */
+    int32_t obs_acc;         /* JMC_ACC_LL / JMC_ACC_MLL                       */
+    int32_t split_acc;       /* JMC_ACC_* (radiatorWeight; shower: LL or MLL)  */
+    int32_t nan_to_num;      /* 1: weights pass through np.nan_to_num          */
+    int32_t shower_groomer;  /* SHOWER: 0 ungroomed, 1 Soft Drop               */
+    int32_t shower_n_emissions; /* SHOWER: 1, 2, ... or 0 = 'all'              */
+    int32_t reserved;
+    double  epsilon;         /* log-sampling cutoff                            */
+    double  z_cut;           /* grooming parameter                             */
+    double  radius;          /* jet radius                                     */
+    double  beta;            /* angular exponent                               */
+    double  f_soft;          /* C_groomed f                                    */
+    double  z_pre;           /* C_groomed scalar z_pre (kinds without a pre sampler) */
+    double  theta_scale;     /* RADIATOR: theta_crit rescaling (1 = none)      */
+    double  lo, hi;          /* SIMPLE: bounds                                 */
+    double  beta_sd;         /* SHOWER: Soft Drop angular exponent             */
+    double  shower_cutoff;   /* SHOWER: continue while z*theta > cutoff        */
+} jmc_integrand;
+
+/* ---- library ---------------------------------------------------------- */
+int         jmc_abi_version(void);
+const char* jmc_last_error(void);
+/* Number of CUDA devices visible; selects `device` for the calling thread. */
+int         jmc_device_count(void);
+int         jmc_set_device(int device);
+/* 148 on B200; used to size persistent grids. */
+int         jmc_sm_count(void);
+/* phase-space area of a sampler (setArea).  ref: samplers.py:30-36,132-138,196-202;
+ * sampler.py:118-122 */
+int         jmc_sampler_area(const jmc_sampler* s, double* area);
+/* number of uniforms one sample of the integrand consumes */
+int         jmc_integrand_uniforms(const jmc_integrand* g);
+/* product of the sampler areas of the integrand */
+int         jmc_integrand_area(const jmc_integrand* g, double* area);
+
+/* ---- sampling on request (replaces sampler.generateSamples,
+ *      montecarlo/sampler.py:30-34 + the addSample of each sampler) -------- */
+/* d_samples: [n] (1-D samplers) or [n,2] row-major (z, theta); d_jac: [n].
+ * Sample i uses Philox-4x32-10 counter (first_index+i, slot), key = seed. */
+int jmc_sample(const jmc_sampler* s, uint64_t n, uint64_t seed, uint64_t first_index,
+               double* d_samples, double* d_jac, void* stream);
+/* raw 53-bit uniforms [n, n_uniform] of the same stream (tests, zero-bin draw) */
+int jmc_uniforms(uint64_t n, uint64_t seed, uint64_t first_index, int n_uniform,
+                 double* d_out, void* stream);
+
+/* ---- replay path: arrays in, arrays out -------------------------------- */
+int jmc_eval_fn(int fn, const jmc_fn_params* p, uint64_t n,
+                const double* d_a0, int64_t stride0, const double* d_a1, int64_t stride1,
+                const double* d_a2, int64_t stride2, const double* d_a3, int64_t stride3,
+                double* d_out, void* stream);
+
+/* Whole-integrand replay on given samples: jac, obs, weight (= pdf weight *
+ * jac, nan_to_num applied if set) and bin index (-1 = dropped) per sample.
+ * d_crit/d_sub: [n,2]; d_pre: [n]; d_zb_u: [n] zero-bin uniforms; unused ones
+ * NULL.  For RADIATOR/SIMPLE the samples go in d_sub / d_pre respectively.
+ * Any output may be NULL.  d_edges may be NULL when d_bin is NULL. */
+int jmc_eval_integrand(const jmc_integrand* g, uint64_t n,
+                       const double* d_crit, const double* d_sub, const double* d_pre,
+                       const double* d_zb_u, const double* d_edges, int n_edges,
+                       double* d_jac, double* d_obs, double* d_weight, int32_t* d_bin,
+                       void* stream);
+
+/* np.histogram(obs, edges) bin index per sample (-1 dropped).
+ * ref: numpy.histogram as called at montecarlo/integrator.py:97-101 */
+int jmc_bin_index(const double* d_obs, uint64_t n, const double* d_edges, int n_edges,
+                  int32_t* d_bin, void* stream);
+
+/* The three histograms of integrator.setDensity (montecarlo/integrator.py:97-101):
+ * sum w, sum w^2, count per bin; n_edges-1 bins.  NaN weights poison their bin
+ * and every higher bin, as NumPy's cumsum-based weighted histogram does.
+ * d_weights may be NULL (count only). */
+int jmc_hist(const double* d_obs, const double* d_weights, uint64_t n,
+             const double* d_edges, int n_edges,
+             double* d_sum_w, double* d_sum_w2, uint64_t* d_count, void* stream);
+
+/* min / max of an array with NumPy NaN propagation -> d_minmax[0..1]
+ * (integrator.setBins, montecarlo/integrator.py:42-46) */
+int jmc_minmax(const double* d_x, uint64_t n, double* d_minmax, void* stream);
+
+/* ---- fused path: generate -> weight -> bin, nothing per-sample in HBM ---- */
+/* Samples first_index .. first_index+n-1 of stream `seed`.  Histograms
+ * accumulate into d_sum_w / d_sum_w2 / d_count (n_edges-1 each).  If d_minmax
+ * is not NULL, min and max of the observable are also merged into
+ * d_minmax[0..1] (caller initialises to +inf, -inf); d_edges may then be NULL
+ * for a min/max-only pass (data-dependent bins, integrator.setBins).
+ * precision: JMC_F64 = NumPy-order FP64 (checkable sample by sample against
+ * the oracle), JMC_F32 = log-space FP32 fast path (statistical parity). */
+int jmc_run(const jmc_integrand* g, uint64_t n, uint64_t seed, uint64_t first_index,
+            int precision, const double* d_edges, int n_edges,
+            double* d_sum_w, double* d_sum_w2, uint64_t* d_count, double* d_minmax,
+            void* stream);
+
+/* density, error, cumulative integral (+ error) from the histograms.
+ * ref: montecarlo/integrator.py:113-124 (density), :129-202 (integrate).
+ * density, density_err, integral_err: n_edges-1; integral: n_edges. */
+int jmc_finalize(const double* d_sum_w, const double* d_sum_w2, const uint64_t* d_count,
+                 const double* d_edges, int n_edges, double area, uint64_t n_total,
+                 int bc_kind, double bc_value,
+                 double* d_density, double* d_density_err,
+                 double* d_integral, double* d_integral_err, void* stream);
+/* d_integral / d_integral_err may both be NULL: density only (setDensity). */
+
+/* integrator.integrate() alone: cumulative integral of a given density.
+ * ref: montecarlo/integrator.py:129-202 */
+int jmc_cumulative(const double* d_density, const double* d_density_err, const double* d_edges,
+                   int n_edges, int bc_kind, double bc_value,
+                   double* d_integral, double* d_integral_err, void* stream);
+
+/* ---- host-buffer entry points (what a reference-side binding calls) ------ */
+/* integrator.setDensity + integrate on host arrays: copies obs/weights to the
+ * device, runs jmc_hist + jmc_finalize, copies the results back.  Any of the
+ * h_sum_w / h_sum_w2 / h_count outputs may be NULL. */
+int jmc_set_density_host(const double* h_obs, const double* h_weights, uint64_t n,
+                         const double* h_edges, int n_edges, double area,
+                         int bc_kind, double bc_value,
+                         double* h_density, double* h_density_err,
+                         double* h_integral, double* h_integral_err,
+                         double* h_sum_w, double* h_sum_w2, uint64_t* h_count);
+
+/* Whole job from a description: fused run of n samples + finalize.  n_total
+ * is the normalisation count (= n on one GPU).  h_edges is read, everything
+ * else is written. */
+int jmc_integrate_host(const jmc_integrand* g, uint64_t n, uint64_t seed, uint64_t first_index,
+                       int precision, const double* h_edges, int n_edges,
+                       int bc_kind, double bc_value,
+                       double* h_density, double* h_density_err,
+                       double* h_integral, double* h_integral_err,
+                       double* h_sum_w, double* h_sum_w2, uint64_t* h_count);
+
+/* sampler.generateSamples into host arrays */
+int jmc_sample_host(const jmc_sampler* s, uint64_t n, uint64_t seed, uint64_t first_index,
+                    double* h_samples, double* h_jac);
+
+/* array function on host arrays (same argument rules as jmc_eval_fn) */
+int jmc_eval_fn_host(int fn, const jmc_fn_params* p, uint64_t n,
+                     const double* h_a0, int64_t stride0, const double* h_a1, int64_t stride1,
+                     const double* h_a2, int64_t stride2, const double* h_a3, int64_t stride3,
+                     double* h_out);
+
+/* number of kernels this library has launched on the calling process so far
+ * (bench.py reports the difference over the timed region as gpu_launches) */
+uint64_t jmc_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JMC_B200_H */

@@ -1,0 +1,89 @@
+"""Build libjmc_b200.so (sm_100a only) in-tree with nvcc.
+
+    python jetmontecarlo_b200/csrc/build.py [--force] [--verbose]
+
+Each translation unit has its own floating-point contract:
+  jmc_exact.cu   --fmad=false   FP64 in NumPy operation order (replay parity, bit-exact bins)
+  jmc_fast.cu    FMA + fast intrinsics: the FP32 log-space throughput path
+  jmc_shower.cu  --fmad=false   veto-algorithm shower (FP64 chain, checkable against the oracle)
+  jmc_host.cu    host plumbing and the host-buffer entry points
+The objects are linked into jetmontecarlo_b200/lib/libjmc_b200.so, which
+travels to the GPU box with the repository snapshot (it is git-ignored).
+"""
+import hashlib
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.dirname(HERE)
+ROOT = os.path.dirname(PKG)
+LIB_DIR = os.path.join(PKG, "lib")
+OBJ_DIR = os.path.join(HERE, "build")
+LIB = os.path.join(LIB_DIR, "libjmc_b200.so")
+
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
+          "-I", os.path.join(ROOT, "include")]
+UNITS = {
+    "jmc_exact.cu": ["--fmad=false"],
+    "jmc_shower.cu": ["--fmad=false"],
+    "jmc_fast.cu": ["--fmad=true"],
+    "jmc_host.cu": [],
+}
+
+
+def _nvcc():
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if cand and (os.path.isabs(cand) and os.path.exists(cand) or not os.path.isabs(cand)):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def _digest():
+    h = hashlib.sha256()
+    names = sorted(f for f in os.listdir(HERE) if f.endswith((".cu", ".cuh", ".py")))
+    for name in names + [os.path.join(ROOT, "include", "jmc_b200.h")]:
+        with open(os.path.join(HERE, name) if not os.path.isabs(name) else name, "rb") as f:
+            h.update(name.encode())
+            h.update(f.read())
+    return h.hexdigest()
+
+
+def build(force=False, verbose=False):
+    """Compile if sources changed; returns the path of the shared library."""
+    os.makedirs(LIB_DIR, exist_ok=True)
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    stamp = os.path.join(LIB_DIR, "libjmc_b200.stamp")
+    digest = _digest()
+    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read().strip() == digest:
+        return LIB
+    nvcc = _nvcc()
+    units = {u: f for u, f in UNITS.items() if os.path.exists(os.path.join(HERE, u))}
+
+    def compile_one(item):
+        unit, flags = item
+        obj = os.path.join(OBJ_DIR, unit.replace(".cu", ".o"))
+        cmd = [nvcc, *ARCH, *COMMON, *flags, *(["-Xptxas", "-v"] if verbose else []),
+               "-c", os.path.join(HERE, unit), "-o", obj]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (unit, res.stdout, res.stderr))
+        if verbose:
+            print(res.stderr)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=len(units)) as pool:
+        objs = list(pool.map(compile_one, units.items()))
+    cmd = [nvcc, *ARCH, "-shared", "-o", LIB, *objs]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("link failed:\n%s\n%s" % (res.stdout, res.stderr))
+    with open(stamp, "w") as f:
+        f.write(digest)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

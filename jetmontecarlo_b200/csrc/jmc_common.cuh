@@ -1,0 +1,58 @@
+// Host-side plumbing shared by the translation units of libjmc_b200.so:
+// error strings, launch accounting, per-device scratch, launch geometry.
+#pragma once
+#include <cuda_runtime.h>
+#include <atomic>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include "../../include/jmc_b200.h"
+
+namespace jmc {
+
+int set_error(int code, const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+void count_launch();
+
+#define JMC_CUDA(call)                                         \
+    do {                                                       \
+        cudaError_t _e = (call);                               \
+        if (_e != cudaSuccess) return ::jmc::cuda_fail(_e, #call); \
+    } while (0)
+
+#define JMC_REQUIRE(cond, ...)                                 \
+    do {                                                       \
+        if (!(cond)) return ::jmc::set_error(JMC_EINVAL, __VA_ARGS__); \
+    } while (0)
+
+// after a kernel launch
+#define JMC_LAUNCHED(name)                                     \
+    do {                                                       \
+        ::jmc::count_launch();                                 \
+        cudaError_t _e = cudaGetLastError();                   \
+        if (_e != cudaSuccess) return ::jmc::cuda_fail(_e, name); \
+    } while (0)
+
+struct DeviceInfo {
+    int device;
+    int sm_count;
+    int max_smem_optin;
+};
+int device_info(DeviceInfo* out);
+
+// small per-(thread, device) device scratch: poison flags, min/max staging, ...
+int scratch(size_t bytes, void** ptr);
+
+// Derived constants of an integrand, computed once per launch on the host.
+struct RunParams {
+    jmc_integrand g;
+    double log_eps;       // ln(epsilon)
+    double lw_crit_z;     // ln(1/2 - z_cut)
+    double lw_radius;     // ln(radius)
+    double lw_half;       // ln(1/2)
+    double lw_pre;        // ln(z_cut)
+    double lw_simple;     // ln(hi - lo)
+};
+int make_run_params(const jmc_integrand* g, RunParams* out);
+
+}  // namespace jmc

@@ -1,0 +1,719 @@
+// FP64 kernels of libjmc_b200.so (compiled with --fmad=false so that the
+// arithmetic is IEEE FP64 in NumPy operation order):
+//   - array functions and whole-integrand replay (jmc_eval_fn, jmc_eval_integrand)
+//   - Philox samplers on request (jmc_sample, jmc_uniforms)
+//   - np.histogram restated: bin index, (sum w, sum w^2, count) with shared-
+//     memory privatisation, NaN poisoning, min/max
+//   - density / cumulative-integral epilogue with a block prefix scan
+//   - the exact (FP64) mode of the fused generate->weight->bin kernel
+#include <cfloat>
+#include <climits>
+#include "jmc_common.cuh"
+#include "jmc_integrand.cuh"
+
+namespace jmc {
+
+static constexpr int kThreads = 256;
+
+// ---------------------------------------------------------------------------
+// array functions
+// ---------------------------------------------------------------------------
+struct FnArgs {
+    const double* a[4];
+    int64_t stride[4];
+    double scalar[4];
+};
+
+__device__ __forceinline__ double fn_arg(const FnArgs& A, int k, uint64_t i) {
+    return A.a[k] ? A.a[k][i * A.stride[k]] : A.scalar[k];
+}
+
+__global__ void __launch_bounds__(kThreads) eval_fn_kernel(int fn, jmc_fn_params p, FnArgs A, uint64_t n,
+                                                            double* __restrict__ out) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double x0 = fn_arg(A, 0, i), x1 = fn_arg(A, 1, i), x2 = fn_arg(A, 2, i), x3 = fn_arg(A, 3, i);
+        double r;
+        switch (fn) {
+            case JMC_FN_ALPHA_S: r = alpha_running(x0, x1); break;
+            case JMC_FN_SPLITTING: r = splitting(x0, p.jet, p.acc); break;
+            case JMC_FN_RADIATOR_WEIGHT: r = weight_radiator(x0, x1, p.jet, p.fixed_coupling, p.acc); break;
+            case JMC_FN_CRIT_PDF_FC: r = pdf_crit_fc(x0, x1, p.z_cut, p.jet); break;
+            case JMC_FN_CRIT_RAD_FC: r = rad_crit_fc(x0, p.z_cut, p.jet); break;
+            case JMC_FN_SUB_RAD_FC: r = rad_sub_fc(x0, p.beta, p.jet, x1); break;
+            case JMC_FN_SUB_RADPRIME_FC: r = radprime_sub_fc(x0, p.beta, p.jet, x1); break;
+            case JMC_FN_SUB_PDF_FC: r = pdf_sub_fc(x0, p.beta, p.jet, x1); break;
+            case JMC_FN_PRE_RAD_FC: r = rad_pre_fc(x0, x1, p.z_cut, p.jet, x2); break;
+            case JMC_FN_CRIT_RAD_RC: r = rad_crit_rc(x0, p.z_cut, p.jet); break;
+            case JMC_FN_CRIT_RADPRIME_RC: r = radprime_crit_rc(x0, p.z_cut, p.jet); break;
+            case JMC_FN_CRIT_PDF_RC: r = pdf_crit_rc(x0, x1, p.z_cut, p.jet); break;
+            case JMC_FN_SUB_RAD_RC: r = rad_sub_rc(x0, p.beta, p.jet, x1); break;
+            case JMC_FN_SUB_RADPRIME_RC: r = radprime_sub_rc(x0, p.beta, p.jet, x1); break;
+            case JMC_FN_SUB_PDF_RC: r = pdf_sub_rc(x0, p.beta, p.jet, x1); break;
+            case JMC_FN_PRE_WEIGHT: r = weight_precritical(x0, x1, p.z_cut, p.jet); break;
+            case JMC_FN_C_GROOMED: r = ecf_groomed(x0, x1, p.z_cut, p.beta, x2, x3, p.acc); break;
+            case JMC_FN_C_UNGROOMED: r = ecf_ungroomed(x0, x1, p.beta, p.acc); break;
+            case JMC_FN_TWO_EMISSION:
+                r = weight_two_emission(x0, x1, x2, x3, p.z_cut, p.beta, p.jet, p.fixed_coupling);
+                break;
+            case JMC_FN_PRE_WEIGHT_ZEROBIN: r = weight_precritical_zerobin(x0, x1, p.z_cut, p.jet, p.epsilon); break;
+            default: r = qnan();
+        }
+        out[i] = r;
+    }
+}
+
+static int grid_for(uint64_t n, int threads, int blocks_per_sm = 8) {
+    DeviceInfo di;
+    if (device_info(&di) != 0) return -1;
+    uint64_t want = (n + threads - 1) / threads;
+    uint64_t cap = (uint64_t)di.sm_count * blocks_per_sm;
+    if (want < 1) want = 1;
+    return (int)(want < cap ? want : cap);
+}
+
+}  // namespace jmc
+
+using namespace jmc;
+
+extern "C" int jmc_eval_fn(int fn, const jmc_fn_params* p, uint64_t n, const double* d_a0, int64_t stride0,
+                           const double* d_a1, int64_t stride1, const double* d_a2, int64_t stride2,
+                           const double* d_a3, int64_t stride3, double* d_out, void* stream) {
+    JMC_REQUIRE(p != nullptr, "jmc_eval_fn: params is NULL");
+    JMC_REQUIRE(fn >= 0 && fn < JMC_FN_COUNT, "jmc_eval_fn: unknown function id %d", fn);
+    JMC_REQUIRE(p->jet == JMC_QUARK || p->jet == JMC_GLUON, "jmc_eval_fn: jet must be quark or gluon");
+    JMC_REQUIRE(p->acc >= JMC_ACC_LL && p->acc <= JMC_ACC_MLL, "jmc_eval_fn: invalid accuracy");
+    if (n == 0) return JMC_OK;
+    JMC_REQUIRE(d_out != nullptr, "jmc_eval_fn: out is NULL");
+    FnArgs A;
+    A.a[0] = d_a0; A.a[1] = d_a1; A.a[2] = d_a2; A.a[3] = d_a3;
+    A.stride[0] = stride0; A.stride[1] = stride1; A.stride[2] = stride2; A.stride[3] = stride3;
+    A.scalar[0] = p->s0; A.scalar[1] = p->s1; A.scalar[2] = p->s2; A.scalar[3] = p->s3;
+    // documented scalar stand-ins
+    if ((fn >= JMC_FN_SUB_RAD_FC && fn <= JMC_FN_SUB_PDF_FC) || (fn >= JMC_FN_SUB_RAD_RC && fn <= JMC_FN_SUB_PDF_RC))
+        A.scalar[1] = p->max_radius;
+    if (fn == JMC_FN_C_GROOMED) { A.scalar[2] = p->z_pre; A.scalar[3] = p->f_soft; }
+    const int grid = grid_for(n, kThreads);
+    if (grid < 0) return JMC_ENODEV;
+    eval_fn_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(fn, *p, A, n, d_out);
+    JMC_LAUNCHED("eval_fn_kernel");
+    return JMC_OK;
+}
+
+// ---------------------------------------------------------------------------
+// sampling on request
+// ---------------------------------------------------------------------------
+namespace jmc {
+
+__global__ void __launch_bounds__(kThreads) uniforms_kernel(uint64_t n, uint64_t seed, uint64_t first, int n_uniform,
+                                                             double* __restrict__ out) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const int n_blocks = (n_uniform + 1) / 2;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        for (int b = 0; b < n_blocks; ++b) {
+            double u0, u1;
+            philox_uniform53x2(first + i, (uint32_t)b, seed, u0, u1);
+            out[i * n_uniform + 2 * b] = u0;
+            if (2 * b + 1 < n_uniform) out[i * n_uniform + 2 * b + 1] = u1;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) sample_kernel(RunParams p, int sampler_kind, uint64_t n, uint64_t seed,
+                                                           uint64_t first, double* __restrict__ samples,
+                                                           double* __restrict__ jac) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const bool is_log = p.g.method == JMC_LOG;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        double u0, u1;
+        philox_uniform53x2(first + i, 0u, seed, u0, u1);
+        double j;
+        if (sampler_kind == JMC_SAMPLER_CRITICAL) {
+            double z, th;
+            sample_critical(p, u0, u1, z, th);
+            samples[2 * i] = z; samples[2 * i + 1] = th;
+            j = is_log ? (z - p.g.z_cut) * th : 1.0;
+        } else if (sampler_kind == JMC_SAMPLER_UNGROOMED) {
+            double z, th;
+            sample_ungroomed(p, u0, u1, z, th);
+            samples[2 * i] = z; samples[2 * i + 1] = th;
+            j = is_log ? z * th : 1.0;
+        } else if (sampler_kind == JMC_SAMPLER_PRECRITICAL) {
+            const double z = sample_precritical(p, u0);
+            samples[i] = z;
+            j = is_log ? z : 1.0;
+        } else {
+            const double x = sample_simple(p, u0);
+            samples[i] = x;
+            j = is_log ? x : 1.0;
+        }
+        if (jac) jac[i] = j;
+    }
+}
+
+}  // namespace jmc
+
+extern "C" int jmc_uniforms(uint64_t n, uint64_t seed, uint64_t first_index, int n_uniform, double* d_out,
+                            void* stream) {
+    JMC_REQUIRE(n_uniform >= 1 && n_uniform <= 64, "jmc_uniforms: n_uniform must be in 1..64");
+    if (n == 0) return JMC_OK;
+    JMC_REQUIRE(d_out != nullptr, "jmc_uniforms: out is NULL");
+    const int grid = grid_for(n, kThreads);
+    if (grid < 0) return JMC_ENODEV;
+    uniforms_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(n, seed, first_index, n_uniform, d_out);
+    JMC_LAUNCHED("uniforms_kernel");
+    return JMC_OK;
+}
+
+static int sampler_to_integrand(const jmc_sampler* s, jmc_integrand* g) {
+    JMC_REQUIRE(s != nullptr, "sampler is NULL");
+    JMC_REQUIRE(s->kind >= JMC_SAMPLER_SIMPLE && s->kind <= JMC_SAMPLER_UNGROOMED, "unknown sampler kind %d", s->kind);
+    *g = jmc_integrand{};
+    g->method = s->method;
+    g->epsilon = s->epsilon;
+    g->z_cut = s->zc;
+    g->radius = s->radius;
+    g->lo = s->lo;
+    g->hi = s->hi;
+    g->beta = 2.0;
+    g->theta_scale = 1.0;
+    g->fixed_coupling = 1;
+    switch (s->kind) {
+        case JMC_SAMPLER_SIMPLE: g->kind = JMC_KIND_SIMPLE; break;
+        case JMC_SAMPLER_CRITICAL: g->kind = JMC_KIND_CRIT; break;
+        case JMC_SAMPLER_PRECRITICAL: g->kind = JMC_KIND_PRE_CRIT_SUB; g->radius = 1.0; break;
+        default: g->kind = JMC_KIND_RADIATOR; break;
+    }
+    return JMC_OK;
+}
+
+extern "C" int jmc_sample(const jmc_sampler* s, uint64_t n, uint64_t seed, uint64_t first_index, double* d_samples,
+                          double* d_jac, void* stream) {
+    jmc_integrand g;
+    int rc = sampler_to_integrand(s, &g);
+    if (rc) return rc;
+    RunParams p;
+    rc = make_run_params(&g, &p);
+    if (rc) return rc;
+    if (n == 0) return JMC_OK;
+    JMC_REQUIRE(d_samples != nullptr, "jmc_sample: samples is NULL");
+    const int grid = grid_for(n, kThreads);
+    if (grid < 0) return JMC_ENODEV;
+    sample_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(p, s->kind, n, seed, first_index, d_samples, d_jac);
+    JMC_LAUNCHED("sample_kernel");
+    return JMC_OK;
+}
+
+// ---------------------------------------------------------------------------
+// whole-integrand replay
+// ---------------------------------------------------------------------------
+namespace jmc {
+
+template <int KIND>
+__global__ void __launch_bounds__(kThreads)
+eval_integrand_kernel(RunParams p, uint64_t n, const double* __restrict__ crit, const double* __restrict__ sub,
+                      const double* __restrict__ pre, const double* __restrict__ zb_u,
+                      const double* __restrict__ edges, int n_edges, double* __restrict__ jac_out,
+                      double* __restrict__ obs_out, double* __restrict__ w_out, int32_t* __restrict__ bin_out) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        SampleSet s;
+        s.z_c = s.th_c = s.z_s = s.th_s = s.z_pre = s.zb_u = 0.0;
+        if (crit) { s.z_c = crit[2 * i]; s.th_c = crit[2 * i + 1]; }
+        if (sub) { s.z_s = sub[2 * i]; s.th_s = sub[2 * i + 1]; }
+        if (pre) s.z_pre = pre[i];
+        if (zb_u) s.zb_u = zb_u[i]; else s.zb_u = 2.0;   // no zero-bin draw -> never zeroed
+        double jac, obs, wj;
+        integrand_eval<KIND>(p, s, jac, obs, wj);
+        if (jac_out) jac_out[i] = jac;
+        if (obs_out) obs_out[i] = obs;
+        if (w_out) w_out[i] = wj;
+        if (bin_out) bin_out[i] = bin_index(obs, edges, n_edges);
+    }
+}
+
+}  // namespace jmc
+
+extern "C" int jmc_eval_integrand(const jmc_integrand* g, uint64_t n, const double* d_crit, const double* d_sub,
+                                  const double* d_pre, const double* d_zb_u, const double* d_edges, int n_edges,
+                                  double* d_jac, double* d_obs, double* d_weight, int32_t* d_bin, void* stream) {
+    RunParams p;
+    int rc = make_run_params(g, &p);
+    if (rc) return rc;
+    JMC_REQUIRE(g->kind != JMC_KIND_SHOWER, "jmc_eval_integrand: the shower has no sample-replay form");
+    if (d_bin) JMC_REQUIRE(d_edges != nullptr && n_edges >= 2, "jmc_eval_integrand: bins requested without edges");
+    const bool need_crit = g->kind == JMC_KIND_CRIT || g->kind == JMC_KIND_CRIT_SUB || g->kind == JMC_KIND_PRE_CRIT_SUB;
+    const bool need_sub = g->kind == JMC_KIND_RADIATOR || g->kind == JMC_KIND_CRIT_SUB || g->kind == JMC_KIND_PRE_CRIT_SUB;
+    const bool need_pre = g->kind == JMC_KIND_PRE_CRIT_SUB || g->kind == JMC_KIND_SIMPLE;
+    if (n == 0) return JMC_OK;
+    JMC_REQUIRE(!need_crit || d_crit, "jmc_eval_integrand: critical samples missing");
+    JMC_REQUIRE(!need_sub || d_sub, "jmc_eval_integrand: subsequent/ungroomed samples missing");
+    JMC_REQUIRE(!need_pre || d_pre, "jmc_eval_integrand: pre-critical/simple samples missing");
+    const int grid = grid_for(n, kThreads);
+    if (grid < 0) return JMC_ENODEV;
+    cudaStream_t st = (cudaStream_t)stream;
+#define JMC_LAUNCH_EVAL(K)                                                                                      \
+    eval_integrand_kernel<K><<<grid, kThreads, 0, st>>>(p, n, d_crit, d_sub, d_pre, d_zb_u, d_edges, n_edges, \
+                                                         d_jac, d_obs, d_weight, d_bin)
+    switch (g->kind) {
+        case JMC_KIND_RADIATOR: JMC_LAUNCH_EVAL(JMC_KIND_RADIATOR); break;
+        case JMC_KIND_CRIT: JMC_LAUNCH_EVAL(JMC_KIND_CRIT); break;
+        case JMC_KIND_CRIT_SUB: JMC_LAUNCH_EVAL(JMC_KIND_CRIT_SUB); break;
+        case JMC_KIND_PRE_CRIT_SUB: JMC_LAUNCH_EVAL(JMC_KIND_PRE_CRIT_SUB); break;
+        default: JMC_LAUNCH_EVAL(JMC_KIND_SIMPLE); break;
+    }
+#undef JMC_LAUNCH_EVAL
+    JMC_LAUNCHED("eval_integrand_kernel");
+    return JMC_OK;
+}
+
+// ---------------------------------------------------------------------------
+// np.histogram restated
+// ---------------------------------------------------------------------------
+namespace jmc {
+
+__global__ void __launch_bounds__(kThreads) bin_index_kernel(const double* __restrict__ obs, uint64_t n,
+                                                              const double* __restrict__ edges, int n_edges,
+                                                              int32_t* __restrict__ bin) {
+    extern __shared__ double s_edges[];
+    for (int k = threadIdx.x; k < n_edges; k += blockDim.x) s_edges[k] = edges[k];
+    __syncthreads();
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        bin[i] = bin_index(obs[i], s_edges, n_edges);
+}
+
+// Shared-memory layout of a privatised histogram block:
+//   double edges[n_edges]; double sum_w[nb]; double sum_w2[nb]; uint32 count[nb]
+struct HistSmem {
+    double* edges;
+    double* sum_w;
+    double* sum_w2;
+    unsigned int* count;
+    __device__ HistSmem(void* base, int n_edges) {
+        const int nb = n_edges - 1;
+        edges = (double*)base;
+        sum_w = edges + n_edges;
+        sum_w2 = sum_w + nb;
+        count = (unsigned int*)(sum_w2 + nb);
+    }
+};
+static size_t hist_smem_bytes(int n_edges) {
+    const size_t nb = (size_t)n_edges - 1;
+    return sizeof(double) * ((size_t)n_edges + 2 * nb) + sizeof(unsigned int) * nb;
+}
+
+__device__ __forceinline__ void hist_init(HistSmem& h, const double* __restrict__ edges, int n_edges) {
+    const int nb = n_edges - 1;
+    for (int k = threadIdx.x; k < n_edges; k += blockDim.x) h.edges[k] = edges[k];
+    for (int k = threadIdx.x; k < nb; k += blockDim.x) {
+        h.sum_w[k] = 0.0;
+        h.sum_w2[k] = 0.0;
+        h.count[k] = 0u;
+    }
+    __syncthreads();
+}
+
+// One sample into the block histogram.  A NaN weight is not added; it lowers
+// the poison bin instead (NumPy: NaN in a cumsum reaches every later bin).
+__device__ __forceinline__ void hist_add(HistSmem& h, int n_edges, double obs, double w, bool has_w,
+                                         int* s_poison) {
+    const int b = bin_index(obs, h.edges, n_edges);
+    if (has_w && w != w) {
+        // obs below the first edge sorts before every bin -> poisons them all;
+        // obs above the last edge or NaN sorts after the last bin -> harmless.
+        int pb = b;
+        if (b < 0) pb = (obs < h.edges[0]) ? 0 : INT_MAX;
+        if (pb != INT_MAX) atomicMin(s_poison, pb);
+        if (b >= 0) atomicAdd(&h.count[b], 1u);
+        return;
+    }
+    if (b < 0) return;
+    atomicAdd(&h.count[b], 1u);
+    if (has_w && w != 0.0) {
+        atomicAdd(&h.sum_w[b], w);
+        atomicAdd(&h.sum_w2[b], w * w);
+    }
+}
+
+__device__ __forceinline__ void hist_flush(HistSmem& h, int n_edges, double* __restrict__ g_sum_w,
+                                           double* __restrict__ g_sum_w2, unsigned long long* __restrict__ g_count,
+                                           int* s_poison, int* g_poison) {
+    __syncthreads();
+    const int nb = n_edges - 1;
+    for (int k = threadIdx.x; k < nb; k += blockDim.x) {
+        const unsigned int c = h.count[k];
+        if (c) {
+            atomicAdd(&g_count[k], (unsigned long long)c);
+            const double sw = h.sum_w[k], sw2 = h.sum_w2[k];
+            if (g_sum_w && sw != 0.0) atomicAdd(&g_sum_w[k], sw);
+            if (g_sum_w2 && sw2 != 0.0) atomicAdd(&g_sum_w2[k], sw2);
+        }
+    }
+    if (threadIdx.x == 0 && *s_poison != INT_MAX) atomicMin(g_poison, *s_poison);
+}
+
+__global__ void __launch_bounds__(kThreads)
+hist_kernel(const double* __restrict__ obs, const double* __restrict__ w, uint64_t n,
+            const double* __restrict__ edges, int n_edges, double* __restrict__ g_sum_w,
+            double* __restrict__ g_sum_w2, unsigned long long* __restrict__ g_count, int* g_poison) {
+    extern __shared__ double s_raw[];
+    __shared__ int s_poison;
+    HistSmem h(s_raw, n_edges);
+    if (threadIdx.x == 0) s_poison = INT_MAX;
+    hist_init(h, edges, n_edges);
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const bool has_w = w != nullptr;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        hist_add(h, n_edges, obs[i], has_w ? w[i] : 1.0, has_w, &s_poison);
+    hist_flush(h, n_edges, g_sum_w, g_sum_w2, g_count, &s_poison, g_poison);
+}
+
+// NaN-fill every bin at or above the poison bin
+__global__ void poison_kernel(const int* g_poison, int nb, double* g_sum_w, double* g_sum_w2) {
+    const int pb = *g_poison;
+    if (pb < 0 || pb >= nb) return;
+    for (int k = pb + blockIdx.x * blockDim.x + threadIdx.x; k < nb; k += gridDim.x * blockDim.x) {
+        if (k < 0) continue;
+        if (g_sum_w) g_sum_w[k] = qnan();
+        if (g_sum_w2) g_sum_w2[k] = qnan();
+    }
+}
+
+// ---- min / max with NaN propagation --------------------------------------
+// staging: double mn, double mx, int has_nan
+__device__ __forceinline__ void atomic_min_double(double* addr, double v) {
+    unsigned long long old = __double_as_longlong(*addr);
+    while (v < __longlong_as_double(old)) {
+        const unsigned long long assumed = old;
+        old = atomicCAS((unsigned long long*)addr, assumed, (unsigned long long)__double_as_longlong(v));
+        if (old == assumed) break;
+    }
+}
+__device__ __forceinline__ void atomic_max_double(double* addr, double v) {
+    unsigned long long old = __double_as_longlong(*addr);
+    while (v > __longlong_as_double(old)) {
+        const unsigned long long assumed = old;
+        old = atomicCAS((unsigned long long*)addr, assumed, (unsigned long long)__double_as_longlong(v));
+        if (old == assumed) break;
+    }
+}
+
+// block-reduce per-thread (mn, mx, nan) and merge into d_minmax[0..1]; a NaN
+// anywhere makes both NaN (np.min / np.max semantics)
+__device__ __forceinline__ void minmax_merge(double mn, double mx, bool has_nan, double* __restrict__ d_minmax) {
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    has_nan = __any_sync(0xffffffffu, has_nan);
+    if ((threadIdx.x & 31) == 0) {
+        if (has_nan) {
+            // NaN is sticky: atomic_min/max never replace it because comparisons fail
+            d_minmax[0] = qnan();
+            d_minmax[1] = qnan();
+        } else {
+            atomic_min_double(&d_minmax[0], mn);
+            atomic_max_double(&d_minmax[1], mx);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) minmax_kernel(const double* __restrict__ x, uint64_t n,
+                                                           double* __restrict__ d_minmax) {
+    double mn = INFINITY, mx = -INFINITY;
+    bool has_nan = false;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double v = x[i];
+        has_nan |= (v != v);
+        mn = fmin(mn, v);
+        mx = fmax(mx, v);
+    }
+    minmax_merge(mn, mx, has_nan, d_minmax);
+}
+
+__global__ void minmax_init_kernel(double* d_minmax) {
+    d_minmax[0] = INFINITY;
+    d_minmax[1] = -INFINITY;
+}
+
+}  // namespace jmc
+
+extern "C" int jmc_bin_index(const double* d_obs, uint64_t n, const double* d_edges, int n_edges, int32_t* d_bin,
+                             void* stream) {
+    JMC_REQUIRE(n_edges >= 2, "jmc_bin_index: need at least 2 edges");
+    JMC_REQUIRE(d_edges != nullptr, "jmc_bin_index: edges is NULL");
+    if (n == 0) return JMC_OK;
+    JMC_REQUIRE(d_obs && d_bin, "jmc_bin_index: NULL array");
+    DeviceInfo di;
+    if (device_info(&di)) return JMC_ENODEV;
+    const size_t smem = sizeof(double) * (size_t)n_edges;
+    if (smem > (size_t)di.max_smem_optin) return set_error(JMC_ELIMIT, "jmc_bin_index: %d edges exceed shared memory", n_edges);
+    JMC_CUDA(cudaFuncSetAttribute(bin_index_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = grid_for(n, kThreads);
+    bin_index_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(d_obs, n, d_edges, n_edges, d_bin);
+    JMC_LAUNCHED("bin_index_kernel");
+    return JMC_OK;
+}
+
+static int check_hist_args(const char* who, const double* d_edges, int n_edges, size_t* smem) {
+    JMC_REQUIRE(n_edges >= 2, "%s: need at least 2 edges", who);
+    JMC_REQUIRE(d_edges != nullptr, "%s: edges is NULL", who);
+    DeviceInfo di;
+    if (device_info(&di)) return JMC_ENODEV;
+    *smem = hist_smem_bytes(n_edges);
+    if (*smem > (size_t)di.max_smem_optin)
+        return set_error(JMC_ELIMIT, "%s: %d edges need %zu B of shared memory (limit %d B, about 8100 edges)", who,
+                         n_edges, *smem, di.max_smem_optin);
+    return JMC_OK;
+}
+
+extern "C" int jmc_hist(const double* d_obs, const double* d_weights, uint64_t n, const double* d_edges, int n_edges,
+                        double* d_sum_w, double* d_sum_w2, uint64_t* d_count, void* stream) {
+    size_t smem;
+    int rc = check_hist_args("jmc_hist", d_edges, n_edges, &smem);
+    if (rc) return rc;
+    JMC_REQUIRE(d_count != nullptr, "jmc_hist: count is NULL");
+    if (n == 0) return JMC_OK;
+    JMC_REQUIRE(d_obs != nullptr, "jmc_hist: obs is NULL");
+    cudaStream_t st = (cudaStream_t)stream;
+    int* d_poison;
+    rc = scratch(sizeof(int), (void**)&d_poison);
+    if (rc) return rc;
+    JMC_CUDA(cudaMemsetAsync(d_poison, 0x7f, sizeof(int), st));   // 0x7f7f7f7f: "no poison"
+    JMC_CUDA(cudaFuncSetAttribute(hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    JMC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hist_kernel, kThreads, smem));
+    if (per_sm < 1) per_sm = 1;
+    const int grid = grid_for(n, kThreads, per_sm);
+    hist_kernel<<<grid, kThreads, smem, st>>>(d_obs, d_weights, n, d_edges, n_edges, d_sum_w, d_sum_w2,
+                                               (unsigned long long*)d_count, d_poison);
+    JMC_LAUNCHED("hist_kernel");
+    if (d_weights) {
+        poison_kernel<<<1, 256, 0, st>>>(d_poison, n_edges - 1, d_sum_w, d_sum_w2);
+        JMC_LAUNCHED("poison_kernel");
+    }
+    return JMC_OK;
+}
+
+extern "C" int jmc_minmax(const double* d_x, uint64_t n, double* d_minmax, void* stream) {
+    JMC_REQUIRE(d_minmax != nullptr, "jmc_minmax: output is NULL");
+    JMC_REQUIRE(n > 0, "jmc_minmax: zero-size array has no minimum");   // np.min raises ValueError
+    JMC_REQUIRE(d_x != nullptr, "jmc_minmax: input is NULL");
+    cudaStream_t st = (cudaStream_t)stream;
+    minmax_init_kernel<<<1, 1, 0, st>>>(d_minmax);
+    JMC_LAUNCHED("minmax_init_kernel");
+    const int grid = grid_for(n, kThreads);
+    minmax_kernel<<<grid, kThreads, 0, st>>>(d_x, n, d_minmax);
+    JMC_LAUNCHED("minmax_kernel");
+    return JMC_OK;
+}
+
+// ---------------------------------------------------------------------------
+// fused path, exact (FP64) mode
+// ---------------------------------------------------------------------------
+namespace jmc {
+
+template <int KIND>
+__global__ void __launch_bounds__(kThreads)
+run_exact_kernel(RunParams p, uint64_t n, uint64_t seed, uint64_t first, const double* __restrict__ edges,
+                 int n_edges, double* __restrict__ g_sum_w, double* __restrict__ g_sum_w2,
+                 unsigned long long* __restrict__ g_count, int* g_poison, double* __restrict__ d_minmax) {
+    extern __shared__ double s_raw[];
+    __shared__ int s_poison;
+    HistSmem h(s_raw, n_edges > 0 ? n_edges : 1);
+    const bool do_hist = edges != nullptr;
+    if (threadIdx.x == 0) s_poison = INT_MAX;
+    if (do_hist) hist_init(h, edges, n_edges); else __syncthreads();
+    double mn = INFINITY, mx = -INFINITY;
+    bool has_nan = false;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        SampleSet s;
+        s.z_c = s.th_c = s.z_s = s.th_s = s.z_pre = 0.0;
+        s.zb_u = 2.0;
+        draw_exact<KIND>(p, first + i, seed, s);
+        double jac, obs, wj;
+        integrand_eval<KIND>(p, s, jac, obs, wj);
+        if (do_hist) hist_add(h, n_edges, obs, wj, true, &s_poison);
+        if (d_minmax) {
+            has_nan |= (obs != obs);
+            mn = fmin(mn, obs);
+            mx = fmax(mx, obs);
+        }
+    }
+    if (do_hist) hist_flush(h, n_edges, g_sum_w, g_sum_w2, g_count, &s_poison, g_poison);
+    if (d_minmax) minmax_merge(mn, mx, has_nan, d_minmax);
+}
+
+template <int KIND>
+static int launch_run_exact(const RunParams& p, uint64_t n, uint64_t seed, uint64_t first, const double* d_edges,
+                            int n_edges, double* d_sum_w, double* d_sum_w2, uint64_t* d_count, int* d_poison,
+                            double* d_minmax, size_t smem, cudaStream_t st) {
+    JMC_CUDA(cudaFuncSetAttribute(run_exact_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    JMC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, run_exact_kernel<KIND>, kThreads, smem));
+    if (per_sm < 1) per_sm = 1;
+    const int grid = grid_for(n, kThreads, per_sm);
+    if (grid < 0) return JMC_ENODEV;
+    run_exact_kernel<KIND><<<grid, kThreads, smem, st>>>(p, n, seed, first, d_edges, n_edges, d_sum_w, d_sum_w2,
+                                                          (unsigned long long*)d_count, d_poison, d_minmax);
+    JMC_LAUNCHED("run_exact_kernel");
+    return JMC_OK;
+}
+
+int run_exact(const jmc_integrand* g, uint64_t n, uint64_t seed, uint64_t first_index, const double* d_edges,
+              int n_edges, double* d_sum_w, double* d_sum_w2, uint64_t* d_count, double* d_minmax, void* stream) {
+    RunParams p;
+    int rc = make_run_params(g, &p);
+    if (rc) return rc;
+    size_t smem = 0;
+    if (d_edges) {
+        rc = check_hist_args("jmc_run", d_edges, n_edges, &smem);
+        if (rc) return rc;
+        JMC_REQUIRE(d_sum_w && d_sum_w2 && d_count, "jmc_run: histogram outputs missing");
+    } else {
+        JMC_REQUIRE(d_minmax != nullptr, "jmc_run: neither edges nor minmax requested");
+    }
+    if (n == 0) return JMC_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    int* d_poison;
+    rc = scratch(sizeof(int), (void**)&d_poison);
+    if (rc) return rc;
+    JMC_CUDA(cudaMemsetAsync(d_poison, 0x7f, sizeof(int), st));
+#define JMC_RUN(K) \
+    rc = launch_run_exact<K>(p, n, seed, first_index, d_edges, n_edges, d_sum_w, d_sum_w2, d_count, d_poison, d_minmax, smem, st)
+    switch (g->kind) {
+        case JMC_KIND_RADIATOR: JMC_RUN(JMC_KIND_RADIATOR); break;
+        case JMC_KIND_CRIT: JMC_RUN(JMC_KIND_CRIT); break;
+        case JMC_KIND_CRIT_SUB: JMC_RUN(JMC_KIND_CRIT_SUB); break;
+        case JMC_KIND_PRE_CRIT_SUB: JMC_RUN(JMC_KIND_PRE_CRIT_SUB); break;
+        case JMC_KIND_SIMPLE: JMC_RUN(JMC_KIND_SIMPLE); break;
+        default: return set_error(JMC_EINVAL, "jmc_run: kind %d has no FP64 sampler form", g->kind);
+    }
+#undef JMC_RUN
+    if (rc) return rc;
+    if (d_edges && !g->nan_to_num) {
+        poison_kernel<<<1, 256, 0, st>>>(d_poison, n_edges - 1, d_sum_w, d_sum_w2);
+        JMC_LAUNCHED("poison_kernel");
+    }
+    return JMC_OK;
+}
+
+// ---------------------------------------------------------------------------
+// density / cumulative integral epilogue
+// ---------------------------------------------------------------------------
+static constexpr int kScanThreads = 1024;
+
+// Exclusive prefix of per-thread totals across the block (two arrays at once).
+__device__ __forceinline__ void block_exclusive_scan2(double& a, double& b, double* s_a, double* s_b) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double ia = a, ib = b;   // inclusive within the warp
+    for (int o = 1; o < 32; o <<= 1) {
+        const double ta = __shfl_up_sync(0xffffffffu, ia, o);
+        const double tb = __shfl_up_sync(0xffffffffu, ib, o);
+        if (lane >= o) { ia += ta; ib += tb; }
+    }
+    if (lane == 31) { s_a[warp] = ia; s_b[warp] = ib; }
+    __syncthreads();
+    if (warp == 0) {
+        double wa = s_a[lane], wb = s_b[lane];
+        for (int o = 1; o < 32; o <<= 1) {
+            const double ta = __shfl_up_sync(0xffffffffu, wa, o);
+            const double tb = __shfl_up_sync(0xffffffffu, wb, o);
+            if (lane >= o) { wa += ta; wb += tb; }
+        }
+        s_a[lane] = wa; s_b[lane] = wb;
+    }
+    __syncthreads();
+    const double oa = warp ? s_a[warp - 1] : 0.0, ob = warp ? s_b[warp - 1] : 0.0;
+    a = oa + (ia - a);
+    b = ob + (ib - b);
+}
+
+// One block.  Bins are processed in scan order: forward for a first-bin
+// boundary condition, reversed for a last-bin one (integrator.py:162-192).
+// FROM_HIST: density and its error are first derived from the histograms
+// (integrator.py:113-124); otherwise they are inputs (integrate() alone).
+template <bool FROM_HIST>
+__global__ void __launch_bounds__(kScanThreads)
+finalize_kernel(const double* __restrict__ sum_w, const double* __restrict__ sum_w2,
+                const unsigned long long* __restrict__ count, const double* __restrict__ edges, int n_edges,
+                double area, double n_total, int bc_kind, double bc_value, double* __restrict__ density,
+                double* __restrict__ density_err, double* __restrict__ integral, double* __restrict__ integral_err) {
+    __shared__ double s_a[32], s_b[32];
+    const int nb = n_edges - 1;
+    const int per = (nb + kScanThreads - 1) / kScanThreads;
+    const bool reverse = bc_kind != JMC_BC_FIRST;
+    const double norm = area / n_total;
+    const int begin = threadIdx.x * per;
+    const int end = min(begin + per, nb);
+    // pass 1: density and per-thread totals of density*width, err*width
+    double ta = 0.0, tb = 0.0;
+    for (int j = begin; j < end; ++j) {
+        const int k = reverse ? nb - 1 - j : j;
+        const double width = edges[k + 1] - edges[k];
+        double d, e;
+        if (FROM_HIST) {
+            d = (sum_w[k] / width) * norm;
+            e = (sqrt(sum_w2[k]) / width) * norm;
+            if (count[k] == 0ull) { d = 0.0; e = 0.0; }
+            density[k] = d;
+            density_err[k] = e;
+        } else {
+            d = density[k];
+            e = density_err[k];
+        }
+        ta += d * width;
+        tb += e * width;
+    }
+    if (integral == nullptr) return;   // density only
+    block_exclusive_scan2(ta, tb, s_a, s_b);
+    // pass 2: running sums from the thread's offset
+    for (int j = begin; j < end; ++j) {
+        const int k = reverse ? nb - 1 - j : j;
+        const double width = edges[k + 1] - edges[k];
+        ta += density[k] * width;
+        tb += density_err[k] * width;
+        integral_err[k] = tb;
+        if (bc_kind == JMC_BC_FIRST) integral[k + 1] = bc_value + ta;
+        else if (bc_kind == JMC_BC_LAST_PLUS) integral[k] = bc_value + ta;
+        else integral[k] = bc_value - ta;
+    }
+    if (threadIdx.x == 0) {
+        if (bc_kind == JMC_BC_FIRST) integral[0] = bc_value;
+        else integral[nb] = bc_value;
+    }
+}
+
+}  // namespace jmc
+
+extern "C" int jmc_finalize(const double* d_sum_w, const double* d_sum_w2, const uint64_t* d_count,
+                            const double* d_edges, int n_edges, double area, uint64_t n_total, int bc_kind,
+                            double bc_value, double* d_density, double* d_density_err, double* d_integral,
+                            double* d_integral_err, void* stream) {
+    JMC_REQUIRE(n_edges >= 2, "jmc_finalize: need at least 2 edges");
+    JMC_REQUIRE(bc_kind >= JMC_BC_FIRST && bc_kind <= JMC_BC_LAST_MINUS, "jmc_finalize: invalid boundary condition");
+    JMC_REQUIRE(d_sum_w && d_sum_w2 && d_count && d_edges, "jmc_finalize: NULL input");
+    JMC_REQUIRE(d_density && d_density_err, "jmc_finalize: NULL output");
+    JMC_REQUIRE((d_integral == nullptr) == (d_integral_err == nullptr), "jmc_finalize: integral and its error go together");
+    finalize_kernel<true><<<1, kScanThreads, 0, (cudaStream_t)stream>>>(
+        d_sum_w, d_sum_w2, (const unsigned long long*)d_count, d_edges, n_edges, area, (double)n_total, bc_kind,
+        bc_value, d_density, d_density_err, d_integral, d_integral_err);
+    JMC_LAUNCHED("finalize_kernel");
+    return JMC_OK;
+}
+
+extern "C" int jmc_cumulative(const double* d_density, const double* d_density_err, const double* d_edges,
+                              int n_edges, int bc_kind, double bc_value, double* d_integral,
+                              double* d_integral_err, void* stream) {
+    JMC_REQUIRE(n_edges >= 2, "jmc_cumulative: need at least 2 edges");
+    JMC_REQUIRE(bc_kind >= JMC_BC_FIRST && bc_kind <= JMC_BC_LAST_MINUS, "jmc_cumulative: invalid boundary condition");
+    JMC_REQUIRE(d_density && d_density_err && d_edges && d_integral && d_integral_err, "jmc_cumulative: NULL argument");
+    finalize_kernel<false><<<1, kScanThreads, 0, (cudaStream_t)stream>>>(
+        nullptr, nullptr, nullptr, d_edges, n_edges, 1.0, 1.0, bc_kind, bc_value, (double*)d_density,
+        (double*)d_density_err, d_integral, d_integral_err);
+    JMC_LAUNCHED("finalize_kernel");
+    return JMC_OK;
+}

@@ -1,0 +1,348 @@
+// Host side of libjmc_b200.so: error strings, device bookkeeping, argument
+// validation shared by all kernels, precision dispatch of the fused path, and
+// the host-buffer entry points a reference-side binding would call.
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "jmc_common.cuh"
+
+namespace jmc {
+
+static thread_local std::string g_error;
+static std::atomic<uint64_t> g_launches{0};
+
+int set_error(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_error = buf;
+    return code;
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+    return set_error(JMC_ECUDA, "CUDA error in %s: %s", what, cudaGetErrorString(e));
+}
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+int device_info(DeviceInfo* out) {
+    static thread_local DeviceInfo cache = {-1, 0, 0};
+    int dev = -1;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+    if (cache.device != dev) {
+        cudaDeviceProp prop;
+        e = cudaGetDeviceProperties(&prop, dev);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceProperties");
+        if (prop.major != 10)
+            return set_error(JMC_ENODEV, "libjmc_b200 is built for sm_100a only; device %d is sm_%d%d", dev, prop.major,
+                             prop.minor);
+        cache.device = dev;
+        cache.sm_count = prop.multiProcessorCount;
+        cache.max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    }
+    *out = cache;
+    return JMC_OK;
+}
+
+// one small scratch allocation per (thread, device); grows on demand
+int scratch(size_t bytes, void** ptr) {
+    struct Slot { int device; void* p; size_t cap; };
+    static thread_local std::vector<Slot> slots;
+    int dev = -1;
+    JMC_CUDA(cudaGetDevice(&dev));
+    for (auto& s : slots) {
+        if (s.device != dev) continue;
+        if (s.cap < bytes) {
+            JMC_CUDA(cudaFree(s.p));
+            s.p = nullptr; s.cap = 0;
+            JMC_CUDA(cudaMalloc(&s.p, bytes));
+            s.cap = bytes;
+        }
+        *ptr = s.p;
+        return JMC_OK;
+    }
+    Slot s{dev, nullptr, bytes < 256 ? 256 : bytes};
+    JMC_CUDA(cudaMalloc(&s.p, s.cap));
+    slots.push_back(s);
+    *ptr = s.p;
+    return JMC_OK;
+}
+
+static bool valid_eps(double e) { return e > 0.0 && e < 1.0; }
+
+// Validation mirrors the reference's assertions; the Python layer raises
+// AssertionError with the reference's own messages before it ever gets here.
+// ref: montecarlo/sampler.py:65-81, numerics/radiators/samplers.py:12-18,116,298
+int make_run_params(const jmc_integrand* g, RunParams* out) {
+    JMC_REQUIRE(g != nullptr, "integrand is NULL");
+    JMC_REQUIRE(g->kind >= 0 && g->kind < JMC_KIND_COUNT, "unknown integrand kind %d", g->kind);
+    JMC_REQUIRE(g->method == JMC_LIN || g->method == JMC_LOG, "%dis not a supported sample method.", g->method);
+    JMC_REQUIRE(g->jet == JMC_QUARK || g->jet == JMC_GLUON, "jet type %d is not a supported jet type.", g->jet);
+    if (g->method == JMC_LOG)
+        JMC_REQUIRE(valid_eps(g->epsilon), "epsilon=%g is invalid for log sampling.", g->epsilon);
+    const bool uses_zc = g->kind == JMC_KIND_CRIT || g->kind == JMC_KIND_CRIT_SUB || g->kind == JMC_KIND_PRE_CRIT_SUB;
+    if (uses_zc) JMC_REQUIRE(g->z_cut > 0.0 && g->z_cut < 0.5, "zc=%g is an invalid grooming parameter.", g->z_cut);
+    if (g->kind != JMC_KIND_SIMPLE) JMC_REQUIRE(g->radius > 0.0, "Jet radius must be greater than zero!");
+    if (g->kind == JMC_KIND_PRE_CRIT_SUB && uses_zc) {
+        JMC_REQUIRE(g->fixed_coupling != 0, "Can only accept fixed coupling for now!");
+        JMC_REQUIRE(g->method != JMC_LOG || valid_eps(g->epsilon), "Weight requires valid cutoff for zero bin.");
+    }
+    JMC_REQUIRE(g->obs_acc == JMC_ACC_LL || g->obs_acc == JMC_ACC_MLL, "Accuracy must be LL or MLL");
+    JMC_REQUIRE(g->split_acc >= JMC_ACC_LL && g->split_acc <= JMC_ACC_MLL, "Invalid accuracy.");
+    RunParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.g = *g;
+    if (g->method == JMC_LOG) {
+        p.log_eps = std::log(g->epsilon);
+        p.lw_crit_z = std::log(0.5 - g->z_cut);
+        p.lw_radius = std::log(g->radius - 0.0);
+        p.lw_half = std::log(0.5 - 0.0);
+        p.lw_pre = g->z_cut > 0.0 ? std::log(g->z_cut - 0.0) : 0.0;
+        p.lw_simple = g->hi > g->lo ? std::log(g->hi - g->lo) : 0.0;
+    }
+    *out = p;
+    return JMC_OK;
+}
+
+int run_exact(const jmc_integrand* g, uint64_t n, uint64_t seed, uint64_t first_index, const double* d_edges,
+              int n_edges, double* d_sum_w, double* d_sum_w2, uint64_t* d_count, double* d_minmax, void* stream);
+int run_fast(const jmc_integrand* g, uint64_t n, uint64_t seed, uint64_t first_index, const double* d_edges,
+             int n_edges, double* d_sum_w, double* d_sum_w2, uint64_t* d_count, double* d_minmax, void* stream);
+int run_shower(const jmc_integrand* g, uint64_t n, uint64_t seed, uint64_t first_index, const double* d_edges,
+               int n_edges, double* d_sum_w, double* d_sum_w2, uint64_t* d_count, double* d_minmax, void* stream);
+
+static int sampler_area(int kind, int method, double eps, double zc, double radius, double lo, double hi,
+                        double* area) {
+    // ref: samplers.py:30-36 (critical), :132-138 (precritical), :196-202 (ungroomed); sampler.py:118-122 (simple)
+    if (method == JMC_LOG) {
+        JMC_REQUIRE(valid_eps(eps), "epsilon=%g is invalid for log sampling.", eps);
+        const double l = std::log(1.0 / eps);
+        *area = (kind == JMC_SAMPLER_CRITICAL || kind == JMC_SAMPLER_UNGROOMED) ? std::pow(l, 2.0) : l;
+        return JMC_OK;
+    }
+    switch (kind) {
+        case JMC_SAMPLER_SIMPLE: *area = hi - lo; break;
+        case JMC_SAMPLER_CRITICAL: *area = (1.0 / 2.0 - zc) * radius; break;
+        case JMC_SAMPLER_PRECRITICAL: *area = zc; break;
+        default: *area = radius / 2.0; break;
+    }
+    return JMC_OK;
+}
+
+}  // namespace jmc
+
+using namespace jmc;
+
+extern "C" int jmc_abi_version(void) { return JMC_ABI_VERSION; }
+extern "C" const char* jmc_last_error(void) { return g_error.c_str(); }
+extern "C" uint64_t jmc_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+extern "C" int jmc_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+extern "C" int jmc_set_device(int device) {
+    JMC_CUDA(cudaSetDevice(device));
+    return JMC_OK;
+}
+extern "C" int jmc_sm_count(void) {
+    DeviceInfo di;
+    if (device_info(&di)) return JMC_ENODEV;
+    return di.sm_count;
+}
+
+extern "C" int jmc_sampler_area(const jmc_sampler* s, double* area) {
+    JMC_REQUIRE(s && area, "jmc_sampler_area: NULL argument");
+    JMC_REQUIRE(s->method == JMC_LIN || s->method == JMC_LOG, "%dis not a supported sample method.", s->method);
+    return sampler_area(s->kind, s->method, s->epsilon, s->zc, s->radius, s->lo, s->hi, area);
+}
+
+extern "C" int jmc_integrand_uniforms(const jmc_integrand* g) {
+    if (!g) return set_error(JMC_EINVAL, "integrand is NULL");
+    switch (g->kind) {
+        case JMC_KIND_RADIATOR: case JMC_KIND_CRIT: return 2;
+        case JMC_KIND_CRIT_SUB: return 4;
+        case JMC_KIND_PRE_CRIT_SUB: return 6;
+        case JMC_KIND_SIMPLE: return 1;
+        case JMC_KIND_SHOWER: return 0;   // variable: 2-3 per veto trial
+        default: return set_error(JMC_EINVAL, "unknown integrand kind %d", g->kind);
+    }
+}
+
+extern "C" int jmc_integrand_area(const jmc_integrand* g, double* area) {
+    JMC_REQUIRE(g && area, "jmc_integrand_area: NULL argument");
+    double a = 1.0, t = 1.0;
+    int rc = JMC_OK;
+    auto mul = [&](int kind) {
+        if (rc) return;
+        rc = sampler_area(kind, g->method, g->epsilon, g->z_cut, g->radius, g->lo, g->hi, &t);
+        a *= t;
+    };
+    switch (g->kind) {
+        case JMC_KIND_RADIATOR: mul(JMC_SAMPLER_UNGROOMED); break;
+        case JMC_KIND_CRIT: mul(JMC_SAMPLER_CRITICAL); break;
+        case JMC_KIND_CRIT_SUB: mul(JMC_SAMPLER_CRITICAL); mul(JMC_SAMPLER_UNGROOMED); break;
+        // order of the reference's product: crit * pre * sub (comparison_utils_probabilistic.py:452-454)
+        case JMC_KIND_PRE_CRIT_SUB: mul(JMC_SAMPLER_CRITICAL); mul(JMC_SAMPLER_PRECRITICAL); mul(JMC_SAMPLER_UNGROOMED); break;
+        case JMC_KIND_SIMPLE: mul(JMC_SAMPLER_SIMPLE); break;
+        case JMC_KIND_SHOWER: a = 1.0; break;
+        default: return set_error(JMC_EINVAL, "unknown integrand kind %d", g->kind);
+    }
+    if (rc) return rc;
+    // RADIATOR, lin sampling: the reference rescales the AREA by theta_crit (generation.py:316-317)
+    if (g->kind == JMC_KIND_RADIATOR && g->method == JMC_LIN) a = a * g->theta_scale;
+    *area = a;
+    return JMC_OK;
+}
+
+extern "C" int jmc_run(const jmc_integrand* g, uint64_t n, uint64_t seed, uint64_t first_index, int precision,
+                       const double* d_edges, int n_edges, double* d_sum_w, double* d_sum_w2, uint64_t* d_count,
+                       double* d_minmax, void* stream) {
+    JMC_REQUIRE(g != nullptr, "jmc_run: integrand is NULL");
+    JMC_REQUIRE(precision == JMC_F64 || precision == JMC_F32, "jmc_run: precision must be JMC_F64 or JMC_F32");
+    if (g->kind == JMC_KIND_SHOWER)
+        return run_shower(g, n, seed, first_index, d_edges, n_edges, d_sum_w, d_sum_w2, d_count, d_minmax, stream);
+    if (precision == JMC_F64)
+        return run_exact(g, n, seed, first_index, d_edges, n_edges, d_sum_w, d_sum_w2, d_count, d_minmax, stream);
+    return run_fast(g, n, seed, first_index, d_edges, n_edges, d_sum_w, d_sum_w2, d_count, d_minmax, stream);
+}
+
+// ---------------------------------------------------------------------------
+// host-buffer entry points
+// ---------------------------------------------------------------------------
+namespace {
+
+// device buffer that frees itself; the host entry points are synchronous
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    int alloc(size_t bytes) {
+        JMC_CUDA(cudaMalloc(&p, bytes ? bytes : 8));
+        return JMC_OK;
+    }
+    template <typename T> T* as() { return (T*)p; }
+};
+
+int finalize_to_host(DevBuf& hist, int n_edges, const double* d_edges, double area, uint64_t n_total, int bc_kind,
+                     double bc_value, double* h_density, double* h_density_err, double* h_integral,
+                     double* h_integral_err, double* h_sum_w, double* h_sum_w2, uint64_t* h_count) {
+    const size_t nb = (size_t)n_edges - 1;
+    double* d_sum_w = hist.as<double>();
+    double* d_sum_w2 = d_sum_w + nb;
+    uint64_t* d_count = (uint64_t*)(d_sum_w2 + nb);
+    DevBuf out;
+    int rc = out.alloc(sizeof(double) * (4 * nb + 1));
+    if (rc) return rc;
+    double* d_density = out.as<double>();
+    double* d_err = d_density + nb;
+    double* d_ierr = d_err + nb;
+    double* d_integral = d_ierr + nb;
+    rc = jmc_finalize(d_sum_w, d_sum_w2, d_count, d_edges, n_edges, area, n_total, bc_kind, bc_value, d_density, d_err,
+                      d_integral, d_ierr, nullptr);
+    if (rc) return rc;
+    if (h_density) JMC_CUDA(cudaMemcpy(h_density, d_density, sizeof(double) * nb, cudaMemcpyDeviceToHost));
+    if (h_density_err) JMC_CUDA(cudaMemcpy(h_density_err, d_err, sizeof(double) * nb, cudaMemcpyDeviceToHost));
+    if (h_integral_err) JMC_CUDA(cudaMemcpy(h_integral_err, d_ierr, sizeof(double) * nb, cudaMemcpyDeviceToHost));
+    if (h_integral) JMC_CUDA(cudaMemcpy(h_integral, d_integral, sizeof(double) * (nb + 1), cudaMemcpyDeviceToHost));
+    if (h_sum_w) JMC_CUDA(cudaMemcpy(h_sum_w, d_sum_w, sizeof(double) * nb, cudaMemcpyDeviceToHost));
+    if (h_sum_w2) JMC_CUDA(cudaMemcpy(h_sum_w2, d_sum_w2, sizeof(double) * nb, cudaMemcpyDeviceToHost));
+    if (h_count) JMC_CUDA(cudaMemcpy(h_count, d_count, sizeof(uint64_t) * nb, cudaMemcpyDeviceToHost));
+    JMC_CUDA(cudaDeviceSynchronize());
+    return JMC_OK;
+}
+
+}  // namespace
+
+extern "C" int jmc_set_density_host(const double* h_obs, const double* h_weights, uint64_t n, const double* h_edges,
+                                    int n_edges, double area, int bc_kind, double bc_value, double* h_density,
+                                    double* h_density_err, double* h_integral, double* h_integral_err,
+                                    double* h_sum_w, double* h_sum_w2, uint64_t* h_count) {
+    JMC_REQUIRE(n_edges >= 2 && h_edges, "jmc_set_density_host: Need bins to produce density histogram.");
+    JMC_REQUIRE(n == 0 || (h_obs && h_weights), "jmc_set_density_host: NULL input array");
+    const size_t nb = (size_t)n_edges - 1;
+    DevBuf in, edges, hist;
+    int rc = in.alloc(sizeof(double) * 2 * n);
+    if (!rc) rc = edges.alloc(sizeof(double) * n_edges);
+    if (!rc) rc = hist.alloc(sizeof(double) * 3 * nb);
+    if (rc) return rc;
+    double* d_obs = in.as<double>();
+    double* d_w = d_obs + n;
+    JMC_CUDA(cudaMemcpy(d_obs, h_obs, sizeof(double) * n, cudaMemcpyHostToDevice));
+    JMC_CUDA(cudaMemcpy(d_w, h_weights, sizeof(double) * n, cudaMemcpyHostToDevice));
+    JMC_CUDA(cudaMemcpy(edges.p, h_edges, sizeof(double) * n_edges, cudaMemcpyHostToDevice));
+    JMC_CUDA(cudaMemset(hist.p, 0, sizeof(double) * 3 * nb));
+    rc = jmc_hist(d_obs, d_w, n, edges.as<double>(), n_edges, hist.as<double>(), hist.as<double>() + nb,
+                  (uint64_t*)(hist.as<double>() + 2 * nb), nullptr);
+    if (rc) return rc;
+    return finalize_to_host(hist, n_edges, edges.as<double>(), area, n, bc_kind, bc_value, h_density, h_density_err,
+                            h_integral, h_integral_err, h_sum_w, h_sum_w2, h_count);
+}
+
+extern "C" int jmc_integrate_host(const jmc_integrand* g, uint64_t n, uint64_t seed, uint64_t first_index,
+                                  int precision, const double* h_edges, int n_edges, int bc_kind, double bc_value,
+                                  double* h_density, double* h_density_err, double* h_integral,
+                                  double* h_integral_err, double* h_sum_w, double* h_sum_w2, uint64_t* h_count) {
+    JMC_REQUIRE(n_edges >= 2 && h_edges, "jmc_integrate_host: Need bins to produce density histogram.");
+    double area;
+    int rc = jmc_integrand_area(g, &area);
+    if (rc) return rc;
+    const size_t nb = (size_t)n_edges - 1;
+    DevBuf edges, hist;
+    rc = edges.alloc(sizeof(double) * n_edges);
+    if (!rc) rc = hist.alloc(sizeof(double) * 3 * nb);
+    if (rc) return rc;
+    JMC_CUDA(cudaMemcpy(edges.p, h_edges, sizeof(double) * n_edges, cudaMemcpyHostToDevice));
+    JMC_CUDA(cudaMemset(hist.p, 0, sizeof(double) * 3 * nb));
+    rc = jmc_run(g, n, seed, first_index, precision, edges.as<double>(), n_edges, hist.as<double>(),
+                 hist.as<double>() + nb, (uint64_t*)(hist.as<double>() + 2 * nb), nullptr, nullptr);
+    if (rc) return rc;
+    return finalize_to_host(hist, n_edges, edges.as<double>(), area, n, bc_kind, bc_value, h_density, h_density_err,
+                            h_integral, h_integral_err, h_sum_w, h_sum_w2, h_count);
+}
+
+extern "C" int jmc_sample_host(const jmc_sampler* s, uint64_t n, uint64_t seed, uint64_t first_index,
+                               double* h_samples, double* h_jac) {
+    JMC_REQUIRE(s != nullptr, "jmc_sample_host: sampler is NULL");
+    const int dim = (s->kind == JMC_SAMPLER_CRITICAL || s->kind == JMC_SAMPLER_UNGROOMED) ? 2 : 1;
+    DevBuf buf;
+    int rc = buf.alloc(sizeof(double) * n * (dim + 1));
+    if (rc) return rc;
+    double* d_samples = buf.as<double>();
+    double* d_jac = d_samples + n * dim;
+    rc = jmc_sample(s, n, seed, first_index, d_samples, d_jac, nullptr);
+    if (rc) return rc;
+    if (n && h_samples) JMC_CUDA(cudaMemcpy(h_samples, d_samples, sizeof(double) * n * dim, cudaMemcpyDeviceToHost));
+    if (n && h_jac) JMC_CUDA(cudaMemcpy(h_jac, d_jac, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    return JMC_OK;
+}
+
+extern "C" int jmc_eval_fn_host(int fn, const jmc_fn_params* p, uint64_t n, const double* h_a0, int64_t stride0,
+                                const double* h_a1, int64_t stride1, const double* h_a2, int64_t stride2,
+                                const double* h_a3, int64_t stride3, double* h_out) {
+    JMC_REQUIRE(n == 0 || h_out, "jmc_eval_fn_host: out is NULL");
+    if (n == 0) return JMC_OK;
+    const double* h[4] = {h_a0, h_a1, h_a2, h_a3};
+    const int64_t st[4] = {stride0, stride1, stride2, stride3};
+    DevBuf in[4], out;
+    const double* d[4] = {nullptr, nullptr, nullptr, nullptr};
+    for (int k = 0; k < 4; ++k) {
+        if (!h[k]) continue;
+        JMC_REQUIRE(st[k] >= 1, "jmc_eval_fn_host: stride of argument %d must be >= 1", k);
+        const size_t count = (size_t)(n - 1) * st[k] + 1;
+        int rc = in[k].alloc(sizeof(double) * count);
+        if (rc) return rc;
+        JMC_CUDA(cudaMemcpy(in[k].p, h[k], sizeof(double) * count, cudaMemcpyHostToDevice));
+        d[k] = in[k].as<double>();
+    }
+    int rc = out.alloc(sizeof(double) * n);
+    if (rc) return rc;
+    rc = jmc_eval_fn(fn, p, n, d[0], st[0], d[1], st[1], d[2], st[2], d[3], st[3], out.as<double>(), nullptr);
+    if (rc) return rc;
+    JMC_CUDA(cudaMemcpy(h_out, out.p, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    return JMC_OK;
+}

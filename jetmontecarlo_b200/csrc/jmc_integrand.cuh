@@ -1,0 +1,134 @@
+// FP64 (NumPy-order) evaluation of one sample of an integrand: samples ->
+// jacobian, observable, weight*jacobian.  Shared by the replay kernel
+// (samples read from device arrays) and the exact mode of the fused kernel
+// (samples drawn from Philox in registers).
+#pragma once
+#include "jmc_common.cuh"
+#include "jmc_philox.cuh"
+#include "jmc_physics.cuh"
+
+namespace jmc {
+
+struct SampleSet {
+    double z_c, th_c;   // critical emission
+    double z_s, th_s;   // subsequent / ungroomed emission
+    double z_pre;       // pre-critical emission (or the simple sampler's x)
+    double zb_u;        // zero-bin uniform
+};
+
+// ---- the sampler formulas, from uniforms ----------------------------------
+// ref: numerics/radiators/samplers.py:38-62 (critical; z is drawn first)
+__device__ __forceinline__ void sample_critical(const RunParams& p, double u0, double u1, double& z, double& th) {
+    if (p.g.method == JMC_LIN) {
+        z = lin_sample(p.g.z_cut, 0.5, u0);
+        th = lin_sample(0.0, p.g.radius, u1);
+    } else {
+        z = log_sample(p.g.z_cut, p.log_eps, p.lw_crit_z, u0);
+        th = log_sample(0.0, p.log_eps, p.lw_radius, u1);
+    }
+}
+// ref: numerics/radiators/samplers.py:204-226 (ungroomed)
+__device__ __forceinline__ void sample_ungroomed(const RunParams& p, double u0, double u1, double& z, double& th) {
+    if (p.g.method == JMC_LIN) {
+        z = lin_sample(0.0, 0.5, u0);
+        th = lin_sample(0.0, p.g.radius, u1);
+    } else {
+        z = log_sample(0.0, p.log_eps, p.lw_half, u0);
+        th = log_sample(0.0, p.log_eps, p.lw_radius, u1);
+    }
+}
+// ref: numerics/radiators/samplers.py:140-158 (precritical)
+__device__ __forceinline__ double sample_precritical(const RunParams& p, double u) {
+    return p.g.method == JMC_LIN ? lin_sample(0.0, p.g.z_cut, u) : log_sample(0.0, p.log_eps, p.lw_pre, u);
+}
+// ref: montecarlo/sampler.py:124-132 (simple)
+__device__ __forceinline__ double sample_simple(const RunParams& p, double u) {
+    return p.g.method == JMC_LIN ? lin_sample(p.g.lo, p.g.hi, u) : log_sample(p.g.lo, p.log_eps, p.lw_simple, u);
+}
+
+// Draw the samples of integrand KIND for global sample index `idx`.
+// Uniform slots: 0,1 critical (z, theta) | 2,3 subsequent (z, theta) | 4 pre | 5 zero-bin;
+// kinds with a single sampler use slots 0,1.
+template <int KIND>
+__device__ __forceinline__ void draw_exact(const RunParams& p, uint64_t idx, uint64_t seed, SampleSet& s) {
+    double u0, u1;
+    philox_uniform53x2(idx, 0u, seed, u0, u1);
+    if (KIND == JMC_KIND_RADIATOR) {
+        sample_ungroomed(p, u0, u1, s.z_s, s.th_s);
+    } else if (KIND == JMC_KIND_SIMPLE) {
+        s.z_pre = sample_simple(p, u0);
+    } else {
+        sample_critical(p, u0, u1, s.z_c, s.th_c);
+    }
+    if (KIND == JMC_KIND_CRIT_SUB || KIND == JMC_KIND_PRE_CRIT_SUB) {
+        philox_uniform53x2(idx, 1u, seed, u0, u1);
+        sample_ungroomed(p, u0, u1, s.z_s, s.th_s);
+    }
+    if (KIND == JMC_KIND_PRE_CRIT_SUB) {
+        philox_uniform53x2(idx, 2u, seed, u0, u1);
+        s.z_pre = sample_precritical(p, u0);
+        s.zb_u = u1;
+    }
+}
+
+// ---- one sample of the integrand -------------------------------------------
+// jac: product of the sampler jacobians (incl. theta_scale for log RADIATOR);
+// obs: the binned observable; wj: weight * jac, nan_to_num applied to the
+// weight first when g.nan_to_num is set.
+template <int KIND>
+__device__ __forceinline__ void integrand_eval(const RunParams& p, const SampleSet& s, double& jac, double& obs,
+                                               double& wj) {
+    const jmc_integrand& g = p.g;
+    const bool is_log = g.method == JMC_LOG;
+    if (KIND == JMC_KIND_RADIATOR) {
+        // ref: numerics/radiators/generation.py:303-335 (theta_scale = theta_crit), weights.py:15-26
+        const double th_em = s.th_s * g.theta_scale;
+        obs = ecf_ungroomed(s.z_s, th_em, g.beta, g.obs_acc);
+        double w = weight_radiator(s.z_s, th_em, g.jet, g.fixed_coupling, g.split_acc);
+        if (g.nan_to_num) w = nan_to_num(w);
+        jac = is_log ? (s.z_s * s.th_s) * g.theta_scale : 1.0;
+        wj = w * jac;
+    } else if (KIND == JMC_KIND_CRIT) {
+        // ref: examples/tests/oneEmission_tests/test_fixedcoupcritsudakov.py:124-220
+        obs = ecf_groomed(s.z_c, s.th_c, g.z_cut, g.beta, g.z_pre, g.f_soft, g.obs_acc);
+        double w = weight_critical(s.z_c, s.th_c, g.z_cut, g.jet, g.fixed_coupling);
+        if (g.nan_to_num) w = nan_to_num(w);
+        jac = is_log ? (s.z_c - g.z_cut) * s.th_c : 1.0;
+        wj = w * jac;
+    } else if (KIND == JMC_KIND_CRIT_SUB) {
+        // ref: numerics/weights.py:63-99; examples/sudakov_comparisons/sudakov_utils.py:525-538
+        const double csub = csub_verbatim(s.z_s, s.th_s, g.beta);
+        const double ccrit = ecf_groomed(s.z_c, s.th_c, g.z_cut, g.beta, g.z_pre, g.f_soft, g.obs_acc);
+        obs = np_max(ccrit, csub);
+        double w = weight_two_emission(s.z_c, s.th_c, s.z_s, s.th_s, g.z_cut, g.beta, g.jet, g.fixed_coupling);
+        if (g.nan_to_num) w = nan_to_num(w);
+        const double jc = is_log ? (s.z_c - g.z_cut) * s.th_c : 1.0;
+        const double js = is_log ? s.z_s * s.th_s : 1.0;
+        jac = jc * js;
+        wj = w * jc * js;
+    } else if (KIND == JMC_KIND_PRE_CRIT_SUB) {
+        // ref: examples/tests/comparison_tests/comparison_utils_probabilistic.py:384-474
+        const double cr = casimir(g.jet);
+        const double cdf_eps = exp(-2.0 * cr * JMC_ALPHA_FIXED / JMC_PI * log(JMC_R0 / s.th_c)
+                                   * log(g.z_cut / g.epsilon));
+        const double zp = (is_log && s.zb_u < cdf_eps) ? 0.0 : s.z_pre;
+        const double thb = np_pow(s.th_c, g.beta);
+        const double c_sub = s.z_s * thb;
+        obs = np_max(ecf_groomed(s.z_c, s.th_c, g.z_cut, g.beta, zp, g.f_soft, g.obs_acc), c_sub);
+        double w = weight_critical(s.z_c, s.th_c, g.z_cut, g.jet, 1)
+                   * pdf_sub_fc(c_sub / thb, g.beta, g.jet, 1.0)
+                   * weight_precritical_zerobin(zp, s.th_c, g.z_cut, g.jet, g.epsilon);
+        if (g.nan_to_num) w = nan_to_num(w);
+        const double jc = is_log ? (s.z_c - g.z_cut) * s.th_c : 1.0;
+        const double js = is_log ? s.z_s * s.th_s : 1.0;
+        const double jp = is_log ? s.z_pre : 1.0;
+        jac = (zp == 0.0) ? jc * js : jc * jp * js;
+        wj = w * jac;
+    } else {  // JMC_KIND_SIMPLE
+        obs = s.z_pre;
+        jac = is_log ? s.z_pre : 1.0;
+        wj = jac;
+    }
+}
+
+}  // namespace jmc

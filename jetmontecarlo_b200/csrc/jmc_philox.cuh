@@ -1,0 +1,67 @@
+// Counter-based RNG of the fused path: Philox-4x32-10 (Salmon et al., SC'11).
+//
+// Replaces the reference's per-coordinate `random.random()` (MT19937) calls at
+// jetmontecarlo/utils/montecarlo_utils.py:28,53.  A counter RNG needs no state
+// in memory: sample i, draw block b is philox(counter=(i_lo, i_hi, b, 0),
+// key=(seed_lo, seed_hi)), so samples live only in registers, any GPU can
+// produce any index range, and the union of samples is the same for every
+// number of GPUs.
+//
+// Uniform conventions (mirrored by oracle/jmc_oracle.py: philox_uniforms53 /
+// philox_words):
+//   f64: block b yields uniforms 2b, 2b+1 = ((w[2j]>>5)*2^26 + (w[2j+1]>>6)) / 2^53
+//        -- the same 53-bit construction CPython's random.random() uses;
+//   f32: block b yields uniforms 4b..4b+3 = ((w[j]>>8) + 0.5) * 2^-24  in (0,1).
+#pragma once
+#include <cstdint>
+
+namespace jmc {
+
+struct PhiloxKey { uint32_t k0, k1; };
+
+__host__ __device__ __forceinline__ void philox_round(uint32_t& c0, uint32_t& c1, uint32_t& c2,
+                                                      uint32_t& c3, uint32_t k0, uint32_t k1) {
+#ifdef __CUDA_ARCH__
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0);
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2);
+#else
+    const uint32_t hi0 = (uint32_t)(((uint64_t)0xD2511F53u * c0) >> 32);
+    const uint32_t hi1 = (uint32_t)(((uint64_t)0xCD9E8D57u * c2) >> 32);
+#endif
+    const uint32_t lo0 = 0xD2511F53u * c0;
+    const uint32_t lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ k0;
+    c1 = lo1;
+    c2 = hi0 ^ c3 ^ k1;
+    c3 = lo0;
+}
+
+// four 32-bit words for (index, block) under key `seed`
+__host__ __device__ __forceinline__ void philox4x32_10(uint64_t index, uint32_t block, uint64_t seed,
+                                                       uint32_t w[4]) {
+    uint32_t c0 = (uint32_t)index, c1 = (uint32_t)(index >> 32), c2 = block, c3 = 0u;
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        philox_round(c0, c1, c2, c3, k0, k1);
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    w[0] = c0; w[1] = c1; w[2] = c2; w[3] = c3;
+}
+
+// two 53-bit uniforms in [0,1) from one block
+__host__ __device__ __forceinline__ void philox_uniform53x2(uint64_t index, uint32_t block, uint64_t seed,
+                                                            double& u0, double& u1) {
+    uint32_t w[4];
+    philox4x32_10(index, block, seed, w);
+    u0 = ((double)(w[0] >> 5) * 67108864.0 + (double)(w[1] >> 6)) / 9007199254740992.0;
+    u1 = ((double)(w[2] >> 5) * 67108864.0 + (double)(w[3] >> 6)) / 9007199254740992.0;
+}
+
+// 24-bit uniform strictly inside (0,1)
+__host__ __device__ __forceinline__ float u32_to_unit_float(uint32_t w) {
+    return ((float)(w >> 8) + 0.5f) * 5.9604644775390625e-08f;
+}
+
+}  // namespace jmc

@@ -1,0 +1,62 @@
+"""Multi-GPU plumbing: one process per GPU, samples sharded by global index,
+histograms combined by ONE all-reduce (NCCL over NVLink on the GPU box; the
+same code runs on gloo in the CPU tests).
+
+Because sample i is a pure function of (seed, i) -- a counter RNG -- the union
+of the ranks' samples is identical for every world size; the result differs
+only by floating-point summation order.
+"""
+import torch
+import torch.distributed as dist
+
+
+def is_distributed(group=None):
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+
+
+def shard_bounds(n, rank, world):
+    """[first, first + count) of rank ``rank``: contiguous, sizes differ by <= 1."""
+    base, rem = divmod(int(n), int(world))
+    first = rank * base + min(rank, rem)
+    return first, base + (1 if rank < rem else 0)
+
+
+def shard(n, group=None):
+    if not is_distributed(group):
+        return 0, int(n)
+    return shard_bounds(n, dist.get_rank(group), dist.get_world_size(group))
+
+
+def pack_histograms(sum_w, sum_w2, count):
+    """One float64 buffer [3, nb]; counts are exact in float64 up to 2^53."""
+    return torch.stack([sum_w, sum_w2, count.to(torch.float64)])
+
+
+def unpack_histograms(buf, sum_w, sum_w2, count):
+    sum_w.copy_(buf[0])
+    sum_w2.copy_(buf[1])
+    count.copy_(buf[2].round().to(count.dtype))
+
+
+def allreduce_histograms(sum_w, sum_w2, count, group=None):
+    """SUM over ranks of (sum w, sum w^2, count), in place, one collective."""
+    if not is_distributed(group):
+        return
+    buf = pack_histograms(sum_w, sum_w2, count)
+    dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+    unpack_histograms(buf, sum_w, sum_w2, count)
+
+
+def allreduce_minmax(minmax, group=None):
+    """minmax = [min, max]: one MAX all-reduce of [-min, max]; NaN propagates."""
+    if not is_distributed(group):
+        return
+    buf = torch.stack([-minmax[0], minmax[1]])
+    has_nan = torch.isnan(buf).any().to(buf.dtype).reshape(1)
+    buf = torch.cat([torch.nan_to_num(buf, nan=float("-inf")), has_nan])
+    dist.all_reduce(buf, op=dist.ReduceOp.MAX, group=group)
+    if buf[2] > 0:
+        minmax.fill_(float("nan"))
+    else:
+        minmax[0] = -buf[0]
+        minmax[1] = buf[1]

@@ -1,0 +1,192 @@
+"""Fused path: describe an integrand, and the GPU generates, weights and bins
+its samples in one kernel (jmc_run) without ever writing a sample to HBM.
+
+An ``Integrand`` names one of the sampler x observable x weight combinations
+the reference's scripts build by hand:
+
+  Integrand.radiator(...)      ungroomedSampler, C_ungroomed, radiatorWeight          (C1, C2, C5)
+  Integrand.critical(...)      criticalSampler, C_groomed, criticalEmissionWeight
+  Integrand.crit_sub(...)      critical x ungroomed, max(C_groomed, csub), twoEmissionWeight   (C3)
+  Integrand.pre_crit_sub(...)  + precriticalSampler with the zero-bin draw            (C4)
+  Integrand.shower(...)        veto-algorithm angularity shower, ECF of the chain     (C2, C3)
+
+``integrate(integrand, n, edges | (numbins, spacing), ...)`` returns a filled
+``integrator``.  With ``torch.distributed`` initialised the sample indices are
+sharded over the ranks and the histograms are summed by one all-reduce.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _device as D
+from . import _lib
+from . import distributed as dist_utils
+
+PRECISIONS = {'f64': _lib.F64, 'f32': _lib.F32}
+
+
+class Integrand:
+    """Plain description of an integrand (mirrors ``jmc_integrand``)."""
+
+    def __init__(self, kind, method, *, jet_type='quark', fixedcoupling=True, obs_acc='LL',
+                 split_acc='LL', nan_to_num=False, epsilon=0., z_cut=0., radius=1., beta=2., f=1.,
+                 z_pre=0., theta_scale=1., bounds=(0., 1.), groomer=0, n_emissions=1, beta_sd=0.,
+                 cutoff=0.):
+        assert method in ('lin', 'log'), str(method) + "is not a supported sample method."
+        assert jet_type in ('quark', 'gluon'), str(jet_type) + "is not a supported jet type."
+        assert obs_acc in ('LL', 'MLL'), "Accuracy must be LL or MLL"
+        assert split_acc in ('LL', 'LL_nonsing', 'MLL'), "Invalid accuracy."
+        eps = 0 if epsilon is None else epsilon
+        if method == 'log':
+            assert 0 < eps < 1., ("epsilon={epsilon} is invalid for {type} sampling."
+                                  .format(epsilon=eps, type=method))
+        self.kind, self.method = kind, method
+        self.jet_type, self.fixedcoupling = jet_type, bool(fixedcoupling)
+        self.obs_acc, self.split_acc, self.nan_to_num = obs_acc, split_acc, bool(nan_to_num)
+        self.epsilon, self.z_cut, self.radius, self.beta = float(eps), float(z_cut), float(radius), float(beta)
+        self.f, self.z_pre, self.theta_scale = float(f), float(z_pre), float(theta_scale)
+        self.bounds = (float(bounds[0]), float(bounds[1]))
+        self.groomer, self.beta_sd, self.cutoff = int(groomer), float(beta_sd), float(cutoff)
+        self.n_emissions = 0 if n_emissions == 'all' else int(n_emissions)
+
+    # ---- constructors ---------------------------------------------------------
+    @classmethod
+    def radiator(cls, method, epsilon=0., radius=1., beta=2., jet_type='quark', fixedcoupling=True,
+                 obs_acc='LL', split_acc='LL', theta_scale=1., nan_to_num=False):
+        assert radius > 0, "Jet radius must be greater than zero!"
+        return cls(_lib.KIND_RADIATOR, method, epsilon=epsilon, radius=radius, beta=beta, jet_type=jet_type,
+                   fixedcoupling=fixedcoupling, obs_acc=obs_acc, split_acc=split_acc, theta_scale=theta_scale,
+                   nan_to_num=nan_to_num)
+
+    @classmethod
+    def critical(cls, method, z_cut, epsilon=0., radius=1., beta=2., jet_type='quark', fixedcoupling=True,
+                 obs_acc='LL', z_pre=0., f=1., nan_to_num=None):
+        _check_zcut(z_cut)
+        nan_to_num = (not fixedcoupling) if nan_to_num is None else nan_to_num
+        return cls(_lib.KIND_CRIT, method, epsilon=epsilon, z_cut=z_cut, radius=radius, beta=beta,
+                   jet_type=jet_type, fixedcoupling=fixedcoupling, obs_acc=obs_acc, z_pre=z_pre, f=f,
+                   nan_to_num=nan_to_num)
+
+    @classmethod
+    def crit_sub(cls, method, z_cut, epsilon=0., radius=1., beta=2., jet_type='quark', fixedcoupling=True,
+                 obs_acc='MLL', z_pre=None, f=0., nan_to_num=True):
+        """Defaults are the Soft Drop / mMDT form ``z_pre=z_cut, f=0``
+        (examples/sudakov_comparisons/sudakov_utils.py:481-486)."""
+        _check_zcut(z_cut)
+        return cls(_lib.KIND_CRIT_SUB, method, epsilon=epsilon, z_cut=z_cut, radius=radius, beta=beta,
+                   jet_type=jet_type, fixedcoupling=fixedcoupling, obs_acc=obs_acc,
+                   z_pre=z_cut if z_pre is None else z_pre, f=f, nan_to_num=nan_to_num)
+
+    @classmethod
+    def pre_crit_sub(cls, method, z_cut, epsilon=0., radius=1., beta=2., jet_type='quark', fixedcoupling=True,
+                     obs_acc='LL', f=1., nan_to_num=False):
+        _check_zcut(z_cut)
+        if not fixedcoupling:
+            raise TypeError("Can only accept fixed coupling for now!")
+        assert method == 'log', "Weight requires valid cutoff for zero bin."
+        return cls(_lib.KIND_PRE_CRIT_SUB, method, epsilon=epsilon, z_cut=z_cut, radius=radius, beta=beta,
+                   jet_type=jet_type, fixedcoupling=True, obs_acc=obs_acc, f=f, nan_to_num=nan_to_num)
+
+    @classmethod
+    def simple(cls, method, bounds=(0., 1.), epsilon=0.):
+        return cls(_lib.KIND_SIMPLE, method, epsilon=epsilon, bounds=bounds)
+
+    @classmethod
+    def shower(cls, beta=2., jet_type='quark', acc='MLL', radius=1., cutoff=None, groomer='ungroomed',
+               z_cut=0., beta_sd=0., obs_acc='LL', n_emissions=1):
+        from .analytics.qcd_utils import MU_NP
+        assert acc in ('LL', 'MLL'), "Invalid accuracy."
+        assert groomer in ('ungroomed', 'softdrop')
+        return cls(_lib.KIND_SHOWER, 'lin', radius=radius, beta=beta, jet_type=jet_type, split_acc=acc,
+                   obs_acc=obs_acc, z_cut=z_cut, groomer=int(groomer == 'softdrop'), n_emissions=n_emissions,
+                   beta_sd=beta_sd, cutoff=MU_NP if cutoff is None else cutoff)
+
+    # ---- C struct and derived quantities ---------------------------------------
+    def c_struct(self):
+        return _lib.Integrand(
+            kind=self.kind, method=_lib.METHODS[self.method], jet=_lib.JETS[self.jet_type],
+            fixed_coupling=int(self.fixedcoupling), obs_acc=_lib.ACCS[self.obs_acc],
+            split_acc=_lib.ACCS[self.split_acc], nan_to_num=int(self.nan_to_num),
+            shower_groomer=self.groomer, shower_n_emissions=self.n_emissions,
+            epsilon=self.epsilon, z_cut=self.z_cut, radius=self.radius, beta=self.beta, f_soft=self.f,
+            z_pre=self.z_pre, theta_scale=self.theta_scale, lo=self.bounds[0], hi=self.bounds[1],
+            beta_sd=self.beta_sd, shower_cutoff=self.cutoff)
+
+    @property
+    def area(self):
+        """Product of the sampler areas, as the reference's scripts multiply them
+        (NumPy arithmetic, so it is bit-identical to ``sampler.area`` products)."""
+        if self.kind == _lib.KIND_SHOWER:
+            return 1.
+        if self.method == 'log':
+            l1 = np.log(1. / self.epsilon)
+            l2 = np.log(1. / self.epsilon) ** 2.
+            return {_lib.KIND_RADIATOR: l2, _lib.KIND_CRIT: l2, _lib.KIND_CRIT_SUB: l2 * l2,
+                    _lib.KIND_PRE_CRIT_SUB: l2 * l1 * l2, _lib.KIND_SIMPLE: l1}[self.kind]
+        crit = (1. / 2. - self.z_cut) * self.radius
+        ung = self.radius / 2.
+        return {_lib.KIND_RADIATOR: ung * self.theta_scale, _lib.KIND_CRIT: crit,
+                _lib.KIND_CRIT_SUB: crit * ung, _lib.KIND_PRE_CRIT_SUB: crit * self.z_cut * ung,
+                _lib.KIND_SIMPLE: self.bounds[1] - self.bounds[0]}[self.kind]
+
+    @property
+    def n_uniform(self):
+        s = self.c_struct()
+        return _lib.check(_lib.lib.jmc_integrand_uniforms(C.byref(s)))
+
+
+def _check_zcut(zc):
+    zc = 0 if zc is None else zc
+    assert 0 < zc < 1. / 2., ("zc={zcut} is an invalid grooming parameter.".format(zcut=zc))
+
+
+def accumulate(integrand, num_samples, seed, precision, edges_dev, sum_w, sum_w2, count, group=None,
+               minmax=None):
+    """Run this rank's share of ``num_samples`` and (if distributed) all-reduce.
+
+    The tensors are CUDA tensors: edges float64 [n_edges], sum_w / sum_w2
+    float64 [n_edges-1], count int64 [n_edges-1]; they are accumulated into."""
+    D.require_cuda()
+    num_samples = int(num_samples)
+    first, n_local = dist_utils.shard(num_samples, group)
+    s = integrand.c_struct()
+    n_edges = 0 if edges_dev is None else int(edges_dev.numel())
+    _lib.check(_lib.lib.jmc_run(C.byref(s), n_local, int(seed) & 0xFFFFFFFFFFFFFFFF, first,
+                                PRECISIONS[precision], D.ptr(edges_dev), n_edges, D.ptr(sum_w), D.ptr(sum_w2),
+                                D.ptr(count), D.ptr(minmax), D.stream()))
+    if edges_dev is not None:
+        dist_utils.allreduce_histograms(sum_w, sum_w2, count, group)
+    if minmax is not None:
+        dist_utils.allreduce_minmax(minmax, group)
+
+
+def observable_range(integrand, num_samples, seed, precision='f64', group=None):
+    """(min, max) of the observable over the job's samples, regenerated from the
+    counter RNG (nothing stored) -- the data-dependent half of setBins."""
+    mm = torch.tensor([np.inf, -np.inf], dtype=torch.float64, device=D.device())
+    accumulate(integrand, num_samples, seed, precision, None, None, None, None, group, minmax=mm)
+    lo, hi = D.to_host(mm)
+    return lo, hi
+
+
+def integrate(integrand, num_samples, *, edges=None, numbins=None, binspacing='log', seed=0, precision='f32',
+              last_bc=None, first_bc=None, min_log_bin=1e-15, group=None):
+    """One call for the whole job; returns an ``integrator`` with density,
+    densityErr, integral and integralErr filled."""
+    from .montecarlo.integrator import integrator
+    it = integrator()
+    if last_bc is not None:
+        it.setLastBinBndCondition(list(last_bc))
+    if first_bc is not None:
+        it.setFirstBinBndCondition(first_bc)
+    if edges is not None:
+        it.bins = np.asarray(edges, dtype=np.float64)
+        it.binspacing = binspacing
+        it.hasBins = True
+    else:
+        it.setBinsFused(numbins, integrand, num_samples, binspacing, seed, min_log_bin=min_log_bin,
+                        precision='f64' if integrand.kind != _lib.KIND_SHOWER else precision, group=group)
+    it.setDensityFused(integrand, num_samples, seed, precision=precision, group=group)
+    it.integrate()
+    return it

@@ -1,0 +1,306 @@
+"""Monte Carlo integrator -- host mirror of jetmontecarlo/montecarlo/integrator.py.
+
+``integrator`` keeps the reference's methods, attributes, flags, assertion
+messages and on-disk formats.  The numerics run in libjmc_b200.so:
+
+  setBins      min / max of the observable       -> jmc_minmax (edges themselves
+               are np.linspace / np.logspace on the host, as in the reference)
+  setDensity   3 x np.histogram + normalisation  -> jmc_hist + jmc_finalize
+  integrate    (reverse) cumulative sums         -> jmc_cumulative (block scan)
+
+Observables and weights may be NumPy arrays (copied to the device) or CUDA
+tensors (used in place).  Additive API for the fused path, where samples are
+never materialised: ``setBinsFused`` / ``setDensityFused`` take an integrand
+description (jetmontecarlo_b200.fused.Integrand) instead of arrays.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from .. import _device as D
+from .. import _lib
+from .sampler import simpleSampler
+
+MIN_LOG_BIN = 1e-15
+
+
+def _bc_args(first_bc, last_bc):
+    """(bc_kind, bc_value) of the C ABI from the reference's two attributes."""
+    use_last = (last_bc is not None) and first_bc is None
+    use_first = (first_bc is not None) and last_bc is None
+    ambiguous = (not (use_last or use_first)) or (use_last and use_first)
+    assert not ambiguous, "Integration requires unambiguous boundary conditions"
+    if use_first:
+        return _lib.BC_FIRST, float(first_bc)
+    assert last_bc[1] in ['plus', 'minus'], \
+        "Integration requires lastBinBndCond (plus or minus)"
+    return (_lib.BC_LAST_PLUS if last_bc[1] == 'plus' else _lib.BC_LAST_MINUS), float(last_bc[0])
+
+
+class integrator():
+    """Weighted histogram -> density +- error -> cumulative integral +- error.
+    ref: montecarlo/integrator.py:21-386"""
+
+    # ------------------
+    # Integration Tools:
+    # ------------------
+    def _device_obs(self, observables):
+        """Device copy of an observable array, cached between setBins and
+        setDensity so a host array crosses PCIe once."""
+        cached = getattr(self, '_obs_cache', None)
+        if cached is not None and cached[0] is observables:
+            return cached[1]
+        dev = D.to_device(observables).reshape(-1)
+        self._obs_cache = (observables, dev)
+        return dev
+
+    def _min_max(self, observables):
+        dev = self._device_obs(observables)
+        if dev.numel() == 0:
+            raise ValueError("zero-size array to reduction operation minimum which has no identity")
+        out = D.empty((2,))
+        _lib.check(_lib.lib.jmc_minmax(D.ptr(dev), dev.numel(), D.ptr(out), D.stream()))
+        lo, hi = D.to_host(out)
+        return lo, hi
+
+    def _edges_from_range(self, numbins, obs_min, obs_max, binspacing, min_log_bin):
+        """ref: montecarlo/integrator.py:41-55"""
+        if binspacing == 'lin':
+            self.bins = np.linspace(min(0, obs_min), obs_max, numbins)
+        elif binspacing == 'log':
+            min_bin = np.log10(max(obs_min, min_log_bin))
+            max_bin = np.log10(obs_max)
+            self.bins = np.logspace(min_bin, max_bin, numbins)
+        self.binspacing = binspacing
+        if self.binspacing == 'lin':
+            self.bin_midpoints = (self.bins[1:] + self.bins[:-1]) / 2.
+        elif self.binspacing == 'log':
+            self.bin_midpoints = np.exp((np.log(self.bins[1:]) + np.log(self.bins[:-1])) / 2.)
+        self.hasBins = True
+
+    def setBins(self, numbins, observables, binspacing, min_log_bin=MIN_LOG_BIN):
+        """Sets the bin edges from the range of the observables; ``numbins`` is
+        the number of EDGES.  ref: montecarlo/integrator.py:37-57"""
+        obs_min, obs_max = self._min_max(observables)
+        self._edges_from_range(numbins, obs_min, obs_max, binspacing, min_log_bin)
+
+    def setLastBinBndCondition(self, bndCond):
+        self.lastBinBndCond = bndCond
+        self.useLastBinBndCond = True
+
+    def setFirstBinBndCondition(self, bndCond):
+        self.firstBinBndCond = bndCond
+        self.useFirstBinBndCond = True
+
+    def setMonotone(self, monotone=True):
+        self.monotone = monotone
+
+    # ------------------
+    # Actual Integration:
+    # ------------------
+    def _density_from_hist(self, area, n_total):
+        """jmc_finalize on the device histograms -> density, densityErr."""
+        nb = len(self.bins) - 1
+        dens, err = D.empty((nb,)), D.empty((nb,))
+        _lib.check(_lib.lib.jmc_finalize(
+            D.ptr(self._sum_w), D.ptr(self._sum_w2), D.ptr(self._count), D.ptr(self._edges_dev), nb + 1,
+            float(area), int(n_total), _lib.BC_FIRST, 0., D.ptr(dens), D.ptr(err), None, None, D.stream()))
+        self.density = D.to_host(dens)
+        self.densityErr = D.to_host(err)
+        self.hasMCDensity = True
+
+    def _alloc_hist(self):
+        edges = np.ascontiguousarray(self.bins, dtype=np.float64)
+        assert edges.ndim == 1 and len(edges) >= 2, "Need bins to produce density histogram."
+        nb = len(edges) - 1
+        self._edges_dev = D.to_device(edges)
+        self._sum_w, self._sum_w2 = D.zeros((nb,)), D.zeros((nb,))
+        self._count = D.zeros((nb,), dtype=torch.int64)
+        return nb
+
+    def setDensity(self, observables, weights, area):
+        """Histogram of weights and squared weights in the observable, normalised
+        to a density with its statistical error.  ref: montecarlo/integrator.py:83-127"""
+        assert self.hasBins, "Need bins to produce density histogram."
+        assert area is not None, "Need a valid area to produce density histogram."
+        obs = self._device_obs(observables)
+        w = D.to_device(weights).reshape(-1)
+        if w.numel() != obs.numel():
+            raise ValueError("weights should have the same shape as a.")
+        nb = self._alloc_hist()
+        _lib.check(_lib.lib.jmc_hist(D.ptr(obs), D.ptr(w), obs.numel(), D.ptr(self._edges_dev), nb + 1,
+                                     D.ptr(self._sum_w), D.ptr(self._sum_w2), D.ptr(self._count), D.stream()))
+        self._density_from_hist(area, obs.numel())
+        self._obs_cache = None
+
+    def integrate(self):
+        """Cumulative integral of the density from the boundary condition.
+        ref: montecarlo/integrator.py:129-202"""
+        assert self.hasMCDensity, \
+            "Need density function to perform integration"
+        bc_kind, bc_value = _bc_args(self.firstBinBndCond, self.lastBinBndCond)
+        self.useLastBinBndCond = bc_kind != _lib.BC_FIRST
+        self.useFirstBinBndCond = bc_kind == _lib.BC_FIRST
+        edges = D.to_device(np.asarray(self.bins, dtype=np.float64))
+        nb = edges.numel() - 1
+        dens = D.to_device(np.asarray(self.density, dtype=np.float64))
+        err = D.to_device(np.asarray(self.densityErr, dtype=np.float64))
+        integral, ierr = D.empty((nb + 1,)), D.empty((nb,))
+        _lib.check(_lib.lib.jmc_cumulative(D.ptr(dens), D.ptr(err), D.ptr(edges), nb + 1, bc_kind, bc_value,
+                                           D.ptr(integral), D.ptr(ierr), D.stream()))
+        # the reference keeps a Python list of length numbins here
+        self.integral = list(D.to_host(integral))
+        self.integralErr = D.to_host(ierr)
+        self.hasMCIntegral = True
+        if self.monotone:
+            arr = np.asarray(self.integral)
+            is_monotone = ((arr[1:] <= arr[:-1]).all() or (arr[1:] >= arr[:-1]).all())
+            assert is_monotone, "User asked for a monotone integral,"\
+                " but the integral is not monotone!"
+
+    # ------------------
+    # Fused path (additive API)
+    # ------------------
+    def setBinsFused(self, numbins, integrand, num_samples, binspacing, seed, min_log_bin=MIN_LOG_BIN,
+                     precision='f64', group=None):
+        """setBins for a described integrand: a min/max pass that regenerates
+        the samples from the counter RNG instead of storing them."""
+        from .. import fused
+        obs_min, obs_max = fused.observable_range(integrand, num_samples, seed, precision, group)
+        self._edges_from_range(numbins, obs_min, obs_max, binspacing, min_log_bin)
+
+    def setDensityFused(self, integrand, num_samples, seed, precision='f32', group=None):
+        """setDensity for a described integrand: generate -> weight -> bin in
+        one kernel; with ``torch.distributed`` initialised the samples are
+        sharded by index over the ranks of ``group`` and the histograms are
+        summed with one all-reduce."""
+        from .. import fused
+        assert self.hasBins, "Need bins to produce density histogram."
+        self._alloc_hist()
+        fused.accumulate(integrand, num_samples, seed, precision, self._edges_dev,
+                         self._sum_w, self._sum_w2, self._count, group)
+        self._density_from_hist(integrand.area, int(num_samples))
+
+    # ------------------
+    # Saved data         (keys of the reference: integrator.py:204-224)
+    # ------------------
+    def montecarlo_data_dict(self, info=None):
+        data_dict = {'bins': self.bins,
+                     'bin midpoints': self.bin_midpoints,
+                     'density': self.density,
+                     'density error': self.densityErr,
+                     'integral': self.integral,
+                     'integral error': self.integralErr}
+        if info is not None:
+            data_dict['info'] = info
+        return data_dict
+
+    def save_montecarlo_data(self, filename, info=None):
+        assert self.hasMCDensity and self.hasMCIntegral, \
+            "Need density function and integral to save MC data"
+        np.savez(filename, **self.montecarlo_data_dict(info=info))
+
+    # ------------------
+    # Interpolation (host, O(bins))
+    # ------------------
+    def makeInterpolatingFn(self, **kwargs):
+        from ..utils.interpolation import get_1d_interpolation
+        assert self.hasMCIntegral, \
+            "Need MC integral to produce interpolation"
+        self.interpFn = get_1d_interpolation(self.bins, self.integral, monotonic=self.monotone, **kwargs)
+        self.hasInterpIntegral = True
+
+    def makeInterpolatingDensity(self, binspacing, monotone=False):
+        from ..utils.interpolation import get_1d_interpolation
+        assert self.hasMCDensity, \
+            "Need MC density to produce interpolation"
+        bins = self.bins
+        self.interpDensity = get_1d_interpolation(self.bin_midpoints, self.density, monotonic=False,
+                                                  bounds=(bins[0], bins[-1]), bound_values=(0., 0.))
+        self.hasInterpDensity = True
+
+    # ------------------
+    # csv save / load    (ref: integrator.py:320-354)
+    # ------------------
+    def saveIntegral(self, intFile, errFile, binFile):
+        assert self.hasMCIntegral, \
+            "No integral histogram to save"
+        np.savetxt(intFile, self.integral, delimiter=',')
+        np.savetxt(errFile, self.integralErr, delimiter=',')
+        np.savetxt(binFile, self.bins, delimiter=',')
+
+    def loadIntegral(self, intFile, errFile, binFile):
+        self.integral = np.loadtxt(intFile, delimiter=',')
+        self.integralErr = np.loadtxt(errFile, delimiter=',')
+        self.bins = np.loadtxt(binFile, delimiter=',')
+        self.hasMCIntegral = True
+
+    def saveDensity(self, denFile, errFile, binFile):
+        assert self.hasMCDensity, \
+            "No density histogram to save"
+        np.savetxt(denFile, self.density, delimiter=',')
+        np.savetxt(errFile, self.densityErr, delimiter=',')
+        np.savetxt(binFile, self.bins, delimiter=',')
+
+    def loadDensity(self, denFile, errFile, binFile):
+        self.density = np.loadtxt(denFile, delimiter=',')
+        self.densityErr = np.loadtxt(errFile, delimiter=',')
+        self.bins = np.loadtxt(binFile, delimiter=',')
+        self.hasMCDensity = True
+
+    def checkValidAttributes(self):
+        pass
+
+    def __init__(self, *args, **kwargs):
+        """ref: montecarlo/integrator.py:367-386"""
+        self.hasBins = False
+        self.hasMCDensity = False
+        self.hasMCIntegral = False
+        self.hasInterpIntegral = False
+        self.hasInterpDensity = False
+        self.firstBinBndCond = None
+        self.useFirstBinBndCond = False
+        self.lastBinBndCond = None
+        self.useLastBinBndCond = False
+        self.monotone = False
+        self.hasAnalyticIntegral = False
+        self.hasAnalyticDensity = False
+        self._obs_cache = None
+        self.checkValidAttributes()
+
+
+def integrate_1d(function, bounds, bin_space='lin', epsilon=1e-10, num_samples=1e5, num_bins=2,
+                 bnd_cond=0, bnd_cond_bin='first'):
+    """1-D Monte Carlo integral of ``function`` over ``bounds``.
+    ref: montecarlo/integrator.py:390-457.  ``function`` is the caller's
+    Python callable, so it runs on the host samples; sampling, histogramming
+    and the cumulative sum run on the GPU."""
+    if bin_space == 'lin':
+        epsilon = None
+    this_sampler = simpleSampler(bin_space, epsilon=epsilon, bounds=bounds)
+    this_sampler.generateSamples(int(num_samples))
+    samples = this_sampler.getSamples()
+
+    this_integrator = integrator()
+    if bnd_cond_bin == 'first':
+        this_integrator.setFirstBinBndCondition(bnd_cond)
+    elif bnd_cond_bin == 'last':
+        this_integrator.setLastBinBndCondition(bnd_cond)
+    else:
+        raise AssertionError("Bin at which we place a boundary condition"
+                             + "must be 'first' or 'last'.")
+
+    this_integrator.setBins(num_bins, samples, bin_space)
+    weights = function(samples)
+    jacs = np.asarray(this_sampler.jacobians)
+    area = this_sampler.area
+    this_integrator.setDensity(samples, weights * jacs, area)
+    this_integrator.integrate()
+
+    integral = this_integrator.integral
+    error = this_integrator.integralErr
+    xs = this_integrator.bins
+    if num_bins == 2:
+        return integral[1], error[0], xs[1]
+    return integral, error, xs

@@ -1,0 +1,171 @@
+"""Phase-space samplers -- host mirror of jetmontecarlo/montecarlo/sampler.py.
+
+Same constructor arguments, methods, attributes and assertion messages as the
+reference.  What changes is ``generateSamples``: the reference runs a Python
+loop calling ``random.random()`` once per coordinate (sampler.py:30-34); here
+one CUDA kernel (jmc_sample) draws all samples from a counter-based Philox
+stream and applies the lin/log inverse transform.  The samples are written to
+HBM only because this API hands them to the caller; the fused path
+(jetmontecarlo_b200.fused) never stores them.
+
+Additive API: ``generateSamples(num, seed=None)``, ``set_seed(seed)``,
+``device_samples`` / ``device_jacobians`` (CUDA tensors of the same data).
+"""
+import ctypes as C
+import itertools
+import os
+from abc import ABC, abstractmethod
+
+import numpy as np
+
+from .. import _device as D
+from .. import _lib
+
+# ---- seeding -----------------------------------------------------------------
+# The reference relies on Python's global MT19937 state.  Here every
+# generateSamples call takes the next 64-bit Philox key of a global sequence
+# seeded by set_seed (or by the OS), so separate samplers are independent.
+_base_seed = int.from_bytes(os.urandom(8), "little")
+_stream = itertools.count()
+
+
+def set_seed(seed):
+    """Seed the global stream sequence (the analogue of ``random.seed``)."""
+    global _base_seed, _stream
+    _base_seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    _stream = itertools.count()
+
+
+def _mix64(x):
+    """splitmix64 finaliser: decorrelates consecutive stream ids."""
+    x = (x + 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+    x = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+    x = ((x ^ (x >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+    return x ^ (x >> 31)
+
+
+def next_key():
+    """Philox key of the next sampler run."""
+    return _mix64(_base_seed + next(_stream))
+
+
+class sampler(ABC):
+    """Abstract Monte Carlo phase-space sampler (ref: montecarlo/sampler.py:8-108)."""
+
+    _kind = None      # _lib.SAMPLER_*
+    _dim = 1
+
+    # ------------------
+    # Sampling Methods:
+    # ------------------
+    @abstractmethod
+    def setArea(self):
+        """Sets the area of the sampled phase space."""
+
+    def _descriptor(self):
+        return _lib.Sampler(kind=self._kind, method=_lib.METHODS[self.sampleMethod],
+                            epsilon=float(self.epsilon or 0.), zc=float(getattr(self, 'zc', 0.) or 0.),
+                            radius=float(getattr(self, 'radius', 1.)),
+                            lo=float(getattr(self, 'bounds', [0, 1])[0]),
+                            hi=float(getattr(self, 'bounds', [0, 1])[1]))
+
+    def _draw(self, num, seed, first_index=0):
+        D.require_cuda()
+        shape = (num, 2) if self._dim == 2 else (num,)
+        samples = D.empty(shape)
+        jac = D.empty((num,))
+        desc = self._descriptor()
+        _lib.check(_lib.lib.jmc_sample(C.byref(desc), num, seed, first_index, D.ptr(samples), D.ptr(jac),
+                                       D.stream()))
+        return samples, jac
+
+    def addSample(self):
+        """Adds a single sample (and its jacobian) to the lists."""
+        samples, jac = self._draw(1, next_key())
+        self.samples.append(D.to_host(samples)[0].tolist() if self._dim == 2 else float(D.to_host(samples)[0]))
+        self.jacobians.append(float(D.to_host(jac)[0]))
+
+    def generateSamples(self, num, seed=None):
+        """Generates ``num`` samples on the GPU (ref: sampler.py:30-34).
+
+        As in the reference, ``samples`` becomes an ndarray, so a second call
+        without ``clearSamples`` fails, and ``jacobians`` keeps growing across
+        calls (``clearSamples`` does not reset it)."""
+        if isinstance(self.samples, np.ndarray):
+            raise AttributeError("'numpy.ndarray' object has no attribute 'append'")
+        num = int(num)
+        self.seed = next_key() if seed is None else int(seed) & 0xFFFFFFFFFFFFFFFF
+        dev_samples, dev_jac = self._draw(num, self.seed)
+        self.device_samples, self.device_jacobians = dev_samples, dev_jac
+        new = D.to_host(dev_samples)
+        if len(self.samples):
+            new = np.concatenate([np.array(self.samples).reshape((-1,) + new.shape[1:]), new])
+        self.samples = new
+        self.jacobians = list(self.jacobians) + D.to_host(dev_jac).tolist()
+
+    def getSamples(self):
+        return self.samples
+
+    def getSampleMethod(self):
+        return self.sampleMethod
+
+    def clearSamples(self):
+        self.samples = []
+
+    # ------------------
+    # Saving/Loading:       (npz layout of the reference: keys 'samples', 'area')
+    # ------------------
+    def saveSamples(self, filename):
+        np.savez(filename, samples=self.samples, area=self.area)
+
+    def loadSamples(self, filename):
+        npzfile = np.load(filename, allow_pickle=True, mmap_mode='c')
+        self.samples = npzfile['samples']
+        self.area = npzfile['area']
+
+    # ------------------
+    # Validity Checks:
+    # ------------------
+    def checkSampleMethod(self):
+        validSampleMethods = ['lin', 'log']
+        assert self.sampleMethod in validSampleMethods, \
+            str(self.sampleMethod) + "is not a supported sample method."
+
+    def checkValidEpsilon(self):
+        eps = self.epsilon
+        eps = 0 if eps is None else eps
+        valid_eps = 0 < eps < 1.
+        if self.sampleMethod == 'log':
+            assert valid_eps, \
+                ("epsilon={epsilon} is invalid for {type} sampling."
+                 .format(epsilon=eps, type=self.sampleMethod))
+
+    @abstractmethod
+    def __init__(self, sampleMethod, epsilon=0., **kwargs):
+        self.sampleMethod = sampleMethod
+        self.epsilon = epsilon
+        self.samples = []
+        self.jacobians = []
+        self.device_samples = None
+        self.device_jacobians = None
+        self.seed = None
+        self.checkSampleMethod()
+        self.checkValidEpsilon()
+        self.setArea()
+        super().__init__(**kwargs)
+
+
+class simpleSampler(sampler):
+    """Samples one variable on ``bounds`` (ref: montecarlo/sampler.py:114-140)."""
+    _kind = _lib.SAMPLER_SIMPLE
+    _dim = 1
+
+    def setArea(self):
+        if self.sampleMethod == 'lin':
+            self.area = self.bounds[1] - self.bounds[0]
+        elif self.sampleMethod == 'log':
+            self.area = np.log(1. / self.epsilon)
+
+    def __init__(self, sampleMethod, bounds=[0, 1], **kwargs):
+        self.bounds = bounds
+        super().__init__(sampleMethod, **kwargs)

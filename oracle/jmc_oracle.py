@@ -594,6 +594,55 @@ def sample_ungroomed(method, u, epsilon=0., radius=1.):
 
 
 # --------------------------------------------------------------------------
+# The reference's sampling LOOP, restated: one Python iteration per sample,
+# one random.random() and scalar np.log / np.exp per coordinate, lists
+# converted to arrays at the end.  This is what the reference actually runs
+# (and where 98-99 % of its time goes); bench.py's CPU baseline times it.
+#                                 ref: montecarlo/sampler.py:30-34,
+#                                      utils/montecarlo_utils.py:12-55,
+#                                      numerics/radiators/samplers.py:38-62,204-226
+# --------------------------------------------------------------------------
+def _get_lin_sample(rng, lo, hi):
+    return lo + rng.random() * (hi - lo)
+
+
+def _get_log_sample(rng, lo, hi, eps):
+    return lo + np.exp(np.log(eps) * rng.random() + np.log(hi - lo))
+
+
+def sample_loop_critical(method, n, zc, epsilon=0., seed=0, radius=1.):
+    check_sampler_args(method, epsilon, zc, radius, needs_zc=True)
+    rng = _pyrandom.Random(seed)
+    samples, jacs = [], []
+    for _ in range(n):
+        if method == 'lin':
+            z, th = _get_lin_sample(rng, zc, 1. / 2.), _get_lin_sample(rng, 0, radius)
+            jac = 1.
+        else:
+            z, th = _get_log_sample(rng, zc, 1. / 2., epsilon), _get_log_sample(rng, 0, radius, epsilon)
+            jac = (z - zc) * th
+        samples.append([z, th])
+        jacs.append(jac)
+    return np.array(samples), np.array(jacs)
+
+
+def sample_loop_ungroomed(method, n, epsilon=0., seed=0, radius=1.):
+    check_sampler_args(method, epsilon, radius=radius)
+    rng = _pyrandom.Random(seed)
+    samples, jacs = [], []
+    for _ in range(n):
+        if method == 'lin':
+            z, th = _get_lin_sample(rng, 0, 1. / 2.), _get_lin_sample(rng, 0, radius)
+            jac = 1.
+        else:
+            z, th = _get_log_sample(rng, 0, 1. / 2., epsilon), _get_log_sample(rng, 0, radius, epsilon)
+            jac = z * th
+        samples.append([z, th])
+        jacs.append(jac)
+    return np.array(samples), np.array(jacs)
+
+
+# --------------------------------------------------------------------------
 # Integrator                                      ref: montecarlo/integrator.py:37-202
 # --------------------------------------------------------------------------
 MIN_LOG_BIN = 1e-15

@@ -25,3 +25,25 @@ def golden():
             cache[name] = dict(np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False))
         return cache[name]
     return load
+
+
+@pytest.fixture(scope="session", autouse=True)
+def built_library():
+    """The CUDA library must exist before the package can be imported.  Building
+    it (nvcc cross-compiles without a GPU) is not a fallback: without it every
+    product import fails."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(
+        "jmc_build", os.path.join(ROOT, "jetmontecarlo_b200", "csrc", "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)      # by path: importing the package needs the library
+    return mod.build()
+
+
+@pytest.fixture(scope="session")
+def cuda():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail("this test is marked gpu but no CUDA device is visible")
+    torch.cuda.set_device(0)
+    return torch.device("cuda", 0)

@@ -1,0 +1,235 @@
+"""CPU-side tests (no GPU): the C-ABI library loads and exports every symbol
+include/jmc_b200.h declares, the ctypes structs match the C layout, the host
+mirror reproduces the reference's argument checks and areas, the product never
+falls back to a CPU path, and the multi-GPU host logic works on gloo with
+world_size 2."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import jmc_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_functions():
+    text = open(os.path.join(ROOT, "include", "jmc_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(jmc_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from jetmontecarlo_b200 import _lib
+    names = _declared_functions()
+    assert len(names) >= 20
+    for name in names:
+        assert hasattr(_lib.lib, name), name + " is declared in include/jmc_b200.h but not exported"
+    assert sorted(_lib.EXPORTS) == names
+    assert _lib.lib.jmc_abi_version() == 1
+
+
+def test_struct_layout_matches_header():
+    """compile a tiny C program against the header and compare sizeof/offsetof"""
+    from jetmontecarlo_b200 import _lib
+    src = r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "jmc_b200.h"
+int main(void) {
+  printf("%zu %zu %zu\n", sizeof(jmc_sampler), sizeof(jmc_fn_params), sizeof(jmc_integrand));
+  printf("%zu %zu %zu\n", offsetof(jmc_sampler, hi), offsetof(jmc_fn_params, s3), offsetof(jmc_integrand, shower_cutoff));
+  printf("%zu %zu\n", offsetof(jmc_integrand, epsilon), offsetof(jmc_fn_params, z_cut));
+  return 0; }'''
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "t.c"), "w").write(src)
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "t.c"), "-o",
+                               os.path.join(d, "t")])
+        out = subprocess.check_output([os.path.join(d, "t")]).decode().split()
+    got = [int(x) for x in out]
+    want = [C.sizeof(_lib.Sampler), C.sizeof(_lib.FnParams), C.sizeof(_lib.Integrand),
+            _lib.Sampler.hi.offset, _lib.FnParams.s3.offset, _lib.Integrand.shower_cutoff.offset,
+            _lib.Integrand.epsilon.offset, _lib.FnParams.z_cut.offset]
+    assert got == want
+
+
+def test_no_cpu_fallback():
+    """without a CUDA device every compute entry point raises instead of computing on the host"""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is visible; the no-GPU behaviour is checked on the CPU box")
+    from jetmontecarlo_b200.montecarlo.integrator import integrator
+    from jetmontecarlo_b200.numerics.observables import C_ungroomed
+    from jetmontecarlo_b200.numerics.radiators.samplers import ungroomedSampler
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        C_ungroomed(np.ones(3), np.ones(3), 2.)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ungroomedSampler('lin').generateSamples(4)
+    it = integrator()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        it.setBins(10, np.ones(4), 'lin')
+    # and the product package never imports the oracle
+    pkg = os.path.join(ROOT, "jetmontecarlo_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+\.*oracle|#include\s+[\"<][^\n]*oracle|import_module\([^)]*oracle",
+                                     text, flags=re.M), os.path.join(dirpath, f)
+
+
+def test_missing_library_fails_loudly(tmp_path):
+    """import of the package without libjmc_b200.so raises ImportError"""
+    code = ("import sys, importlib.util, os\n"
+            "sys.path.insert(0, %r)\n"
+            "import jetmontecarlo_b200._lib as L\n" % ROOT)
+    env = dict(os.environ)
+    # run in a copy of the package that has no lib/ directory
+    import shutil
+    dst = tmp_path / "jetmontecarlo_b200"
+    shutil.copytree(os.path.join(ROOT, "jetmontecarlo_b200"), dst,
+                    ignore=shutil.ignore_patterns("lib", "build", "__pycache__"))
+    res = subprocess.run([sys.executable, "-c", "import sys; sys.path.insert(0, %r); import jetmontecarlo_b200"
+                          % str(tmp_path)], capture_output=True, text=True, env=env)
+    assert res.returncode != 0 and "no CPU fallback" in res.stderr
+
+
+def test_sampler_argument_checks_and_areas():
+    """same assertions and messages as the reference (sampler.py:65-81, samplers.py:12-18,116,298;
+    areas: simple_tests/test_jetSamplers.py:50,83,120,151)"""
+    from jetmontecarlo_b200.montecarlo.sampler import simpleSampler
+    from jetmontecarlo_b200.numerics.radiators.samplers import (criticalSampler, precriticalSampler,
+                                                                ungroomedSampler)
+    with pytest.raises(AssertionError, match="is not a supported sample method"):
+        ungroomedSampler('cubic')
+    for eps in (0., 1., -1., None, 2.):
+        with pytest.raises(AssertionError, match="is invalid for log sampling"):
+            criticalSampler('log', zc=.1, epsilon=eps)
+    for zc in (0., .5, .7, -1, None):
+        with pytest.raises(AssertionError, match="invalid grooming parameter"):
+            criticalSampler('lin', zc=zc)
+        with pytest.raises(AssertionError, match="invalid grooming parameter"):
+            precriticalSampler('lin', zc=zc)
+    with pytest.raises(AssertionError, match="radius must be greater than zero"):
+        ungroomedSampler('lin', radius=0.)
+    assert criticalSampler('lin', zc=.1, radius=.8).area == (1. / 2. - .1) * .8
+    assert criticalSampler('log', zc=.1, epsilon=1e-10).area == np.log(1. / 1e-10) ** 2.
+    assert precriticalSampler('lin', zc=.2).area == .2
+    assert precriticalSampler('log', zc=.2, epsilon=1e-5).area == np.log(1. / 1e-5)
+    assert ungroomedSampler('lin', radius=.6).area == .6 / 2.
+    assert ungroomedSampler('log', epsilon=1e-3).area == np.log(1. / 1e-3) ** 2.
+    assert simpleSampler('lin', bounds=[.1, .5]).area == .5 - .1
+    assert simpleSampler('log', epsilon=1e-8).area == np.log(1. / 1e-8)
+    s = criticalSampler('lin', zc=.1)
+    assert s.samples == [] and s.jacobians == [] and s.getSampleMethod() == 'lin'
+    # C-side area agrees with the NumPy one
+    from jetmontecarlo_b200 import _lib
+    a = C.c_double()
+    d = _lib.Sampler(kind=_lib.SAMPLER_CRITICAL, method=_lib.LOG, epsilon=1e-10, zc=.1, radius=1.)
+    assert _lib.lib.jmc_sampler_area(C.byref(d), C.byref(a)) == 0 and a.value == s.__class__('log', .1, 1e-10).area
+
+
+def test_integrand_descriptions():
+    from jetmontecarlo_b200 import _lib
+    from jetmontecarlo_b200.fused import Integrand
+    g = Integrand.crit_sub('log', .1, 1e-10, fixedcoupling=False)
+    assert g.n_uniform == 4 and g.z_pre == .1 and g.f == 0. and g.nan_to_num
+    l2 = np.log(1. / 1e-10) ** 2.
+    assert g.area == l2 * l2
+    a = C.c_double()
+    s = g.c_struct()
+    assert _lib.lib.jmc_integrand_area(C.byref(s), C.byref(a)) == 0 and abs(a.value / g.area - 1) < 1e-15
+    assert Integrand.pre_crit_sub('log', .1, 1e-10).n_uniform == 6
+    assert Integrand.radiator('lin', radius=.8, theta_scale=.5).area == .8 / 2. * .5
+    with pytest.raises(TypeError):
+        Integrand.pre_crit_sub('log', .1, 1e-10, fixedcoupling=False)
+    with pytest.raises(AssertionError):
+        Integrand.crit_sub('log', .6, 1e-10)
+    with pytest.raises(AssertionError):
+        Integrand.radiator('log', epsilon=0.)
+    # C-side validation returns JMC_EINVAL with the reference's wording
+    bad = g.c_struct()
+    bad.z_cut = .7
+    rc = _lib.lib.jmc_run(C.byref(bad), 10, 0, 0, 0, None, 0, None, None, None, None, None)
+    assert rc == -1 and b"invalid grooming parameter" in _lib.lib.jmc_last_error()
+    with pytest.raises(_lib.JmcError):
+        _lib.check(rc)
+
+
+def test_host_helpers_match_oracle(golden):
+    from jetmontecarlo_b200.analytics import qcd_utils as Q
+    from jetmontecarlo_b200.numerics.observables import C_ungroomed_max
+    from jetmontecarlo_b200.utils.interpolation import lin_log_mixed_list
+    assert (Q.CF, Q.CA, Q.TF, Q.N_F, Q.beta_0, Q.alpha_fixed, Q.MU_NP) == (
+        O.CF, O.CA, O.TF, O.N_F, O.BETA_0, O.ALPHA_FIXED, O.MU_NP)
+    assert Q.CR('quark') == O.CF and Q.CR('gluon') == O.CA
+    with pytest.raises(AssertionError, match="is not a supported jet type"):
+        Q.CR('photon')
+    g = golden("lin_log_mixed")
+    np.testing.assert_array_equal(lin_log_mixed_list(1e-10, 1., 12), g['a'])
+    np.testing.assert_array_equal(lin_log_mixed_list(1e-15, 1., 501), g['b'])
+    assert C_ungroomed_max(2., .5, 'LL') == O.ecf_ungroomed_max(2., .5, 'LL')
+    assert C_ungroomed_max(3., .5, 'MLL') == O.ecf_ungroomed_max(3., .5, 'MLL')
+
+
+def test_shard_bounds_cover_the_job():
+    from jetmontecarlo_b200.distributed import shard_bounds
+    for n in (0, 1, 7, 10 ** 10, 10 ** 9 + 3):
+        for world in (1, 2, 3, 8):
+            nxt = 0
+            for r in range(world):
+                first, cnt = shard_bounds(n, r, world)
+                assert first == nxt and cnt in (n // world, n // world + 1)
+                nxt += cnt
+            assert nxt == n
+
+
+_GLOO_WORKER = r'''
+import os, sys
+sys.path.insert(0, %(root)r)
+import torch, torch.distributed as dist
+from jetmontecarlo_b200 import distributed as du
+rank = int(os.environ["RANK"])
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%(port)d", rank=rank, world_size=2)
+first, cnt = du.shard(1001)
+assert (first, cnt) == ((0, 501) if rank == 0 else (501, 500))
+sw = torch.arange(5, dtype=torch.float64) * (rank + 1)
+sw2 = torch.ones(5, dtype=torch.float64) * (rank + 1)
+cnt_t = torch.tensor([1, 2, 3, 2 ** 40, 0], dtype=torch.int64) * (rank + 1)
+du.allreduce_histograms(sw, sw2, cnt_t)
+assert torch.equal(sw, torch.arange(5, dtype=torch.float64) * 3)
+assert torch.equal(sw2, torch.full((5,), 3., dtype=torch.float64))
+assert torch.equal(cnt_t, torch.tensor([3, 6, 9, 3 * 2 ** 40, 0], dtype=torch.int64))
+mm = torch.tensor([0.5 + rank, 7. - rank], dtype=torch.float64)
+du.allreduce_minmax(mm)
+assert mm.tolist() == [0.5, 7.0]
+mm = torch.tensor([float("nan") if rank == 1 else 1., 2.], dtype=torch.float64)
+du.allreduce_minmax(mm)
+assert torch.isnan(mm).all()
+dist.barrier()
+dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def test_gloo_world_size_2():
+    """sharding + the single histogram all-reduce + min/max merge on two CPU ranks"""
+    import socket
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    code = _GLOO_WORKER % dict(root=ROOT, port=port)
+    procs = []
+    for rank in range(2):
+        env = dict(os.environ, RANK=str(rank), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.PIPE, text=True))
+    for p in procs:
+        out, err = p.communicate(timeout=180)
+        assert p.returncode == 0, err
+        assert "ok" in out
