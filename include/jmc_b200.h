@@ -232,6 +232,15 @@ int jmc_run(const jmc_integrand* g, uint64_t n, uint64_t seed, uint64_t first_in
             double* d_sum_w, double* d_sum_w2, uint64_t* d_count, double* d_minmax,
             void* stream);
 
+/* Samples on request: the per-sample view of the same streams jmc_run bins, written to HBM only when a
+ * caller asks for it (sampler.getSamples() on a fused job; parity tests).  d_samples: [n,8] = z_crit,
+ * theta_crit, z_sub, theta_sub, z_pre, zero-bin uniform, delta = z_crit - z_cut (in FP32 mode the sampled
+ * quantity itself, free of the reference's cancellation), jacobian (FP64 mode); unused slots 0.  In FP32
+ * mode z_pre is 0 for a zero-binned sample.  d_obs, d_weight (= weight * jacobian): [n].  Any output may
+ * be NULL. */
+int jmc_dump(const jmc_integrand* g, uint64_t n, uint64_t seed, uint64_t first_index, int precision,
+             double* d_samples, double* d_obs, double* d_weight, void* stream);
+
 /* density, error, cumulative integral (+ error) from the histograms.
  * ref: montecarlo/integrator.py:113-124 (density), :129-202 (integrate).
  * density, density_err, integral_err: n_edges-1; integral: n_edges. */

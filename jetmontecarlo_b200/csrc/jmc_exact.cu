@@ -601,6 +601,52 @@ int run_exact(const jmc_integrand* g, uint64_t n, uint64_t seed, uint64_t first_
     return JMC_OK;
 }
 
+// samples on request: per-sample samples / observable / weight*jac of the FP64 path
+template <int KIND>
+__global__ void __launch_bounds__(kThreads)
+dump_exact_kernel(RunParams p, uint64_t n, uint64_t seed, uint64_t first, double* __restrict__ samples,
+                  double* __restrict__ obs_out, double* __restrict__ w_out) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        SampleSet s;
+        s.z_c = s.th_c = s.z_s = s.th_s = s.z_pre = 0.0;
+        s.zb_u = 2.0;
+        draw_exact<KIND>(p, first + i, seed, s);
+        double jac, obs, wj;
+        integrand_eval<KIND>(p, s, jac, obs, wj);
+        if (samples) {
+            double* o = samples + 8 * i;
+            o[0] = s.z_c; o[1] = s.th_c; o[2] = s.z_s; o[3] = s.th_s; o[4] = s.z_pre; o[5] = s.zb_u;
+            o[6] = s.z_c - p.g.z_cut; o[7] = jac;
+        }
+        if (obs_out) obs_out[i] = obs;
+        if (w_out) w_out[i] = wj;
+    }
+}
+
+int dump_exact(const jmc_integrand* g, uint64_t n, uint64_t seed, uint64_t first_index, double* d_samples,
+               double* d_obs, double* d_weight, void* stream) {
+    RunParams p;
+    int rc = make_run_params(g, &p);
+    if (rc) return rc;
+    if (n == 0) return JMC_OK;
+    const int grid = grid_for(n, kThreads);
+    if (grid < 0) return JMC_ENODEV;
+    cudaStream_t st = (cudaStream_t)stream;
+#define JMC_DUMP(K) dump_exact_kernel<K><<<grid, kThreads, 0, st>>>(p, n, seed, first_index, d_samples, d_obs, d_weight)
+    switch (g->kind) {
+        case JMC_KIND_RADIATOR: JMC_DUMP(JMC_KIND_RADIATOR); break;
+        case JMC_KIND_CRIT: JMC_DUMP(JMC_KIND_CRIT); break;
+        case JMC_KIND_CRIT_SUB: JMC_DUMP(JMC_KIND_CRIT_SUB); break;
+        case JMC_KIND_PRE_CRIT_SUB: JMC_DUMP(JMC_KIND_PRE_CRIT_SUB); break;
+        case JMC_KIND_SIMPLE: JMC_DUMP(JMC_KIND_SIMPLE); break;
+        default: return set_error(JMC_EINVAL, "jmc_dump: kind %d has no FP64 sampler form", g->kind);
+    }
+#undef JMC_DUMP
+    JMC_LAUNCHED("dump_exact_kernel");
+    return JMC_OK;
+}
+
 // ---------------------------------------------------------------------------
 // density / cumulative integral epilogue
 // ---------------------------------------------------------------------------

@@ -112,6 +112,10 @@ int run_exact(const jmc_integrand* g, uint64_t n, uint64_t seed, uint64_t first_
               int n_edges, double* d_sum_w, double* d_sum_w2, uint64_t* d_count, double* d_minmax, void* stream);
 int run_fast(const jmc_integrand* g, uint64_t n, uint64_t seed, uint64_t first_index, const double* d_edges,
              int n_edges, double* d_sum_w, double* d_sum_w2, uint64_t* d_count, double* d_minmax, void* stream);
+int dump_exact(const jmc_integrand* g, uint64_t n, uint64_t seed, uint64_t first_index, double* d_samples,
+               double* d_obs, double* d_weight, void* stream);
+int dump_fast(const jmc_integrand* g, uint64_t n, uint64_t seed, uint64_t first_index, double* d_samples,
+              double* d_obs, double* d_weight, void* stream);
 int run_shower(const jmc_integrand* g, uint64_t n, uint64_t seed, uint64_t first_index, const double* d_edges,
                int n_edges, double* d_sum_w, double* d_sum_w2, uint64_t* d_count, double* d_minmax, void* stream);
 
@@ -210,6 +214,15 @@ extern "C" int jmc_run(const jmc_integrand* g, uint64_t n, uint64_t seed, uint64
     if (precision == JMC_F64)
         return run_exact(g, n, seed, first_index, d_edges, n_edges, d_sum_w, d_sum_w2, d_count, d_minmax, stream);
     return run_fast(g, n, seed, first_index, d_edges, n_edges, d_sum_w, d_sum_w2, d_count, d_minmax, stream);
+}
+
+extern "C" int jmc_dump(const jmc_integrand* g, uint64_t n, uint64_t seed, uint64_t first_index, int precision,
+                        double* d_samples, double* d_obs, double* d_weight, void* stream) {
+    JMC_REQUIRE(g != nullptr, "jmc_dump: integrand is NULL");
+    JMC_REQUIRE(precision == JMC_F64 || precision == JMC_F32, "jmc_dump: precision must be JMC_F64 or JMC_F32");
+    JMC_REQUIRE(g->kind != JMC_KIND_SHOWER, "jmc_dump: use jmc_shower_dump for the shower");
+    if (precision == JMC_F64) return dump_exact(g, n, seed, first_index, d_samples, d_obs, d_weight, stream);
+    return dump_fast(g, n, seed, first_index, d_samples, d_obs, d_weight, stream);
 }
 
 // ---------------------------------------------------------------------------

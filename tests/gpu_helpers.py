@@ -86,3 +86,12 @@ def finalize(sw, sw2, cnt, edges, area, n_total, bc_kind, bc_value):
     _lib.check(L.jmc_finalize(D.ptr(sw), D.ptr(sw2), D.ptr(cnt), D.ptr(e), nb + 1, float(area), int(n_total),
                               bc_kind, float(bc_value), D.ptr(d), D.ptr(de), D.ptr(integ), D.ptr(ie), D.stream()))
     return d.cpu().numpy(), de.cpu().numpy(), integ.cpu().numpy(), ie.cpu().numpy()
+
+
+def dump(g, n, seed, precision='f64', first=0):
+    """per-sample view of the fused streams: samples [n,8], obs [n], weight*jac [n]"""
+    s = g.c_struct()
+    samples, obs, w = D.empty((n, 8)), D.empty((n,)), D.empty((n,))
+    _lib.check(L.jmc_dump(C.byref(s), n, seed, first, {'f64': 0, 'f32': 1}[precision], D.ptr(samples), D.ptr(obs),
+                          D.ptr(w), D.stream()))
+    return samples.cpu().numpy(), obs.cpu().numpy(), w.cpu().numpy()

@@ -1,0 +1,264 @@
+"""GPU tests of the FP32 log-space mode of the fused kernel (the throughput path).
+
+Parity contract for fresh samples (BASELINE.json north_star): pdf and cdf agree
+with the CPU output within 3 sigma per bin and the cdf within 1e-3 absolute at
+1e7 samples.  On top of that statistical statement the per-sample dump
+(jmc_dump) lets the oracle evaluate the FP64 reference formulas on exactly the
+samples the FP32 path drew, so the active-branch / Landau-predicate logic is
+checked sample by sample:
+  * observable within 2e-5 relative (FP32 log2/exp2 round trip),
+  * weight within 2e-4 relative where the reference weight is finite (plus 3e-5/|x| next to the kinematic
+    end point x = ln(2C/theta_c^beta) -> 0 of the fixed-coupling pdfs, where the weight itself vanishes
+    like |x| and FP32 rounding of the logarithms is an absolute error on x),
+  * zero weight exactly where the reference is NaN (np.nan_to_num), except
+    within 1e-5 (relative, in the log argument) of a Landau threshold.
+"""
+import numpy as np
+import pytest
+from numpy.testing import assert_allclose, assert_array_equal
+
+from oracle import jmc_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+EPS, ZC, BETA = 1e-10, .1, 2.
+
+
+def _endpoint_x(kind, samples, fc, beta=BETA):
+    """|x| of the fixed-coupling subsequent pdf (inf where there is no such end point)"""
+    thc, zs, ths = samples[:, 1], samples[:, 2], samples[:, 3]
+    with np.errstate(all='ignore'):
+        if kind == 'crit_sub' and fc:
+            return np.abs(np.log(2. * zs * ths ** (2 * beta) / thc ** beta))
+        if kind == 'pre_crit_sub':
+            return np.abs(np.log(2. * zs))
+    return np.full(len(samples), np.inf)
+
+
+def _oracle_on_dump(kind, samples, jet, fc, acc, zc=ZC, beta=BETA, eps=EPS, z_pre=None, f=None, theta_scale=1.):
+    zc_, thc, zs, ths, zpre, zbu, delta = (samples[:, k] for k in range(7))
+    with np.errstate(all='ignore'):
+        if kind == 'radiator':
+            th_em = ths            # the dump holds theta_em = theta * theta_scale
+            obs = O.ecf_ungroomed(zs, th_em, beta, acc)
+            w = O.weight_radiator(zs, th_em, jet, fc, acc) * (zs * th_em)
+            return obs, w
+        jc = delta * thc          # (z - z_c) theta with the sampled delta: no cancellation
+        if kind == 'crit':
+            obs = O.ecf_groomed(zc_, thc, zc, beta, z_pre=0. if z_pre is None else z_pre,
+                                f=1. if f is None else f, acc=acc)
+            if z_pre in (None, 0.) and f in (None, 1.):
+                # zmin - z_c is delta itself; recompute without cancellation for the comparison
+                obs = (delta * thc ** beta / (1. - zc) ** 2. if acc == 'LL'
+                       else delta * (1. - zc_) * thc ** beta / (1. - zc) ** 2.)
+            w = O.weight_critical(zc_, thc, zc, jet, fc) * jc
+            return obs, w
+        js = zs * ths
+        if kind == 'crit_sub':
+            csub = zs * ths ** beta * ths ** beta
+            obs = np.maximum(O.ecf_groomed(zc_, thc, zc, beta, z_pre=zc, f=0., acc=acc), csub)
+            crit, sub = np.stack([zc_, thc], 1), np.stack([zs, ths], 1)
+            w = O.weight_two_emission(crit, sub, zc, beta, jet, fc) * jc * js
+            return obs, w
+        # pre_crit_sub: the dump's z_pre is already 0 for zero-binned samples
+        zp = zpre
+        c_sub = zs * thc ** beta
+        a = delta + np.where(zp == 0, 0., zp)       # f = 1: zmin - (z_c - z_pre) = delta + z_pre
+        obs = np.maximum(a * thc ** beta / (1. - zc) ** 2., c_sub)
+        w = (O.weight_critical(zc_, thc, zc, jet, True) * O.pdf_sub_fc(c_sub / thc ** beta, beta, jet)
+             * O.weight_precritical_zerobin(zp, thc, zc, jet, eps))
+        jp = np.where(zp == 0, 1., zp)
+        return obs, w * jc * js * jp
+
+
+CASES = [
+    ('radiator', 'quark', True, 'LL'), ('radiator', 'gluon', False, 'MLL'), ('radiator', 'quark', False, 'MLL'),
+    ('crit', 'quark', True, 'LL'), ('crit', 'quark', False, 'LL'), ('crit', 'gluon', False, 'MLL'),
+    ('crit_sub', 'quark', False, 'MLL'), ('crit_sub', 'gluon', False, 'MLL'), ('crit_sub', 'quark', True, 'MLL'),
+    ('crit_sub', 'gluon', True, 'LL'),
+    ('pre_crit_sub', 'quark', True, 'LL'), ('pre_crit_sub', 'gluon', True, 'LL'),
+]
+
+
+def _integrand(kind, jet, fc, acc, eps=EPS, **kw):
+    from jetmontecarlo_b200.fused import Integrand
+    if kind == 'radiator':
+        return Integrand.radiator('log', eps, beta=BETA, jet_type=jet, fixedcoupling=fc, obs_acc=acc, split_acc=acc,
+                                  nan_to_num=True, **kw)
+    if kind == 'crit':
+        return Integrand.critical('log', ZC, eps, beta=BETA, jet_type=jet, fixedcoupling=fc, obs_acc=acc,
+                                  nan_to_num=True)
+    if kind == 'crit_sub':
+        return Integrand.crit_sub('log', ZC, eps, beta=BETA, jet_type=jet, fixedcoupling=fc, obs_acc=acc)
+    return Integrand.pre_crit_sub('log', ZC, eps, beta=BETA, jet_type=jet, nan_to_num=True)
+
+
+@pytest.mark.parametrize("kind,jet,fc,acc", CASES)
+@pytest.mark.parametrize("eps", [1e-10, 1e-3])
+def test_fast_per_sample_vs_oracle(cuda, kind, jet, fc, acc, eps):
+    import gpu_helpers as H
+    if kind == 'pre_crit_sub' and eps != 1e-10:
+        eps = 1e-6
+    ig = _integrand(kind, jet, fc, acc, eps)
+    n = 400000
+    samples, obs, w = H.dump(ig, n, 31337, 'f32')
+    obs_ref, w_ref = _oracle_on_dump(kind, samples, jet, fc, acc, eps=eps)
+    # observable
+    ok = np.isfinite(obs_ref) & (obs_ref > 0)
+    assert ok.mean() > .999
+    assert_allclose(obs[ok], obs_ref[ok], rtol=2e-5)
+    # weights: zero exactly where the reference is NaN ...
+    nan_ref = np.isnan(w_ref)
+    mism = (nan_ref != (w == 0)) & ~((w_ref == 0) & (w == 0))
+    # ... except next to a Landau threshold (FP32 vs FP64 on the log argument) and FP32 underflow of tiny weights
+    tiny = np.abs(np.nan_to_num(w_ref)) < 1e-30
+    assert (mism & ~tiny).sum() <= max(3, 2e-5 * n), "%d samples disagree on NaN-ness" % (mism & ~tiny).sum()
+    good = ~nan_ref & (w != 0) & (np.abs(w_ref) > 1e-30)
+    if kind in ('crit', 'crit_sub') and not fc and eps < 1e-5:
+        assert nan_ref.mean() > .3            # the Landau region is exercised
+        assert good.sum() > 100
+    tol = 2e-4 + 3e-5 / _endpoint_x(kind, samples, fc)
+    assert np.all(np.abs(w[good] - w_ref[good]) <= tol[good] * np.abs(w_ref[good])), \
+        "max rel weight error %.3g" % np.max(np.abs(w[good] / w_ref[good] - 1))
+    # and in aggregate the weighted totals agree much better than per sample
+    assert abs(w[good].sum() / w_ref[good].sum() - 1) < 2e-5
+
+
+def test_fast_radiator_theta_scale(cuda):
+    """gen_crit_sub_num_rad rescaling: theta_em = theta * theta_crit, jac * theta_crit"""
+    import gpu_helpers as H
+    ig = _integrand('radiator', 'gluon', False, 'MLL', theta_scale=.01)
+    samples, obs, w = H.dump(ig, 100000, 5, 'f32')
+    obs_ref, w_ref = _oracle_on_dump('radiator', samples, 'gluon', False, 'MLL')
+    assert_allclose(obs, obs_ref, rtol=2e-5)
+    assert_allclose(w, w_ref, rtol=2e-4)
+    assert samples[:, 3].max() <= .01 * (1 + 1e-6)
+
+
+@pytest.mark.parametrize("kind,jet,fc,acc", [CASES[0], CASES[1], CASES[4], CASES[6], CASES[8], CASES[10]])
+def test_fast_histogram_equals_histogram_of_its_dump(cuda, kind, jet, fc, acc):
+    """the fused FP32 kernel bins exactly the per-sample values it would dump: counts are identical to
+    np.histogram of the dumped observable up to FP32 edge ties, sums agree to FP64 summation order"""
+    import gpu_helpers as H
+    ig = _integrand(kind, jet, fc, acc)
+    n, seed = 300000, 77
+    edges = np.logspace(-11, np.log10(.5), 100)
+    _, obs, w = H.dump(ig, n, seed, 'f32')
+    r = H.run(ig, n, seed, edges, 'f32')
+    cnt = r['count'].cpu().numpy()
+    # the kernel compares log2(obs) with log2(edges) in FP32: restate exactly that
+    l2 = np.log2(obs).astype(np.float32)
+    e32 = np.log2(edges).astype(np.float32)
+    idx = np.searchsorted(e32, l2, side='right').astype(np.int64) - 1
+    idx[l2 == e32[-1]] = len(edges) - 2
+    keep = (idx >= 0) & (idx <= len(edges) - 2)
+    ref_cnt = np.bincount(idx[keep], minlength=len(edges) - 1)
+    assert_array_equal(cnt, ref_cnt)
+    assert abs(cnt - np.histogram(obs, edges)[0]).sum() <= 1e-4 * n     # and FP64 binning differs only at edge ties
+    ref_sw = np.bincount(idx[keep], weights=w[keep], minlength=len(edges) - 1)
+    ref_sw2 = np.bincount(idx[keep], weights=w[keep] ** 2, minlength=len(edges) - 1)
+    assert_allclose(r['sum_w'].cpu().numpy(), ref_sw, rtol=1e-11, atol=1e-13 * np.abs(ref_sw).max())
+    assert_allclose(r['sum_w2'].cpu().numpy(), ref_sw2, rtol=1e-11, atol=1e-13 * np.abs(ref_sw2).max())
+
+
+def _pulls(a, ea, b, eb):
+    err = np.sqrt(ea ** 2 + eb ** 2)
+    m = err > 0
+    return (a[m] - b[m]) / err[m]
+
+
+@pytest.mark.parametrize("kind,jet,fc,acc", [CASES[0], CASES[1], CASES[3], CASES[4], CASES[6], CASES[8], CASES[10]])
+def test_fast_vs_exact_fresh_samples(cuda, kind, jet, fc, acc):
+    """fresh-sample agreement: FP32 path vs FP64 path on DIFFERENT streams, 1e7 samples each:
+    <= 3 sigma per bin (allowing the expected handful of 3-sigma outliers over ~200 bins; none above 5),
+    cdf within 1e-3 absolute"""
+    from jetmontecarlo_b200 import fused
+    ig = _integrand(kind, jet, fc, acc)
+    n = 10_000_000
+    edges = np.logspace(-11, np.log10(.5), 100)
+    bc = [0., 'plus'] if kind == 'radiator' else [1., 'minus']
+    a = fused.integrate(ig, n, edges=edges, seed=1, precision='f32', last_bc=bc)
+    b = fused.integrate(ig, n, edges=edges, seed=2, precision='f64', last_bc=bc)
+    p = _pulls(a.density, a.densityErr, b.density, b.densityErr)
+    assert np.abs(p).max() < 5. and (np.abs(p) > 3.).sum() <= 3, "pdf pulls: max %.2f" % np.abs(p).max()
+    ia, ib = np.asarray(a.integral), np.asarray(b.integral)
+    q = _pulls(ia[:-1], a.integralErr, ib[:-1], b.integralErr)
+    assert np.abs(q).max() < 4.
+    if kind != 'radiator':                      # cdfs (the radiator integral is not bounded by 1)
+        assert np.abs(ia - ib).max() < 1e-3 + 3 * np.sqrt(a.integralErr.max() ** 2 + b.integralErr.max() ** 2)
+
+
+def test_fast_same_stream_is_much_closer_than_statistics(cuda):
+    """same sample indices in both precisions (24-bit vs 53-bit uniforms from the same Philox words):
+    this is NOT the same sample set, but the headline C3 cdf must agree within errors; and the FP32 run is
+    reproducible bit for bit and additive over index ranges"""
+    import gpu_helpers as H
+    ig = _integrand('crit_sub', 'quark', False, 'MLL')
+    edges = np.logspace(-11, np.log10(.5), 100)
+    n = 4_000_000
+    r1 = H.run(ig, n, 9, edges, 'f32')
+    r2 = H.run(ig, n, 9, edges, 'f32')
+    assert_array_equal(r1['count'].cpu().numpy(), r2['count'].cpu().numpy())
+    assert_allclose(r1['sum_w'].cpu().numpy(), r2['sum_w'].cpu().numpy(), rtol=1e-12)
+    acc = None
+    for first, cnt in ((0, 1_500_000), (1_500_000, 2_500_000)):
+        rr = H.run(ig, cnt, 9, edges, 'f32', first=first, accumulate_into=acc)
+        acc = (rr['sum_w'], rr['sum_w2'], rr['count'])
+    assert_array_equal(acc[2].cpu().numpy(), r1['count'].cpu().numpy())
+    assert_allclose(acc[0].cpu().numpy(), r1['sum_w'].cpu().numpy(), rtol=1e-11)
+
+
+def test_fast_nonuniform_and_linear_edges(cuda):
+    """general edge arrays: non-uniform (binary search), linear edges starting at 0 (linear compare domain),
+    5000 edges (params.py NUM_RAD_BINS)"""
+    import gpu_helpers as H
+    ig = _integrand('crit', 'quark', True, 'LL')
+    n, seed = 500000, 3
+    _, obs, w = H.dump(ig, n, seed, 'f32')
+    rng = np.random.RandomState(0)
+    for edges in (np.sort(np.exp(rng.uniform(np.log(1e-12), np.log(.6), 40))),
+                  np.linspace(0., .3, 50),
+                  np.logspace(-12, 0, 5000)):
+        r = H.run(ig, n, seed, edges, 'f32')
+        cnt = r['count'].cpu().numpy()
+        ref = np.histogram(obs, edges)[0]
+        assert abs(cnt - ref).sum() <= 2e-4 * n + 2
+        assert_allclose(r['sum_w'].cpu().numpy().sum(), np.histogram(obs, edges, weights=w)[0].sum(), rtol=1e-6)
+
+
+def test_fast_minmax_and_unsupported(cuda):
+    import gpu_helpers as H
+    from jetmontecarlo_b200 import _lib
+    from jetmontecarlo_b200.fused import Integrand
+    ig = _integrand('crit_sub', 'quark', True, 'MLL')
+    n = 200000
+    _, obs, _ = H.dump(ig, n, 4, 'f32')
+    r = H.run(ig, n, 4, None, 'f32', want_minmax=True)
+    assert_allclose(r['minmax'], [obs.min(), obs.max()], rtol=1e-6)
+    with pytest.raises(_lib.JmcError, match="log-sampling path"):
+        H.run(Integrand.critical('lin', .1), 10, 0, np.linspace(0, 1, 5), 'f32')
+
+
+def test_c3_headline_against_cpu_oracle(cuda):
+    """the headline workload end to end: FP32 fused path vs the oracle on CPU-generated (MT19937) samples"""
+    from jetmontecarlo_b200 import fused
+    n_cpu, n_gpu = 1_000_000, 20_000_000
+    edges = np.logspace(np.log10(EPS) - 1, np.log10(.5), 100)
+    for fc in (False, True):
+        u = O.mt_uniforms(20260101 + int(fc), 4 * n_cpu)
+        crit, jc, ac = O.sample_critical('log', u[:2 * n_cpu].reshape(n_cpu, 2), ZC, EPS)
+        sub, js, as_ = O.sample_ungroomed('log', u[2 * n_cpu:].reshape(n_cpu, 2), EPS)
+        with np.errstate(all='ignore'):
+            csub = sub[:, 0] * sub[:, 1] ** BETA * sub[:, 1] ** BETA
+            obs = np.maximum(O.ecf_groomed(crit[:, 0], crit[:, 1], ZC, BETA, z_pre=ZC, f=0., acc='MLL'), csub)
+            w = np.nan_to_num(O.weight_two_emission(crit, sub, ZC, BETA, 'quark', fc)) * jc * js
+        ref = O.integrate_hist(obs, w, edges, ac * as_, last_bc=[1., 'minus'])
+        ig = _integrand('crit_sub', 'quark', fc, 'MLL')
+        it = fused.integrate(ig, n_gpu, edges=edges, seed=5, precision='f32', last_bc=[1., 'minus'])
+        p = _pulls(it.density, it.densityErr, ref['density'], ref['density_err'])
+        assert np.abs(p).max() < 5. and (np.abs(p) > 3.).sum() <= 2
+        q = _pulls(np.asarray(it.integral)[:-1], it.integralErr, ref['integral'][:-1], ref['integral_err'])
+        assert np.abs(q).max() < 4.
+        # SURVEY 8(d) caveat values: total integral 0.2705 (rc) / 0.5881 (fc) at eps = 1e-10
+        total = 1. - it.integral[0]
+        assert abs(total - (.5881 if fc else .2705)) < 4 * it.integralErr[0] + 2e-3
