@@ -29,7 +29,8 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
 UNITS = {
     "jmc_exact.cu": ["--fmad=false"],
     "jmc_shower.cu": ["--fmad=false"],
-    "jmc_fast.cu": ["--fmad=true"],
+    "jmc_fast.cu": ["--fmad=true"] + (["-DJMC_FAST_MIN_BLOCKS=" + os.environ["JMC_FAST_MIN_BLOCKS"]]
+                                      if os.environ.get("JMC_FAST_MIN_BLOCKS") else []),
     "jmc_host.cu": [],
 }
 
@@ -44,6 +45,7 @@ def _nvcc():
 def _digest():
     h = hashlib.sha256()
     names = sorted(f for f in os.listdir(HERE) if f.endswith((".cu", ".cuh", ".py")))
+    h.update(os.environ.get("JMC_FAST_MIN_BLOCKS", "").encode())
     for name in names + [os.path.join(ROOT, "include", "jmc_b200.h")]:
         with open(os.path.join(HERE, name) if not os.path.isabs(name) else name, "rb") as f:
             h.update(name.encode())

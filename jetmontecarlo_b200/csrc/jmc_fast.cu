@@ -36,6 +36,12 @@
 namespace jmc {
 
 static constexpr int kFastThreads = 256;
+static constexpr int kQueueFields = 5, kQueueSlots = 64;   // per-warp compaction queue (see run_fast_kernel)
+// resident blocks per SM the register allocation must allow: 3 x 256 threads = 24 warps (<= 80 registers): measured fastest (2..6 blocks differ by < 5 %).
+// The rarely executed running-coupling radiator code may spill; the per-sample light path must not.
+#ifndef JMC_FAST_MIN_BLOCKS
+#define JMC_FAST_MIN_BLOCKS 3
+#endif
 #define JMC_LN2F 0.69314718055994531f
 #define JMC_INV_LN2F 1.4426950408889634f
 
@@ -49,6 +55,7 @@ struct FastParams {
     int kind, jet, fixed, obs_mll, split_acc, nan_to_num;
     // sampling, base-2 logs
     float L2;          // log2(eps)
+    float sL2;         // 2^-32 log2(eps): maps a 32-bit word straight to u * log2(eps)
     float l2w_cz;      // log2(1/2 - z_cut)
     float l2R;         // log2(radius) (+ log2(theta_scale) for RADIATOR)
     float l2zc;        // log2(z_cut)
@@ -76,17 +83,25 @@ struct FastParams {
     int crit_always_nan;
     // running coupling, subsequent radiator
     float lnknee, bbar_knee;
+    float l2tc_min;          // log2 of the smallest theta_c at which the CRIT_SUB weight is not NaN
     // binning
     int dom_log;             // 1: compare log2(obs) with log2(edges); 0: compare obs with edges
     int uniform;             // edges equally spaced in that domain
     int n_edges;
     float b0, inv_d;
+    float mb0_inv_d;         // -b0 * inv_d
+    float e_first, e_last;   // first / last edge in the compare domain
 };
 
 __device__ __forceinline__ float ex2(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float lg2(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float lnf_(float x) { return JMC_LN2F * lg2(x); }
 __device__ __forceinline__ float rcp(float x) { return __fdividef(1.0f, x); }
+// ln(1 + t), accurate for small |t| where lg2.approx(1 + t) only has absolute accuracy
+__device__ __forceinline__ float log1p_f(float t) {
+    if (fabsf(t) < 0.03f) return t * (1.0f - t * (0.5f - t * (0.33333334f - t * 0.25f)));
+    return lnf_(1.0f + t);
+}
 __device__ __forceinline__ float wlog(float x) { return x * lnf_(x); }     // W(x) = x ln x, qcd_utils.py:211-216
 __device__ __forceinline__ float fnan() { return __int_as_float(0x7fc00000); }
 
@@ -181,7 +196,10 @@ __device__ __forceinline__ bool sub_rc(const FastParams& P, float lc, float Lc, 
     R = (C < 0.5f) ? soft + hard : 0.0f;
     // derivative
     const float lm = fmaxf(lc, fminf((beta * P.lnMU - lc) / bm1, -JMC_LN2F));
-    const float sc = lnf_(aC2 / (1.0f + k * (lc + bm1 * lm) * ib)) * beta / (bm1 * k) + (lm - lc) / one_kMU;
+    // ln(aC2 / aM) with aM = 1 + k (lc + (beta-1) lm)/beta and aC2 - aM = -k (beta-1)(ln2 + lm)/beta formed
+    // directly: at m = 1/2 the ratio is exactly 1 and R' changes sign nearby, so no cancellation is allowed here
+    const float aM = 1.0f + k * (lc + bm1 * lm) * ib;
+    const float sc = log1p_f(-k * bm1 * (JMC_LN2F + lm) * ib / aM) * beta / (bm1 * k) + (lm - lc) / one_kMU;
     const float hc = rcp(1.0f + k * fmaxf(-bm1 * ib * JMC_LN2F + lc * ib, P.lnMU));
     rp = aR * (P.twoCR * sc + bC * hc) / ((float)H_PI * beta);
     return true;
@@ -191,130 +209,159 @@ struct FastSample {            // what a dump shows for one sample
     float z_c, th_c, z_s, th_s, z_pre, zb_u, delta;
 };
 
-// One sample: returns log2(observable) and weight*jacobian (0 where the
-// reference's nan_to_num'd weight is 0; NaN if nan_to_num is off).
-template <int KIND>
-__device__ __forceinline__ void eval_fast(const FastParams& P, uint64_t idx, uint64_t seed, float& l2obs, float& w,
-                                          FastSample* dump) {
+// The draws of one sample, kept in registers between the two stages below.
+struct Draw {
+    float l2d, l2tc, l2zs, l2ts, l2zp;   // base-2 logs of delta, theta_c, z_s, theta_s, z_pre
+    float delta, z;                      // delta = z_crit - z_cut (sampled), z = z_cut + delta
+    float u5, cdf;                       // zero-bin uniform and zero-bin probability (PRE_CRIT_SUB)
+    float lcl2;                          // log2(csub / theta_c^beta)
+};
+
+// uniform in [0,1] from a 32-bit word folded into the log-sampling FMA:
+// l2x = u * log2(eps) + log2(width) = float(w) * (2^-32 log2 eps) + log2(width)
+__device__ __forceinline__ float l2_sample(uint32_t w, float sL2, float l2w) {
+    return fmaf(__uint2float_rn(w), sL2, l2w);
+}
+
+// Stage 1 ("light"): draw the sample, form log2(observable) and decide whether the weight can be
+// non-zero.  Everything here is executed for every sample; it is straight-line code.
+// FIXED selects the coupling at compile time so that the other branch costs nothing.
+template <int KIND, bool FIXED, bool OBS_MLL>
+__device__ __forceinline__ bool light(const FastParams& P, uint64_t idx, uint64_t seed, Draw& d, float& l2obs) {
     uint32_t r[4];
     philox4x32_10(idx, 0u, seed, r);
-    const float u0 = u32_to_unit_float(r[0]), u1 = u32_to_unit_float(r[1]);
-    const float u2 = u32_to_unit_float(r[2]), u3 = u32_to_unit_float(r[3]);
-    const float nanw = P.nan_to_num ? 0.0f : fnan();
-
     if (KIND == JMC_KIND_RADIATOR) {
-        // ungroomedSampler (samplers.py:204-226), C_ungroomed (observables.py:82-109),
-        // radiatorWeight (weights.py:15-26); theta_em = theta * theta_scale (generation.py:303-335)
-        const float l2z = u0 * P.L2 - 1.0f;
-        const float l2t = u1 * P.L2 + P.l2R;             // log2(theta_em)
-        const float z = ex2(l2z);
-        l2obs = l2z + P.beta * l2t;
-        if (P.obs_mll) l2obs += lg2(1.0f - z);
-        float zp;
-        if (P.split_acc == JMC_ACC_LL) zp = P.twoCR;
-        else if (P.split_acc == JMC_ACC_LL_NONSING) zp = z_times_p(z, P.jet);
-        else zp = z_times_p(z, P.jet) + z * p_of(1.0f - z, P.jet);
-        const float alpha = P.fixed ? (float)H_ALPHA : alpha_from_lnmu(P, P.lnPT + JMC_LN2F * (l2z + l2t));
-        w = zp * alpha * (float)(1.0 / H_PI);            // splitting * alpha / (theta pi) * z theta
-        if (dump) { dump->z_s = z; dump->th_s = ex2(l2t); }
-        return;
+        // ungroomedSampler (samplers.py:204-226), C_ungroomed (observables.py:82-109)
+        d.l2zs = l2_sample(r[0], P.sL2, -1.0f);
+        d.l2ts = l2_sample(r[1], P.sL2, P.l2R);          // log2(theta_em), theta_scale folded into l2R
+        d.z = ex2(d.l2zs);
+        l2obs = fmaf(P.beta, d.l2ts, d.l2zs);
+        if (OBS_MLL) l2obs += lg2(1.0f - d.z);
+        return true;
     }
-
     // critical emission: z = z_c + delta, delta log-sampled (samplers.py:38-62)
-    const float l2d = u0 * P.L2 + P.l2w_cz;
-    const float l2tc = u1 * P.L2 + P.l2R;
-    const float delta = ex2(l2d);
-    const float z = P.zc + delta;
-    const float l2z = lg2(z);
-    const float Lc = JMC_LN2F * l2tc;
-    if (dump) { dump->z_c = z; dump->th_c = ex2(l2tc); dump->delta = delta; }
-
+    d.l2d = l2_sample(r[0], P.sL2, P.l2w_cz);
+    d.l2tc = l2_sample(r[1], P.sL2, P.l2R);
+    d.delta = ex2(d.l2d);
+    d.z = P.zc + d.delta;
+    const float onorm = fmaf(P.beta, d.l2tc, P.l2_onorm);            // log2(theta_c^beta / (1 - z_cut)^2)
     if (KIND == JMC_KIND_CRIT) {
-        // C_groomed (observables.py:15-79), criticalEmissionWeight (weights.py:31-41)
-        const float a = delta + P.c0;
-        const float b = P.obs_mll ? (1.0f - z) - P.omf_zcl : P.one_m;
-        l2obs = lg2(a * b) + P.beta * l2tc + P.l2_onorm;
-        if (P.fixed) {
-            w = P.g * ex2(l2d - l2z + P.A * l2tc);       // 2 C_R a/(pi theta z) theta^A * (z - z_c) theta
-        } else {
-            float R;
-            if (!crit_rad_rc(P, Lc, R)) { w = nanw; return; }
-            const float alpha = alpha_from_lnmu(P, P.lnPT + JMC_LN2F * l2z + Lc);
-            w = p_bar(z, P.jet) * delta * alpha * (float)(1.0 / H_PI) * ex2(-R * JMC_INV_LN2F);
-        }
-        return;
+        // C_groomed (observables.py:15-79)
+        const float a = d.delta + P.c0;
+        const float b = OBS_MLL ? (1.0f - d.z) - P.omf_zcl : P.one_m;
+        l2obs = lg2(a * b) + onorm;
+        if (FIXED) return true;
+        return fmaf(P.k, fmaf(JMC_LN2F, d.l2tc, P.lzc), 1.0f) > 0.0f && !P.crit_always_nan;   // 1 + Lambda(z_c theta) > 0
     }
-
     // subsequent emission from the ungroomed sampler
-    const float l2zs = u2 * P.L2 - 1.0f;
-    const float l2ts = u3 * P.L2 + P.l2R;
-    if (dump) { dump->z_s = ex2(l2zs); dump->th_s = ex2(l2ts); }
-
+    d.l2zs = l2_sample(r[2], P.sL2, -1.0f);
+    d.l2ts = l2_sample(r[3], P.sL2, P.l2R);
     if (KIND == JMC_KIND_CRIT_SUB) {
-        // twoEmissionWeight (weights.py:63-99) with csub = z_s th_s^b th_s^b as written at :74
-        const float a = delta + P.c0;
-        const float b = P.obs_mll ? (1.0f - z) - P.omf_zcl : P.one_m;
-        const float l2cc = lg2(a * b) + P.beta * l2tc + P.l2_onorm;
-        const float l2cs = l2zs + 2.0f * P.beta * l2ts;
+        // observable of twoEmissionWeight's integrand: max(C_groomed, csub), csub = z_s th_s^b th_s^b (weights.py:74)
+        const float a = d.delta + P.c0;
+        const float b = OBS_MLL ? (1.0f - d.z) - P.omf_zcl : P.one_m;
+        const float l2cc = lg2(a * b) + onorm;
+        const float l2cs = fmaf(2.0f * P.beta, d.l2ts, d.l2zs);
         l2obs = fmaxf(l2cc, l2cs);
-        const float lc = JMC_LN2F * (l2cs - P.beta * l2tc);          // ln(csub / theta_c^beta)
-        if (P.fixed) {
-            // critPDF_fc * subPDF_fc(csub, maxRadius=theta_c) * th_s^b th_c^b * jacobians
-            const float x = JMC_LN2F + lc;                           // ln(2 csub / theta_c^beta)
-            if (!(x < 0.0f)) { w = 0.0f; return; }
-            const float e2 = l2d - l2z + (P.A + P.beta) * l2tc + (1.0f - P.beta) * l2ts - P.c1 * x * x * JMC_INV_LN2F;
-            w = P.g * 2.0f * P.c1 * (-x) * ex2(e2);
-        } else {
-            float Rc, Rs, rp;
-            if (!sub_rc(P, lc, Lc, Rs, rp) || !crit_rad_rc(P, Lc, Rc)) { w = nanw; return; }
-            const float alpha = alpha_from_lnmu(P, P.lnPT + JMC_LN2F * l2z + Lc);
-            const float lin = p_bar(z, P.jet) * delta * alpha * (float)(1.0 / H_PI) * rp;
-            w = lin * ex2(P.beta * l2tc + (1.0f - P.beta) * l2ts - (Rc + Rs) * JMC_INV_LN2F);
-        }
-        return;
+        d.lcl2 = fmaf(-P.beta, d.l2tc, l2cs);                        // log2(csub / theta_c^beta)
+        if (FIXED) return d.lcl2 < -1.0f;                            // subPDF_fc mask: C < theta_c^beta / 2
+        // "the reference is not NaN": theta_c above both Landau thresholds (a constant), C < 1, and
+        // 1 + Lambda(C, alpha(theta_c)) > 0, which after multiplying by alpha's positive denominator is linear
+        // in the logarithms:  1 + ca (max(ln P_T theta_c, 0) - ln M_Z + ln C) > 0
+        const float mu = fmaxf(fmaf(JMC_LN2F, d.l2tc, P.lnPT), 0.0f);
+        const float t = fmaf(JMC_LN2F, d.lcl2, mu - P.lnMZ);
+        return (d.l2tc > P.l2tc_min) & (d.lcl2 < 0.0f) & (fmaf(P.ca, t, 1.0f) > 0.0f);
     }
-
     if (KIND == JMC_KIND_PRE_CRIT_SUB) {
         // all-emission integrand with the zero bin
-        // (examples/tests/comparison_tests/comparison_utils_probabilistic.py:82-98, 384-474)
+        // (examples/tests/comparison_tests/comparison_utils_probabilistic.py:384-474)
         uint32_t r2[4];
         philox4x32_10(idx, 1u, seed, r2);
-        const float u4 = u32_to_unit_float(r2[0]), u5 = u32_to_unit_float(r2[1]);
-        const float E = -P.g * Lc;                                   // 2 C_R a/pi ln(R0/theta_c)
-        const float cdf = ex2(-E * P.ln_zc_eps * JMC_INV_LN2F);
-        const float l2zp = u4 * P.L2 + P.l2zc;
-        const bool zero_bin = u5 < cdf;
-        const float zp = zero_bin ? 0.0f : ex2(l2zp);
-        const float zcl = P.zc - zp;
-        // zmin - f (z_cut - z_pre) = delta + (1-f) z_cut + f z_pre: summed without passing through z_cut - z_pre,
-        // which would swallow a z_pre below the FP32 spacing of z_cut
-        const float a = delta + P.omf_zc + P.f * zp;
-        const float b = P.obs_mll ? (1.0f - z) - (1.0f - P.f) * zcl : 1.0f - (1.0f - P.f) * zcl;
-        const float l2cc = lg2(a * b) + P.beta * l2tc + P.l2_onorm;
-        const float l2cs = l2zs + P.beta * l2tc;                     // c_sub = z_s theta_c^beta
+        d.l2zp = l2_sample(r2[0], P.sL2, P.l2zc);
+        d.u5 = __uint2float_rn(r2[1]) * 2.3283064365386963e-10f;
+        const float E2 = -P.g * d.l2tc;                              // E / ln2, E = 2 C_R a/pi ln(R0/theta_c)
+        d.cdf = ex2(-E2 * P.ln_zc_eps);                              // exp(-E ln(z_cut/eps))
+        const bool zero_bin = d.u5 < d.cdf;
+        const float zp = zero_bin ? 0.0f : ex2(d.l2zp);
+        // zmin - f (z_cut - z_pre) = delta + (1-f) z_cut + f z_pre, summed without passing through
+        // z_cut - z_pre, which would swallow a z_pre below the FP32 spacing of z_cut
+        const float a = d.delta + P.omf_zc + P.f * zp;
+        const float omf_zcl = (1.0f - P.f) * (P.zc - zp);
+        const float b = OBS_MLL ? (1.0f - d.z) - omf_zcl : 1.0f - omf_zcl;
+        const float l2cc = lg2(a * b) + onorm;
+        const float l2cs = fmaf(P.beta, d.l2tc, d.l2zs);            // c_sub = z_s theta_c^beta
         l2obs = fmaxf(l2cc, l2cs);
-        const float x = JMC_LN2F * (1.0f + l2zs);                    // ln(2 z_s) < 0
-        const float pre = zero_bin ? cdf : E * ex2(-E * (P.l2zc - l2zp));
-        const float e2 = l2d - l2z + P.A * l2tc + l2ts - P.c1 * x * x * JMC_INV_LN2F;
-        w = P.g * 2.0f * P.c1 * (-x) * pre * ex2(e2);
-        if (dump) { dump->z_pre = zp; dump->zb_u = u5; }
-        return;
+        return true;
     }
+    return false;
+}
+
+// Stage 2 ("heavy"): weight * jacobian of a sample whose weight can be non-zero.
+template <int KIND, bool FIXED>
+__device__ __forceinline__ float heavy(const FastParams& P, const Draw& d) {
+    const float inv_pi = (float)(1.0 / H_PI);
+    if (KIND == JMC_KIND_RADIATOR) {
+        // radiatorWeight (weights.py:15-26) * z theta: theta cancels, z multiplies the splitting function
+        float zp;
+        if (P.split_acc == JMC_ACC_LL) zp = P.twoCR;
+        else if (P.split_acc == JMC_ACC_LL_NONSING) zp = z_times_p(d.z, P.jet);
+        else zp = z_times_p(d.z, P.jet) + d.z * p_of(1.0f - d.z, P.jet);
+        const float alpha = FIXED ? (float)H_ALPHA : alpha_from_lnmu(P, fmaf(JMC_LN2F, d.l2zs + d.l2ts, P.lnPT));
+        return zp * alpha * inv_pi;
+    }
+    const float l2z = lg2(d.z);
+    const float Lc = JMC_LN2F * d.l2tc;
+    if (KIND == JMC_KIND_CRIT) {
+        // criticalEmissionWeight (weights.py:31-41) * (z - z_c) theta
+        if (FIXED) return P.g * ex2(d.l2d - l2z + P.A * d.l2tc);
+        float R;
+        if (!crit_rad_rc(P, Lc, R)) return fnan();
+        const float alpha = alpha_from_lnmu(P, P.lnPT + JMC_LN2F * l2z + Lc);
+        return p_bar(d.z, P.jet) * d.delta * alpha * inv_pi * ex2(-R * JMC_INV_LN2F);
+    }
+    if (KIND == JMC_KIND_CRIT_SUB) {
+        // twoEmissionWeight (weights.py:63-99) * jacobians
+        const float lc = JMC_LN2F * d.lcl2;
+        if (FIXED) {
+            // critPDF_fc * subPDF_fc(csub, maxRadius=theta_c) * th_s^b th_c^b * (z - z_c) th_c z_s th_s
+            const float x = JMC_LN2F + lc;                           // ln(2 csub / theta_c^beta) < 0
+            const float e2 = d.l2d - l2z + (P.A + P.beta) * d.l2tc + (1.0f - P.beta) * d.l2ts
+                             - P.c1 * x * x * JMC_INV_LN2F;
+            return P.g * 2.0f * P.c1 * (-x) * ex2(e2);
+        }
+        float Rc, Rs, rp;
+        if (!sub_rc(P, lc, Lc, Rs, rp) || !crit_rad_rc(P, Lc, Rc)) return fnan();
+        const float alpha = alpha_from_lnmu(P, P.lnPT + JMC_LN2F * l2z + Lc);
+        const float lin = p_bar(d.z, P.jet) * d.delta * alpha * inv_pi * rp;
+        return lin * ex2(P.beta * d.l2tc + (1.0f - P.beta) * d.l2ts - (Rc + Rs) * JMC_INV_LN2F);
+    }
+    if (KIND == JMC_KIND_PRE_CRIT_SUB) {
+        // critPDF_fc * subPDF_fc(z_s) * precriticalEmissionWeight_zerobin * jacobians
+        // (comparison_utils_probabilistic.py:82-98, 432-464)
+        const float E = -P.g * Lc;
+        const bool zero_bin = d.u5 < d.cdf;
+        const float x = JMC_LN2F * (1.0f + d.l2zs);                  // ln(2 z_s) < 0
+        const float pre = zero_bin ? d.cdf : E * ex2(-E * (P.l2zc - d.l2zp));
+        const float e2 = d.l2d - l2z + P.A * d.l2tc + d.l2ts - P.c1 * x * x * JMC_INV_LN2F;
+        return P.g * 2.0f * P.c1 * (-x) * pre * ex2(e2);
+    }
+    return 0.0f;
 }
 
 // ---- binning ---------------------------------------------------------------
-// s_edges: edges in the compare domain (log2 or linear), FP32.
+// s_edges: edges in the compare domain (log2 or linear), FP32.  Returns -1 for a dropped sample.
+// UNILOG: edges known at compile time to be equally spaced in log2 (np.logspace bins, the common case).
+template <bool UNILOG>
 __device__ __forceinline__ int bin_fast(const FastParams& P, float l2obs, const float* __restrict__ s_edges) {
-    const float v = P.dom_log ? l2obs : ex2(l2obs);
+    const float v = (UNILOG || P.dom_log) ? l2obs : ex2(l2obs);
     const int ne = P.n_edges;
-    if (!(v >= s_edges[0]) || !(v <= s_edges[ne - 1])) return -1;
     int idx;
-    if (P.uniform) {
-        idx = (int)((v - P.b0) * P.inv_d);
+    if (UNILOG || P.uniform) {
+        // affine guess, then settle against the stored edges (FP32 rounding of the map can be off by one)
+        idx = __float2int_rd(fmaf(v, P.inv_d, P.mb0_inv_d));
         idx = max(0, min(idx, ne - 2));
-        // FP32 rounding of the affine map can be off by one: settle against the edges themselves
-        if (v < s_edges[idx]) --idx;
-        else if (idx < ne - 2 && v >= s_edges[idx + 1]) ++idx;
+        const float e_lo = s_edges[idx], e_hi = s_edges[idx + 1];
+        idx += (int)((v >= e_hi) & (idx < ne - 2)) - (int)(v < e_lo);
     } else {
         int lo = 0, hi = ne;
         while (lo < hi) {
@@ -323,11 +370,14 @@ __device__ __forceinline__ int bin_fast(const FastParams& P, float l2obs, const 
         }
         idx = min(lo - 1, ne - 2);
     }
-    return idx;
+    const bool in_range = (v >= P.e_first) & (v <= P.e_last);       // NaN fails both
+    return in_range ? idx : -1;
 }
 
-template <int KIND>
-__global__ void __launch_bounds__(kFastThreads)
+// HOT: histogram only (no min/max tracking) into np.logspace-like bins -- the form every large job has; the
+// generic instantiation reads those choices from FastParams at run time.
+template <int KIND, bool FIXED, bool OBS_MLL, bool HOT>
+__global__ void __launch_bounds__(kFastThreads, JMC_FAST_MIN_BLOCKS)
 run_fast_kernel(FastParams P, uint64_t n, uint64_t seed, uint64_t first, const float* __restrict__ g_edges,
                 double* __restrict__ g_sum_w, double* __restrict__ g_sum_w2,
                 unsigned long long* __restrict__ g_count, int* g_poison, double* __restrict__ d_minmax) {
@@ -338,34 +388,110 @@ run_fast_kernel(FastParams P, uint64_t n, uint64_t seed, uint64_t first, const f
     double* s_sum_w2 = s_sum_w + nb;
     unsigned int* s_count = (unsigned int*)(s_sum_w2 + nb);
     float* s_edges = (float*)(s_count + nb);
-    const bool do_hist = g_edges != nullptr;
+    const bool do_hist = HOT || g_edges != nullptr;
+    const bool do_minmax = !HOT && d_minmax != nullptr;
     if (threadIdx.x == 0) s_poison = INT_MAX;
     for (int k = threadIdx.x; k < nb; k += blockDim.x) { s_sum_w[k] = 0.0; s_sum_w2[k] = 0.0; s_count[k] = 0u; }
     for (int k = threadIdx.x; k < ne; k += blockDim.x) s_edges[k] = g_edges[k];
     __syncthreads();
     float mn = INFINITY, mx = -INFINITY;
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        float l2obs, w;
-        eval_fast<KIND>(P, first + i, seed, l2obs, w, nullptr);
-        if (do_hist) {
-            const int b = bin_fast(P, l2obs, s_edges);
-            if (w != w) {                                // NaN weight (nan_to_num off): NumPy poisons bins >= b
-                const float v = P.dom_log ? l2obs : ex2(l2obs);
-                const int pb = b >= 0 ? b : (v < s_edges[0] ? 0 : INT_MAX);
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const uint32_t iters = n > tid ? (uint32_t)((n - tid + stride - 1) / stride) : 0u;
+    uint64_t idx = first + tid;
+
+    // weight * jacobian of one sample into the block histogram (bq: bin, or -1 / -2 for a sample below /
+    // above the binned range, which matters only for NumPy's NaN poisoning)
+    auto accumulate = [&](float w, int bq) {
+        if (w != w) {                                    // NaN: 0 under nan_to_num, else NumPy poisons bins >= bq
+            if (!P.nan_to_num) {
+                const int pb = bq >= 0 ? bq : (bq == -1 ? 0 : INT_MAX);
                 if (pb != INT_MAX) atomicMin(&s_poison, pb);
-                if (b >= 0) atomicAdd(&s_count[b], 1u);
-            } else if (b >= 0) {
-                atomicAdd(&s_count[b], 1u);
-                if (w != 0.0f) {
-                    const double wd = (double)w;
-                    atomicAdd(&s_sum_w[b], wd);
-                    atomicAdd(&s_sum_w2[b], wd * wd);
+            }
+        } else if (bq >= 0 && w != 0.0f) {
+            const double wd = (double)w;
+            atomicAdd(&s_sum_w[bq], wd);
+            atomicAdd(&s_sum_w2[bq], wd * wd);
+        }
+    };
+
+    // Warp-level compaction of the rare samples whose weight is not NaN -> 0.  In the running-coupling
+    // critical x subsequent integrand 0.3 % of the samples are active, i.e. 9 % of the warps would run the
+    // ~330-instruction radiator code with one or two live lanes.  Instead the active draws are appended to a
+    // per-warp shared-memory queue (ballot + popc, no atomics) and evaluated 32 at a time with every lane busy.
+    constexpr bool COMPACT = (KIND == JMC_KIND_CRIT_SUB) && !FIXED;
+    const unsigned lane = threadIdx.x & 31u;
+    float* q = (float*)(s_edges + ((ne + 3) & ~3)) + (threadIdx.x >> 5) * (kQueueFields * kQueueSlots);
+    int qn = 0;                                          // warp-uniform queue length
+    auto heavy_from_queue = [&](int slot) {
+        Draw d;
+        d.l2d = q[0 * kQueueSlots + slot];
+        d.l2tc = q[1 * kQueueSlots + slot];
+        d.l2zs = q[2 * kQueueSlots + slot];
+        d.l2ts = q[3 * kQueueSlots + slot];
+        const int bq = __float_as_int(q[4 * kQueueSlots + slot]);
+        d.delta = ex2(d.l2d);
+        d.z = P.zc + d.delta;
+        d.lcl2 = fmaf(-P.beta, d.l2tc, fmaf(2.0f * P.beta, d.l2ts, d.l2zs));
+        accumulate(heavy<KIND, FIXED>(P, d), bq);
+    };
+    // everything after the draw for one sample: min/max, bin, count, weight (directly or through the queue)
+    auto handle = [&](const Draw& d, float l2obs, bool active, bool valid) {
+        if (do_minmax && valid) {
+            mn = fminf(mn, l2obs);
+            mx = fmaxf(mx, l2obs);
+        }
+        if (!do_hist) return;
+        int b = bin_fast<HOT>(P, l2obs, s_edges);
+        if (!valid) { b = -1; active = false; }
+        if (b >= 0) atomicAdd(&s_count[b], 1u);
+        const float v = (HOT || P.dom_log) ? l2obs : ex2(l2obs);
+        const int bq = b >= 0 ? b : (v < P.e_first ? -1 : -2);
+        if (COMPACT) {
+            if (!P.nan_to_num && !active && valid) accumulate(fnan(), bq);   // inactive = "the reference weight is NaN"
+            const unsigned m = __ballot_sync(0xffffffffu, active);
+            if (m) {
+                if (active) {
+                    const int slot = qn + __popc(m & ((1u << lane) - 1u));
+                    q[0 * kQueueSlots + slot] = d.l2d;
+                    q[1 * kQueueSlots + slot] = d.l2tc;
+                    q[2 * kQueueSlots + slot] = d.l2zs;
+                    q[3 * kQueueSlots + slot] = d.l2ts;
+                    q[4 * kQueueSlots + slot] = __int_as_float(bq);
+                }
+                qn += __popc(m);
+                __syncwarp();
+                if (qn >= 32) {
+                    qn -= 32;
+                    heavy_from_queue(qn + (int)lane);
+                    __syncwarp();
                 }
             }
+        } else if (active) {
+            accumulate(heavy<KIND, FIXED>(P, d), bq);
+        } else if (!FIXED && !P.nan_to_num && valid) {
+            accumulate(fnan(), bq);                      // inactive under running coupling = NaN weight
         }
-        mn = fminf(mn, l2obs);
-        mx = fmaxf(mx, l2obs);
+    };
+
+    // Two samples per trip: their Philox chains are independent, so the scheduler interleaves them (the
+    // generator is a 10-deep dependent chain of IMAD.WIDE -> LOP3), and the warp-uniform work of a trip (round
+    // keys, constant loads, loop control) is paid once per two samples.  The ballots in handle() need every
+    // lane of the warp in every trip, so all lanes run to the warp's longest trip count.
+    const uint32_t my_trips = (iters + 1u) >> 1;
+    const uint32_t trips = __shfl_sync(0xffffffffu, my_trips, 0);
+    const uint64_t stride2 = 2ull * stride;
+    for (uint32_t j = 0; j < trips; ++j, idx += stride2) {
+        Draw d0, d1;
+        float o0, o1;
+        const bool a0 = light<KIND, FIXED, OBS_MLL>(P, idx, seed, d0, o0);
+        const bool a1 = light<KIND, FIXED, OBS_MLL>(P, idx + stride, seed, d1, o1);
+        handle(d0, o0, a0, 2u * j < iters);
+        handle(d1, o1, a1, 2u * j + 1u < iters);
+    }
+    if (COMPACT && do_hist) {
+        __syncwarp();
+        if ((int)lane < qn) heavy_from_queue((int)lane);
     }
     __syncthreads();
     if (do_hist) {
@@ -380,7 +506,7 @@ run_fast_kernel(FastParams P, uint64_t n, uint64_t seed, uint64_t first, const f
         }
         if (threadIdx.x == 0 && s_poison != INT_MAX) atomicMin(g_poison, s_poison);
     }
-    if (d_minmax) {
+    if (do_minmax) {
         for (int o = 16; o > 0; o >>= 1) {
             mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
             mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -416,19 +542,33 @@ __global__ void poison_fast_kernel(const int* g_poison, int nb, double* g_sum_w,
 }
 
 // samples on request: per-sample samples / observable / weight of the FP32 path
-template <int KIND>
+template <int KIND, bool FIXED>
 __global__ void __launch_bounds__(kFastThreads)
 dump_fast_kernel(FastParams P, uint64_t n, uint64_t seed, uint64_t first, double* __restrict__ samples,
                  double* __restrict__ obs, double* __restrict__ weight) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        FastSample s = {0.f, 0.f, 0.f, 0.f, 0.f, 2.f, 0.f};
-        float l2obs, w;
-        eval_fast<KIND>(P, first + i, seed, l2obs, w, &s);
+        Draw d;
+        d.l2d = d.l2tc = d.l2zs = d.l2ts = d.l2zp = -INFINITY;
+        d.delta = d.z = d.cdf = 0.0f;
+        d.u5 = 2.0f;
+        float l2obs;
+        const bool active = P.obs_mll ? light<KIND, FIXED, true>(P, first + i, seed, d, l2obs)
+                                      : light<KIND, FIXED, false>(P, first + i, seed, d, l2obs);
+        float w = active ? heavy<KIND, FIXED>(P, d) : (FIXED ? 0.0f : fnan());
+        if (w != w && P.nan_to_num) w = 0.0f;
         if (samples) {
             double* o = samples + 8 * i;
-            o[0] = s.z_c; o[1] = s.th_c; o[2] = s.z_s; o[3] = s.th_s; o[4] = s.z_pre; o[5] = s.zb_u;
-            o[6] = s.delta; o[7] = 0.0;
+            const bool has_crit = KIND != JMC_KIND_RADIATOR;
+            const bool zero_bin = KIND == JMC_KIND_PRE_CRIT_SUB && d.u5 < d.cdf;
+            o[0] = has_crit ? d.z : 0.0;
+            o[1] = has_crit ? ex2(d.l2tc) : 0.0;
+            o[2] = KIND == JMC_KIND_RADIATOR ? d.z : ex2(d.l2zs);
+            o[3] = ex2(d.l2ts);
+            o[4] = KIND == JMC_KIND_PRE_CRIT_SUB ? (zero_bin ? 0.0 : ex2(d.l2zp)) : 0.0;
+            o[5] = d.u5;
+            o[6] = has_crit ? d.delta : 0.0;
+            o[7] = 0.0;
         }
         if (obs) obs[i] = exp2((double)l2obs);
         if (weight) weight[i] = (double)w;
@@ -462,6 +602,7 @@ static int make_fast_params(const jmc_integrand* g, const double* h_edges, int n
     P.kind = g->kind; P.jet = g->jet; P.fixed = g->fixed_coupling; P.obs_mll = g->obs_acc == JMC_ACC_MLL;
     P.split_acc = g->split_acc; P.nan_to_num = g->nan_to_num;
     P.L2 = (float)std::log2(g->epsilon);
+    P.sL2 = (float)(std::log2(g->epsilon) * 2.3283064365386963e-10);
     P.l2w_cz = (float)std::log2(0.5 - g->z_cut);
     P.l2R = (float)(std::log2(g->radius) + (g->kind == JMC_KIND_RADIATOR ? std::log2(g->theta_scale) : 0.0));
     P.l2zc = g->z_cut > 0 ? (float)std::log2(g->z_cut) : 0.f;
@@ -515,6 +656,16 @@ static int make_fast_params(const jmc_integrand* g, const double* h_edges, int n
     const double knee = std::pow(H_MU, g->beta) * std::pow(2.0, g->beta - 1.0);
     P.lnknee = (float)std::log(knee);
     P.bbar_knee = (float)h_bbar(knee, g->jet);
+    {
+        // CRIT_SUB, running coupling: the weight is NaN unless 1 + Lambda(MU_NP, alpha(theta_c)) > 0, i.e.
+        // 1 + ca (ln(P_T theta_c) - ln M_Z + ln MU_NP) > 0 (theta_c above the freezing scale there), and unless
+        // the critical radiator's 1 + Lambda(z_c theta_c) > 0.
+        const double ca = 2.0 * H_AMZ * H_BETA0;
+        const double ln_th_sub = -1.0 / ca + std::log(H_MZ) - std::log(H_MU) - std::log(H_PT);
+        const double k = 2.0 * H_ALPHA * H_BETA0;
+        const double ln_th_crit = g->z_cut > 0 ? -1.0 / k - std::log(g->z_cut) : -INFINITY;
+        P.l2tc_min = (float)(std::fmax(ln_th_sub, ln_th_crit) / ln2);
+    }
     // ---- binning domain
     P.n_edges = n_edges;
     if (h_edges) {
@@ -534,7 +685,10 @@ static int make_fast_params(const jmc_integrand* g, const double* h_edges, int n
         P.uniform = uniform;
         P.b0 = (float)dom[0];
         P.inv_d = (float)(1.0 / d);
+        P.mb0_inv_d = (float)(-dom[0] / d);
         for (int k = 0; k < n_edges; ++k) (*edges_f)[k] = (float)dom[k];
+        P.e_first = (*edges_f)[0];
+        P.e_last = (*edges_f)[n_edges - 1];
         for (int k = 1; k < n_edges; ++k)
             if (!((*edges_f)[k] > (*edges_f)[k - 1]))
                 return set_error(JMC_ELIMIT, "jmc_run: bin edges %d and %d coincide in FP32; use JMC_F64 for bins this fine",
@@ -546,11 +700,13 @@ static int make_fast_params(const jmc_integrand* g, const double* h_edges, int n
 
 static size_t fast_smem_bytes(int n_edges) {
     const size_t nb = n_edges > 0 ? (size_t)n_edges - 1 : 0;
-    return sizeof(double) * 2 * nb + sizeof(unsigned int) * nb + sizeof(float) * (size_t)(n_edges > 0 ? n_edges : 0);
+    const size_t ne_pad = ((size_t)(n_edges > 0 ? n_edges : 0) + 3) & ~(size_t)3;
+    return sizeof(double) * 2 * nb + sizeof(unsigned int) * nb + sizeof(float) * ne_pad
+           + sizeof(float) * (kFastThreads / 32) * kQueueFields * kQueueSlots;
 }
 
-template <int KIND>
-static int launch_fast(const FastParams& P, uint64_t n, uint64_t seed, uint64_t first, const float* d_edges_f,
+template <int KIND, bool FIXED, bool OBS_MLL, bool HOT>
+static int launch_fast_t(const FastParams& P, uint64_t n, uint64_t seed, uint64_t first, const float* d_edges_f,
                        double* d_sum_w, double* d_sum_w2, uint64_t* d_count, int* d_poison, double* d_minmax,
                        cudaStream_t st) {
     DeviceInfo di;
@@ -559,19 +715,30 @@ static int launch_fast(const FastParams& P, uint64_t n, uint64_t seed, uint64_t 
     if (smem > (size_t)di.max_smem_optin)
         return set_error(JMC_ELIMIT, "jmc_run: %d edges need %zu B of shared memory (limit %d B)", P.n_edges, smem,
                          di.max_smem_optin);
-    JMC_CUDA(cudaFuncSetAttribute(run_fast_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    JMC_CUDA(cudaFuncSetAttribute(run_fast_kernel<KIND, FIXED, OBS_MLL, HOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    JMC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, run_fast_kernel<KIND>, kFastThreads, smem));
+    JMC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, run_fast_kernel<KIND, FIXED, OBS_MLL, HOT>, kFastThreads, smem));
     if (per_sm < 1) per_sm = 1;
     uint64_t want = (n + kFastThreads - 1) / kFastThreads;
     const uint64_t cap = (uint64_t)di.sm_count * per_sm;      // persistent: one wave of resident blocks
     const int grid = (int)(want < cap ? want : cap);
     FastParams Q = P;
     if (!d_edges_f) Q.n_edges = 0;
-    run_fast_kernel<KIND><<<grid, kFastThreads, smem, st>>>(Q, n, seed, first, d_edges_f, d_sum_w, d_sum_w2,
+    run_fast_kernel<KIND, FIXED, OBS_MLL, HOT><<<grid, kFastThreads, smem, st>>>(Q, n, seed, first, d_edges_f, d_sum_w, d_sum_w2,
                                                              (unsigned long long*)d_count, d_poison, d_minmax);
     JMC_LAUNCHED("run_fast_kernel");
     return JMC_OK;
+}
+
+template <int KIND, bool FIXED>
+static int launch_fast(const FastParams& P, uint64_t n, uint64_t seed, uint64_t first, const float* d_edges_f,
+                       double* d_sum_w, double* d_sum_w2, uint64_t* d_count, int* d_poison, double* d_minmax,
+                       cudaStream_t st) {
+    const bool hot = d_edges_f != nullptr && d_minmax == nullptr && P.dom_log && P.uniform;
+#define JMC_GO(M, H) launch_fast_t<KIND, FIXED, M, H>(P, n, seed, first, d_edges_f, d_sum_w, d_sum_w2, d_count, d_poison, d_minmax, st)
+    if (P.obs_mll) return hot ? JMC_GO(true, true) : JMC_GO(true, false);
+    return hot ? JMC_GO(false, true) : JMC_GO(false, false);
+#undef JMC_GO
 }
 
 int run_fast(const jmc_integrand* g, uint64_t n, uint64_t seed, uint64_t first_index, const double* d_edges,
@@ -607,12 +774,18 @@ int run_fast(const jmc_integrand* g, uint64_t n, uint64_t seed, uint64_t first_i
         JMC_CUDA(cudaMemcpyAsync(d_edges_f, edges_f.data(), sizeof(float) * n_edges, cudaMemcpyHostToDevice, st));
         JMC_CUDA(cudaStreamSynchronize(st));     // edges_f goes out of scope at return
     }
-#define JMC_RUNF(K) rc = launch_fast<K>(P, n, seed, first_index, d_edges_f, d_sum_w, d_sum_w2, d_count, d_poison, d_minmax, st)
+#define JMC_RUNF(K)                                                                                                   \
+    rc = g->fixed_coupling                                                                                            \
+             ? launch_fast<K, true>(P, n, seed, first_index, d_edges_f, d_sum_w, d_sum_w2, d_count, d_poison, d_minmax, st) \
+             : launch_fast<K, false>(P, n, seed, first_index, d_edges_f, d_sum_w, d_sum_w2, d_count, d_poison, d_minmax, st)
     switch (g->kind) {
         case JMC_KIND_RADIATOR: JMC_RUNF(JMC_KIND_RADIATOR); break;
         case JMC_KIND_CRIT: JMC_RUNF(JMC_KIND_CRIT); break;
         case JMC_KIND_CRIT_SUB: JMC_RUNF(JMC_KIND_CRIT_SUB); break;
-        case JMC_KIND_PRE_CRIT_SUB: JMC_RUNF(JMC_KIND_PRE_CRIT_SUB); break;
+        case JMC_KIND_PRE_CRIT_SUB:
+            rc = launch_fast<JMC_KIND_PRE_CRIT_SUB, true>(P, n, seed, first_index, d_edges_f, d_sum_w, d_sum_w2, d_count,
+                                                          d_poison, d_minmax, st);
+            break;
         default: return set_error(JMC_EINVAL, "jmc_run: kind %d has no FP32 form", g->kind);
     }
 #undef JMC_RUNF
@@ -637,12 +810,21 @@ int dump_fast(const jmc_integrand* g, uint64_t n, uint64_t seed, uint64_t first_
     const uint64_t cap = (uint64_t)di.sm_count * 8;
     const int grid = (int)(want < cap ? want : cap);
     cudaStream_t st = (cudaStream_t)stream;
-#define JMC_DUMPF(K) dump_fast_kernel<K><<<grid, kFastThreads, 0, st>>>(P, n, seed, first_index, d_samples, d_obs, d_weight)
+#define JMC_DUMPF(K)                                                                                              \
+    do {                                                                                                          \
+        if (g->fixed_coupling)                                                                                    \
+            dump_fast_kernel<K, true><<<grid, kFastThreads, 0, st>>>(P, n, seed, first_index, d_samples, d_obs, d_weight); \
+        else                                                                                                      \
+            dump_fast_kernel<K, false><<<grid, kFastThreads, 0, st>>>(P, n, seed, first_index, d_samples, d_obs, d_weight); \
+    } while (0)
     switch (g->kind) {
         case JMC_KIND_RADIATOR: JMC_DUMPF(JMC_KIND_RADIATOR); break;
         case JMC_KIND_CRIT: JMC_DUMPF(JMC_KIND_CRIT); break;
         case JMC_KIND_CRIT_SUB: JMC_DUMPF(JMC_KIND_CRIT_SUB); break;
-        case JMC_KIND_PRE_CRIT_SUB: JMC_DUMPF(JMC_KIND_PRE_CRIT_SUB); break;
+        case JMC_KIND_PRE_CRIT_SUB:
+            dump_fast_kernel<JMC_KIND_PRE_CRIT_SUB, true><<<grid, kFastThreads, 0, st>>>(P, n, seed, first_index, d_samples,
+                                                                                         d_obs, d_weight);
+            break;
         default: return set_error(JMC_EINVAL, "jmc_dump: kind %d has no FP32 form", g->kind);
     }
 #undef JMC_DUMPF

@@ -117,8 +117,16 @@ def test_fast_per_sample_vs_oracle(cuda, kind, jet, fc, acc, eps):
     if kind in ('crit', 'crit_sub') and not fc and eps < 1e-5:
         assert nan_ref.mean() > .3            # the Landau region is exercised
         assert good.sum() > 100
-    tol = 2e-4 + 3e-5 / _endpoint_x(kind, samples, fc)
-    assert np.all(np.abs(w[good] - w_ref[good]) <= tol[good] * np.abs(w_ref[good])), \
+    # backward-error statement: the FP32 weight equals the reference function within 2e-4 relative, or is the
+    # reference function at inputs moved by ~1e-5 relative (FP32 rounding of the carried logarithms).  The
+    # second term only matters where the weight vanishes or changes sign (kinematic end point x -> 0 of the
+    # fixed-coupling pdf, zero of R' of the running-coupling subsequent radiator near C = 1/2).
+    moved = samples.copy()
+    moved[:, 2] *= 1. + 1e-5
+    _, w_moved = _oracle_on_dump(kind, moved, jet, fc, acc, eps=eps)
+    tol = 2e-4 * np.abs(w_ref) + 3. * np.abs(np.nan_to_num(w_moved) - np.nan_to_num(w_ref)) \
+        + 3e-5 / _endpoint_x(kind, samples, fc) * np.abs(w_ref)
+    assert np.all(np.abs(w[good] - w_ref[good]) <= tol[good]), \
         "max rel weight error %.3g" % np.max(np.abs(w[good] / w_ref[good] - 1))
     # and in aggregate the weighted totals agree much better than per sample
     assert abs(w[good].sum() / w_ref[good].sum() - 1) < 2e-5
@@ -157,8 +165,10 @@ def test_fast_histogram_equals_histogram_of_its_dump(cuda, kind, jet, fc, acc):
     assert abs(cnt - np.histogram(obs, edges)[0]).sum() <= 1e-4 * n     # and FP64 binning differs only at edge ties
     ref_sw = np.bincount(idx[keep], weights=w[keep], minlength=len(edges) - 1)
     ref_sw2 = np.bincount(idx[keep], weights=w[keep] ** 2, minlength=len(edges) - 1)
-    assert_allclose(r['sum_w'].cpu().numpy(), ref_sw, rtol=1e-11, atol=1e-13 * np.abs(ref_sw).max())
-    assert_allclose(r['sum_w2'].cpu().numpy(), ref_sw2, rtol=1e-11, atol=1e-13 * np.abs(ref_sw2).max())
+    # the dump and the histogram kernel are separate instantiations of the same FP32 code; FMA contraction
+    # may differ between them in the last place of a weight, hence FP32-ulp level agreement of the sums
+    assert_allclose(r['sum_w'].cpu().numpy(), ref_sw, rtol=2e-6, atol=1e-7 * np.abs(ref_sw).max())
+    assert_allclose(r['sum_w2'].cpu().numpy(), ref_sw2, rtol=4e-6, atol=1e-7 * np.abs(ref_sw2).max())
 
 
 def _pulls(a, ea, b, eb):
