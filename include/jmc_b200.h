@@ -241,6 +241,12 @@ int jmc_run(const jmc_integrand* g, uint64_t n, uint64_t seed, uint64_t first_in
 int jmc_dump(const jmc_integrand* g, uint64_t n, uint64_t seed, uint64_t first_index, int precision,
              double* d_samples, double* d_obs, double* d_weight, void* stream);
 
+/* Per-jet view of the shower streams: ECF observable, number of accepted emissions and number of veto trials of
+ * jets first_index .. first_index+n-1 (outputs indexed 0..n-1; any may be NULL).
+ * ref: utils/partonshower_utils.py:130-328 (gen_jets), :445-499, :676-790 (getECFs_*) */
+int jmc_shower_dump(const jmc_integrand* g, uint64_t n, uint64_t seed, uint64_t first_index, int precision,
+                    double* d_obs, int32_t* d_n_emissions, int32_t* d_n_trials, void* stream);
+
 /* density, error, cumulative integral (+ error) from the histograms.
  * ref: montecarlo/integrator.py:113-124 (density), :129-202 (integrate).
  * density, density_err, integral_err: n_edges-1; integral: n_edges. */

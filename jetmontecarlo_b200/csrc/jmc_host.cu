@@ -116,8 +116,9 @@ int dump_exact(const jmc_integrand* g, uint64_t n, uint64_t seed, uint64_t first
                double* d_obs, double* d_weight, void* stream);
 int dump_fast(const jmc_integrand* g, uint64_t n, uint64_t seed, uint64_t first_index, double* d_samples,
               double* d_obs, double* d_weight, void* stream);
-int run_shower(const jmc_integrand* g, uint64_t n, uint64_t seed, uint64_t first_index, const double* d_edges,
-               int n_edges, double* d_sum_w, double* d_sum_w2, uint64_t* d_count, double* d_minmax, void* stream);
+int run_shower(const jmc_integrand* g, uint64_t n, uint64_t seed, uint64_t first_index, int precision,
+               const double* d_edges, int n_edges, double* d_sum_w, double* d_sum_w2, uint64_t* d_count,
+               double* d_minmax, void* stream);
 
 static int sampler_area(int kind, int method, double eps, double zc, double radius, double lo, double hi,
                         double* area) {
@@ -210,7 +211,8 @@ extern "C" int jmc_run(const jmc_integrand* g, uint64_t n, uint64_t seed, uint64
     JMC_REQUIRE(g != nullptr, "jmc_run: integrand is NULL");
     JMC_REQUIRE(precision == JMC_F64 || precision == JMC_F32, "jmc_run: precision must be JMC_F64 or JMC_F32");
     if (g->kind == JMC_KIND_SHOWER)
-        return run_shower(g, n, seed, first_index, d_edges, n_edges, d_sum_w, d_sum_w2, d_count, d_minmax, stream);
+        return run_shower(g, n, seed, first_index, precision, d_edges, n_edges, d_sum_w, d_sum_w2, d_count, d_minmax,
+                          stream);
     if (precision == JMC_F64)
         return run_exact(g, n, seed, first_index, d_edges, n_edges, d_sum_w, d_sum_w2, d_count, d_minmax, stream);
     return run_fast(g, n, seed, first_index, d_edges, n_edges, d_sum_w, d_sum_w2, d_count, d_minmax, stream);

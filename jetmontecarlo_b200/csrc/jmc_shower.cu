@@ -1,7 +1,383 @@
-// placeholder until the shower lands
+// Angularity-ordered parton shower with the MLL veto (acceptance-rejection)
+// algorithm, fused with the ECF observable and the histogram.
+//
+// What it replaces: gen_jets -> angularity_shower -> angularity_split
+// (jetmontecarlo/utils/partonshower_utils.py:130-328) followed by
+// getECFs_ungroomed (:445-499) or getECFs_softdrop (:676-790).  The reference
+// builds a tree of Parton objects with 3-vectors per jet; with split_soft=False
+// (:321) the geometry is redundant -- the opening angle of the daughters IS
+// theta and the softer momentum fraction IS z -- so a jet is just its ordered
+// chain of (z, theta), and the observables are running maxima / sums over
+// that chain.  Nothing per jet is stored.
+//
+// Device design: one jet per lane, but lanes do not wait for each other: the
+// kernel loops over veto TRIALS, and a lane whose chain ends bins its
+// observable and immediately starts its next jet (persistent lanes with
+// refill).  Trial counts per jet are geometric (about 30 for quark, 57 for
+// gluon jets at the 1 GeV cutoff), so lock-step jets would idle most lanes.
+//
+// Two arithmetic modes:
+//   FP64: the reference's operation sequence on 53-bit Philox uniforms, jet by
+//         jet comparable with oracle/jmc_oracle.py: shower_emissions;
+//   FP32: ln(2 ang) carried instead of ang, one Philox block (r1, r2, r3) per
+//         trial, MUFU transcendentals.
+// compiled with --fmad=false (shared flag of the NumPy-order translation units)
+#include <climits>
+#include <cmath>
+#include <vector>
 #include "jmc_common.cuh"
+#include "jmc_philox.cuh"
+#include "jmc_physics.cuh"
+
 namespace jmc {
-int run_shower(const jmc_integrand*, uint64_t, uint64_t, uint64_t, const double*, int, double*, double*, uint64_t*, double*, void*) {
-    return set_error(JMC_EINVAL, "jmc_run: shower not built");
+
+static constexpr int kShowerThreads = 128;
+static constexpr int kMaxEmissions = 64;     // as the oracle; the reference recurses until the cutoff
+static constexpr int kTopN = 4;              // n_emissions up to 4 (+ 'all')
+
+struct ShowerParams {
+    int jet, mll_shower, obs_mll, groomer, n_emissions;
+    double beta, radius, cutoff, z_cut, beta_sd;
+    double alpha;          // alpha_fixed (LL) or the veto overestimate 1.5 (MLL)
+    double kfac;           // pi beta / (C_R alpha)
+    double cr;
+};
+
+// sequential uniforms of one jet: block b of the jet's Philox stream yields uniforms 2b, 2b+1
+struct UStream {
+    uint64_t jet, seed;
+    uint32_t blk;
+    bool have;
+    double buf;
+    __device__ __forceinline__ void reset(uint64_t j, uint64_t s) { jet = j; seed = s; blk = 0u; have = false; }
+    __device__ __forceinline__ double next() {
+        if (have) { have = false; return buf; }
+        double u0;
+        philox_uniform53x2(jet, blk++, seed, u0, buf);
+        have = true;
+        return u0;
+    }
+};
+
+// running top-N / sum of the chain's ECFs, in the order the reference adds them
+struct EcfAcc {
+    double top[kTopN];   // largest values seen, descending (ungroomed: all; soft drop: the ones after the first kept)
+    double sum_all;      // running sum in chain order
+    double first;        // soft drop: the critical emission's value
+    bool dropping;       // soft drop: still below the grooming condition
+    int n;
+    __device__ __forceinline__ void reset(int groomer) {
+#pragma unroll
+        for (int k = 0; k < kTopN; ++k) top[k] = -1.0;
+        // getECFs_ungroomed starts its list with 1e-50 (:459); soft drop appends its two 1e-50 at the end
+        sum_all = groomer ? 0.0 : 1e-50;
+        first = -1.0;
+        dropping = true;
+        n = 0;
+        if (!groomer) insert(1e-50);
+    }
+    __device__ __forceinline__ void insert(double c) {
+#pragma unroll
+        for (int k = 0; k < kTopN; ++k) {
+            if (c > top[k]) { const double t = top[k]; top[k] = c; c = t; }
+        }
+    }
+    __device__ __forceinline__ void add(double c, double z, double theta, const ShowerParams& p) {
+        if (!p.groomer) {                      // ref: partonshower_utils.py:445-499
+            insert(c);
+            sum_all += c;
+            return;
+        }
+        // ref: partonshower_utils.py:676-790: the first emission with z > z_cut theta^beta_sd is critical,
+        // every later one is subsequent
+        if (dropping) {
+            if (!(z > p.z_cut * np_pow(theta, p.beta_sd))) return;
+            dropping = false;
+            first = c;
+            sum_all = c;
+            return;
+        }
+        insert(c);
+        sum_all += c;
+    }
+    __device__ __forceinline__ double result(const ShowerParams& p) {
+        if (!p.groomer) {
+            if (p.n_emissions == 0) return sum_all;
+            double s = 0.0;                    // sum(cs[:n]) over the descending list
+            for (int k = 0; k < kTopN && k < p.n_emissions; ++k) if (top[k] >= 0.0) s += top[k];
+            return s;
+        }
+        // c_list += [1e-50, 1e-50]
+        if (dropping) {                        // nothing survived grooming: c_list = [1e-50, 1e-50]
+            if (p.n_emissions == 0) return 1e-50 + 1e-50;
+            if (p.n_emissions == 1) return 1e-50;
+            double s = 1e-50;
+            for (int k = 1; k < p.n_emissions && k < 2; ++k) s += 1e-50;
+            return s;
+        }
+        if (p.n_emissions == 0) return (sum_all + 1e-50) + 1e-50;
+        if (p.n_emissions == 1) return first;
+        insert(1e-50);
+        insert(1e-50);
+        double s = first;                      // sum([c0] + rest[:n-1])
+        for (int k = 0; k < kTopN && k < p.n_emissions - 1; ++k) if (top[k] >= 0.0) s += top[k];
+        return s;
+    }
+};
+
+// One veto trial in the reference's FP64 operation order.  Returns true if the emission is accepted.
+// ref: partonshower_utils.py:168-209
+__device__ __forceinline__ bool trial_exact(const ShowerParams& p, UStream& us, double& ang, double& z, double& theta,
+                                            int* error_flag) {
+    const double r1 = us.next(), r2 = us.next();
+    const double l = log(2.0 * ang);
+    const double ang_f = exp(-sqrt(l * l - p.kfac * log(r1))) / 2.0;
+    z = pow(2.0 * ang_f, r2) / 2.0;
+    theta = pow(2.0 * ang_f, (1 - r2) / p.beta);
+    ang = ang_f;
+    if (!p.mll_shower) return true;
+    const double cut = alpha_running(z, theta) * splitting(z, p.jet, JMC_ACC_MLL) / (2.0 * p.cr * p.alpha / z);
+    if (cut > 1.0) *error_flag = 1;            // the reference raises ValueError here
+    return us.next() < cut;
 }
+
+template <bool EXACT>
+__global__ void __launch_bounds__(kShowerThreads)
+shower_kernel(ShowerParams p, uint64_t n, uint64_t seed, uint64_t first, const double* __restrict__ edges,
+              int n_edges, unsigned long long* __restrict__ g_count, double* __restrict__ d_minmax,
+              double* __restrict__ dump_obs, int* __restrict__ dump_n, int* __restrict__ dump_trials,
+              int* error_flag) {
+    extern __shared__ double s_raw[];
+    const int nb = n_edges > 0 ? n_edges - 1 : 0;
+    double* s_edges = s_raw;
+    unsigned int* s_count = (unsigned int*)(s_edges + (n_edges > 0 ? n_edges : 0));
+    for (int k = threadIdx.x; k < n_edges; k += blockDim.x) s_edges[k] = edges[k];
+    for (int k = threadIdx.x; k < nb; k += blockDim.x) s_count[k] = 0u;
+    __syncthreads();
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double mn = INFINITY, mx = -INFINITY;
+
+    // per-lane jet state
+    UStream us;
+    EcfAcc acc;
+    double ang = 0.0, z = 0.0, theta = 0.0;
+    float lf = 0.0f;                            // FP32 mode: ln(2 ang)
+    int n_em = 0, n_trials = 0;
+    uint32_t blk32 = 0u;
+    bool in_veto_loop = false;
+    bool alive = j < n;
+    auto start_jet = [&]() {
+        us.reset(first + j, seed);
+        acc.reset(p.groomer);
+        ang = pow(p.radius, p.beta) / 2.0;     // ang_init = R^beta / 2, z_init = 1/2, theta_init = R (:316-321)
+        lf = (float)(p.beta * log(p.radius));
+        z = 0.5;
+        theta = p.radius;
+        n_em = 0;
+        n_trials = 0;
+        blk32 = 0u;
+        in_veto_loop = false;
+    };
+    if (alive) start_jet();
+    const float kfac_f = (float)p.kfac, inv_beta_f = (float)(1.0 / p.beta), ln_cut_f = (float)log(p.cutoff);
+    const float lnPT_f = (float)log(JMC_PT), lnMZ_f = (float)log(JMC_MZ), ca_f = (float)(2.0 * JMC_ALPHA_MZ * JMC_BETA0);
+    const float veto_norm_f = (float)(1.0 / (2.0 * p.cr * p.alpha));
+
+    while (__any_sync(0xffffffffu, alive)) {
+        if (!alive) continue;
+        // does the chain continue?  (angularity_shower: recurse while z theta > cutoff, :262-279).  The cutoff is
+        // tested on ACCEPTED emissions only: inside angularity_split the veto loop keeps trying without it (:188-209)
+        bool finished = in_veto_loop ? false : (!(z * theta > p.cutoff) || n_em >= kMaxEmissions);
+        if (!finished) {
+            bool accepted;
+            ++n_trials;
+            if (EXACT) {
+                accepted = trial_exact(p, us, ang, z, theta, error_flag);
+            } else {
+                // FP32: l' = -sqrt(l^2 - K ln r1); ln z = r2 l' - ln 2; ln theta = (1 - r2) l' / beta
+                uint32_t r[4];
+                philox4x32_10(first + j, blk32++, seed, r);
+                const float r1 = u32_to_unit_float(r[0]), r2 = u32_to_unit_float(r[1]), r3 = u32_to_unit_float(r[2]);
+                const float lp = -sqrtf(fmaf(lf, lf, -kfac_f * __logf(r1)));
+                const float lnz = fmaf(r2, lp, -0.69314718f);
+                const float lnth = (1.0f - r2) * lp * inv_beta_f;
+                lf = lp;
+                const float zf = __expf(lnz);
+                z = (double)zf;
+                theta = (double)__expf(lnth);
+                accepted = true;
+                if (p.mll_shower) {
+                    const float alpha = 0.118f / (1.0f + ca_f * (fmaxf(lnPT_f + lnz + lnth, 0.0f) - lnMZ_f));
+                    const float omz = 1.0f - zf;
+                    float zp;                    // z * (P(z) + P(1-z))
+                    if (p.jet == JMC_QUARK) {
+                        zp = (float)JMC_CF * ((1.0f + omz * omz) + zf * (1.0f + zf * zf) / omz);
+                    } else {
+                        const float pz = (float)JMC_CA * (2.0f * omz + zf * zf * omz)
+                                         + (float)(JMC_TF * JMC_NF) * zf * (zf * zf + omz * omz);
+                        const float p1 = ((float)JMC_CA * (2.0f * zf + omz * omz * zf)
+                                          + (float)(JMC_TF * JMC_NF) * omz * (zf * zf + omz * omz)) / omz;
+                        zp = pz + zf * p1;
+                    }
+                    const float cut = alpha * zp * veto_norm_f;
+                    if (cut > 1.0f) *error_flag = 1;
+                    accepted = r3 < cut;
+                }
+            }
+            in_veto_loop = !accepted;
+            if (accepted) {
+                ++n_em;
+                acc.add(ecf_ungroomed(z, theta, p.beta, p.obs_mll ? JMC_ACC_MLL : JMC_ACC_LL), z, theta, p);
+            }
+            continue;
+        }
+        // jet finished: observable -> histogram, then take the next jet
+        const double obs = acc.result(p);
+        if (dump_obs) dump_obs[j] = obs;
+        if (dump_n) dump_n[j] = n_em;
+        if (dump_trials) dump_trials[j] = n_trials;
+        if (n_edges > 0) {
+            const int b = bin_index(obs, s_edges, n_edges);
+            if (b >= 0) atomicAdd(&s_count[b], 1u);
+        }
+        mn = fmin(mn, obs);
+        mx = fmax(mx, obs);
+        j += stride;
+        alive = j < n;
+        if (alive) start_jet();
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < nb; k += blockDim.x)
+        if (s_count[k]) atomicAdd(&g_count[k], (unsigned long long)s_count[k]);
+    if (d_minmax) {
+        for (int o = 16; o > 0; o >>= 1) {
+            mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+            mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        }
+        if ((threadIdx.x & 31) == 0 && mn <= mx) {
+            unsigned long long* a0 = (unsigned long long*)&d_minmax[0];
+            unsigned long long* a1 = (unsigned long long*)&d_minmax[1];
+            unsigned long long old = *a0;
+            while (mn < __longlong_as_double(old)) {
+                const unsigned long long as = old;
+                old = atomicCAS(a0, as, (unsigned long long)__double_as_longlong(mn));
+                if (old == as) break;
+            }
+            old = *a1;
+            while (mx > __longlong_as_double(old)) {
+                const unsigned long long as = old;
+                old = atomicCAS(a1, as, (unsigned long long)__double_as_longlong(mx));
+                if (old == as) break;
+            }
+        }
+    }
+}
+
+// weight 1 per jet: sum w = sum w^2 = count
+__global__ void shower_sums_kernel(const unsigned long long* __restrict__ before, const unsigned long long* __restrict__ after,
+                                   int nb, double* __restrict__ sum_w, double* __restrict__ sum_w2) {
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nb; k += gridDim.x * blockDim.x) {
+        const double d = (double)(after[k] - before[k]);
+        sum_w[k] += d;
+        sum_w2[k] += d;
+    }
+}
+
+static int make_shower_params(const jmc_integrand* g, ShowerParams* out) {
+    JMC_REQUIRE(g != nullptr, "integrand is NULL");
+    JMC_REQUIRE(g->jet == JMC_QUARK || g->jet == JMC_GLUON, "jet type %d is not a supported jet type.", g->jet);
+    JMC_REQUIRE(g->split_acc == JMC_ACC_LL || g->split_acc == JMC_ACC_MLL, "shower accuracy must be LL or MLL");
+    JMC_REQUIRE(g->obs_acc == JMC_ACC_LL || g->obs_acc == JMC_ACC_MLL, "Accuracy must be LL or MLL");
+    JMC_REQUIRE(g->radius > 0.0, "Jet radius must be greater than zero!");
+    JMC_REQUIRE(g->beta > 0.0, "shower: beta must be positive");
+    JMC_REQUIRE(g->shower_cutoff > 0.0, "shower: cutoff must be positive");
+    JMC_REQUIRE(g->shower_n_emissions >= 0 && g->shower_n_emissions <= kTopN, "shower: n_emissions must be 1..%d or 0 ('all')", kTopN);
+    if (g->shower_groomer) JMC_REQUIRE(g->z_cut > 0.0 && g->z_cut < 0.5, "zc=%g is an invalid grooming parameter.", g->z_cut);
+    ShowerParams p;
+    p.jet = g->jet;
+    p.mll_shower = g->split_acc == JMC_ACC_MLL;
+    p.obs_mll = g->obs_acc == JMC_ACC_MLL;
+    p.groomer = g->shower_groomer;
+    p.n_emissions = g->shower_n_emissions;
+    p.beta = g->beta; p.radius = g->radius; p.cutoff = g->shower_cutoff; p.z_cut = g->z_cut; p.beta_sd = g->beta_sd;
+    p.cr = g->jet == JMC_QUARK ? JMC_CF : JMC_CA;
+    p.alpha = p.mll_shower ? JMC_ALPHA_VETO : JMC_ALPHA_FIXED;
+    p.kfac = JMC_PI * g->beta / (p.cr * p.alpha);
+    *out = p;
+    return JMC_OK;
+}
+
+static int shower_launch(const jmc_integrand* g, uint64_t n, uint64_t seed, uint64_t first_index, int precision,
+                         const double* d_edges, int n_edges, double* d_sum_w, double* d_sum_w2, uint64_t* d_count,
+                         double* d_minmax, double* d_obs, int* d_n_em, int* d_trials, void* stream) {
+    ShowerParams p;
+    int rc = make_shower_params(g, &p);
+    if (rc) return rc;
+    if (d_edges) {
+        JMC_REQUIRE(n_edges >= 2, "jmc_run: need at least 2 edges");
+        JMC_REQUIRE(d_sum_w && d_sum_w2 && d_count, "jmc_run: histogram outputs missing");
+    } else {
+        n_edges = 0;
+    }
+    if (n == 0) return JMC_OK;
+    DeviceInfo di;
+    if (device_info(&di)) return JMC_ENODEV;
+    const size_t nb = n_edges > 0 ? (size_t)n_edges - 1 : 0;
+    const size_t smem = sizeof(double) * (size_t)n_edges + sizeof(unsigned int) * nb;
+    if (smem > (size_t)di.max_smem_optin)
+        return set_error(JMC_ELIMIT, "jmc_run: %d edges exceed shared memory", n_edges);
+    cudaStream_t st = (cudaStream_t)stream;
+    char* scr;
+    rc = scratch(256 + sizeof(unsigned long long) * nb, (void**)&scr);
+    if (rc) return rc;
+    int* d_err = (int*)scr;
+    unsigned long long* d_before = (unsigned long long*)(scr + 256);
+    JMC_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int), st));
+    if (nb) JMC_CUDA(cudaMemcpyAsync(d_before, d_count, sizeof(unsigned long long) * nb, cudaMemcpyDeviceToDevice, st));
+    uint64_t want = (n + kShowerThreads - 1) / kShowerThreads;
+    const uint64_t cap = (uint64_t)di.sm_count * 8;
+    const int grid = (int)(want < cap ? want : cap);
+    if (precision == JMC_F64) {
+        JMC_CUDA(cudaFuncSetAttribute(shower_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        shower_kernel<true><<<grid, kShowerThreads, smem, st>>>(p, n, seed, first_index, d_edges, n_edges,
+                                                                 (unsigned long long*)d_count, d_minmax, d_obs, d_n_em,
+                                                                 d_trials, d_err);
+    } else {
+        JMC_CUDA(cudaFuncSetAttribute(shower_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        shower_kernel<false><<<grid, kShowerThreads, smem, st>>>(p, n, seed, first_index, d_edges, n_edges,
+                                                                  (unsigned long long*)d_count, d_minmax, d_obs, d_n_em,
+                                                                  d_trials, d_err);
+    }
+    JMC_LAUNCHED("shower_kernel");
+    if (nb) {
+        shower_sums_kernel<<<(int)((nb + 255) / 256), 256, 0, st>>>(d_before, (const unsigned long long*)d_count, (int)nb,
+                                                                     d_sum_w, d_sum_w2);
+        JMC_LAUNCHED("shower_sums_kernel");
+    }
+    // the reference raises inside the veto loop when the overestimate fails; report it the same way
+    int h_err = 0;
+    JMC_CUDA(cudaMemcpyAsync(&h_err, d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
+    JMC_CUDA(cudaStreamSynchronize(st));
+    if (h_err) return set_error(JMC_EDOMAIN, "The pdf must be everywhere less than the proposed pdf!");
+    return JMC_OK;
+}
+
+int run_shower(const jmc_integrand* g, uint64_t n, uint64_t seed, uint64_t first_index, int precision,
+               const double* d_edges, int n_edges, double* d_sum_w, double* d_sum_w2, uint64_t* d_count,
+               double* d_minmax, void* stream) {
+    JMC_REQUIRE(d_edges != nullptr || d_minmax != nullptr, "jmc_run: neither edges nor minmax requested");
+    return shower_launch(g, n, seed, first_index, precision, d_edges, n_edges, d_sum_w, d_sum_w2, d_count, d_minmax,
+                         nullptr, nullptr, nullptr, stream);
+}
+
+}  // namespace jmc
+
+extern "C" int jmc_shower_dump(const jmc_integrand* g, uint64_t n, uint64_t seed, uint64_t first_index, int precision,
+                               double* d_obs, int32_t* d_n_emissions, int32_t* d_n_trials, void* stream) {
+    JMC_REQUIRE(g != nullptr && g->kind == JMC_KIND_SHOWER, "jmc_shower_dump: integrand must be a shower");
+    JMC_REQUIRE(precision == JMC_F64 || precision == JMC_F32, "jmc_shower_dump: precision must be JMC_F64 or JMC_F32");
+    // the output arrays are indexed by the local jet number 0..n-1; jet i is stream index first_index + i
+    return jmc::shower_launch(g, n, seed, first_index, precision, nullptr, 0, nullptr, nullptr, nullptr, nullptr, d_obs,
+                              d_n_emissions, d_n_trials, stream);
 }
