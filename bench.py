@@ -149,7 +149,7 @@ def run_reference_arm(args):
         return
     import multiprocessing as mp
     cores = os.cpu_count() or 1
-    n_per_proc = int(args.cpu_samples) if args.cpu_samples else 12000
+    n_per_proc = int(args.cpu_samples) if args.cpu_samples else 60000
     ctx = mp.get_context("fork")
     with ctx.Pool(cores) as pool:
         for w in range(args.warmup):

@@ -88,7 +88,10 @@ enum {
     JMC_FN_TWO_EMISSION = 18,    /* a0=z_c a1=th_c a2=z_s a3=th_s    numerics/weights.py:63-99 */
     JMC_FN_PRE_WEIGHT_ZEROBIN = 19, /* a0=z_pre a1=theta_crit  examples/tests/comparison_tests/
                                        comparison_utils_probabilistic.py:82-98 */
-    JMC_FN_COUNT = 20
+    JMC_FN_ALPHA_SPLITTING = 20, /* a0=z a1=theta: alpha * splittingFn(z)   numerics/splitting.py:34-39,52-58 */
+    JMC_FN_MUL = 21,             /* a0 * a1 (weights * jacobians, e.g. montecarlo/integrator.py:447)        */
+    JMC_FN_MASK_FINITE = 22,     /* a0=w a1=v: w if both finite else 0 (make_finite of utils/hist_utils.py:103-108) */
+    JMC_FN_COUNT = 23
 };
 
 typedef struct jmc_fn_params {
@@ -214,6 +217,22 @@ int jmc_bin_index(const double* d_obs, uint64_t n, const double* d_edges, int n_
 int jmc_hist(const double* d_obs, const double* d_weights, uint64_t n,
              const double* d_edges, int n_edges,
              double* d_sum_w, double* d_sum_w2, uint64_t* d_count, void* stream);
+
+/* The three 2-D histograms of integrator_2d.setDensity (np.histogram2d, montecarlo/integrator.py:539-545):
+ * row-major [nx_edges-1, ny_edges-1] sum w, sum w^2, count; half-open bins, last bin closed, outliers and NaN
+ * dropped (histogramdd semantics: a NaN weight stays in its own bin).  d_weights may be NULL. */
+int jmc_hist2d(const double* d_x, const double* d_y, const double* d_weights, uint64_t n,
+               const double* d_edges_x, int nx_edges, const double* d_edges_y, int ny_edges,
+               double* d_sum_w, double* d_sum_w2, uint64_t* d_count, void* stream);
+
+/* integrator_2d: density, error (both stored transposed, [ny-1, nx-1], as the reference keeps them after
+ * its .T at :577-578) and the double cumulative sum with boundary condition (multidim_cumsum, :463-467,
+ * integrate :584-648).  d_integral / d_integral_err may both be NULL (density only). */
+int jmc_finalize2d(const double* d_sum_w, const double* d_sum_w2, const uint64_t* d_count,
+                   const double* d_edges_x, int nx_edges, const double* d_edges_y, int ny_edges,
+                   double area, uint64_t n_total, int bc_kind, double bc_value,
+                   double* d_density, double* d_density_err, double* d_integral, double* d_integral_err,
+                   void* stream);
 
 /* min / max of an array with NumPy NaN propagation -> d_minmax[0..1]
  * (integrator.setBins, montecarlo/integrator.py:42-46) */

@@ -20,7 +20,7 @@ SAMPLER_SIMPLE, SAMPLER_CRITICAL, SAMPLER_PRECRITICAL, SAMPLER_UNGROOMED = 0, 1,
 (FN_ALPHA_S, FN_SPLITTING, FN_RADIATOR_WEIGHT, FN_CRIT_PDF_FC, FN_CRIT_RAD_FC, FN_SUB_RAD_FC,
  FN_SUB_RADPRIME_FC, FN_SUB_PDF_FC, FN_PRE_RAD_FC, FN_CRIT_RAD_RC, FN_CRIT_RADPRIME_RC,
  FN_CRIT_PDF_RC, FN_SUB_RAD_RC, FN_SUB_RADPRIME_RC, FN_SUB_PDF_RC, FN_PRE_WEIGHT, FN_C_GROOMED,
- FN_C_UNGROOMED, FN_TWO_EMISSION, FN_PRE_WEIGHT_ZEROBIN) = range(20)
+ FN_C_UNGROOMED, FN_TWO_EMISSION, FN_PRE_WEIGHT_ZEROBIN, FN_ALPHA_SPLITTING, FN_MUL, FN_MASK_FINITE) = range(23)
 KIND_RADIATOR, KIND_CRIT, KIND_CRIT_SUB, KIND_PRE_CRIT_SUB, KIND_SIMPLE, KIND_SHOWER = range(6)
 
 METHODS = {'lin': LIN, 'log': LOG}
@@ -30,7 +30,7 @@ ACCS = {'LL': ACC_LL, 'LL_nonsing': ACC_LL_NONSING, 'MLL': ACC_MLL}
 EXPORTS = (
     "jmc_abi_version", "jmc_last_error", "jmc_device_count", "jmc_set_device", "jmc_sm_count",
     "jmc_sampler_area", "jmc_integrand_uniforms", "jmc_integrand_area", "jmc_sample", "jmc_uniforms",
-    "jmc_eval_fn", "jmc_eval_integrand", "jmc_bin_index", "jmc_hist", "jmc_minmax", "jmc_run", "jmc_dump", "jmc_shower_dump",
+    "jmc_eval_fn", "jmc_eval_integrand", "jmc_bin_index", "jmc_hist", "jmc_hist2d", "jmc_finalize2d", "jmc_minmax", "jmc_run", "jmc_dump", "jmc_shower_dump",
     "jmc_finalize", "jmc_cumulative", "jmc_set_density_host", "jmc_integrate_host", "jmc_sample_host",
     "jmc_eval_fn_host", "jmc_launch_count",
 )
@@ -87,6 +87,8 @@ def _load():
         "jmc_eval_integrand": (i32, [P(Integrand), u64, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp]),
         "jmc_bin_index": (i32, [vp, u64, vp, i32, vp, vp]),
         "jmc_hist": (i32, [vp, vp, u64, vp, i32, vp, vp, vp, vp]),
+        "jmc_hist2d": (i32, [vp, vp, vp, u64, vp, i32, vp, i32, vp, vp, vp, vp]),
+        "jmc_finalize2d": (i32, [vp, vp, vp, vp, i32, vp, i32, dbl, u64, i32, dbl, vp, vp, vp, vp, vp]),
         "jmc_minmax": (i32, [vp, u64, vp, vp]),
         "jmc_run": (i32, [P(Integrand), u64, u64, u64, i32, vp, i32, vp, vp, vp, vp, vp]),
         "jmc_dump": (i32, [P(Integrand), u64, u64, u64, i32, vp, vp, vp, vp]),

@@ -57,6 +57,11 @@ __global__ void __launch_bounds__(kThreads) eval_fn_kernel(int fn, jmc_fn_params
                 r = weight_two_emission(x0, x1, x2, x3, p.z_cut, p.beta, p.jet, p.fixed_coupling);
                 break;
             case JMC_FN_PRE_WEIGHT_ZEROBIN: r = weight_precritical_zerobin(x0, x1, p.z_cut, p.jet, p.epsilon); break;
+            case JMC_FN_ALPHA_SPLITTING:
+                r = (p.fixed_coupling ? JMC_ALPHA_FIXED : alpha_running(x0, x1)) * splitting(x0, p.jet, p.acc);
+                break;
+            case JMC_FN_MUL: r = x0 * x1; break;
+            case JMC_FN_MASK_FINITE: r = (isfinite(x0) && isfinite(x1)) ? x0 : 0.0; break;
             default: r = qnan();
         }
         out[i] = r;
@@ -507,6 +512,140 @@ extern "C" int jmc_minmax(const double* d_x, uint64_t n, double* d_minmax, void*
     const int grid = grid_for(n, kThreads);
     minmax_kernel<<<grid, kThreads, 0, st>>>(d_x, n, d_minmax);
     JMC_LAUNCHED("minmax_kernel");
+    return JMC_OK;
+}
+
+// ---------------------------------------------------------------------------
+// 2-D histogram and epilogue (integrator_2d; used by the pre-critical radiator, generation.py:143-250)
+// ---------------------------------------------------------------------------
+namespace jmc {
+
+__global__ void __launch_bounds__(kThreads)
+hist2d_kernel(const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ w, uint64_t n,
+              const double* __restrict__ ex, int nxe, const double* __restrict__ ey, int nye,
+              double* __restrict__ g_sum_w, double* __restrict__ g_sum_w2, unsigned long long* __restrict__ g_count) {
+    extern __shared__ double s_e[];
+    double* s_ex = s_e;
+    double* s_ey = s_e + nxe;
+    for (int k = threadIdx.x; k < nxe; k += blockDim.x) s_ex[k] = ex[k];
+    for (int k = threadIdx.x; k < nye; k += blockDim.x) s_ey[k] = ey[k];
+    __syncthreads();
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const int nby = nye - 1;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int bx = bin_index(x[i], s_ex, nxe), by = bin_index(y[i], s_ey, nye);
+        if (bx < 0 || by < 0) continue;
+        const size_t b = (size_t)bx * nby + by;
+        // (nx-1)(ny-1) bins do not fit shared memory in general: L2-resident global atomics (REDG.F64 / .64)
+        atomicAdd(&g_count[b], 1ull);
+        if (w) {
+            const double wi = w[i];
+            atomicAdd(&g_sum_w[b], wi);
+            atomicAdd(&g_sum_w2[b], wi * wi);
+        }
+    }
+}
+
+// density[iy][ix] (transposed, as the reference stores it) and running sums along x then y
+__global__ void density2d_kernel(const double* __restrict__ sum_w, const double* __restrict__ sum_w2,
+                                 const unsigned long long* __restrict__ count, const double* __restrict__ ex, int nxe,
+                                 const double* __restrict__ ey, int nye, double norm, double* __restrict__ density,
+                                 double* __restrict__ density_err) {
+    const int nbx = nxe - 1, nby = nye - 1;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nbx * nby; t += gridDim.x * blockDim.x) {
+        const int ix = t / nby, iy = t % nby;
+        // areafactor = area / (N * binArea)                          integrator.py:562-566
+        const double bin_area = (ex[ix + 1] - ex[ix]) * (ey[iy + 1] - ey[iy]);
+        const double f = norm / bin_area;
+        double d = sum_w[t] * f, e = sqrt(sum_w2[t]) * f;
+        if (count[t] == 0ull) { d = 0.0; e = 0.0; }
+        density[(size_t)iy * nbx + ix] = d;
+        density_err[(size_t)iy * nbx + ix] = e;
+    }
+}
+
+// multidim_cumsum of density*binArea on the [nby, nbx] (transposed) array: cumsum along the last axis (x), then
+// along y; `reverse` flips both axes (np.flip before and after).  One thread per line; the arrays are tiny.
+__global__ void cumsum2d_kernel(const double* __restrict__ density, const double* __restrict__ density_err,
+                                const double* __restrict__ ex, int nxe, const double* __restrict__ ey, int nye,
+                                int bc_kind, double bc_value, double* __restrict__ integral,
+                                double* __restrict__ integral_err, int pass) {
+    const int nbx = nxe - 1, nby = nye - 1;
+    const bool reverse = bc_kind != JMC_BC_FIRST;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pass == 0) {                    // along x for each row iy
+        if (t >= nby) return;
+        const int iy = t;
+        double a = 0.0, b = 0.0;
+        for (int j = 0; j < nbx; ++j) {
+            const int ix = reverse ? nbx - 1 - j : j;
+            const double area = (ex[ix + 1] - ex[ix]) * (ey[iy + 1] - ey[iy]);
+            a += density[(size_t)iy * nbx + ix] * area;
+            b += density_err[(size_t)iy * nbx + ix] * area;
+            integral[(size_t)iy * nbx + ix] = a;
+            integral_err[(size_t)iy * nbx + ix] = b;
+        }
+    } else {                            // along y for each column ix, then apply the boundary condition
+        if (t >= nbx) return;
+        const int ix = t;
+        double a = 0.0, b = 0.0;
+        for (int j = 0; j < nby; ++j) {
+            const int iy = reverse ? nby - 1 - j : j;
+            a += integral[(size_t)iy * nbx + ix];
+            b += integral_err[(size_t)iy * nbx + ix];
+            integral_err[(size_t)iy * nbx + ix] = b;
+            integral[(size_t)iy * nbx + ix] = bc_kind == JMC_BC_LAST_MINUS ? bc_value - a : bc_value + a;
+        }
+    }
+}
+
+}  // namespace jmc
+
+extern "C" int jmc_hist2d(const double* d_x, const double* d_y, const double* d_weights, uint64_t n,
+                          const double* d_edges_x, int nx_edges, const double* d_edges_y, int ny_edges,
+                          double* d_sum_w, double* d_sum_w2, uint64_t* d_count, void* stream) {
+    JMC_REQUIRE(nx_edges >= 2 && ny_edges >= 2, "jmc_hist2d: need at least 2 edges per axis");
+    JMC_REQUIRE(d_edges_x && d_edges_y && d_count, "jmc_hist2d: NULL argument");
+    JMC_REQUIRE(!d_weights || (d_sum_w && d_sum_w2), "jmc_hist2d: weighted histogram outputs missing");
+    if (n == 0) return JMC_OK;
+    JMC_REQUIRE(d_x && d_y, "jmc_hist2d: NULL input array");
+    DeviceInfo di;
+    if (device_info(&di)) return JMC_ENODEV;
+    const size_t smem = sizeof(double) * ((size_t)nx_edges + ny_edges);
+    if (smem > (size_t)di.max_smem_optin) return set_error(JMC_ELIMIT, "jmc_hist2d: edges exceed shared memory");
+    JMC_CUDA(cudaFuncSetAttribute(hist2d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = grid_for(n, kThreads);
+    hist2d_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(d_x, d_y, d_weights, n, d_edges_x, nx_edges, d_edges_y,
+                                                                   ny_edges, d_sum_w, d_sum_w2,
+                                                                   (unsigned long long*)d_count);
+    JMC_LAUNCHED("hist2d_kernel");
+    return JMC_OK;
+}
+
+extern "C" int jmc_finalize2d(const double* d_sum_w, const double* d_sum_w2, const uint64_t* d_count,
+                              const double* d_edges_x, int nx_edges, const double* d_edges_y, int ny_edges,
+                              double area, uint64_t n_total, int bc_kind, double bc_value, double* d_density,
+                              double* d_density_err, double* d_integral, double* d_integral_err, void* stream) {
+    JMC_REQUIRE(nx_edges >= 2 && ny_edges >= 2, "jmc_finalize2d: need at least 2 edges per axis");
+    JMC_REQUIRE(bc_kind >= JMC_BC_FIRST && bc_kind <= JMC_BC_LAST_MINUS, "jmc_finalize2d: invalid boundary condition");
+    JMC_REQUIRE(d_sum_w && d_sum_w2 && d_count && d_edges_x && d_edges_y, "jmc_finalize2d: NULL input");
+    JMC_REQUIRE(d_density && d_density_err, "jmc_finalize2d: NULL output");
+    JMC_REQUIRE((d_integral == nullptr) == (d_integral_err == nullptr), "jmc_finalize2d: integral and its error go together");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nbx = nx_edges - 1, nby = ny_edges - 1;
+    const int cells = nbx * nby;
+    density2d_kernel<<<(cells + 255) / 256, 256, 0, st>>>(d_sum_w, d_sum_w2, (const unsigned long long*)d_count,
+                                                           d_edges_x, nx_edges, d_edges_y, ny_edges,
+                                                           area / (double)n_total, d_density, d_density_err);
+    JMC_LAUNCHED("density2d_kernel");
+    if (d_integral) {
+        cumsum2d_kernel<<<(nby + 127) / 128, 128, 0, st>>>(d_density, d_density_err, d_edges_x, nx_edges, d_edges_y,
+                                                            ny_edges, bc_kind, bc_value, d_integral, d_integral_err, 0);
+        JMC_LAUNCHED("cumsum2d_kernel");
+        cumsum2d_kernel<<<(nbx + 127) / 128, 128, 0, st>>>(d_density, d_density_err, d_edges_x, nx_edges, d_edges_y,
+                                                            ny_edges, bc_kind, bc_value, d_integral, d_integral_err, 1);
+        JMC_LAUNCHED("cumsum2d_kernel");
+    }
     return JMC_OK;
 }
 

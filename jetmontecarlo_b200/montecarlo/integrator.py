@@ -304,3 +304,174 @@ def integrate_1d(function, bounds, bin_space='lin', epsilon=1e-10, num_samples=1
     if num_bins == 2:
         return integral[1], error[0], xs[1]
     return integral, error, xs
+
+
+#######################################
+# 2 dimensional integrator
+#######################################
+class integrator_2d():
+    """2-D version of ``integrator`` (ref: montecarlo/integrator.py:469-778; used by gen_pre_num_rad).
+    np.histogram2d -> jmc_hist2d, normalisation and the double cumulative sum -> jmc_finalize2d.  The reference's
+    quirks are kept: 'lin' bins of both axes start at min(0, min over BOTH observables) (:494-495), log
+    bin_midpoints end up holding the y axis only (:508-511), density and integral are stored transposed
+    ([y bin, x bin], :577-578)."""
+
+    def _min_max(self, arr):
+        dev = D.to_device(arr).reshape(-1)
+        out = D.empty((2,))
+        _lib.check(_lib.lib.jmc_minmax(D.ptr(dev), dev.numel(), D.ptr(out), D.stream()))
+        return D.to_host(out)
+
+    def setBins(self, numbins, observables, binspacing, min_log_bin=MIN_LOG_BIN):
+        rng = [self._min_max(observables[i]) for i in range(2)]
+        both_min = min(rng[0][0], rng[1][0]) if not (np.isnan(rng[0][0]) or np.isnan(rng[1][0])) else np.nan
+        bins = []
+        for i in range(2):
+            if binspacing == 'lin':
+                bins.append(np.linspace(min(0, both_min), rng[i][1], numbins))
+            elif binspacing == 'log':
+                min_bin = np.log10(max(rng[i][0], min_log_bin))
+                max_bin = np.log10(rng[i][1])
+                bins.append(np.logspace(min_bin, max_bin, numbins))
+        self.bins = bins
+        self.bin_midpoints = [[], []]
+        xs, ys = bins[0], bins[1]
+        if binspacing == 'lin':
+            self.bin_midpoints[0] = (xs[1:] + xs[:-1]) / 2
+            self.bin_midpoints[1] = (ys[1:] + ys[:-1]) / 2
+        elif binspacing == 'log':
+            self.bin_midpoints = np.exp((np.log(xs[1:]) + np.log(xs[:-1])) / 2.)
+            self.bin_midpoints = np.exp((np.log(ys[1:]) + np.log(ys[:-1])) / 2.)
+        self.hasBins = True
+
+    def setLastBinBndCondition(self, bndCond):
+        self.lastBinBndCond = bndCond
+        self.useLastBinBndCond = True
+
+    def setFirstBinBndCondition(self, bndCond):
+        self.firstBinBndCond = bndCond
+        self.useFirstBinBndCond = True
+
+    def _finalize(self, area, n_total, bc_kind, bc_value, with_integral):
+        nbx, nby = len(self.bins[0]) - 1, len(self.bins[1]) - 1
+        dens, err = D.empty((nby, nbx)), D.empty((nby, nbx))
+        integ = D.empty((nby, nbx)) if with_integral else None
+        ierr = D.empty((nby, nbx)) if with_integral else None
+        _lib.check(_lib.lib.jmc_finalize2d(
+            D.ptr(self._sum_w), D.ptr(self._sum_w2), D.ptr(self._count), D.ptr(self._ex), nbx + 1, D.ptr(self._ey),
+            nby + 1, float(area), int(n_total), bc_kind, float(bc_value), D.ptr(dens), D.ptr(err), D.ptr(integ),
+            D.ptr(ierr), D.stream()))
+        return dens, err, integ, ierr
+
+    def setDensity(self, observables, weights, area):
+        assert self.hasBins, "Need bins to produce density histogram."
+        x = D.to_device(observables[0]).reshape(-1)
+        y = D.to_device(observables[1]).reshape(-1)
+        w = D.to_device(weights).reshape(-1)
+        self._ex = D.to_device(np.asarray(self.bins[0], dtype=np.float64))
+        self._ey = D.to_device(np.asarray(self.bins[1], dtype=np.float64))
+        nbx, nby = self._ex.numel() - 1, self._ey.numel() - 1
+        self._sum_w, self._sum_w2 = D.zeros((nbx, nby)), D.zeros((nbx, nby))
+        self._count = D.zeros((nbx, nby), dtype=torch.int64)
+        _lib.check(_lib.lib.jmc_hist2d(D.ptr(x), D.ptr(y), D.ptr(w), x.numel(), D.ptr(self._ex), nbx + 1,
+                                       D.ptr(self._ey), nby + 1, D.ptr(self._sum_w), D.ptr(self._sum_w2),
+                                       D.ptr(self._count), D.stream()))
+        self._area, self._n_total = area, x.numel()
+        dens, err, _, _ = self._finalize(area, x.numel(), _lib.BC_FIRST, 0., False)
+        self.density, self.densityErr = D.to_host(dens), D.to_host(err)
+        self.hasMCDensity = True
+
+    def integrate(self):
+        assert self.hasMCDensity, \
+            "Need density function to perform integration"
+        bc_kind, bc_value = _bc_args(self.firstBinBndCond, self.lastBinBndCond)
+        self.useLastBinBndCond = bc_kind != _lib.BC_FIRST
+        self.useFirstBinBndCond = bc_kind == _lib.BC_FIRST
+        _, _, integ, ierr = self._finalize(self._area, self._n_total, bc_kind, bc_value, True)
+        self.integral, self.integralErr = D.to_host(integ), D.to_host(ierr)
+        self.hasMCIntegral = True
+        self.set_extended_integral()
+
+    def set_extended_integral(self):
+        """integral with its boundary values appended (ref: integrator.py:650-685); host array assembly"""
+        assert self.hasMCIntegral, "Cannot set extension of"\
+            + " the integration to the boundaries without an integral."
+        nx = len(self.bins[0])
+        if self.useFirstBinBndCond:
+            bc = self.firstBinBndCond
+            z = [np.ones(nx) * bc] + [np.append(bc, z_i) for z_i in self.integral]
+            zerr = [np.zeros(nx)] + [np.append(0, z_i) for z_i in self.integralErr]
+        else:
+            bc = self.lastBinBndCond[0]
+            z = [np.append(z_i, bc) for z_i in self.integral] + [np.ones(nx) * bc]
+            zerr = [np.append(0, z_i) for z_i in self.integralErr] + [np.zeros(nx)]
+        self.extended_integral = np.array(z).T
+        self.extended_integralErr = np.array(zerr).T
+
+    def montecarlo_data_dict(self, info=None):
+        data_dict = {'bins': self.bins,
+                     'density': self.density,
+                     'density error': self.densityErr,
+                     'integral': self.extended_integral,
+                     'integral error': self.extended_integralErr}
+        if info is not None:
+            data_dict['info'] = info
+        return data_dict
+
+    def save_montecarlo_data(self, filename, info=None):
+        assert self.hasMCDensity and self.hasMCIntegral, \
+            "Need density function and integral to save MC data"
+        np.savez(filename, **self.montecarlo_data_dict(info=info))
+
+    def makeInterpolatingFn(self, **kwargs):
+        from ..utils.interpolation import get_2d_interpolation
+        assert self.hasMCIntegral, \
+            "Need MC integral to produce interpolation"
+        self.interpFn = get_2d_interpolation(self.bins[0], self.bins[1], self.extended_integral, **kwargs)
+        self.interpErr = None
+        self.hasInterpIntegral = True
+
+    def __init__(self, *args, **kwargs):
+        self.hasBins = False
+        self.hasMCDensity = False
+        self.hasMCIntegral = False
+        self.hasInterpIntegral = False
+        self.hasInterpDensity = False
+        self.firstBinBndCond = None
+        self.useFirstBinBndCond = False
+        self.lastBinBndCond = None
+        self.useLastBinBndCond = False
+        self.hasAnalyticIntegral = False
+        self.hasAnalyticDensity = False
+
+
+def integrate_2d(function, bounds, bin_space='lin', epsilon=1e-10, num_samples=1e5, num_bins=2, bnd_cond=0,
+                 bnd_cond_bin='first'):
+    """2-D Monte Carlo integral over [[xmin, xmax], [ymin, ymax]].  ref: montecarlo/integrator.py:780-858"""
+    if bin_space == 'lin':
+        epsilon = None
+    s1 = simpleSampler(bin_space, bounds=bounds[0], epsilon=epsilon)
+    s1.generateSamples(int(num_samples))
+    s2 = simpleSampler(bin_space, bounds=bounds[1], epsilon=epsilon)
+    s2.generateSamples(int(num_samples))
+    x, y = s1.getSamples(), s2.getSamples()
+    it = integrator_2d()
+    if bnd_cond_bin == 'first':
+        it.setFirstBinBndCondition(bnd_cond)
+    elif bnd_cond_bin == 'last':
+        it.setLastBinBndCondition(bnd_cond)
+    else:
+        raise AssertionError("Bin at which we place a boundary condition"
+                             + "must be 'first' or 'last'.")
+    it.setBins(num_bins, [x, y], bin_space)
+    weights = function(x, y)
+    it.setDensity([x, y], weights, s1.area * s2.area)
+    it.integrate()
+    integral, error = it.integral, it.integralErr
+    if bnd_cond_bin == 'first':
+        xs, ys = it.bins[0][1:], it.bins[1][1:]
+    else:
+        xs, ys = it.bins[0][:-1], it.bins[1][:-1]
+    if num_bins == 2:
+        return integral[0][0], error[0][0], xs[0], ys[0]
+    return integral, error, xs, ys

@@ -79,6 +79,10 @@ class sampler(ABC):
                                        D.stream()))
         return samples, jac
 
+    @staticmethod
+    def _next_key():
+        return next_key()
+
     def addSample(self):
         """Adds a single sample (and its jacobian) to the lists."""
         samples, jac = self._draw(1, next_key())

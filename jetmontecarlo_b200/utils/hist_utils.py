@@ -1,0 +1,49 @@
+"""``vals_to_pdf`` -- host mirror of jetmontecarlo/utils/hist_utils.py:94-144: weighted pdf of a sample on fixed
+lin bins on [0,1] or log bins down to ``log_cutoff`` with a zero bin [1e-100, cutoff), normalised to unit
+integral and, for log bins, multiplied by x ln 10 (density in log10 x).  The per-sample work (finite mask,
+histogram) runs on the GPU (JMC_FN_MASK_FINITE, jmc_hist); the O(bins) normalisation is NumPy as in the reference.
+"""
+from warnings import warn
+
+import numpy as np
+import torch
+
+from .. import _device as D
+from .. import _lib
+from .._arrayfn import eval_fn
+
+
+def vals_to_pdf(vals, num_bins, weights=None, bin_space='log', log_cutoff=None, make_finite=True):
+    """ref: utils/hist_utils.py:94-144"""
+    v = D.to_device(vals).reshape(-1)
+    w = D.to_device(np.ones(v.numel()) if weights is None else weights).reshape(-1)
+    if make_finite:
+        # a removed sample == a sample of weight 0 (the pdf is normalised by the histogram's own sum)
+        w = eval_fn(_lib.FN_MASK_FINITE, [w, v])
+        if not bool(torch.isfinite(v).any()):
+            warn("No finite values in `vals`, the values given to "
+                 "vals_to_pdf. Returning empty arrays.")
+            return np.array([]), np.array([])
+    if bin_space == 'lin':
+        bins = np.linspace(0, 1, num_bins)
+        xs = (bins[:-1] + bins[1:]) / 2
+    elif bin_space == 'log':
+        assert log_cutoff is not None,\
+            "log cutoff required for logarithmic"\
+            " bins (you could try, say, -10)."
+        bins = np.logspace(np.log10(log_cutoff), 0, num_bins)
+        bins = np.insert(bins, 0, 1e-100)  # zero bin
+        xs = np.sqrt(bins[1:-1] * bins[2:])
+        xs = np.insert(xs, 0, 1e-50)  # zero bin
+    e = D.to_device(bins)
+    nb = e.numel() - 1
+    sw, sw2 = D.zeros((nb,)), D.zeros((nb,))
+    cnt = D.zeros((nb,), dtype=torch.int64)
+    _lib.check(_lib.lib.jmc_hist(D.ptr(v), D.ptr(w), v.numel(), D.ptr(e), nb + 1, D.ptr(sw), D.ptr(sw2), D.ptr(cnt),
+                                 D.stream()))
+    pdf = D.to_host(sw)
+    dx = np.array(np.diff(bins), float)
+    pdf = pdf / dx / pdf.sum()
+    if bin_space == 'log':
+        pdf = xs * pdf * np.log(10)
+    return xs, pdf

@@ -724,6 +724,50 @@ def integrate_hist(obs, weights, edges, area, first_bc=None, last_bc=None):
                 integral=integ, integral_err=ierr)
 
 
+def make_edges_2d(numbins, obs, spacing, min_log_bin=MIN_LOG_BIN):
+    """ref: montecarlo/integrator.py:486-500 ('lin' bins of both axes start at min(0, min over BOTH arrays))"""
+    bins = []
+    for i in range(2):
+        if spacing == 'lin':
+            bins.append(np.linspace(min(0, np.min(obs)), np.max(obs[i]), numbins))
+        else:
+            bins.append(np.logspace(np.log10(max(np.min(obs[i]), min_log_bin)), np.log10(np.max(obs[i])), numbins))
+    return bins
+
+
+def integrate_hist_2d(x, y, weights, bins, area, first_bc=None, last_bc=None):
+    """integrator_2d.setDensity + integrate + set_extended_integral.
+    ref: montecarlo/integrator.py:463-467 (multidim_cumsum), :525-685"""
+    h, _, _ = np.histogram2d(x, y, bins, weights=weights)
+    h2, _, _ = np.histogram2d(x, y, bins, weights=np.square(weights))
+    n, _, _ = np.histogram2d(x, y, bins)
+    w1, w2 = np.meshgrid(bins[0][1:] - bins[0][:-1], bins[1][1:] - bins[1][:-1])
+    areas = w1 * w2
+    factor = area / (len(x) * areas.T)
+    dens = np.where(n == 0, 0, h * factor).T
+    err = np.where(n == 0, 0, np.sqrt(h2) * factor).T
+
+    def mcumsum(a):
+        out = a.cumsum(-1)
+        np.cumsum(out, axis=-2, out=out)
+        return out
+    nx = len(bins[0])
+    if first_bc is not None:
+        integ = first_bc + mcumsum(dens * areas)
+        ierr = mcumsum(err * areas)
+        ext = np.array([np.ones(nx) * first_bc] + [np.append(first_bc, r) for r in integ]).T
+        ext_err = np.array([np.zeros(nx)] + [np.append(0, r) for r in ierr]).T
+    else:
+        value, sign = last_bc
+        rev = np.flip(mcumsum(np.flip(dens * areas)))
+        integ = value + rev if sign == 'plus' else value - rev
+        ierr = np.flip(mcumsum(np.flip(err * areas)))
+        ext = np.array([np.append(r, value) for r in integ] + [np.ones(nx) * value]).T
+        ext_err = np.array([np.append(0, r) for r in ierr] + [np.zeros(nx)]).T
+    return dict(density=dens, density_err=err, integral=integ, integral_err=ierr, ext=ext, ext_err=ext_err,
+                sum_w=h, sum_w2=h2, count=n)
+
+
 def lin_log_mixed_list(lower, upper, num):
     """ref: utils/interpolation.py:18-41"""
     vals = np.logspace(np.log10(lower), np.log10(upper), int(num / 2) + 2)
@@ -732,10 +776,25 @@ def lin_log_mixed_list(lower, upper, num):
     return vals[~np.isnan(vals)]
 
 
-def vals_to_pdf_log(vals, num_bins, weights, log_cutoff):
-    """Log-binned weighted pdf with an underflow ("zero") bin.
-    ref: utils/hist_utils.py:94-144 (bin_space='log')"""
-    raise NotImplementedError  # filled in by the "next" rows (SURVEY 8f)
+def vals_to_pdf(vals, num_bins, weights=None, bin_space='log', log_cutoff=None):
+    """Weighted pdf on fixed bins; log bins get an underflow ("zero") bin.
+    ref: utils/hist_utils.py:94-144"""
+    vals = np.asarray(vals, dtype=float)
+    weights = np.ones_like(vals) if weights is None else np.asarray(weights, dtype=float)
+    good = np.isfinite(vals) & np.isfinite(weights)
+    vals, weights = vals[good], weights[good]
+    if bin_space == 'lin':
+        bins = np.linspace(0, 1, num_bins)
+        xs = (bins[:-1] + bins[1:]) / 2
+    else:
+        bins = np.logspace(np.log10(log_cutoff), 0, num_bins)
+        bins = np.insert(bins, 0, 1e-100)
+        xs = np.insert(np.sqrt(bins[1:-1] * bins[2:]), 0, 1e-50)
+    pdf, _ = np.histogram(vals, bins, weights=weights)
+    pdf = pdf / np.array(np.diff(bins), float) / pdf.sum()
+    if bin_space == 'log':
+        pdf = xs * pdf * np.log(10)
+    return xs, pdf
 
 
 # --------------------------------------------------------------------------

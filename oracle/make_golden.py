@@ -396,7 +396,7 @@ def misc():
     save("vals_to_pdf", vals=vals, weights=wts, xs=xs, pdf=pdf)
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and len(sys.argv) == 1:
     os.makedirs(OUT, exist_ok=True)
     kats()
     function_vectors()
@@ -407,3 +407,66 @@ if __name__ == "__main__":
     simple_integrals()
     shower()
     misc()
+
+
+# ------------------------------------------------------------------ round 1b: 2-D integrator and grid callers ----
+def callers():
+    """integrator_2d and the numerical-radiator generators (the batched callers of the hot path).
+    Run alone with ``python oracle/make_golden.py callers`` (keeps the other fixtures untouched)."""
+    from jetmontecarlo.montecarlo.integrator import integrator_2d
+    from jetmontecarlo.numerics.radiators import generation as GEN
+    n, zc, eps = 3000, .1, 1e-8
+    for method in ('lin', 'log'):
+        random.seed(SEED + 80)
+        e = eps if method == 'log' else 0.
+        cs = criticalSampler(method, zc=zc, epsilon=e)
+        cs.generateSamples(n)
+        ps = precriticalSampler(method, zc=zc, epsilon=e)
+        ps.generateSamples(n)
+        us = ungroomedSampler(method, epsilon=e)
+        us.generateSamples(n)
+        out = dict(seed=SEED + 80, crit=np.asarray(cs.samples), pre=np.asarray(ps.samples), sub=np.asarray(us.samples),
+                   jac_crit=np.asarray(cs.jacobians, float), jac_pre=np.asarray(ps.jacobians, float),
+                   jac_sub=np.asarray(us.jacobians, float), area_crit=cs.area, area_pre=ps.area, area_sub=us.area,
+                   epsilon=e, z_cut=zc)
+        # plain integrator_2d
+        x, y = np.asarray(ps.samples), np.asarray(cs.samples)[:, 1]
+        w = W.radiatorWeight(x, y, 'quark', fixedcoupling=True, acc='LL') * (x * y if method == 'log' else 1.)
+        for bc_name, setter in (('last', lambda it: it.setLastBinBndCondition([0., 'plus'])),
+                                ('lastminus', lambda it: it.setLastBinBndCondition([1., 'minus'])),
+                                ('first', lambda it: it.setFirstBinBndCondition(0.))):
+            it = integrator_2d()
+            setter(it)
+            it.setBins(12, [x, y], method)
+            it.setDensity([x, y], w, 2.5)
+            it.integrate()
+            t = f'i2d_{bc_name}:'
+            out[t + 'bins0'], out[t + 'bins1'] = it.bins[0], it.bins[1]
+            out[t + 'density'], out[t + 'density_err'] = it.density, it.densityErr
+            out[t + 'integral'], out[t + 'integral_err'] = it.integral, it.integralErr
+            out[t + 'ext'], out[t + 'ext_err'] = it.extended_integral, it.extended_integralErr
+        out['i2d_weights'] = w
+        # gen_numerical_radiator
+        for jet, fc, acc in (('quark', True, 'LL'), ('gluon', False, 'MLL')):
+            tag = f"{jet}_{'fc' if fc else 'rc'}:"
+            _, d = GEN.gen_numerical_radiator(cs, 'crit', jet_type=jet, obs_accuracy=acc, splitfn_accuracy=acc,
+                                              bin_space=method, fixed_coupling=fc, num_bins=30)
+            for k, v in d.items():
+                out[tag + 'crit:' + k] = np.asarray(v, float)
+            _, d = GEN.gen_numerical_radiator(us, 'sub', jet_type=jet, obs_accuracy=acc, splitfn_accuracy=acc,
+                                              beta=2., bin_space=method, fixed_coupling=fc, num_bins=30)
+            for k, v in d.items():
+                out[tag + 'sub:' + k] = np.asarray(v, float)
+            _, d = GEN.gen_pre_num_rad(ps, cs, jet_type=jet, splitfn_accuracy=acc, bin_space=method,
+                                       fixed_coupling=fc, num_bins=10)
+            for k, v in d.items():
+                out[tag + 'pre:' + k] = np.asarray(v, float)
+            _, d = GEN.gen_crit_sub_num_rad(us, jet_type=jet, obs_accuracy=acc, splitfn_accuracy=acc, beta=2.,
+                                            epsilon=eps, bin_space=method, fixed_coupling=fc, num_bins=10)
+            for k, v in d.items():
+                out[tag + 'critsub:' + k] = np.asarray(v, float)
+        save(f"callers_{method}", **out)
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "callers":
+    callers()

@@ -309,6 +309,82 @@ def test_lin_log_mixed(golden):
     assert_array_equal(O.lin_log_mixed_list(1e-15, 1., 501), g['b'])
 
 
+@pytest.mark.parametrize("method", ['lin', 'log'])
+def test_integrator_2d_and_grid_callers(golden, method):
+    """integrator_2d and the numerical-radiator generators, restated with the oracle's pieces"""
+    g = golden(f"callers_{method}")
+    x, y, w = g['pre'], g['crit'][:, 1], g['i2d_weights']
+    bins = O.make_edges_2d(12, [x, y], method)
+    for name, kw in (('last', dict(last_bc=[0., 'plus'])), ('lastminus', dict(last_bc=[1., 'minus'])),
+                     ('first', dict(first_bc=0.))):
+        t = f'i2d_{name}:'
+        assert_array_equal(bins[0], g[t + 'bins0'])
+        assert_array_equal(bins[1], g[t + 'bins1'])
+        r = O.integrate_hist_2d(x, y, w, bins, 2.5, **kw)
+        for k in ('density', 'density_err', 'integral', 'integral_err', 'ext', 'ext_err'):
+            assert_array_equal(r[k], g[t + k])
+    # gen_numerical_radiator: bins from the whole (N,2) sample array, observable theta or C_ungroomed
+    for jet, fc, acc in (('quark', True, 'LL'), ('gluon', False, 'MLL')):
+        tag = f"{jet}_{'fc' if fc else 'rc'}:"
+        for em, s, jac, area in (('crit', g['crit'], g['jac_crit'], float(g['area_crit'])),
+                                 ('sub', g['sub'], g['jac_sub'], float(g['area_sub']))):
+            z, th = s[:, 0], s[:, 1]
+            obs = th if em == 'crit' else O.ecf_ungroomed(z, th, 2., acc)
+            edges, mids = O.make_edges(30, s, method)
+            assert_array_equal(edges, g[tag + em + ':bins'])
+            r = O.integrate_hist(obs, O.weight_radiator(z, th, jet, fc, acc) * jac, edges, area, last_bc=[0., 'plus'])
+            assert_array_equal(r['density'], g[tag + em + ':density'])
+            assert_array_equal(r['integral'], g[tag + em + ':integral'])
+            assert_array_equal(r['integral_err'], g[tag + em + ':integral error'])
+        # gen_pre_num_rad
+        z_em, th_c = g['pre'], g['crit'][:, 1]
+        b2 = O.make_edges_2d(10, [z_em, th_c], method)
+        wts = O.weight_radiator(z_em, th_c, jet, fc, acc)
+        if method == 'lin':
+            area, jacs = float(g['z_cut']), np.ones(len(th_c))
+        else:
+            area, jacs = np.log(1. / float(g['epsilon'])) * np.log(1. / float(g['epsilon'])), z_em * th_c
+        r = O.integrate_hist_2d(z_em, th_c, wts * jacs, b2, area, last_bc=[0., 'plus'])
+        assert_array_equal(np.array(b2), g[tag + 'pre:bins'])
+        assert_array_equal(r['density'], g[tag + 'pre:density'])
+        assert_array_equal(r['ext'], g[tag + 'pre:integral'])
+        assert_array_equal(r['ext_err'], g[tag + 'pre:integral error'])
+        # gen_crit_sub_num_rad loop
+        grid = O.lin_log_mixed_list(float(g['epsilon']) if method == 'log' else 1e-8, 1., 10)
+        s, jac, area0 = g['sub'], g['jac_sub'], float(g['area_sub'])
+        xs_all, rads_all = [], []
+        for thc in grid:
+            th_em = s[:, 1] * thc
+            obs = O.ecf_ungroomed(s[:, 0], th_em, 2., acc)
+            edges, _ = O.make_edges(10, obs, method, thc ** 2. * 1e-15)
+            area, jj = (area0 * thc, jac) if method == 'lin' else (area0, jac * thc)
+            r = O.integrate_hist(obs, O.weight_radiator(s[:, 0], th_em, jet, fc, acc) * jj, edges, area,
+                                 last_bc=[0., 'plus'])
+            xs_all.append(edges)
+            rads_all.append(r['integral'])
+        assert_array_equal(np.array(xs_all).flatten(), g[tag + 'critsub:xs'])
+        assert_array_equal(np.array(rads_all).flatten(), g[tag + 'critsub:integral'])
+
+
+def test_vals_to_pdf(golden):
+    g = golden("vals_to_pdf")
+    xs, pdf = O.vals_to_pdf(g['vals'], 50, weights=g['weights'], log_cutoff=1e-10)
+    assert_array_equal(xs, g['xs'])
+    assert_array_equal(pdf, g['pdf'])
+
+
+def test_loop_samplers_equal_vectorised_samplers():
+    """the Python-loop restatement timed by bench.py's CPU baseline draws exactly the vectorised samples"""
+    n = 500
+    s, j = O.sample_loop_critical('log', n, .1, 1e-10, seed=5)
+    s2, j2, _ = O.sample_critical('log', O.mt_uniforms(5, 2 * n).reshape(n, 2), .1, 1e-10)
+    assert_array_equal(s, s2)
+    assert_array_equal(j, j2)
+    s, j = O.sample_loop_ungroomed('lin', n, seed=6, radius=.7)
+    s2, j2, _ = O.sample_ungroomed('lin', O.mt_uniforms(6, 2 * n).reshape(n, 2), radius=.7)
+    assert_array_equal(s, s2)
+
+
 def test_bin_index_is_numpy_histogram():
     rng = np.random.RandomState(3)
     edges = np.logspace(-11, np.log10(.5), 100)
