@@ -40,7 +40,7 @@ FLOP_EQ = {"c3_rc": 390., "c3_fc": 230.}
 SFU_OPS = {"c3_rc": 28., "c3_fc": 14.}
 # work of a sample whose reference weight is NaN -> 0 (99.7 % of C3-rc samples): Philox
 # (100 int), 4 exp, observable, Landau predicate, log-bin, count  ("algorithmic work")
-FLOP_EQ_ZERO_WEIGHT, SFU_ZERO_WEIGHT = 150., 6.
+FLOP_EQ_ZERO_WEIGHT, SFU_ZERO_WEIGHT = 155., 2.
 
 
 def edges_c3():
@@ -360,6 +360,14 @@ def main():
                            "MEASURED_PEAKS.json has no FP32/SFU figure, its HBM peak does not bound a kernel "
                            "with ~0 B/sample of DRAM traffic" % (sm_count, sm_mhz),
         }
+        try:      # ncu-derived companions of the figure above (DRAM traffic, issue-slot utilisation, pipes)
+            with open(os.path.join(ROOT, "profiles", "roofline_inputs.json")) as f:
+                prof = json.load(f)["run_fast_kernel"]
+            if args.precision == "f32" and args.variant == "c3_rc":
+                roofline["traffic"] = prof["dram_bytes_per_launch"]
+                roofline["ncu"] = prof
+        except (OSError, KeyError, ValueError):
+            pass
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",

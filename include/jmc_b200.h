@@ -188,6 +188,13 @@ int jmc_sample(const jmc_sampler* s, uint64_t n, uint64_t seed, uint64_t first_i
 int jmc_uniforms(uint64_t n, uint64_t seed, uint64_t first_index, int n_uniform,
                  double* d_out, void* stream);
 
+/* Inverse-transform sampling from a tabulated cdf: out[i] = interp1d(cdf_vals, x_vals, fill_value='extrapolate')(u_i)
+ * with u_i the first uniform of stream index first_index + i.  The table (n_table >= 2 points) must be sorted by
+ * cdf value (scipy's interp1d sorts it; the host wrapper does the same).
+ * ref: utils/montecarlo_utils.py:377-399 (inverse_transform_samples) */
+int jmc_inverse_transform(const double* d_cdf_vals, const double* d_x_vals, int n_table, uint64_t n, uint64_t seed,
+                          uint64_t first_index, double* d_out, void* stream);
+
 /* ---- replay path: arrays in, arrays out -------------------------------- */
 int jmc_eval_fn(int fn, const jmc_fn_params* p, uint64_t n,
                 const double* d_a0, int64_t stride0, const double* d_a1, int64_t stride1,

@@ -29,7 +29,7 @@ ACCS = {'LL': ACC_LL, 'LL_nonsing': ACC_LL_NONSING, 'MLL': ACC_MLL}
 
 EXPORTS = (
     "jmc_abi_version", "jmc_last_error", "jmc_device_count", "jmc_set_device", "jmc_sm_count",
-    "jmc_sampler_area", "jmc_integrand_uniforms", "jmc_integrand_area", "jmc_sample", "jmc_uniforms",
+    "jmc_sampler_area", "jmc_integrand_uniforms", "jmc_integrand_area", "jmc_sample", "jmc_uniforms", "jmc_inverse_transform",
     "jmc_eval_fn", "jmc_eval_integrand", "jmc_bin_index", "jmc_hist", "jmc_hist2d", "jmc_finalize2d", "jmc_minmax", "jmc_run", "jmc_dump", "jmc_shower_dump",
     "jmc_finalize", "jmc_cumulative", "jmc_set_density_host", "jmc_integrate_host", "jmc_sample_host",
     "jmc_eval_fn_host", "jmc_launch_count",
@@ -83,6 +83,7 @@ def _load():
         "jmc_integrand_area": (i32, [P(Integrand), P(dbl)]),
         "jmc_sample": (i32, [P(Sampler), u64, u64, u64, vp, vp, vp]),
         "jmc_uniforms": (i32, [u64, u64, u64, i32, vp, vp]),
+        "jmc_inverse_transform": (i32, [vp, vp, i32, u64, u64, u64, vp, vp]),
         "jmc_eval_fn": (i32, [i32, P(FnParams), u64, vp, i64, vp, i64, vp, i64, vp, i64, vp, vp]),
         "jmc_eval_integrand": (i32, [P(Integrand), u64, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp]),
         "jmc_bin_index": (i32, [vp, u64, vp, i32, vp, vp]),

@@ -209,6 +209,52 @@ extern "C" int jmc_sample(const jmc_sampler* s, uint64_t n, uint64_t seed, uint6
     return JMC_OK;
 }
 
+// inverse-transform sampling from a tabulated cdf (scipy interp1d semantics: linear, extrapolating)
+namespace jmc {
+__global__ void __launch_bounds__(kThreads)
+inverse_transform_kernel(const double* __restrict__ cdf, const double* __restrict__ xs, int nt, uint64_t n,
+                         uint64_t seed, uint64_t first, double* __restrict__ out) {
+    extern __shared__ double s_tab[];
+    double* s_c = s_tab;
+    double* s_x = s_tab + nt;
+    for (int k = threadIdx.x; k < nt; k += blockDim.x) { s_c[k] = cdf[k]; s_x[k] = xs[k]; }
+    __syncthreads();
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        double u, unused;
+        philox_uniform53x2(first + i, 0u, seed, u, unused);
+        int lo = 0, hi = nt;                   // searchsorted(cdf, u, 'left')
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (s_c[mid] < u) lo = mid + 1; else hi = mid;
+        }
+        int idx = lo < 1 ? 1 : (lo > nt - 1 ? nt - 1 : lo);
+        const double c_lo = s_c[idx - 1], c_hi = s_c[idx], x_lo = s_x[idx - 1], x_hi = s_x[idx];
+        const double slope = (x_hi - x_lo) / (c_hi - c_lo);
+        out[i] = slope * (u - c_lo) + x_lo;
+    }
+}
+}  // namespace jmc
+
+extern "C" int jmc_inverse_transform(const double* d_cdf_vals, const double* d_x_vals, int n_table, uint64_t n,
+                                     uint64_t seed, uint64_t first_index, double* d_out, void* stream) {
+    JMC_REQUIRE(n_table >= 2, "jmc_inverse_transform: need at least two table points");
+    JMC_REQUIRE(d_cdf_vals && d_x_vals, "jmc_inverse_transform: NULL table");
+    if (n == 0) return JMC_OK;
+    JMC_REQUIRE(d_out != nullptr, "jmc_inverse_transform: out is NULL");
+    DeviceInfo di;
+    if (device_info(&di)) return JMC_ENODEV;
+    const size_t smem = sizeof(double) * 2 * (size_t)n_table;
+    if (smem > (size_t)di.max_smem_optin)
+        return set_error(JMC_ELIMIT, "jmc_inverse_transform: table of %d points exceeds shared memory", n_table);
+    JMC_CUDA(cudaFuncSetAttribute(inverse_transform_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = grid_for(n, kThreads);
+    inverse_transform_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(d_cdf_vals, d_x_vals, n_table, n, seed,
+                                                                              first_index, d_out);
+    JMC_LAUNCHED("inverse_transform_kernel");
+    return JMC_OK;
+}
+
 // ---------------------------------------------------------------------------
 // whole-integrand replay
 // ---------------------------------------------------------------------------

@@ -147,3 +147,25 @@ def test_integrate_2d(cuda):
     set_seed(9)
     val, err, x, y = integrate_2d(lambda a, b: a * b, [[0, 1], [0, 1]], num_samples=400000)
     assert abs(val - x ** 2 * y ** 2 / 4.) < 5 * err + 1e-3
+
+
+def test_inverse_transform_samples(cuda):
+    """jmc_inverse_transform == scipy interp1d(cdf, x, 'extrapolate') at the same Philox uniforms; the samples follow
+    the tabulated distribution (inverse-transform Sudakov sampling)"""
+    from scipy import interpolate
+    from jetmontecarlo_b200.utils.montecarlo_utils import getLinSample, getLogSample, inverse_transform_samples
+    xs = np.logspace(-6, 0, 200)
+    cdf = np.exp(-O.rad_sub_fc(xs / 2., 2., 'quark'))           # an LL Sudakov factor as the cdf table
+    n, seed = 200000, 17
+    got = inverse_transform_samples(cdf, xs, n, seed=seed)
+    u = O.philox_uniforms53(seed, 0, n, 1)[:, 0]
+    ref = interpolate.interp1d(cdf, xs, fill_value='extrapolate')(u)
+    assert_allclose(got, ref, rtol=1e-12, atol=1e-15)
+    # unsorted table, values outside the table (extrapolation)
+    perm = np.random.RandomState(0).permutation(len(xs))
+    got2 = inverse_transform_samples(cdf[perm], xs[perm], n, seed=seed)
+    assert_allclose(got2, ref, rtol=1e-12, atol=1e-15)
+    assert (u < cdf.min()).any()
+    # scalar primitives stay in range
+    assert 2. <= getLinSample(2., 3.) <= 3.
+    assert 1. < getLogSample(1., 2., 1e-5) <= 2.
