@@ -210,12 +210,24 @@ extern "C" int jmc_run(const jmc_integrand* g, uint64_t n, uint64_t seed, uint64
                        double* d_minmax, void* stream) {
     JMC_REQUIRE(g != nullptr, "jmc_run: integrand is NULL");
     JMC_REQUIRE(precision == JMC_F64 || precision == JMC_F32, "jmc_run: precision must be JMC_F64 or JMC_F32");
-    if (g->kind == JMC_KIND_SHOWER)
-        return run_shower(g, n, seed, first_index, precision, d_edges, n_edges, d_sum_w, d_sum_w2, d_count, d_minmax,
-                          stream);
-    if (precision == JMC_F64)
-        return run_exact(g, n, seed, first_index, d_edges, n_edges, d_sum_w, d_sum_w2, d_count, d_minmax, stream);
-    return run_fast(g, n, seed, first_index, d_edges, n_edges, d_sum_w, d_sum_w2, d_count, d_minmax, stream);
+    // Per-block bin counts are 32-bit in shared memory; one launch therefore takes at most 2^38 samples
+    // (< 2^32 per block on any grid >= 64 blocks) and larger jobs are issued as consecutive index ranges.
+    const uint64_t kMaxPerLaunch = 1ull << 38;
+    do {
+        const uint64_t chunk = n < kMaxPerLaunch ? n : kMaxPerLaunch;
+        int rc;
+        if (g->kind == JMC_KIND_SHOWER)
+            rc = run_shower(g, chunk, seed, first_index, precision, d_edges, n_edges, d_sum_w, d_sum_w2, d_count,
+                            d_minmax, stream);
+        else if (precision == JMC_F64)
+            rc = run_exact(g, chunk, seed, first_index, d_edges, n_edges, d_sum_w, d_sum_w2, d_count, d_minmax, stream);
+        else
+            rc = run_fast(g, chunk, seed, first_index, d_edges, n_edges, d_sum_w, d_sum_w2, d_count, d_minmax, stream);
+        if (rc) return rc;
+        n -= chunk;
+        first_index += chunk;
+    } while (n > 0);
+    return JMC_OK;
 }
 
 extern "C" int jmc_dump(const jmc_integrand* g, uint64_t n, uint64_t seed, uint64_t first_index, int precision,

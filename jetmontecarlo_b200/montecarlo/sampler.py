@@ -87,7 +87,7 @@ class sampler(ABC):
         """Adds a single sample (and its jacobian) to the lists."""
         samples, jac = self._draw(1, next_key())
         self.samples.append(D.to_host(samples)[0].tolist() if self._dim == 2 else float(D.to_host(samples)[0]))
-        self.jacobians.append(float(D.to_host(jac)[0]))
+        self.jacobians = list(self.jacobians) + [float(D.to_host(jac)[0])]
 
     def generateSamples(self, num, seed=None):
         """Generates ``num`` samples on the GPU (ref: sampler.py:30-34).
@@ -105,7 +105,11 @@ class sampler(ABC):
         if len(self.samples):
             new = np.concatenate([np.array(self.samples).reshape((-1,) + new.shape[1:]), new])
         self.samples = new
-        self.jacobians = list(self.jacobians) + D.to_host(dev_jac).tolist()
+        # kept as an ndarray (the reference appends Python floats to a list; building a list of 1e7 floats would
+        # cost more than drawing the samples): np.array(s.jacobians), weights * s.jacobians, len() work unchanged
+        new_jac = D.to_host(dev_jac)
+        self.jacobians = new_jac if len(self.jacobians) == 0 else np.concatenate([np.asarray(self.jacobians, float),
+                                                                                   new_jac])
 
     def getSamples(self):
         return self.samples

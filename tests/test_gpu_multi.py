@@ -1,0 +1,70 @@
+"""Multi-GPU: the sharded job equals the single-GPU job (same sample indices; counts exact).  Needs >= 2 GPUs;
+on a single-GPU box the same code path is covered by two ranks sharing cuda:0 over gloo."""
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+_WORKER = r'''
+import os, sys
+sys.path.insert(0, %(root)r)
+import numpy as np, torch, torch.distributed as dist
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+ngpu = torch.cuda.device_count()
+torch.cuda.set_device(rank %% ngpu)
+backend = "nccl" if ngpu >= world else "gloo"
+dist.init_process_group(backend, init_method="tcp://127.0.0.1:%(port)d", rank=rank, world_size=world)
+from jetmontecarlo_b200 import fused, distributed as du
+from jetmontecarlo_b200.fused import Integrand
+if backend == "gloo":            # gloo reduces host tensors: route the packed histogram through the host
+    _ar = dist.all_reduce
+    def all_reduce(t, op=dist.ReduceOp.SUM, group=None):
+        h = t.cpu(); _ar(h, op=op, group=group); t.copy_(h)
+    dist.all_reduce = all_reduce
+ig = Integrand.crit_sub('log', .1, 1e-10, jet_type='quark', fixedcoupling=False, obs_acc='MLL')
+edges = np.logspace(-11, np.log10(.5), 100)
+n = 20_000_001
+it = fused.integrate(ig, n, edges=edges, seed=3, precision='f32', last_bc=[1., 'minus'])
+it2 = fused.integrate(ig, n, numbins=50, binspacing='log', seed=3, precision='f64', last_bc=[1., 'minus'])
+if rank == 0:
+    np.savez(%(out)r, count=it._count.cpu().numpy(), sum_w=it._sum_w.cpu().numpy(), integral=np.asarray(it.integral),
+             bins2=it2.bins, count2=it2._count.cpu().numpy(), backend=backend)
+dist.barrier()
+dist.destroy_process_group()
+'''
+
+
+def test_two_ranks_equal_one(cuda, tmp_path):
+    import torch
+    from jetmontecarlo_b200 import fused
+    from jetmontecarlo_b200.fused import Integrand
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    out = str(tmp_path / "multi.npz")
+    code = _WORKER % dict(root=ROOT, port=port, out=out)
+    procs = []
+    for rank in range(2):
+        env = dict(os.environ, RANK=str(rank), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.PIPE, text=True))
+    for p in procs:
+        _, err = p.communicate(timeout=600)
+        assert p.returncode == 0, err[-3000:]
+    got = np.load(out)
+    ig = Integrand.crit_sub('log', .1, 1e-10, jet_type='quark', fixedcoupling=False, obs_acc='MLL')
+    edges = np.logspace(-11, np.log10(.5), 100)
+    n = 20_000_001
+    one = fused.integrate(ig, n, edges=edges, seed=3, precision='f32', last_bc=[1., 'minus'])
+    np.testing.assert_array_equal(got['count'], one._count.cpu().numpy())
+    np.testing.assert_allclose(got['sum_w'], one._sum_w.cpu().numpy(), rtol=1e-9)
+    np.testing.assert_allclose(got['integral'], np.asarray(one.integral), rtol=1e-9, atol=1e-12)
+    one2 = fused.integrate(ig, n, numbins=50, binspacing='log', seed=3, precision='f64', last_bc=[1., 'minus'])
+    np.testing.assert_array_equal(got['bins2'], one2.bins)          # data-dependent edges via the min/max all-reduce
+    np.testing.assert_array_equal(got['count2'], one2._count.cpu().numpy())
