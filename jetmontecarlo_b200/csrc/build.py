@@ -29,8 +29,8 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
 UNITS = {
     "jmc_exact.cu": ["--fmad=false"],
     "jmc_shower.cu": ["--fmad=false"],
-    "jmc_fast.cu": ["--fmad=true"] + (["-DJMC_FAST_MIN_BLOCKS=" + os.environ["JMC_FAST_MIN_BLOCKS"]]
-                                      if os.environ.get("JMC_FAST_MIN_BLOCKS") else []),
+    "jmc_fast.cu": ["--fmad=true"] + ["-D%s=%s" % (k, os.environ[k]) for k in
+                                      ("JMC_FAST_MIN_BLOCKS", "JMC_FAST_UNROLL", "JMC_FAST_PIN_KEYS") if os.environ.get(k)],
     "jmc_host.cu": [],
 }
 
@@ -45,7 +45,8 @@ def _nvcc():
 def _digest():
     h = hashlib.sha256()
     names = sorted(f for f in os.listdir(HERE) if f.endswith((".cu", ".cuh", ".py")))
-    h.update(os.environ.get("JMC_FAST_MIN_BLOCKS", "").encode())
+    for k in ("JMC_FAST_MIN_BLOCKS", "JMC_FAST_UNROLL", "JMC_FAST_PIN_KEYS"):
+        h.update(os.environ.get(k, "").encode())
     for name in names + [os.path.join(ROOT, "include", "jmc_b200.h")]:
         with open(os.path.join(HERE, name) if not os.path.isabs(name) else name, "rb") as f:
             h.update(name.encode())

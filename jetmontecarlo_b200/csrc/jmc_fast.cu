@@ -42,6 +42,12 @@ static constexpr int kQueueFields = 5, kQueueSlots = 64;   // per-warp compactio
 #ifndef JMC_FAST_MIN_BLOCKS
 #define JMC_FAST_MIN_BLOCKS 3
 #endif
+#ifndef JMC_FAST_UNROLL
+#define JMC_FAST_UNROLL 2        // samples per loop trip
+#endif
+#ifndef JMC_FAST_PIN_KEYS
+#define JMC_FAST_PIN_KEYS 1      // keep the Philox round keys in registers across the loop
+#endif
 #define JMC_LN2F 0.69314718055994531f
 #define JMC_INV_LN2F 1.4426950408889634f
 
@@ -227,9 +233,9 @@ __device__ __forceinline__ float l2_sample(uint32_t w, float sL2, float l2w) {
 // non-zero.  Everything here is executed for every sample; it is straight-line code.
 // FIXED selects the coupling at compile time so that the other branch costs nothing.
 template <int KIND, bool FIXED, bool OBS_MLL>
-__device__ __forceinline__ bool light(const FastParams& P, uint64_t idx, uint64_t seed, Draw& d, float& l2obs) {
+__device__ __forceinline__ bool light(const FastParams& P, uint64_t idx, const PhiloxKeys& keys, Draw& d, float& l2obs) {
     uint32_t r[4];
-    philox4x32_10(idx, 0u, seed, r);
+    philox4x32_10(idx, 0u, keys, r);
     if (KIND == JMC_KIND_RADIATOR) {
         // ungroomedSampler (samplers.py:204-226), C_ungroomed (observables.py:82-109)
         d.l2zs = l2_sample(r[0], P.sL2, -1.0f);
@@ -276,7 +282,7 @@ __device__ __forceinline__ bool light(const FastParams& P, uint64_t idx, uint64_
         // all-emission integrand with the zero bin
         // (examples/tests/comparison_tests/comparison_utils_probabilistic.py:384-474)
         uint32_t r2[4];
-        philox4x32_10(idx, 1u, seed, r2);
+        philox4x32_10(idx, 1u, keys, r2);
         d.l2zp = l2_sample(r2[0], P.sL2, P.l2zc);
         d.u5 = __uint2float_rn(r2[1]) * 2.3283064365386963e-10f;
         const float E2 = -P.g * d.l2tc;                              // E / ln2, E = 2 C_R a/pi ln(R0/theta_c)
@@ -478,16 +484,22 @@ run_fast_kernel(FastParams P, uint64_t n, uint64_t seed, uint64_t first, const f
     // generator is a 10-deep dependent chain of IMAD.WIDE -> LOP3), and the warp-uniform work of a trip (round
     // keys, constant loads, loop control) is paid once per two samples.  The ballots in handle() need every
     // lane of the warp in every trip, so all lanes run to the warp's longest trip count.
-    const uint32_t my_trips = (iters + 1u) >> 1;
+    PhiloxKeys keys(seed);
+#if JMC_FAST_PIN_KEYS
+    keys.pin();
+#endif
+    constexpr int U = JMC_FAST_UNROLL;
+    const uint32_t my_trips = (iters + (uint32_t)(U - 1)) / (uint32_t)U;
     const uint32_t trips = __shfl_sync(0xffffffffu, my_trips, 0);
-    const uint64_t stride2 = 2ull * stride;
-    for (uint32_t j = 0; j < trips; ++j, idx += stride2) {
-        Draw d0, d1;
-        float o0, o1;
-        const bool a0 = light<KIND, FIXED, OBS_MLL>(P, idx, seed, d0, o0);
-        const bool a1 = light<KIND, FIXED, OBS_MLL>(P, idx + stride, seed, d1, o1);
-        handle(d0, o0, a0, 2u * j < iters);
-        handle(d1, o1, a1, 2u * j + 1u < iters);
+    const uint64_t strideU = (uint64_t)U * stride;
+    for (uint32_t j = 0; j < trips; ++j, idx += strideU) {
+        Draw d[U];
+        float o[U];
+        bool a[U];
+#pragma unroll
+        for (int k = 0; k < U; ++k) a[k] = light<KIND, FIXED, OBS_MLL>(P, idx + (uint64_t)k * stride, keys, d[k], o[k]);
+#pragma unroll
+        for (int k = 0; k < U; ++k) handle(d[k], o[k], a[k], (uint32_t)U * j + (uint32_t)k < iters);
     }
     if (COMPACT && do_hist) {
         __syncwarp();
@@ -553,8 +565,9 @@ dump_fast_kernel(FastParams P, uint64_t n, uint64_t seed, uint64_t first, double
         d.delta = d.z = d.cdf = 0.0f;
         d.u5 = 2.0f;
         float l2obs;
-        const bool active = P.obs_mll ? light<KIND, FIXED, true>(P, first + i, seed, d, l2obs)
-                                      : light<KIND, FIXED, false>(P, first + i, seed, d, l2obs);
+        const PhiloxKeys keys(seed);
+        const bool active = P.obs_mll ? light<KIND, FIXED, true>(P, first + i, keys, d, l2obs)
+                                      : light<KIND, FIXED, false>(P, first + i, keys, d, l2obs);
         float w = active ? heavy<KIND, FIXED>(P, d) : (FIXED ? 0.0f : fnan());
         if (w != w && P.nan_to_num) w = 0.0f;
         if (samples) {

@@ -55,6 +55,34 @@ __host__ __device__ __forceinline__ void philox4x32_10(uint64_t index, uint32_t 
     w[0] = c0; w[1] = c1; w[2] = c2; w[3] = c3;
 }
 
+// The ten round keys of a launch (key schedule k += W per round).  A kernel that calls the generator in a hot
+// loop computes them once; pin() makes them opaque to the compiler, which otherwise prefers to recompute the
+// schedule with uniform-datapath adds in every iteration (10 issue slots per sample).
+struct PhiloxKeys {
+    uint32_t k0[10], k1[10];
+    __device__ __forceinline__ explicit PhiloxKeys(uint64_t seed) {
+        uint32_t a = (uint32_t)seed, b = (uint32_t)(seed >> 32);
+#pragma unroll
+        for (int r = 0; r < 10; ++r) {
+            k0[r] = a; k1[r] = b;
+            a += 0x9E3779B9u; b += 0xBB67AE85u;
+        }
+    }
+    __device__ __forceinline__ void pin() {
+#ifdef __CUDA_ARCH__
+#pragma unroll
+        for (int r = 0; r < 10; ++r) asm volatile("" : "+r"(k0[r]), "+r"(k1[r]));
+#endif
+    }
+};
+
+__device__ __forceinline__ void philox4x32_10(uint64_t index, uint32_t block, const PhiloxKeys& K, uint32_t w[4]) {
+    uint32_t c0 = (uint32_t)index, c1 = (uint32_t)(index >> 32), c2 = block, c3 = 0u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) philox_round(c0, c1, c2, c3, K.k0[r], K.k1[r]);
+    w[0] = c0; w[1] = c1; w[2] = c2; w[3] = c3;
+}
+
 // two 53-bit uniforms in [0,1) from one block
 __host__ __device__ __forceinline__ void philox_uniform53x2(uint64_t index, uint32_t block, uint64_t seed,
                                                             double& u0, double& u1) {

@@ -124,3 +124,27 @@ def test_shower_mll_f32_vs_f64(cuda):
         pulls = (a.density[m] - b.density[m]) / err[m]
         assert np.abs(pulls).max() < 5. and (np.abs(pulls) > 3).sum() <= 2
         assert abs(np.asarray(a.integral)[-1] - 1.) < 1e-9 and abs(np.asarray(b.integral)[-1] - 1.) < 1e-9
+
+
+@pytest.mark.parametrize("jet", ['quark', 'gluon'])
+def test_c2_veto_shower_against_integrated_radiator(cuda, jet):
+    """BASELINE config 2 at full size (1e8 jets): the two forms of the ungroomed MLL calculation must agree.
+    Veto form: cdf of the leading-emission angularity of the MLL shower.  Integration form: exp(-R(C)) with
+    R(C) the Monte Carlo integral of radiatorWeight (running coupling, reduced splitting function) over
+    z theta^beta > C.  (The reference validates its shower the same way:
+    examples/tests/partonshower_tests/test_partonshower_angularities.py:180-209.)"""
+    from jetmontecarlo_b200 import fused
+    from jetmontecarlo_b200.fused import Integrand
+    n_jets, n_samples = 100_000_000, 2_000_000_000
+    edges = np.logspace(-7, np.log10(.5), 50)
+    sh = Integrand.shower(beta=2., jet_type=jet, acc='MLL', obs_acc='LL', n_emissions=1)
+    it = fused.integrate(sh, n_jets, edges=edges, seed=21, precision='f32', first_bc=0.)
+    counts = np.asarray(it.density) * np.diff(edges) * n_jets
+    cdf = ((n_jets - counts.sum()) + np.cumsum(counts)) / n_jets          # P(C_lead < edge_k), k = 1..
+    rad = Integrand.radiator('log', 1e-10, beta=2., jet_type=jet, fixedcoupling=False, obs_acc='LL', split_acc='MLL')
+    rt = fused.integrate(rad, n_samples, edges=edges, seed=22, precision='f32', last_bc=[0., 'plus'])
+    R, dR = np.asarray(rt.integral)[1:], np.append(rt.integralErr[1:], 0.)
+    sud = np.exp(-R)
+    sigma = np.sqrt(cdf * (1 - cdf) / n_jets + (sud * dR) ** 2) + 2e-5
+    assert np.abs((cdf - sud) / sigma).max() < 5., np.abs((cdf - sud) / sigma).max()
+    assert np.abs(cdf - sud).max() < 1e-3
