@@ -258,6 +258,22 @@ int jmc_run(const jmc_integrand* g, uint64_t n, uint64_t seed, uint64_t first_in
             double* d_sum_w, double* d_sum_w2, uint64_t* d_count, double* d_minmax,
             void* stream);
 
+/* A grid of parameter points in ONE launch (BASELINE config 5; the theta_crit loop of gen_crit_sub_num_rad,
+ * numerics/radiators/generation.py:303-359, and z_cut / beta sweeps).  g: n_points integrands sharing kind,
+ * coupling and observable accuracy; every point sees the same sample stream (seed, first_index), as the reference
+ * re-weights one stored sample set per grid point.  h_edges: HOST array [n_points, n_edges] (each point has its
+ * own bins) or NULL for a min/max-only pass; d_sum_w, d_sum_w2, d_count: DEVICE [n_points, n_edges-1],
+ * accumulated into; d_minmax: DEVICE [n_points, 2] or NULL (caller initialises to +inf, -inf). */
+int jmc_run_batch(const jmc_integrand* g, int n_points, uint64_t n, uint64_t seed, uint64_t first_index,
+                  int precision, const double* h_edges, int n_edges, double* d_sum_w, double* d_sum_w2,
+                  uint64_t* d_count, double* d_minmax, void* stream);
+
+/* jmc_finalize for n_jobs histograms at once: every array has a leading n_jobs dimension; d_area: [n_jobs]. */
+int jmc_finalize_batch(int n_jobs, const double* d_sum_w, const double* d_sum_w2, const uint64_t* d_count,
+                       const double* d_edges, int n_edges, const double* d_area, uint64_t n_total,
+                       int bc_kind, double bc_value, double* d_density, double* d_density_err,
+                       double* d_integral, double* d_integral_err, void* stream);
+
 /* Samples on request: the per-sample view of the same streams jmc_run bins, written to HBM only when a
  * caller asks for it (sampler.getSamples() on a fused job; parity tests).  d_samples: [n,8] = z_crit,
  * theta_crit, z_sub, theta_sub, z_pre, zero-bin uniform, delta = z_crit - z_cut (in FP32 mode the sampled

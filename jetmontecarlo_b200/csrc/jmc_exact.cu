@@ -871,10 +871,20 @@ template <bool FROM_HIST>
 __global__ void __launch_bounds__(kScanThreads)
 finalize_kernel(const double* __restrict__ sum_w, const double* __restrict__ sum_w2,
                 const unsigned long long* __restrict__ count, const double* __restrict__ edges, int n_edges,
-                double area, double n_total, int bc_kind, double bc_value, double* __restrict__ density,
-                double* __restrict__ density_err, double* __restrict__ integral, double* __restrict__ integral_err) {
+                double area, const double* __restrict__ area_per_job, double n_total, int bc_kind, double bc_value,
+                double* __restrict__ density, double* __restrict__ density_err, double* __restrict__ integral,
+                double* __restrict__ integral_err) {
     __shared__ double s_a[32], s_b[32];
     const int nb = n_edges - 1;
+    // blockIdx.x = job of a batch (jmc_finalize_batch); a single job is a batch of one
+    {
+        const size_t job = blockIdx.x;
+        if (FROM_HIST) { sum_w += job * nb; sum_w2 += job * nb; count += job * nb; }
+        edges += job * n_edges;
+        density += job * nb; density_err += job * nb;
+        if (integral) { integral += job * (nb + 1); integral_err += job * nb; }
+        if (area_per_job) area = area_per_job[job];
+    }
     const int per = (nb + kScanThreads - 1) / kScanThreads;
     const bool reverse = bc_kind != JMC_BC_FIRST;
     const double norm = area / n_total;
@@ -930,7 +940,23 @@ extern "C" int jmc_finalize(const double* d_sum_w, const double* d_sum_w2, const
     JMC_REQUIRE(d_density && d_density_err, "jmc_finalize: NULL output");
     JMC_REQUIRE((d_integral == nullptr) == (d_integral_err == nullptr), "jmc_finalize: integral and its error go together");
     finalize_kernel<true><<<1, kScanThreads, 0, (cudaStream_t)stream>>>(
-        d_sum_w, d_sum_w2, (const unsigned long long*)d_count, d_edges, n_edges, area, (double)n_total, bc_kind,
+        d_sum_w, d_sum_w2, (const unsigned long long*)d_count, d_edges, n_edges, area, nullptr, (double)n_total, bc_kind,
+        bc_value, d_density, d_density_err, d_integral, d_integral_err);
+    JMC_LAUNCHED("finalize_kernel");
+    return JMC_OK;
+}
+
+extern "C" int jmc_finalize_batch(int n_jobs, const double* d_sum_w, const double* d_sum_w2, const uint64_t* d_count,
+                                  const double* d_edges, int n_edges, const double* d_area, uint64_t n_total,
+                                  int bc_kind, double bc_value, double* d_density, double* d_density_err,
+                                  double* d_integral, double* d_integral_err, void* stream) {
+    JMC_REQUIRE(n_jobs >= 1, "jmc_finalize_batch: need at least one job");
+    JMC_REQUIRE(n_edges >= 2, "jmc_finalize_batch: need at least 2 edges");
+    JMC_REQUIRE(bc_kind >= JMC_BC_FIRST && bc_kind <= JMC_BC_LAST_MINUS, "jmc_finalize_batch: invalid boundary condition");
+    JMC_REQUIRE(d_sum_w && d_sum_w2 && d_count && d_edges && d_area, "jmc_finalize_batch: NULL input");
+    JMC_REQUIRE(d_density && d_density_err && d_integral && d_integral_err, "jmc_finalize_batch: NULL output");
+    finalize_kernel<true><<<n_jobs, kScanThreads, 0, (cudaStream_t)stream>>>(
+        d_sum_w, d_sum_w2, (const unsigned long long*)d_count, d_edges, n_edges, 0.0, d_area, (double)n_total, bc_kind,
         bc_value, d_density, d_density_err, d_integral, d_integral_err);
     JMC_LAUNCHED("finalize_kernel");
     return JMC_OK;
@@ -943,7 +969,7 @@ extern "C" int jmc_cumulative(const double* d_density, const double* d_density_e
     JMC_REQUIRE(bc_kind >= JMC_BC_FIRST && bc_kind <= JMC_BC_LAST_MINUS, "jmc_cumulative: invalid boundary condition");
     JMC_REQUIRE(d_density && d_density_err && d_edges && d_integral && d_integral_err, "jmc_cumulative: NULL argument");
     finalize_kernel<false><<<1, kScanThreads, 0, (cudaStream_t)stream>>>(
-        nullptr, nullptr, nullptr, d_edges, n_edges, 1.0, 1.0, bc_kind, bc_value, (double*)d_density,
+        nullptr, nullptr, nullptr, d_edges, n_edges, 1.0, nullptr, 1.0, bc_kind, bc_value, (double*)d_density,
         (double*)d_density_err, d_integral, d_integral_err);
     JMC_LAUNCHED("finalize_kernel");
     return JMC_OK;

@@ -383,11 +383,10 @@ __device__ __forceinline__ int bin_fast(const FastParams& P, float l2obs, const 
 // HOT: histogram only (no min/max tracking) into np.logspace-like bins -- the form every large job has; the
 // generic instantiation reads those choices from FastParams at run time.
 template <int KIND, bool FIXED, bool OBS_MLL, bool HOT>
-__global__ void __launch_bounds__(kFastThreads, JMC_FAST_MIN_BLOCKS)
-run_fast_kernel(FastParams P, uint64_t n, uint64_t seed, uint64_t first, const float* __restrict__ g_edges,
-                double* __restrict__ g_sum_w, double* __restrict__ g_sum_w2,
-                unsigned long long* __restrict__ g_count, int* g_poison, double* __restrict__ d_minmax) {
-    extern __shared__ double s_raw[];
+__device__ __forceinline__ void
+fast_body(const FastParams& P, uint64_t n, uint64_t seed, uint64_t first, const float* __restrict__ g_edges,
+          double* __restrict__ g_sum_w, double* __restrict__ g_sum_w2, unsigned long long* __restrict__ g_count,
+          int* g_poison, double* __restrict__ d_minmax, double* s_raw) {
     __shared__ int s_poison;
     const int ne = P.n_edges, nb = ne > 0 ? ne - 1 : 0;
     double* s_sum_w = s_raw;
@@ -542,6 +541,40 @@ run_fast_kernel(FastParams P, uint64_t n, uint64_t seed, uint64_t first, const f
             }
         }
     }
+}
+
+// one job: parameters in the constant bank
+template <int KIND, bool FIXED, bool OBS_MLL, bool HOT>
+__global__ void __launch_bounds__(kFastThreads, JMC_FAST_MIN_BLOCKS)
+run_fast_kernel(FastParams P, uint64_t n, uint64_t seed, uint64_t first, const float* __restrict__ g_edges,
+                double* __restrict__ g_sum_w, double* __restrict__ g_sum_w2,
+                unsigned long long* __restrict__ g_count, int* g_poison, double* __restrict__ d_minmax) {
+    extern __shared__ double s_dyn[];
+    fast_body<KIND, FIXED, OBS_MLL, HOT>(P, n, seed, first, g_edges, g_sum_w, g_sum_w2, g_count, g_poison, d_minmax, s_dyn);
+}
+
+// A grid of parameter points in one launch (BASELINE config 5: gen_crit_sub_num_rad's theta_crit loop,
+// generation.py:303-359, z_cut / beta sweeps): blockIdx.y selects the point, its parameters are staged in shared
+// memory, and every point regenerates the same sample stream -- the reference re-weights one stored sample set
+// per grid point, here the "stored set" is the counter RNG.
+template <int KIND, bool FIXED, bool OBS_MLL, bool HOT>
+__global__ void __launch_bounds__(kFastThreads, JMC_FAST_MIN_BLOCKS)
+run_fast_batch_kernel(const FastParams* __restrict__ params, uint64_t n, uint64_t seed, uint64_t first,
+                      const float* __restrict__ edges_all, int n_edges, double* __restrict__ sum_w_all,
+                      double* __restrict__ sum_w2_all, unsigned long long* __restrict__ count_all, int* poison_all,
+                      double* __restrict__ minmax_all) {
+    extern __shared__ double s_dyn[];
+    __shared__ FastParams sP;
+    const int point = blockIdx.y;
+    const int words = (int)(sizeof(FastParams) / sizeof(int));
+    for (int k = threadIdx.x; k < words; k += blockDim.x) ((int*)&sP)[k] = ((const int*)&params[point])[k];
+    __syncthreads();
+    const size_t nb = n_edges > 0 ? (size_t)n_edges - 1 : 0;
+    fast_body<KIND, FIXED, OBS_MLL, HOT>(
+        sP, n, seed, first, edges_all ? edges_all + (size_t)point * n_edges : nullptr,
+        sum_w_all ? sum_w_all + point * nb : nullptr, sum_w2_all ? sum_w2_all + point * nb : nullptr,
+        count_all ? count_all + point * nb : nullptr, poison_all + point,
+        minmax_all ? minmax_all + 2 * (size_t)point : nullptr, s_dyn);
 }
 
 __global__ void poison_fast_kernel(const int* g_poison, int nb, double* g_sum_w, double* g_sum_w2) {
@@ -806,6 +839,112 @@ int run_fast(const jmc_integrand* g, uint64_t n, uint64_t seed, uint64_t first_i
     if (d_edges && !g->nan_to_num) {
         poison_fast_kernel<<<1, 256, 0, st>>>(d_poison, n_edges - 1, d_sum_w, d_sum_w2);
         JMC_LAUNCHED("poison_fast_kernel");
+    }
+    return JMC_OK;
+}
+
+__global__ void poison_batch_kernel(const int* poison_all, int nb, double* sum_w_all, double* sum_w2_all) {
+    const int point = blockIdx.x;
+    const int pb = poison_all[point];
+    if (pb < 0 || pb >= nb) return;
+    for (int k = pb + threadIdx.x; k < nb; k += blockDim.x) {
+        sum_w_all[(size_t)point * nb + k] = __longlong_as_double(0x7ff8000000000000LL);
+        sum_w2_all[(size_t)point * nb + k] = __longlong_as_double(0x7ff8000000000000LL);
+    }
+}
+
+template <int KIND, bool FIXED, bool OBS_MLL, bool HOT>
+static int launch_fast_batch_t(const FastParams* d_params, int n_points, int n_edges, uint64_t n, uint64_t seed,
+                               uint64_t first, const float* d_edges_f, double* d_sum_w, double* d_sum_w2,
+                               uint64_t* d_count, int* d_poison, double* d_minmax, cudaStream_t st) {
+    DeviceInfo di;
+    if (device_info(&di)) return JMC_ENODEV;
+    const size_t smem = fast_smem_bytes(d_edges_f ? n_edges : 0);
+    if (smem > (size_t)di.max_smem_optin)
+        return set_error(JMC_ELIMIT, "jmc_run_batch: %d edges need %zu B of shared memory (limit %d B)", n_edges, smem,
+                         di.max_smem_optin);
+    auto kern = run_fast_batch_kernel<KIND, FIXED, OBS_MLL, HOT>;
+    JMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    JMC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kFastThreads, smem));
+    if (per_sm < 1) per_sm = 1;
+    const uint64_t cap = (uint64_t)di.sm_count * per_sm;
+    // enough blocks for ~8 full waves (the tail wave then costs little), but at least ~128 samples per thread so
+    // that zeroing and flushing the block histogram stays negligible
+    uint64_t per_point = (8 * cap + (uint64_t)n_points - 1) / (uint64_t)n_points;
+    const uint64_t most = n / ((uint64_t)kFastThreads * 128);
+    if (per_point > most) per_point = most;
+    if (per_point < 1) per_point = 1;
+    dim3 grid((unsigned)per_point, (unsigned)n_points);
+    kern<<<grid, kFastThreads, smem, st>>>(d_params, n, seed, first, d_edges_f, n_edges, d_sum_w, d_sum_w2,
+                                           (unsigned long long*)d_count, d_poison, d_minmax);
+    JMC_LAUNCHED("run_fast_batch_kernel");
+    return JMC_OK;
+}
+
+int run_fast_batch(const jmc_integrand* g, int n_points, uint64_t n, uint64_t seed, uint64_t first_index,
+                   const double* h_edges, int n_edges, double* d_sum_w, double* d_sum_w2, uint64_t* d_count,
+                   double* d_minmax, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    JMC_REQUIRE(g != nullptr && n_points >= 1 && n_points <= 65535, "jmc_run_batch: need 1..65535 parameter points");
+    if (h_edges) {
+        JMC_REQUIRE(n_edges >= 2, "jmc_run_batch: need at least 2 edges");
+        JMC_REQUIRE(d_sum_w && d_sum_w2 && d_count, "jmc_run_batch: histogram outputs missing");
+    } else {
+        JMC_REQUIRE(d_minmax != nullptr, "jmc_run_batch: neither edges nor minmax requested");
+        n_edges = 0;
+    }
+    std::vector<FastParams> params(n_points);
+    std::vector<float> edges_all((size_t)n_points * n_edges), one;
+    bool hot = h_edges != nullptr && d_minmax == nullptr;
+    for (int i = 0; i < n_points; ++i) {
+        JMC_REQUIRE(g[i].kind == g[0].kind && g[i].fixed_coupling == g[0].fixed_coupling && g[i].obs_acc == g[0].obs_acc,
+                    "jmc_run_batch: all points must share kind, coupling and observable accuracy (point %d differs)", i);
+        int rc = make_fast_params(&g[i], h_edges ? h_edges + (size_t)i * n_edges : nullptr, n_edges, &params[i], &one);
+        if (rc) return rc;
+        if (h_edges) std::memcpy(&edges_all[(size_t)i * n_edges], one.data(), sizeof(float) * n_edges);
+        hot = hot && params[i].dom_log && params[i].uniform;
+        if (!h_edges) params[i].n_edges = 0;
+    }
+    if (n == 0) return JMC_OK;
+    const size_t bytes_params = sizeof(FastParams) * (size_t)n_points;
+    const size_t off_edges = (bytes_params + 255) & ~(size_t)255;
+    const size_t bytes_edges = sizeof(float) * edges_all.size();
+    const size_t off_poison = (off_edges + bytes_edges + 255) & ~(size_t)255;
+    char* scr;
+    int rc = scratch(off_poison + sizeof(int) * (size_t)n_points, (void**)&scr);
+    if (rc) return rc;
+    FastParams* d_params = (FastParams*)scr;
+    float* d_edges_f = h_edges ? (float*)(scr + off_edges) : nullptr;
+    int* d_poison = (int*)(scr + off_poison);
+    JMC_CUDA(cudaMemcpyAsync(d_params, params.data(), bytes_params, cudaMemcpyHostToDevice, st));
+    if (h_edges) JMC_CUDA(cudaMemcpyAsync(d_edges_f, edges_all.data(), bytes_edges, cudaMemcpyHostToDevice, st));
+    JMC_CUDA(cudaMemsetAsync(d_poison, 0x7f, sizeof(int) * (size_t)n_points, st));
+    JMC_CUDA(cudaStreamSynchronize(st));           // the staging vectors die at return
+    const bool mll = g[0].obs_acc == JMC_ACC_MLL, fixed = g[0].fixed_coupling != 0;
+#define JMC_B(K, F, M, H) \
+    rc = launch_fast_batch_t<K, F, M, H>(d_params, n_points, n_edges, n, seed, first_index, d_edges_f, d_sum_w, d_sum_w2, d_count, d_poison, d_minmax, st)
+#define JMC_BK(K)                                                              \
+    do {                                                                       \
+        if (fixed) { if (mll) { if (hot) JMC_B(K, true, true, true); else JMC_B(K, true, true, false); }     \
+                     else { if (hot) JMC_B(K, true, false, true); else JMC_B(K, true, false, false); } }      \
+        else { if (mll) { if (hot) JMC_B(K, false, true, true); else JMC_B(K, false, true, false); }         \
+               else { if (hot) JMC_B(K, false, false, true); else JMC_B(K, false, false, false); } }          \
+    } while (0)
+    switch (g[0].kind) {
+        case JMC_KIND_RADIATOR: JMC_BK(JMC_KIND_RADIATOR); break;
+        case JMC_KIND_CRIT: JMC_BK(JMC_KIND_CRIT); break;
+        case JMC_KIND_CRIT_SUB: JMC_BK(JMC_KIND_CRIT_SUB); break;
+        default: return set_error(JMC_EINVAL, "jmc_run_batch: kind %d is not batched", g[0].kind);
+    }
+#undef JMC_BK
+#undef JMC_B
+    if (rc) return rc;
+    bool any_nan_semantics = false;
+    for (int i = 0; i < n_points; ++i) any_nan_semantics = any_nan_semantics || !g[i].nan_to_num;
+    if (h_edges && any_nan_semantics) {
+        poison_batch_kernel<<<n_points, 128, 0, st>>>(d_poison, n_edges - 1, d_sum_w, d_sum_w2);
+        JMC_LAUNCHED("poison_batch_kernel");
     }
     return JMC_OK;
 }

@@ -112,6 +112,9 @@ int run_exact(const jmc_integrand* g, uint64_t n, uint64_t seed, uint64_t first_
               int n_edges, double* d_sum_w, double* d_sum_w2, uint64_t* d_count, double* d_minmax, void* stream);
 int run_fast(const jmc_integrand* g, uint64_t n, uint64_t seed, uint64_t first_index, const double* d_edges,
              int n_edges, double* d_sum_w, double* d_sum_w2, uint64_t* d_count, double* d_minmax, void* stream);
+int run_fast_batch(const jmc_integrand* g, int n_points, uint64_t n, uint64_t seed, uint64_t first_index,
+                   const double* h_edges, int n_edges, double* d_sum_w, double* d_sum_w2, uint64_t* d_count,
+                   double* d_minmax, void* stream);
 int dump_exact(const jmc_integrand* g, uint64_t n, uint64_t seed, uint64_t first_index, double* d_samples,
                double* d_obs, double* d_weight, void* stream);
 int dump_fast(const jmc_integrand* g, uint64_t n, uint64_t seed, uint64_t first_index, double* d_samples,
@@ -119,6 +122,16 @@ int dump_fast(const jmc_integrand* g, uint64_t n, uint64_t seed, uint64_t first_
 int run_shower(const jmc_integrand* g, uint64_t n, uint64_t seed, uint64_t first_index, int precision,
                const double* d_edges, int n_edges, double* d_sum_w, double* d_sum_w2, uint64_t* d_count,
                double* d_minmax, void* stream);
+
+// device buffer freed at scope exit (host-side helpers below synchronise before returning)
+struct DevBufE {
+    void* p = nullptr;
+    ~DevBufE() { if (p) cudaFree(p); }
+    int alloc(size_t bytes) {
+        JMC_CUDA(cudaMalloc(&p, bytes ? bytes : 8));
+        return JMC_OK;
+    }
+};
 
 static int sampler_area(int kind, int method, double eps, double zc, double radius, double lo, double hi,
                         double* area) {
@@ -227,6 +240,34 @@ extern "C" int jmc_run(const jmc_integrand* g, uint64_t n, uint64_t seed, uint64
         n -= chunk;
         first_index += chunk;
     } while (n > 0);
+    return JMC_OK;
+}
+
+extern "C" int jmc_run_batch(const jmc_integrand* g, int n_points, uint64_t n, uint64_t seed, uint64_t first_index,
+                             int precision, const double* h_edges, int n_edges, double* d_sum_w, double* d_sum_w2,
+                             uint64_t* d_count, double* d_minmax, void* stream) {
+    JMC_REQUIRE(g != nullptr && n_points >= 1, "jmc_run_batch: need at least one parameter point");
+    JMC_REQUIRE(precision == JMC_F64 || precision == JMC_F32, "jmc_run_batch: precision must be JMC_F64 or JMC_F32");
+    if (precision == JMC_F32 && g[0].kind != JMC_KIND_SHOWER && g[0].kind != JMC_KIND_PRE_CRIT_SUB
+        && g[0].kind != JMC_KIND_SIMPLE)
+        return run_fast_batch(g, n_points, n, seed, first_index, h_edges, n_edges, d_sum_w, d_sum_w2, d_count, d_minmax,
+                              stream);
+    // FP64 (and the kinds without a batched kernel): one launch per point on the same stream
+    const size_t nb = n_edges > 0 ? (size_t)n_edges - 1 : 0;
+    DevBufE edges;
+    if (h_edges) {
+        int rc = edges.alloc(sizeof(double) * (size_t)n_points * n_edges);
+        if (rc) return rc;
+        JMC_CUDA(cudaMemcpyAsync(edges.p, h_edges, sizeof(double) * (size_t)n_points * n_edges, cudaMemcpyHostToDevice,
+                                 (cudaStream_t)stream));
+    }
+    for (int i = 0; i < n_points; ++i) {
+        int rc = jmc_run(&g[i], n, seed, first_index, precision, h_edges ? (const double*)edges.p + (size_t)i * n_edges : nullptr,
+                         n_edges, d_sum_w ? d_sum_w + i * nb : nullptr, d_sum_w2 ? d_sum_w2 + i * nb : nullptr,
+                         d_count ? d_count + i * nb : nullptr, d_minmax ? d_minmax + 2 * (size_t)i : nullptr, stream);
+        if (rc) return rc;
+    }
+    JMC_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
     return JMC_OK;
 }
 

@@ -185,8 +185,70 @@ def integrate(integrand, num_samples, *, edges=None, numbins=None, binspacing='l
         it.binspacing = binspacing
         it.hasBins = True
     else:
+        # same arithmetic mode for both passes: the min/max pass must see the samples the histogram pass bins
         it.setBinsFused(numbins, integrand, num_samples, binspacing, seed, min_log_bin=min_log_bin,
-                        precision='f64' if integrand.kind != _lib.KIND_SHOWER else precision, group=group)
+                        precision=precision, group=group)
     it.setDensityFused(integrand, num_samples, seed, precision=precision, group=group)
     it.integrate()
     return it
+
+
+def _as_struct_array(integrands):
+    arr = (_lib.Integrand * len(integrands))()
+    for i, ig in enumerate(integrands):
+        arr[i] = ig.c_struct()
+    return arr
+
+
+def integrate_batch(integrands, num_samples, *, edges=None, numbins=None, binspacing='log', min_log_bins=None,
+                    seed=0, precision='f32', last_bc=None, first_bc=None, group=None):
+    """A grid of parameter points in one launch per pass (BASELINE config 5).
+
+    ``integrands``: list of Integrand sharing kind / coupling / observable accuracy (e.g. one ``theta_scale`` per
+    theta_crit of gen_crit_sub_num_rad).  Every point sees the same sample stream.  ``edges``: array
+    [n_points, n_edges]; or ``numbins`` + ``binspacing`` (+ per-point ``min_log_bins``) for the reference's
+    data-dependent bins, found by a batched min/max pass.  Returns a dict of arrays with a leading n_points axis:
+    bins, density, densityErr, integral, integralErr (same conventions as ``integrator``)."""
+    from .montecarlo.integrator import _bc_args
+    D.require_cuda()
+    npts = len(integrands)
+    arr = _as_struct_array(integrands)
+    num_samples = int(num_samples)
+    first, n_local = dist_utils.shard(num_samples, group)
+    prec, key = PRECISIONS[precision], int(seed) & 0xFFFFFFFFFFFFFFFF
+    if edges is None:
+        mm = torch.empty((npts, 2), dtype=torch.float64, device=D.device())
+        mm[:, 0], mm[:, 1] = float('inf'), float('-inf')
+        _lib.check(_lib.lib.jmc_run_batch(arr, npts, n_local, key, first, prec, None, 0, None, None, None, D.ptr(mm),
+                                          D.stream()))
+        if dist_utils.is_distributed(group):
+            for i in range(npts):
+                dist_utils.allreduce_minmax(mm[i], group)
+        mm = D.to_host(mm)
+        mlb = np.full(npts, 1e-15) if min_log_bins is None else np.asarray(min_log_bins, dtype=float)
+        rows = []
+        for i in range(npts):                       # integrator.setBins, one row per point (host, O(bins))
+            lo, hi = mm[i]
+            if binspacing == 'lin':
+                rows.append(np.linspace(min(0, lo), hi, numbins))
+            else:
+                rows.append(np.logspace(np.log10(max(lo, mlb[i])), np.log10(hi), numbins))
+        edges = np.array(rows)
+    edges = np.ascontiguousarray(edges, dtype=np.float64)
+    ne = edges.shape[1]
+    nb = ne - 1
+    sum_w, sum_w2 = D.zeros((npts, nb)), D.zeros((npts, nb))
+    count = D.zeros((npts, nb), dtype=torch.int64)
+    _lib.check(_lib.lib.jmc_run_batch(arr, npts, n_local, key, first, prec, edges.ctypes.data_as(C.c_void_p), ne,
+                                      D.ptr(sum_w), D.ptr(sum_w2), D.ptr(count), None, D.stream()))
+    dist_utils.allreduce_histograms(sum_w, sum_w2, count, group)
+    bc_kind, bc_value = _bc_args(first_bc, None if last_bc is None else list(last_bc))
+    edges_dev = D.to_device(edges)
+    areas = D.to_device(np.array([ig.area for ig in integrands], dtype=np.float64))
+    dens, err = D.empty((npts, nb)), D.empty((npts, nb))
+    integ, ierr = D.empty((npts, ne)), D.empty((npts, nb))
+    _lib.check(_lib.lib.jmc_finalize_batch(npts, D.ptr(sum_w), D.ptr(sum_w2), D.ptr(count), D.ptr(edges_dev), ne,
+                                           D.ptr(areas), num_samples, bc_kind, bc_value, D.ptr(dens), D.ptr(err),
+                                           D.ptr(integ), D.ptr(ierr), D.stream()))
+    return dict(bins=edges, density=D.to_host(dens), densityErr=D.to_host(err), integral=D.to_host(integ),
+                integralErr=D.to_host(ierr), count=D.to_host(count))

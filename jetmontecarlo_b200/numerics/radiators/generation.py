@@ -121,3 +121,34 @@ def gen_crit_sub_num_rad(rad_sampler, jet_type='quark', obs_accuracy='LL', split
 
     data_dict = {'xs': xs_all.flatten(), 'ys': thetas_all.flatten(), 'integral': rads_all.flatten()}
     return bounded_interp_function, data_dict
+
+
+def gen_crit_sub_num_rad_fused(num_samples, jet_type='quark', obs_accuracy='LL', splitfn_accuracy='LL', beta=2.,
+                               epsilon=1e-15, bin_space='log', fixed_coupling=True, num_bins=1000, radius=1.,
+                               sample_epsilon=None, seed=0, precision='f32', group=None):
+    """``gen_crit_sub_num_rad`` without a stored sample set: the whole theta_crit grid runs as two batched launches
+    (min/max for the reference's data-dependent bins, then the histograms), each grid point regenerating the same
+    ``num_samples`` ungroomed-sampler draws from the counter RNG.  Same return value as the reference function
+    (numerics/radiators/generation.py:253-400)."""
+    from ... import fused
+    theta_calc_list = lin_log_mixed_list(epsilon, 1., num_bins)
+    eps = epsilon if sample_epsilon is None else sample_epsilon
+    igs = [fused.Integrand.radiator(bin_space, eps, radius=radius, beta=beta, jet_type=jet_type,
+                                    fixedcoupling=fixed_coupling, obs_acc=obs_accuracy, split_acc=splitfn_accuracy,
+                                    theta_scale=float(t)) for t in theta_calc_list]
+    res = fused.integrate_batch(igs, num_samples, numbins=num_bins, binspacing=bin_space,
+                                min_log_bins=theta_calc_list ** beta * 1e-15, seed=seed, precision=precision,
+                                last_bc=[0., 'plus'], group=group)
+    xs_all = res['bins']
+    thetas_all = np.repeat(theta_calc_list[:, None], xs_all.shape[1], axis=1)
+    rads_all = res['integral']
+    unbounded_interp_function = get_2d_interpolation(xs_all.flatten(), thetas_all.flatten(), rads_all.flatten(),
+                                                     interpolation_method='nearest')
+
+    def bounded_interp_function(x, theta):
+        return unbounded_interp_function(x, theta) * (x >= 0) * (theta >= 0) *\
+            (x <= C_ungroomed_max(beta, radius=theta, acc=obs_accuracy))
+
+    data_dict = {'xs': xs_all.flatten(), 'ys': thetas_all.flatten(), 'integral': rads_all.flatten(),
+                 'integral error': res['integralErr']}
+    return bounded_interp_function, data_dict
