@@ -361,8 +361,14 @@ template <bool UNILOG>
 __device__ __forceinline__ int bin_fast(const FastParams& P, float l2obs, const float* __restrict__ s_edges) {
     const float v = (UNILOG || P.dom_log) ? l2obs : ex2(l2obs);
     const int ne = P.n_edges;
+    const bool in_range = (v >= P.e_first) & (v <= P.e_last);       // NaN fails both
     int idx;
-    if (UNILOG || P.uniform) {
+    if (UNILOG) {
+        // np.logspace bins: the bin is the floor of an affine map of log2(obs).  (The stored FP32 edges are that
+        // same map rounded; settling against them would cost ten more instructions per sample for samples within
+        // 1e-7 of an edge, which FP32 cannot place with respect to the FP64 edges anyway.)
+        idx = min(max(__float2int_rd(fmaf(v, P.inv_d, P.mb0_inv_d)), 0), ne - 2);
+    } else if (P.uniform) {
         // affine guess, then settle against the stored edges (FP32 rounding of the map can be off by one)
         idx = __float2int_rd(fmaf(v, P.inv_d, P.mb0_inv_d));
         idx = max(0, min(idx, ne - 2));
@@ -376,7 +382,6 @@ __device__ __forceinline__ int bin_fast(const FastParams& P, float l2obs, const 
         }
         idx = min(lo - 1, ne - 2);
     }
-    const bool in_range = (v >= P.e_first) & (v <= P.e_last);       // NaN fails both
     return in_range ? idx : -1;
 }
 
@@ -391,12 +396,13 @@ fast_body(const FastParams& P, uint64_t n, uint64_t seed, uint64_t first, const 
     const int ne = P.n_edges, nb = ne > 0 ? ne - 1 : 0;
     double* s_sum_w = s_raw;
     double* s_sum_w2 = s_sum_w + nb;
-    unsigned int* s_count = (unsigned int*)(s_sum_w2 + nb);
-    float* s_edges = (float*)(s_count + nb);
+    unsigned int* s_count = (unsigned int*)(s_sum_w2 + nb);       // nb bins + 32 dummy slots for dropped samples
+    float* s_edges = (float*)(s_count + nb + 32);
     const bool do_hist = HOT || g_edges != nullptr;
     const bool do_minmax = !HOT && d_minmax != nullptr;
     if (threadIdx.x == 0) s_poison = INT_MAX;
     for (int k = threadIdx.x; k < nb; k += blockDim.x) { s_sum_w[k] = 0.0; s_sum_w2[k] = 0.0; s_count[k] = 0u; }
+    if (threadIdx.x < 32) s_count[nb + threadIdx.x] = 0u;
     for (int k = threadIdx.x; k < ne; k += blockDim.x) s_edges[k] = g_edges[k];
     __syncthreads();
     float mn = INFINITY, mx = -INFINITY;
@@ -449,7 +455,9 @@ fast_body(const FastParams& P, uint64_t n, uint64_t seed, uint64_t first, const 
         if (!do_hist) return;
         int b = bin_fast<HOT>(P, l2obs, s_edges);
         if (!valid) { b = -1; active = false; }
-        if (b >= 0) atomicAdd(&s_count[b], 1u);
+        // dropped samples count into a per-lane dummy slot behind the bins: no branch around the atomic, and no
+        // same-address serialisation among the lanes that miss
+        atomicAdd(&s_count[b >= 0 ? b : nb + (int)lane], 1u);
         const float v = (HOT || P.dom_log) ? l2obs : ex2(l2obs);
         const int bq = b >= 0 ? b : (v < P.e_first ? -1 : -2);
         if (COMPACT) {
@@ -747,7 +755,7 @@ static int make_fast_params(const jmc_integrand* g, const double* h_edges, int n
 static size_t fast_smem_bytes(int n_edges) {
     const size_t nb = n_edges > 0 ? (size_t)n_edges - 1 : 0;
     const size_t ne_pad = ((size_t)(n_edges > 0 ? n_edges : 0) + 3) & ~(size_t)3;
-    return sizeof(double) * 2 * nb + sizeof(unsigned int) * nb + sizeof(float) * ne_pad
+    return sizeof(double) * 2 * nb + sizeof(unsigned int) * (nb + 32) + sizeof(float) * ne_pad
            + sizeof(float) * (kFastThreads / 32) * kQueueFields * kQueueSlots;
 }
 

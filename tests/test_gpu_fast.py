@@ -154,12 +154,16 @@ def test_fast_histogram_equals_histogram_of_its_dump(cuda, kind, jet, fc, acc):
     _, obs, w = H.dump(ig, n, seed, 'f32')
     r = H.run(ig, n, seed, edges, 'f32')
     cnt = r['count'].cpu().numpy()
-    # the kernel compares log2(obs) with log2(edges) in FP32: restate exactly that
+    # restate the kernel's binning exactly: np.logspace edges -> bin = floor of an affine map of log2(obs) in
+    # FP32 (one FMA), clamped, with the range test against the FP32 log2 edges
     l2 = np.log2(obs).astype(np.float32)
-    e32 = np.log2(edges).astype(np.float32)
-    idx = np.searchsorted(e32, l2, side='right').astype(np.int64) - 1
-    idx[l2 == e32[-1]] = len(edges) - 2
-    keep = (idx >= 0) & (idx <= len(edges) - 2)
+    dom = np.log2(edges)
+    e32 = dom.astype(np.float32)
+    d = (dom[-1] - dom[0]) / (len(edges) - 1)
+    inv_d, mb0 = np.float32(1. / d), np.float32(-dom[0] / d)
+    fma = (l2.astype(np.float64) * np.float64(inv_d) + np.float64(mb0)).astype(np.float32)
+    idx = np.clip(np.floor(fma).astype(np.int64), 0, len(edges) - 2)
+    keep = (l2 >= e32[0]) & (l2 <= e32[-1])
     ref_cnt = np.bincount(idx[keep], minlength=len(edges) - 1)
     assert_array_equal(cnt, ref_cnt)
     assert abs(cnt - np.histogram(obs, edges)[0]).sum() <= 1e-4 * n     # and FP64 binning differs only at edge ties
