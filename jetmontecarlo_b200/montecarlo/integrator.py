@@ -221,51 +221,46 @@ class integrator():
         self.hasInterpDensity = True
 
     # ------------------
-    # csv save / load    (ref: integrator.py:320-354)
+    # csv save / load    (three files: values, errors, bin edges; ref: integrator.py:320-354)
     # ------------------
+    @staticmethod
+    def _write_csv(files, arrays):
+        for name, arr in zip(files, arrays):
+            np.savetxt(name, arr, delimiter=',')
+
+    @staticmethod
+    def _read_csv(files):
+        return [np.loadtxt(name, delimiter=',') for name in files]
+
     def saveIntegral(self, intFile, errFile, binFile):
         assert self.hasMCIntegral, \
             "No integral histogram to save"
-        np.savetxt(intFile, self.integral, delimiter=',')
-        np.savetxt(errFile, self.integralErr, delimiter=',')
-        np.savetxt(binFile, self.bins, delimiter=',')
+        self._write_csv((intFile, errFile, binFile), (self.integral, self.integralErr, self.bins))
 
     def loadIntegral(self, intFile, errFile, binFile):
-        self.integral = np.loadtxt(intFile, delimiter=',')
-        self.integralErr = np.loadtxt(errFile, delimiter=',')
-        self.bins = np.loadtxt(binFile, delimiter=',')
+        self.integral, self.integralErr, self.bins = self._read_csv((intFile, errFile, binFile))
         self.hasMCIntegral = True
 
     def saveDensity(self, denFile, errFile, binFile):
         assert self.hasMCDensity, \
             "No density histogram to save"
-        np.savetxt(denFile, self.density, delimiter=',')
-        np.savetxt(errFile, self.densityErr, delimiter=',')
-        np.savetxt(binFile, self.bins, delimiter=',')
+        self._write_csv((denFile, errFile, binFile), (self.density, self.densityErr, self.bins))
 
     def loadDensity(self, denFile, errFile, binFile):
-        self.density = np.loadtxt(denFile, delimiter=',')
-        self.densityErr = np.loadtxt(errFile, delimiter=',')
-        self.bins = np.loadtxt(binFile, delimiter=',')
+        self.density, self.densityErr, self.bins = self._read_csv((denFile, errFile, binFile))
         self.hasMCDensity = True
 
     def checkValidAttributes(self):
         pass
 
+    # state flags of the reference (integrator.py:367-386): nothing known yet
+    _FLAGS = ('hasBins', 'hasMCDensity', 'hasMCIntegral', 'hasInterpIntegral', 'hasInterpDensity',
+              'useFirstBinBndCond', 'useLastBinBndCond', 'monotone', 'hasAnalyticIntegral', 'hasAnalyticDensity')
+
     def __init__(self, *args, **kwargs):
-        """ref: montecarlo/integrator.py:367-386"""
-        self.hasBins = False
-        self.hasMCDensity = False
-        self.hasMCIntegral = False
-        self.hasInterpIntegral = False
-        self.hasInterpDensity = False
-        self.firstBinBndCond = None
-        self.useFirstBinBndCond = False
-        self.lastBinBndCond = None
-        self.useLastBinBndCond = False
-        self.monotone = False
-        self.hasAnalyticIntegral = False
-        self.hasAnalyticDensity = False
+        for flag in self._FLAGS:
+            setattr(self, flag, False)
+        self.firstBinBndCond = self.lastBinBndCond = None
         self._obs_cache = None
         self.checkValidAttributes()
 
@@ -432,17 +427,10 @@ class integrator_2d():
         self.hasInterpIntegral = True
 
     def __init__(self, *args, **kwargs):
-        self.hasBins = False
-        self.hasMCDensity = False
-        self.hasMCIntegral = False
-        self.hasInterpIntegral = False
-        self.hasInterpDensity = False
-        self.firstBinBndCond = None
-        self.useFirstBinBndCond = False
-        self.lastBinBndCond = None
-        self.useLastBinBndCond = False
-        self.hasAnalyticIntegral = False
-        self.hasAnalyticDensity = False
+        for flag in integrator._FLAGS:
+            if flag != 'monotone':
+                setattr(self, flag, False)
+        self.firstBinBndCond = self.lastBinBndCond = None
 
 
 def integrate_2d(function, bounds, bin_space='lin', epsilon=1e-10, num_samples=1e5, num_bins=2, bnd_cond=0,
