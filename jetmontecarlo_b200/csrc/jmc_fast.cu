@@ -37,16 +37,19 @@ namespace jmc {
 
 static constexpr int kFastThreads = 256;
 static constexpr int kQueueFields = 5, kQueueSlots = 64;   // per-warp compaction queue (see run_fast_kernel)
-// resident blocks per SM the register allocation must allow: 3 x 256 threads = 24 warps (<= 80 registers): measured fastest (2..6 blocks differ by < 5 %).
+// resident blocks per SM the register allocation must allow: 2 x 256 threads (<= 128 registers, 16-32 resident warps): measured fastest with pinned parameters and 4 samples per trip.
 // The rarely executed running-coupling radiator code may spill; the per-sample light path must not.
 #ifndef JMC_FAST_MIN_BLOCKS
-#define JMC_FAST_MIN_BLOCKS 3
+#define JMC_FAST_MIN_BLOCKS 2
 #endif
 #ifndef JMC_FAST_UNROLL
-#define JMC_FAST_UNROLL 2        // samples per loop trip
+#define JMC_FAST_UNROLL 4        // samples per loop trip
 #endif
 #ifndef JMC_FAST_PIN_KEYS
 #define JMC_FAST_PIN_KEYS 1      // keep the Philox round keys in registers across the loop
+#endif
+#ifndef JMC_FAST_PIN_PARAMS
+#define JMC_FAST_PIN_PARAMS 1    // keep the per-sample parameters in registers across the loop
 #endif
 #define JMC_LN2F 0.69314718055994531f
 #define JMC_INV_LN2F 1.4426950408889634f
@@ -389,10 +392,21 @@ __device__ __forceinline__ int bin_fast(const FastParams& P, float l2obs, const 
 // generic instantiation reads those choices from FastParams at run time.
 template <int KIND, bool FIXED, bool OBS_MLL, bool HOT>
 __device__ __forceinline__ void
-fast_body(const FastParams& P, uint64_t n, uint64_t seed, uint64_t first, const float* __restrict__ g_edges,
+fast_body(const FastParams& P_in, uint64_t n, uint64_t seed, uint64_t first, const float* __restrict__ g_edges,
           double* __restrict__ g_sum_w, double* __restrict__ g_sum_w2, unsigned long long* __restrict__ g_count,
           int* g_poison, double* __restrict__ d_minmax, double* s_raw) {
     __shared__ int s_poison;
+    // The per-sample code reads ~17 parameters.  Left alone the compiler reloads them from the constant bank
+    // (or shared memory, in the batch kernel) in every trip -- 8 issue slots per sample; a local copy whose hot
+    // fields are made opaque stays in registers for the whole loop.
+    FastParams P = P_in;
+#if JMC_FAST_PIN_PARAMS
+#define JMC_PIN(x) asm volatile("" : "+f"(x))
+    JMC_PIN(P.sL2); JMC_PIN(P.l2w_cz); JMC_PIN(P.l2R); JMC_PIN(P.zc); JMC_PIN(P.beta); JMC_PIN(P.c0);
+    JMC_PIN(P.omf_zcl); JMC_PIN(P.one_m); JMC_PIN(P.l2_onorm); JMC_PIN(P.lnPT); JMC_PIN(P.lnMZ); JMC_PIN(P.ca);
+    JMC_PIN(P.l2tc_min); JMC_PIN(P.inv_d); JMC_PIN(P.mb0_inv_d); JMC_PIN(P.e_first); JMC_PIN(P.e_last);
+#undef JMC_PIN
+#endif
     const int ne = P.n_edges, nb = ne > 0 ? ne - 1 : 0;
     double* s_sum_w = s_raw;
     double* s_sum_w2 = s_sum_w + nb;
@@ -448,6 +462,7 @@ fast_body(const FastParams& P, uint64_t n, uint64_t seed, uint64_t first, const 
     };
     // everything after the draw for one sample: min/max, bin, count, weight (directly or through the queue)
     auto handle = [&](const Draw& d, float l2obs, bool active, bool valid) {
+        // `valid` is a compile-time true in the main loop (see below) and a run-time flag only in the tail trip
         if (do_minmax && valid) {
             mn = fminf(mn, l2obs);
             mx = fmaxf(mx, l2obs);
@@ -458,10 +473,14 @@ fast_body(const FastParams& P, uint64_t n, uint64_t seed, uint64_t first, const 
         // dropped samples count into a per-lane dummy slot behind the bins: no branch around the atomic, and no
         // same-address serialisation among the lanes that miss
         atomicAdd(&s_count[b >= 0 ? b : nb + (int)lane], 1u);
-        const float v = (HOT || P.dom_log) ? l2obs : ex2(l2obs);
-        const int bq = b >= 0 ? b : (v < P.e_first ? -1 : -2);
+        // bin for the weight, or -1 / -2 for a sample below / above the binned range (NaN poisoning only); needed
+        // for the few samples that reach a weight, so it is formed inside those branches
+        auto bq_of = [&]() {
+            const float v = (HOT || P.dom_log) ? l2obs : ex2(l2obs);
+            return b >= 0 ? b : (v < P.e_first ? -1 : -2);
+        };
         if (COMPACT) {
-            if (!P.nan_to_num && !active && valid) accumulate(fnan(), bq);   // inactive = "the reference weight is NaN"
+            if (!P.nan_to_num && !active && valid) accumulate(fnan(), bq_of());   // inactive = "the reference weight is NaN"
             const unsigned m = __ballot_sync(0xffffffffu, active);
             if (m) {
                 if (active) {
@@ -470,7 +489,7 @@ fast_body(const FastParams& P, uint64_t n, uint64_t seed, uint64_t first, const 
                     q[1 * kQueueSlots + slot] = d.l2tc;
                     q[2 * kQueueSlots + slot] = d.l2zs;
                     q[3 * kQueueSlots + slot] = d.l2ts;
-                    q[4 * kQueueSlots + slot] = __int_as_float(bq);
+                    q[4 * kQueueSlots + slot] = __int_as_float(bq_of());
                 }
                 qn += __popc(m);
                 __syncwarp();
@@ -481,9 +500,9 @@ fast_body(const FastParams& P, uint64_t n, uint64_t seed, uint64_t first, const 
                 }
             }
         } else if (active) {
-            accumulate(heavy<KIND, FIXED>(P, d), bq);
+            accumulate(heavy<KIND, FIXED>(P, d), bq_of());
         } else if (!FIXED && !P.nan_to_num && valid) {
-            accumulate(fnan(), bq);                      // inactive under running coupling = NaN weight
+            accumulate(fnan(), bq_of());                 // inactive under running coupling = NaN weight
         }
     };
 
@@ -496,17 +515,28 @@ fast_body(const FastParams& P, uint64_t n, uint64_t seed, uint64_t first, const 
     keys.pin();
 #endif
     constexpr int U = JMC_FAST_UNROLL;
-    const uint32_t my_trips = (iters + (uint32_t)(U - 1)) / (uint32_t)U;
-    const uint32_t trips = __shfl_sync(0xffffffffu, my_trips, 0);
     const uint64_t strideU = (uint64_t)U * stride;
-    for (uint32_t j = 0; j < trips; ++j, idx += strideU) {
+    // Main loop: trips in which every lane of the warp has all U samples (no validity tests); then at most two
+    // checked trips for the ragged end.  Lanes of a warp differ by at most one sample (consecutive tid).
+    const uint32_t full = __shfl_sync(0xffffffffu, iters, 31) / (uint32_t)U;
+    const uint32_t trips = (__shfl_sync(0xffffffffu, iters, 0) + (uint32_t)(U - 1)) / (uint32_t)U;
+    for (uint32_t j = 0; j < full; ++j, idx += strideU) {
         Draw d[U];
         float o[U];
         bool a[U];
 #pragma unroll
         for (int k = 0; k < U; ++k) a[k] = light<KIND, FIXED, OBS_MLL>(P, idx + (uint64_t)k * stride, keys, d[k], o[k]);
 #pragma unroll
-        for (int k = 0; k < U; ++k) handle(d[k], o[k], a[k], (uint32_t)U * j + (uint32_t)k < iters);
+        for (int k = 0; k < U; ++k) handle(d[k], o[k], a[k], true);
+    }
+    for (uint32_t j = full; j < trips; ++j, idx += strideU) {
+#pragma unroll 1
+        for (int k = 0; k < U; ++k) {
+            Draw d;
+            float o;
+            const bool a = light<KIND, FIXED, OBS_MLL>(P, idx + (uint64_t)k * stride, keys, d, o);
+            handle(d, o, a, (uint32_t)U * j + (uint32_t)k < iters);
+        }
     }
     if (COMPACT && do_hist) {
         __syncwarp();

@@ -298,7 +298,9 @@ def test_full_size_properties(cuda):
         rr = H.run(ig, c, 5, edges, 'f32', first=first, accumulate_into=acc)
         acc = (rr['sum_w'], rr['sum_w2'], rr['count'])
     assert_array_equal(acc[2].cpu().numpy(), cnt)
-    assert_allclose(acc[0].cpu().numpy(), r['sum_w'].cpu().numpy(), rtol=1e-9)
+    # (the main loop and the ragged-end trips are separate instantiations of the FP32 code, so a sample that
+    # changes position between them may change its weight in the last place: 1e-7 relative on a few samples)
+    assert_allclose(acc[0].cpu().numpy(), r['sum_w'].cpu().numpy(), rtol=1e-7)
     big = fused.integrate(ig, n, edges=edges, seed=5, precision='f32', last_bc=[1., 'minus'])
     small = fused.integrate(ig, n // 100, edges=edges, seed=6, precision='f32', last_bc=[1., 'minus'])
     integ = np.asarray(big.integral)
