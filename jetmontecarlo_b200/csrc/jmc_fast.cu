@@ -35,7 +35,8 @@
 
 namespace jmc {
 
-static constexpr int kFastThreads = 256;
+static constexpr int kFastThreads = 256, kFastThreadsBig = 1024;
+static constexpr size_t kBigSmemThreshold = 72 * 1024;     // block histograms above this use the 1024-thread kernels
 static constexpr int kQueueFields = 5, kQueueSlots = 64;   // per-warp compaction queue (see run_fast_kernel)
 // resident blocks per SM the register allocation must allow: 2 x 256 threads (<= 128 registers, 16-32 resident warps): measured fastest with pinned parameters and 4 samples per trip.
 // The rarely executed running-coupling radiator code may spill; the per-sample light path must not.
@@ -582,8 +583,10 @@ fast_body(const FastParams& P_in, uint64_t n, uint64_t seed, uint64_t first, con
 }
 
 // one job: parameters in the constant bank
-template <int KIND, bool FIXED, bool OBS_MLL, bool HOT>
-__global__ void __launch_bounds__(kFastThreads, JMC_FAST_MIN_BLOCKS)
+// BIG: 1024-thread blocks, one per SM, for histograms that need most of an SM's shared memory (the reference's
+// default of 5000 radiator bins is 130 KB per block): 32 warps then share one histogram instead of 8.
+template <int KIND, bool FIXED, bool OBS_MLL, bool HOT, bool BIG>
+__global__ void __launch_bounds__(BIG ? kFastThreadsBig : kFastThreads, BIG ? 1 : JMC_FAST_MIN_BLOCKS)
 run_fast_kernel(FastParams P, uint64_t n, uint64_t seed, uint64_t first, const float* __restrict__ g_edges,
                 double* __restrict__ g_sum_w, double* __restrict__ g_sum_w2,
                 unsigned long long* __restrict__ g_count, int* g_poison, double* __restrict__ d_minmax) {
@@ -595,8 +598,8 @@ run_fast_kernel(FastParams P, uint64_t n, uint64_t seed, uint64_t first, const f
 // generation.py:303-359, z_cut / beta sweeps): blockIdx.y selects the point, its parameters are staged in shared
 // memory, and every point regenerates the same sample stream -- the reference re-weights one stored sample set
 // per grid point, here the "stored set" is the counter RNG.
-template <int KIND, bool FIXED, bool OBS_MLL, bool HOT>
-__global__ void __launch_bounds__(kFastThreads, JMC_FAST_MIN_BLOCKS)
+template <int KIND, bool FIXED, bool OBS_MLL, bool HOT, bool BIG>
+__global__ void __launch_bounds__(BIG ? kFastThreadsBig : kFastThreads, BIG ? 1 : JMC_FAST_MIN_BLOCKS)
 run_fast_batch_kernel(const FastParams* __restrict__ params, uint64_t n, uint64_t seed, uint64_t first,
                       const float* __restrict__ edges_all, int n_edges, double* __restrict__ sum_w_all,
                       double* __restrict__ sum_w2_all, unsigned long long* __restrict__ count_all, int* poison_all,
@@ -782,34 +785,36 @@ static int make_fast_params(const jmc_integrand* g, const double* h_edges, int n
     return JMC_OK;
 }
 
-static size_t fast_smem_bytes(int n_edges) {
+static size_t fast_smem_bytes(int n_edges, int threads = kFastThreads) {
     const size_t nb = n_edges > 0 ? (size_t)n_edges - 1 : 0;
     const size_t ne_pad = ((size_t)(n_edges > 0 ? n_edges : 0) + 3) & ~(size_t)3;
     return sizeof(double) * 2 * nb + sizeof(unsigned int) * (nb + 32) + sizeof(float) * ne_pad
-           + sizeof(float) * (kFastThreads / 32) * kQueueFields * kQueueSlots;
+           + sizeof(float) * (threads / 32) * kQueueFields * kQueueSlots;
 }
 
-template <int KIND, bool FIXED, bool OBS_MLL, bool HOT>
+template <int KIND, bool FIXED, bool OBS_MLL, bool HOT, bool BIG>
 static int launch_fast_t(const FastParams& P, uint64_t n, uint64_t seed, uint64_t first, const float* d_edges_f,
                        double* d_sum_w, double* d_sum_w2, uint64_t* d_count, int* d_poison, double* d_minmax,
                        cudaStream_t st) {
     DeviceInfo di;
     if (device_info(&di)) return JMC_ENODEV;
-    const size_t smem = fast_smem_bytes(d_edges_f ? P.n_edges : 0);
+    constexpr int threads = BIG ? kFastThreadsBig : kFastThreads;
+    const size_t smem = fast_smem_bytes(d_edges_f ? P.n_edges : 0, threads);
     if (smem > (size_t)di.max_smem_optin)
         return set_error(JMC_ELIMIT, "jmc_run: %d edges need %zu B of shared memory (limit %d B)", P.n_edges, smem,
                          di.max_smem_optin);
-    JMC_CUDA(cudaFuncSetAttribute(run_fast_kernel<KIND, FIXED, OBS_MLL, HOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    auto kern = run_fast_kernel<KIND, FIXED, OBS_MLL, HOT, BIG>;
+    JMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    JMC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, run_fast_kernel<KIND, FIXED, OBS_MLL, HOT>, kFastThreads, smem));
+    JMC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
     if (per_sm < 1) per_sm = 1;
-    uint64_t want = (n + kFastThreads - 1) / kFastThreads;
+    uint64_t want = (n + threads - 1) / threads;
     const uint64_t cap = (uint64_t)di.sm_count * per_sm;      // persistent: one wave of resident blocks
     const int grid = (int)(want < cap ? want : cap);
     FastParams Q = P;
     if (!d_edges_f) Q.n_edges = 0;
-    run_fast_kernel<KIND, FIXED, OBS_MLL, HOT><<<grid, kFastThreads, smem, st>>>(Q, n, seed, first, d_edges_f, d_sum_w, d_sum_w2,
-                                                             (unsigned long long*)d_count, d_poison, d_minmax);
+    kern<<<grid, threads, smem, st>>>(Q, n, seed, first, d_edges_f, d_sum_w, d_sum_w2, (unsigned long long*)d_count,
+                                      d_poison, d_minmax);
     JMC_LAUNCHED("run_fast_kernel");
     return JMC_OK;
 }
@@ -819,9 +824,10 @@ static int launch_fast(const FastParams& P, uint64_t n, uint64_t seed, uint64_t 
                        double* d_sum_w, double* d_sum_w2, uint64_t* d_count, int* d_poison, double* d_minmax,
                        cudaStream_t st) {
     const bool hot = d_edges_f != nullptr && d_minmax == nullptr && P.dom_log && P.uniform;
-#define JMC_GO(M, H) launch_fast_t<KIND, FIXED, M, H>(P, n, seed, first, d_edges_f, d_sum_w, d_sum_w2, d_count, d_poison, d_minmax, st)
-    if (P.obs_mll) return hot ? JMC_GO(true, true) : JMC_GO(true, false);
-    return hot ? JMC_GO(false, true) : JMC_GO(false, false);
+    const bool big = hot && fast_smem_bytes(P.n_edges) > kBigSmemThreshold;
+#define JMC_GO(M, H, B) launch_fast_t<KIND, FIXED, M, H, B>(P, n, seed, first, d_edges_f, d_sum_w, d_sum_w2, d_count, d_poison, d_minmax, st)
+    if (P.obs_mll) return hot ? (big ? JMC_GO(true, true, true) : JMC_GO(true, true, false)) : JMC_GO(true, false, false);
+    return hot ? (big ? JMC_GO(false, true, true) : JMC_GO(false, true, false)) : JMC_GO(false, false, false);
 #undef JMC_GO
 }
 
@@ -891,31 +897,32 @@ __global__ void poison_batch_kernel(const int* poison_all, int nb, double* sum_w
     }
 }
 
-template <int KIND, bool FIXED, bool OBS_MLL, bool HOT>
+template <int KIND, bool FIXED, bool OBS_MLL, bool HOT, bool BIG>
 static int launch_fast_batch_t(const FastParams* d_params, int n_points, int n_edges, uint64_t n, uint64_t seed,
                                uint64_t first, const float* d_edges_f, double* d_sum_w, double* d_sum_w2,
                                uint64_t* d_count, int* d_poison, double* d_minmax, cudaStream_t st) {
     DeviceInfo di;
     if (device_info(&di)) return JMC_ENODEV;
-    const size_t smem = fast_smem_bytes(d_edges_f ? n_edges : 0);
+    constexpr int threads = BIG ? kFastThreadsBig : kFastThreads;
+    const size_t smem = fast_smem_bytes(d_edges_f ? n_edges : 0, threads);
     if (smem > (size_t)di.max_smem_optin)
         return set_error(JMC_ELIMIT, "jmc_run_batch: %d edges need %zu B of shared memory (limit %d B)", n_edges, smem,
                          di.max_smem_optin);
-    auto kern = run_fast_batch_kernel<KIND, FIXED, OBS_MLL, HOT>;
+    auto kern = run_fast_batch_kernel<KIND, FIXED, OBS_MLL, HOT, BIG>;
     JMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    JMC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kFastThreads, smem));
+    JMC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
     if (per_sm < 1) per_sm = 1;
     const uint64_t cap = (uint64_t)di.sm_count * per_sm;
     // enough blocks for ~8 full waves (the tail wave then costs little), but at least ~128 samples per thread so
     // that zeroing and flushing the block histogram stays negligible
     uint64_t per_point = (8 * cap + (uint64_t)n_points - 1) / (uint64_t)n_points;
-    const uint64_t most = n / ((uint64_t)kFastThreads * 128);
+    const uint64_t most = n / ((uint64_t)threads * 128);
     if (per_point > most) per_point = most;
     if (per_point < 1) per_point = 1;
     dim3 grid((unsigned)per_point, (unsigned)n_points);
-    kern<<<grid, kFastThreads, smem, st>>>(d_params, n, seed, first, d_edges_f, n_edges, d_sum_w, d_sum_w2,
-                                           (unsigned long long*)d_count, d_poison, d_minmax);
+    kern<<<grid, threads, smem, st>>>(d_params, n, seed, first, d_edges_f, n_edges, d_sum_w, d_sum_w2,
+                                      (unsigned long long*)d_count, d_poison, d_minmax);
     JMC_LAUNCHED("run_fast_batch_kernel");
     return JMC_OK;
 }
@@ -960,8 +967,12 @@ int run_fast_batch(const jmc_integrand* g, int n_points, uint64_t n, uint64_t se
     JMC_CUDA(cudaMemsetAsync(d_poison, 0x7f, sizeof(int) * (size_t)n_points, st));
     JMC_CUDA(cudaStreamSynchronize(st));           // the staging vectors die at return
     const bool mll = g[0].obs_acc == JMC_ACC_MLL, fixed = g[0].fixed_coupling != 0;
-#define JMC_B(K, F, M, H) \
-    rc = launch_fast_batch_t<K, F, M, H>(d_params, n_points, n_edges, n, seed, first_index, d_edges_f, d_sum_w, d_sum_w2, d_count, d_poison, d_minmax, st)
+    const bool big = hot && fast_smem_bytes(n_edges) > kBigSmemThreshold;
+#define JMC_B(K, F, M, H)                                                                                              \
+    rc = (H && big) ? launch_fast_batch_t<K, F, M, H, H>(d_params, n_points, n_edges, n, seed, first_index, d_edges_f, \
+                                                         d_sum_w, d_sum_w2, d_count, d_poison, d_minmax, st)             \
+                    : launch_fast_batch_t<K, F, M, H, false>(d_params, n_points, n_edges, n, seed, first_index,         \
+                                                             d_edges_f, d_sum_w, d_sum_w2, d_count, d_poison, d_minmax, st)
 #define JMC_BK(K)                                                              \
     do {                                                                       \
         if (fixed) { if (mll) { if (hot) JMC_B(K, true, true, true); else JMC_B(K, true, true, false); }     \
