@@ -24,6 +24,7 @@
 // compiled with --fmad=false (shared flag of the NumPy-order translation units)
 #include <climits>
 #include <cmath>
+#include <type_traits>
 #include <vector>
 #include "jmc_common.cuh"
 #include "jmc_philox.cuh"
@@ -41,6 +42,10 @@ struct ShowerParams {
     double alpha;          // alpha_fixed (LL) or the veto overestimate 1.5 (MLL)
     double kfac;           // pi beta / (C_R alpha)
     double cr;
+    double ang_init;       // R^beta / 2
+    float lf_init;         // ln(2 ang_init) = beta ln R
+    BinGuess guess;        // affine first guess of the bin (exact walk decides); mode 0 = binary search
+    int guess_offset;      // the guess describes edges[guess_offset:] (a leading zero-bin edge is skipped)
 };
 
 // sequential uniforms of one jet: block b of the jet's Philox stream yields uniforms 2b, 2b+1
@@ -59,31 +64,37 @@ struct UStream {
     }
 };
 
-// running top-N / sum of the chain's ECFs, in the order the reference adds them
+// running top-N / sum of the chain's ECFs, in the order the reference adds them.  T = double in the FP64 mode
+// (bit-for-bit the reference's sums); T = float in the FP32 mode, where the reference's 1e-50 place holders
+// (below FP32 range) are carried as 0 and restored when the result is formed.
+template <typename T>
 struct EcfAcc {
-    double top[kTopN];   // largest values seen, descending (ungroomed: all; soft drop: the ones after the first kept)
-    double sum_all;      // running sum in chain order
-    double first;        // soft drop: the critical emission's value
+    T top[kTopN];        // largest values seen, descending (ungroomed: all; soft drop: the ones after the first kept)
+    T sum_all;           // running sum in chain order
+    T first;             // soft drop: the critical emission's value
     bool dropping;       // soft drop: still below the grooming condition
-    int n;
+    static __device__ __forceinline__ T tiny() { return sizeof(T) == 8 ? (T)1e-50 : (T)0; }
+    static __device__ __forceinline__ double wide(T v) { return (sizeof(T) == 4 && v == (T)0) ? 1e-50 : (double)v; }
     __device__ __forceinline__ void reset(int groomer) {
 #pragma unroll
-        for (int k = 0; k < kTopN; ++k) top[k] = -1.0;
+        for (int k = 0; k < kTopN; ++k) top[k] = (T)-1;
         // getECFs_ungroomed starts its list with 1e-50 (:459); soft drop appends its two 1e-50 at the end
-        sum_all = groomer ? 0.0 : 1e-50;
-        first = -1.0;
+        sum_all = groomer ? (T)0 : tiny();
+        first = (T)-1;
         dropping = true;
-        n = 0;
-        if (!groomer) insert(1e-50);
+        if (!groomer) insert(tiny());
     }
-    __device__ __forceinline__ void insert(double c) {
+    // branch-free insertion into the descending top-N (a bubble of max/min pairs)
+    __device__ __forceinline__ void insert(T c) {
 #pragma unroll
         for (int k = 0; k < kTopN; ++k) {
-            if (c > top[k]) { const double t = top[k]; top[k] = c; c = t; }
+            const T hi = c > top[k] ? c : top[k];
+            c = c > top[k] ? top[k] : c;
+            top[k] = hi;
         }
     }
-    __device__ __forceinline__ void add(double c, double z, double theta, const ShowerParams& p) {
-        if (!p.groomer) {                      // ref: partonshower_utils.py:445-499
+    __device__ __forceinline__ void add(T c, bool passes_groomer, int groomer) {
+        if (!groomer) {                        // ref: partonshower_utils.py:445-499
             insert(c);
             sum_all += c;
             return;
@@ -91,7 +102,7 @@ struct EcfAcc {
         // ref: partonshower_utils.py:676-790: the first emission with z > z_cut theta^beta_sd is critical,
         // every later one is subsequent
         if (dropping) {
-            if (!(z > p.z_cut * np_pow(theta, p.beta_sd))) return;
+            if (!passes_groomer) return;
             dropping = false;
             first = c;
             sum_all = c;
@@ -102,9 +113,9 @@ struct EcfAcc {
     }
     __device__ __forceinline__ double result(const ShowerParams& p) {
         if (!p.groomer) {
-            if (p.n_emissions == 0) return sum_all;
+            if (p.n_emissions == 0) return (double)sum_all + (sizeof(T) == 4 ? 1e-50 : 0.0);
             double s = 0.0;                    // sum(cs[:n]) over the descending list
-            for (int k = 0; k < kTopN && k < p.n_emissions; ++k) if (top[k] >= 0.0) s += top[k];
+            for (int k = 0; k < kTopN && k < p.n_emissions; ++k) if (top[k] >= (T)0) s += wide(top[k]);
             return s;
         }
         // c_list += [1e-50, 1e-50]
@@ -115,12 +126,12 @@ struct EcfAcc {
             for (int k = 1; k < p.n_emissions && k < 2; ++k) s += 1e-50;
             return s;
         }
-        if (p.n_emissions == 0) return (sum_all + 1e-50) + 1e-50;
-        if (p.n_emissions == 1) return first;
-        insert(1e-50);
-        insert(1e-50);
-        double s = first;                      // sum([c0] + rest[:n-1])
-        for (int k = 0; k < kTopN && k < p.n_emissions - 1; ++k) if (top[k] >= 0.0) s += top[k];
+        if (p.n_emissions == 0) return ((double)sum_all + 1e-50) + 1e-50;
+        if (p.n_emissions == 1) return (double)first;
+        insert(tiny());
+        insert(tiny());
+        double s = (double)first;              // sum([c0] + rest[:n-1])
+        for (int k = 0; k < kTopN && k < p.n_emissions - 1; ++k) if (top[k] >= (T)0) s += wide(top[k]);
         return s;
     }
 };
@@ -158,10 +169,19 @@ shower_kernel(ShowerParams p, uint64_t n, uint64_t seed, uint64_t first, const d
     uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     double mn = INFINITY, mx = -INFINITY;
 
+    // launch constants of the FP32 mode
+    const float kfac_f = (float)p.kfac, inv_beta_f = (float)(1.0 / p.beta), ln_cut_f = (float)log(p.cutoff);
+    const float beta_f = (float)p.beta, beta_sd_f = (float)p.beta_sd;
+    const float ln_zcut_f = p.z_cut > 0.0 ? (float)log(p.z_cut) : -INFINITY;
+    const float lnPT_f = (float)log(JMC_PT), lnMZ_f = (float)log(JMC_MZ), ca_f = (float)(2.0 * JMC_ALPHA_MZ * JMC_BETA0);
+    const float veto_norm_f = (float)(1.0 / (2.0 * p.cr * p.alpha));
+
     // per-lane jet state
     UStream us;
-    EcfAcc acc;
+    EcfAcc<typename std::conditional<EXACT, double, float>::type> acc;
     double ang = 0.0, z = 0.0, theta = 0.0;
+    float zf = 0.5f, lnz = 0.0f, lnth = 0.0f;   // FP32 mode: the last trial's z, ln z, ln theta
+    const PhiloxKeys keys(seed);
     float lf = 0.0f;                            // FP32 mode: ln(2 ang)
     int n_em = 0, n_trials = 0;
     uint32_t blk32 = 0u;
@@ -170,25 +190,27 @@ shower_kernel(ShowerParams p, uint64_t n, uint64_t seed, uint64_t first, const d
     auto start_jet = [&]() {
         us.reset(first + j, seed);
         acc.reset(p.groomer);
-        ang = pow(p.radius, p.beta) / 2.0;     // ang_init = R^beta / 2, z_init = 1/2, theta_init = R (:316-321)
-        lf = (float)(p.beta * log(p.radius));
+        ang = p.ang_init;                       // ang_init = R^beta / 2, z_init = 1/2, theta_init = R (:316-321)
+        lf = p.lf_init;
         z = 0.5;
         theta = p.radius;
+        zf = 0.5f;
+        lnz = -0.69314718f;
+        lnth = lf * inv_beta_f;                 // ln R
         n_em = 0;
         n_trials = 0;
         blk32 = 0u;
         in_veto_loop = false;
     };
     if (alive) start_jet();
-    const float kfac_f = (float)p.kfac, inv_beta_f = (float)(1.0 / p.beta), ln_cut_f = (float)log(p.cutoff);
-    const float lnPT_f = (float)log(JMC_PT), lnMZ_f = (float)log(JMC_MZ), ca_f = (float)(2.0 * JMC_ALPHA_MZ * JMC_BETA0);
-    const float veto_norm_f = (float)(1.0 / (2.0 * p.cr * p.alpha));
 
     while (__any_sync(0xffffffffu, alive)) {
         if (!alive) continue;
         // does the chain continue?  (angularity_shower: recurse while z theta > cutoff, :262-279).  The cutoff is
         // tested on ACCEPTED emissions only: inside angularity_split the veto loop keeps trying without it (:188-209)
-        bool finished = in_veto_loop ? false : (!(z * theta > p.cutoff) || n_em >= kMaxEmissions);
+        bool finished;
+        if (EXACT) finished = in_veto_loop ? false : (!(z * theta > p.cutoff) || n_em >= kMaxEmissions);
+        else finished = in_veto_loop ? false : (!(lnz + lnth > ln_cut_f) || n_em >= kMaxEmissions);
         if (!finished) {
             bool accepted;
             ++n_trials;
@@ -197,15 +219,13 @@ shower_kernel(ShowerParams p, uint64_t n, uint64_t seed, uint64_t first, const d
             } else {
                 // FP32: l' = -sqrt(l^2 - K ln r1); ln z = r2 l' - ln 2; ln theta = (1 - r2) l' / beta
                 uint32_t r[4];
-                philox4x32_10(first + j, blk32++, seed, r);
+                philox4x32_10(first + j, blk32++, keys, r);
                 const float r1 = u32_to_unit_float(r[0]), r2 = u32_to_unit_float(r[1]), r3 = u32_to_unit_float(r[2]);
                 const float lp = -sqrtf(fmaf(lf, lf, -kfac_f * __logf(r1)));
-                const float lnz = fmaf(r2, lp, -0.69314718f);
-                const float lnth = (1.0f - r2) * lp * inv_beta_f;
+                lnz = fmaf(r2, lp, -0.69314718f);
+                lnth = (1.0f - r2) * lp * inv_beta_f;
                 lf = lp;
-                const float zf = __expf(lnz);
-                z = (double)zf;
-                theta = (double)__expf(lnth);
+                zf = __expf(lnz);
                 accepted = true;
                 if (p.mll_shower) {
                     const float alpha = 0.118f / (1.0f + ca_f * (fmaxf(lnPT_f + lnz + lnth, 0.0f) - lnMZ_f));
@@ -228,7 +248,15 @@ shower_kernel(ShowerParams p, uint64_t n, uint64_t seed, uint64_t first, const d
             in_veto_loop = !accepted;
             if (accepted) {
                 ++n_em;
-                acc.add(ecf_ungroomed(z, theta, p.beta, p.obs_mll ? JMC_ACC_MLL : JMC_ACC_LL), z, theta, p);
+                if (EXACT) {
+                    acc.add(ecf_ungroomed(z, theta, p.beta, p.obs_mll ? JMC_ACC_MLL : JMC_ACC_LL),
+                            z > p.z_cut * np_pow(theta, p.beta_sd), p.groomer);
+                } else {
+                    // C = z theta^beta [(1 - z)], grooming condition ln z > ln z_cut + beta_sd ln theta
+                    float c = __expf(fmaf(beta_f, lnth, lnz));
+                    if (p.obs_mll) c *= 1.0f - zf;
+                    acc.add(c, lnz > fmaf(beta_sd_f, lnth, ln_zcut_f), p.groomer);
+                }
             }
             continue;
         }
@@ -238,7 +266,14 @@ shower_kernel(ShowerParams p, uint64_t n, uint64_t seed, uint64_t first, const d
         if (dump_n) dump_n[j] = n_em;
         if (dump_trials) dump_trials[j] = n_trials;
         if (n_edges > 0) {
-            const int b = bin_index(obs, s_edges, n_edges);
+            // the jets' bins: np.logspace edges, usually behind one zero-bin edge (plot_comparisons.py:296-298)
+            int b;
+            if (p.guess.mode == 0 || obs < s_edges[p.guess_offset]) {
+                b = bin_index(obs, s_edges, n_edges);
+            } else {
+                b = bin_index_guided(obs, s_edges + p.guess_offset, n_edges - p.guess_offset, p.guess);
+                if (b >= 0) b += p.guess_offset;
+            }
             if (b >= 0) atomicAdd(&s_count[b], 1u);
         }
         mn = fmin(mn, obs);
@@ -304,8 +339,29 @@ static int make_shower_params(const jmc_integrand* g, ShowerParams* out) {
     p.cr = g->jet == JMC_QUARK ? JMC_CF : JMC_CA;
     p.alpha = p.mll_shower ? JMC_ALPHA_VETO : JMC_ALPHA_FIXED;
     p.kfac = JMC_PI * g->beta / (p.cr * p.alpha);
+    p.ang_init = std::pow(g->radius, g->beta) / 2.0;
+    p.lf_init = (float)(g->beta * std::log(g->radius));
+    p.guess = BinGuess{0, 0.f, 0.f};
+    p.guess_offset = 0;
     *out = p;
     return JMC_OK;
+}
+
+// log-uniform edges (possibly after a first zero-bin edge) get an affine first guess
+static void shower_bin_guess(const std::vector<double>& e, ShowerParams* p) {
+    const int ne = (int)e.size();
+    for (int off = 0; off <= 1; ++off) {
+        const int m = ne - off;
+        if (m < 8 || !(e[off] > 1e-30 && e[ne - 1] < 1e30)) continue;
+        const double b0 = std::log2(e[off]), d = (std::log2(e[ne - 1]) - b0) / (m - 1);
+        bool ok = d > 0.0 && std::isfinite(d);
+        for (int k = 0; ok && k < m; ++k) ok = std::fabs(std::log2(e[off + k]) - (b0 + k * d)) < 0.25 * d;
+        if (ok) {
+            p->guess = BinGuess{2, (float)b0, (float)(1.0 / d)};
+            p->guess_offset = off;
+            return;
+        }
+    }
 }
 
 static int shower_launch(const jmc_integrand* g, uint64_t n, uint64_t seed, uint64_t first_index, int precision,
@@ -323,6 +379,12 @@ static int shower_launch(const jmc_integrand* g, uint64_t n, uint64_t seed, uint
     if (n == 0) return JMC_OK;
     DeviceInfo di;
     if (device_info(&di)) return JMC_ENODEV;
+    if (n_edges >= 8 && n >= (1u << 16)) {
+        std::vector<double> e(n_edges);
+        JMC_CUDA(cudaMemcpyAsync(e.data(), d_edges, sizeof(double) * n_edges, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+        JMC_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+        shower_bin_guess(e, &p);
+    }
     const size_t nb = n_edges > 0 ? (size_t)n_edges - 1 : 0;
     const size_t smem = sizeof(double) * (size_t)n_edges + sizeof(unsigned int) * nb;
     if (smem > (size_t)di.max_smem_optin)
