@@ -75,7 +75,7 @@ class ClockSampler:
         self.rows, self.proc = [], None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(gpu_index)], stdout=subprocess.PIPE,
+                                          "-lms", "20", "-i", str(gpu_index)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -179,9 +179,9 @@ def run_reference_arm(args):
 
 def cpu_baseline_quick():
     """single-thread port of the reference path on a bounded sample (~10-20 s)"""
-    n = 150000
+    n = 1000000          # SURVEY 8(d): the full reference path at N = 1e6 (about 8 s) ...
     _, _, _, t_loop = _cpu_chunk((n, 42, True))
-    nv = 2000000
+    nv = 10000000        # ... and its vectorised stage alone at N = 1e7 (about 6 s)
     _, _, _, t_vec = _cpu_chunk((nv, 43, False))
     return {"value": n / t_loop, "unit": UNIT, "cores": 1, "kind": "port",
             "sample": "%d C3 samples, single thread: Python-loop sampling (sampler.py:30-34 restated) + NumPy "

@@ -49,9 +49,6 @@ static constexpr int kQueueFields = 5, kQueueSlots = 64;   // per-warp compactio
 #ifndef JMC_FAST_PIN_KEYS
 #define JMC_FAST_PIN_KEYS 1      // keep the Philox round keys in registers across the loop
 #endif
-#ifndef JMC_FAST_PIN_PARAMS
-#define JMC_FAST_PIN_PARAMS 1    // keep the per-sample parameters in registers across the loop
-#endif
 #define JMC_LN2F 0.69314718055994531f
 #define JMC_INV_LN2F 1.4426950408889634f
 
@@ -397,17 +394,10 @@ fast_body(const FastParams& P_in, uint64_t n, uint64_t seed, uint64_t first, con
           double* __restrict__ g_sum_w, double* __restrict__ g_sum_w2, unsigned long long* __restrict__ g_count,
           int* g_poison, double* __restrict__ d_minmax, double* s_raw) {
     __shared__ int s_poison;
-    // The per-sample code reads ~17 parameters.  Left alone the compiler reloads them from the constant bank
-    // (or shared memory, in the batch kernel) in every trip -- 8 issue slots per sample; a local copy whose hot
-    // fields are made opaque stays in registers for the whole loop.
-    FastParams P = P_in;
-#if JMC_FAST_PIN_PARAMS
-#define JMC_PIN(x) asm volatile("" : "+f"(x))
-    JMC_PIN(P.sL2); JMC_PIN(P.l2w_cz); JMC_PIN(P.l2R); JMC_PIN(P.zc); JMC_PIN(P.beta); JMC_PIN(P.c0);
-    JMC_PIN(P.omf_zcl); JMC_PIN(P.one_m); JMC_PIN(P.l2_onorm); JMC_PIN(P.lnPT); JMC_PIN(P.lnMZ); JMC_PIN(P.ca);
-    JMC_PIN(P.l2tc_min); JMC_PIN(P.inv_d); JMC_PIN(P.mb0_inv_d); JMC_PIN(P.e_first); JMC_PIN(P.e_last);
-#undef JMC_PIN
-#endif
+    // (The ~17 per-sample parameters are re-read from the constant bank once per trip -- about 6 issue slots per
+    // sample.  Pinning them in registers through opaque inline asm does not survive ptxas, which rematerialises
+    // parameter loads; measured: no effect.)
+    const FastParams& P = P_in;
     const int ne = P.n_edges, nb = ne > 0 ? ne - 1 : 0;
     double* s_sum_w = s_raw;
     double* s_sum_w2 = s_sum_w + nb;
