@@ -289,6 +289,13 @@ int jmc_dump(const jmc_integrand* g, uint64_t n, uint64_t seed, uint64_t first_i
 int jmc_shower_dump(const jmc_integrand* g, uint64_t n, uint64_t seed, uint64_t first_index, int precision,
                     double* d_obs, int32_t* d_n_emissions, int32_t* d_n_trials, void* stream);
 
+/* The shower's event record on request: d_chains [n, max_emissions, 2] = (z, theta) of each accepted emission in
+ * emission order (entries beyond a jet's length are left untouched), d_n_emissions [n] (may exceed max_emissions;
+ * the record is then truncated).  With split_soft=False (partonshower_utils.py:321) this chain is the whole jet:
+ * the reference's Parton tree and 3-vectors are functions of it.  ref: utils/partonshower_utils.py:224-328 */
+int jmc_shower_chains(const jmc_integrand* g, uint64_t n, uint64_t seed, uint64_t first_index, int precision,
+                      int max_emissions, double* d_chains, int32_t* d_n_emissions, void* stream);
+
 /* density, error, cumulative integral (+ error) from the histograms.
  * ref: montecarlo/integrator.py:113-124 (density), :129-202 (integrate).
  * density, density_err, integral_err: n_edges-1; integral: n_edges. */

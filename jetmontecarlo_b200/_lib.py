@@ -30,7 +30,7 @@ ACCS = {'LL': ACC_LL, 'LL_nonsing': ACC_LL_NONSING, 'MLL': ACC_MLL}
 EXPORTS = (
     "jmc_abi_version", "jmc_last_error", "jmc_device_count", "jmc_set_device", "jmc_sm_count",
     "jmc_sampler_area", "jmc_integrand_uniforms", "jmc_integrand_area", "jmc_sample", "jmc_uniforms", "jmc_inverse_transform",
-    "jmc_eval_fn", "jmc_eval_integrand", "jmc_bin_index", "jmc_hist", "jmc_hist2d", "jmc_finalize2d", "jmc_minmax", "jmc_run", "jmc_run_batch", "jmc_finalize_batch", "jmc_dump", "jmc_shower_dump",
+    "jmc_eval_fn", "jmc_eval_integrand", "jmc_bin_index", "jmc_hist", "jmc_hist2d", "jmc_finalize2d", "jmc_minmax", "jmc_run", "jmc_run_batch", "jmc_finalize_batch", "jmc_dump", "jmc_shower_dump", "jmc_shower_chains",
     "jmc_finalize", "jmc_cumulative", "jmc_set_density_host", "jmc_integrate_host", "jmc_sample_host",
     "jmc_eval_fn_host", "jmc_launch_count",
 )
@@ -96,6 +96,7 @@ def _load():
         "jmc_finalize_batch": (i32, [i32, vp, vp, vp, vp, i32, vp, u64, i32, dbl, vp, vp, vp, vp, vp]),
         "jmc_dump": (i32, [P(Integrand), u64, u64, u64, i32, vp, vp, vp, vp]),
         "jmc_shower_dump": (i32, [P(Integrand), u64, u64, u64, i32, vp, vp, vp, vp]),
+        "jmc_shower_chains": (i32, [P(Integrand), u64, u64, u64, i32, i32, vp, vp, vp]),
         "jmc_finalize": (i32, [vp, vp, vp, vp, i32, dbl, u64, i32, dbl, vp, vp, vp, vp, vp]),
         "jmc_cumulative": (i32, [vp, vp, vp, i32, i32, dbl, vp, vp, vp]),
         "jmc_set_density_host": (i32, [vp, vp, u64, vp, i32, dbl, i32, dbl, vp, vp, vp, vp, vp, vp, vp]),

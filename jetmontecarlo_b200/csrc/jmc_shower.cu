@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(kShowerThreads)
 shower_kernel(ShowerParams p, uint64_t n, uint64_t seed, uint64_t first, const double* __restrict__ edges,
               int n_edges, unsigned long long* __restrict__ g_count, double* __restrict__ d_minmax,
               double* __restrict__ dump_obs, int* __restrict__ dump_n, int* __restrict__ dump_trials,
-              int* error_flag) {
+              double* __restrict__ dump_chain, int chain_cap, int* error_flag) {
     extern __shared__ double s_raw[];
     const int nb = n_edges > 0 ? n_edges - 1 : 0;
     double* s_edges = s_raw;
@@ -247,6 +247,11 @@ shower_kernel(ShowerParams p, uint64_t n, uint64_t seed, uint64_t first, const d
             }
             in_veto_loop = !accepted;
             if (accepted) {
+                if (dump_chain && n_em < chain_cap) {        // event record on request: (z, theta) of emission n_em
+                    double* c = dump_chain + ((size_t)j * chain_cap + n_em) * 2;
+                    c[0] = EXACT ? z : (double)zf;
+                    c[1] = EXACT ? theta : (double)__expf(lnth);
+                }
                 ++n_em;
                 if (EXACT) {
                     acc.add(ecf_ungroomed(z, theta, p.beta, p.obs_mll ? JMC_ACC_MLL : JMC_ACC_LL),
@@ -366,7 +371,8 @@ static void shower_bin_guess(const std::vector<double>& e, ShowerParams* p) {
 
 static int shower_launch(const jmc_integrand* g, uint64_t n, uint64_t seed, uint64_t first_index, int precision,
                          const double* d_edges, int n_edges, double* d_sum_w, double* d_sum_w2, uint64_t* d_count,
-                         double* d_minmax, double* d_obs, int* d_n_em, int* d_trials, void* stream) {
+                         double* d_minmax, double* d_obs, int* d_n_em, int* d_trials, void* stream,
+                         double* d_chain = nullptr, int chain_cap = 0) {
     ShowerParams p;
     int rc = make_shower_params(g, &p);
     if (rc) return rc;
@@ -404,12 +410,12 @@ static int shower_launch(const jmc_integrand* g, uint64_t n, uint64_t seed, uint
         JMC_CUDA(cudaFuncSetAttribute(shower_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         shower_kernel<true><<<grid, kShowerThreads, smem, st>>>(p, n, seed, first_index, d_edges, n_edges,
                                                                  (unsigned long long*)d_count, d_minmax, d_obs, d_n_em,
-                                                                 d_trials, d_err);
+                                                                 d_trials, d_chain, chain_cap, d_err);
     } else {
         JMC_CUDA(cudaFuncSetAttribute(shower_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         shower_kernel<false><<<grid, kShowerThreads, smem, st>>>(p, n, seed, first_index, d_edges, n_edges,
                                                                   (unsigned long long*)d_count, d_minmax, d_obs, d_n_em,
-                                                                  d_trials, d_err);
+                                                                  d_trials, d_chain, chain_cap, d_err);
     }
     JMC_LAUNCHED("shower_kernel");
     if (nb) {
@@ -442,4 +448,13 @@ extern "C" int jmc_shower_dump(const jmc_integrand* g, uint64_t n, uint64_t seed
     // the output arrays are indexed by the local jet number 0..n-1; jet i is stream index first_index + i
     return jmc::shower_launch(g, n, seed, first_index, precision, nullptr, 0, nullptr, nullptr, nullptr, nullptr, d_obs,
                               d_n_emissions, d_n_trials, stream);
+}
+
+extern "C" int jmc_shower_chains(const jmc_integrand* g, uint64_t n, uint64_t seed, uint64_t first_index, int precision,
+                                 int max_emissions, double* d_chains, int32_t* d_n_emissions, void* stream) {
+    JMC_REQUIRE(g != nullptr && g->kind == JMC_KIND_SHOWER, "jmc_shower_chains: integrand must be a shower");
+    JMC_REQUIRE(precision == JMC_F64 || precision == JMC_F32, "jmc_shower_chains: precision must be JMC_F64 or JMC_F32");
+    JMC_REQUIRE(max_emissions >= 1 && d_chains && d_n_emissions, "jmc_shower_chains: need room for at least one emission");
+    return jmc::shower_launch(g, n, seed, first_index, precision, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr,
+                              d_n_emissions, nullptr, stream, d_chains, max_emissions);
 }

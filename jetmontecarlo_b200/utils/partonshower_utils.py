@@ -50,6 +50,20 @@ class JetList:
                                             D.ptr(n_em), D.ptr(n_tr), D.stream()))
         return obs, n_em, n_tr
 
+    def chains(self, max_emissions=64, precision='f64'):
+        """The event record: (lengths [n], z [n, max_emissions], theta [n, max_emissions]) of the ordered emission
+        chains (NaN beyond a jet's length).  This is everything the reference's Parton trees hold when
+        split_soft=False; any per-jet observable can be formed from it."""
+        D.require_cuda()
+        n = self.num_events
+        chains = torch.full((n, int(max_emissions), 2), float('nan'), dtype=torch.float64, device=D.device())
+        lens = D.empty((n,), dtype=torch.int32)
+        s = self._integrand().c_struct()
+        _lib.check(_lib.lib.jmc_shower_chains(C.byref(s), n, self.seed, 0, PRECISIONS[precision], int(max_emissions),
+                                              D.ptr(chains), D.ptr(lens), D.stream()))
+        c = D.to_host(chains)
+        return D.to_host(lens), c[:, :, 0], c[:, :, 1]
+
     def emission_counts(self):
         """(accepted emissions, veto trials) per jet"""
         _, n_em, n_tr = self._dump(self._integrand())

@@ -54,6 +54,14 @@ def test_shower_f64_jet_by_jet(cuda, jet, acc):
             assert_allclose(got, ref, rtol=1e-12)
         ref = [O.ecf_from_chain_softdrop(c, .1, 2., 1., oacc, 1) for c in chains]
         assert_allclose(PS.getECFs_softdrop(jets, .1, beta=2., beta_sd=1., obs_acc=oacc, n_emissions=1), ref, rtol=1e-12)
+    # the event record itself
+    lens, zs, ths = jets.chains(max_emissions=32)
+    assert_array_equal(lens, n_em)
+    for i in (0, 1, 17, n - 1):
+        ref_chain = np.array(chains[i]).reshape(-1, 2)
+        assert_allclose(zs[i, :lens[i]], ref_chain[:, 0], rtol=1e-13)
+        assert_allclose(ths[i, :lens[i]], ref_chain[:, 1], rtol=1e-13)
+        assert np.isnan(zs[i, lens[i]:]).all()
     # mean multiplicities of the survey (section 6): 2.6 / 3.9 emissions per quark jet (LL / MLL), ~30 MLL trials
     if jet == 'quark':
         assert abs(n_em.mean() - (2.6 if acc == 'LL' else 3.9)) < .5
