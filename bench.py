@@ -67,12 +67,26 @@ def workload_config(args, world):
 # clocks
 # ---------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock and throttle reasons during the timed region: NVML polled every few ms from a thread (the timed
+    region is only tens of ms long, too short for `nvidia-smi -lms`); nvidia-smi as the fallback."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, gpu_index):
-        self.rows, self.proc = [], None
+        self.rows, self.proc, self.nvml, self.stop_flag = [], None, None, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
                                           "-lms", "20", "-i", str(gpu_index)], stdout=subprocess.PIPE,
@@ -82,11 +96,35 @@ class ClockSampler:
         except OSError:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        while not self.stop_flag:
+            try:
+                mhz = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                try:
+                    mask = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                except Exception:
+                    mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                watts = n.nvmlDeviceGetPowerUsage(self.handle) / 1000.
+                self.rows.append((time.perf_counter(), float(mhz), int(mask), watts))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
 
     def stop(self, t0, t1):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=1.)
+            rows = [r for r in self.rows if t0 <= r[0] <= t1] or self.rows
+            if not rows:
+                return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["no samples"]}
+            reasons = sorted({name for r in rows for bit, name in self.REASONS.items() if r[2] & bit})
+            return {"sm_mhz": statistics.median(r[1] for r in rows), "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                    "samples": len(rows), "power_w_max": max(r[3] for r in rows), "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -101,7 +139,7 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": float(rows[0][2]), "reasons": sorted(reasons),
-                "samples": len(rows), "power_w_max": max(float(r[3]) for r in rows)}
+                "samples": len(rows), "power_w_max": max(float(r[3]) for r in rows), "source": "nvidia-smi"}
 
 
 # ---------------------------------------------------------------------------
