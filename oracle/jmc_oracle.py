@@ -209,6 +209,28 @@ def rad_pre_fc(z_pre, theta_crit, z_cut, jet=QUARK, max_radius=1.):
             * (0. < theta_crit) * (theta_crit < max_radius))
 
 
+def sudakov_crit_fc(C, z_c, beta, jet, f=1., alpha=None):
+    """Closed-form cdf of one fixed-coupling critical emission in C = (z - f z_c) theta^beta (mpmath 2F1).
+    ref: analytics/sudakov_factors/fixedcoupling.py:11-51 (critSudakov_fc_LL)"""
+    import mpmath
+    alpha = ALPHA_FIXED if alpha is None else alpha
+    cr = casimir(jet)
+    eta = (2. * cr * alpha) / (beta * np.pi) * np.log(1. / (2. * f * z_c))
+    C = np.atleast_1d(np.asarray(C, dtype=float))
+    Cs, zc = C / (1. - (1. - f) * z_c), f * z_c
+    h = np.frompyfunc(lambda x: float(mpmath.hyp2f1(1., 1. - eta, 2. - eta, x)), 1, 1)
+    with np.errstate(all='ignore'):
+        simple = (Cs / (1. / 2. - zc)) ** eta
+        prefac = (2. * cr * alpha / (beta * np.pi)) * (Cs / zc) ** eta / (eta * (eta - 1.))
+        c1 = (zc / Cs) ** (eta - 1.) * np.asarray(h(-Cs / zc), dtype=float)
+        c2 = (zc / Cs) ** eta * (eta - 1.) * np.log(1. + Cs / zc)
+        c3 = -(zc / (1. / 2. - zc)) ** (eta - 1.) * float(mpmath.hyp2f1(1., 1. - eta, 2. - eta, 1. - 1. / (2. * zc)))
+        c4 = -(zc / (1. / 2. - zc)) ** eta * (eta - 1.) * np.log(1. / (2. * zc))
+        full = simple + prefac * (c1 + c2 + c3 + c4)
+    c_max = 1. / 2. - f * z_c
+    return full * (C < c_max) + 1. * (C > c_max)
+
+
 # --------------------------------------------------------------------------
 # Running-coupling analytics                      ref: analytics/radiators/running_coupling.py
 # Every region is evaluated and then masked, exactly as the reference does, so

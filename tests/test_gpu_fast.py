@@ -424,3 +424,26 @@ def test_fast_per_sample_other_parameters(cuda, kind, jet, fc, acc, zc, beta, z_
     # bulk agreement; the rare outliers sit next to zeros of the weight (see test_fast_per_sample_vs_oracle)
     assert np.quantile(rel, .999) < 3e-4 and np.median(rel) < 2e-5, (np.quantile(rel, .999), np.median(rel))
     assert abs(w[good].sum() / w_ref[good].sum() - 1) < 1e-4
+
+
+@pytest.mark.parametrize("jet,zc,beta", [('quark', .1, 2.), ('gluon', .05, 3.), ('quark', .2, 4.)])
+def test_critical_sudakov_against_closed_form(cuda, jet, zc, beta):
+    """The reference validates its critical-emission integration by plotting it over critSudakov_fc_LL
+    (examples/tests/oneEmission_tests/test_fixedcoupcritsudakov.py:124-220).  Here as a number: the closed form is
+    the exact cdf of (z - z_c) theta^beta, and C_groomed = that / (1 - z_c)^2, so the Monte Carlo cdf at edge x
+    must equal the closed form at x (1 - z_c)^2 -- within 1e-3 absolute at 1e7 samples (north star) and within
+    errors at 1e9."""
+    from jetmontecarlo_b200 import fused
+    from jetmontecarlo_b200.fused import Integrand
+    ig = Integrand.critical('log', zc, 1e-10, beta=beta, jet_type=jet, fixedcoupling=True)
+    edges = np.logspace(-8, np.log10(.5), 60)
+    exact = O.sudakov_crit_fc(edges * (1. - zc) ** 2., zc, beta, jet)
+    for n, prec, seed in ((10_000_000, 'f32', 1), (10_000_000, 'f64', 2), (1_000_000_000, 'f32', 3)):
+        it = fused.integrate(ig, n, edges=edges, seed=seed, precision=prec, last_bc=[1., 'minus'])
+        integ = np.asarray(it.integral)
+        # 1e-3 absolute on the cdf, plus the run's own statistical error where that is not yet below 1e-3
+        # (log sampling at 1e7 samples: sigma ~ 1e-3 on the cdf of this integrand)
+        assert np.abs(integ - exact).max() < 1e-3 + (3. * it.integralErr.max() if n < 10 ** 8 else 0.), \
+            (n, prec, np.abs(integ - exact).max())
+        pull = (integ[:-1] - exact[:-1]) / (it.integralErr + 1e-7)
+        assert np.abs(pull).max() < 4.5, (n, prec, np.abs(pull).max())

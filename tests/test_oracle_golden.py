@@ -56,6 +56,22 @@ def test_kats(golden):
     assert kat['C_ungroomed(.2,.3,2,MLL)'] == O.ecf_ungroomed(.2, .3, 2, 'MLL')
 
 
+def test_closed_form_critical_sudakov(golden):
+    """critSudakov_fc_LL (mpmath hyp2f1): the closed form the reference plots its critical-emission MC against"""
+    g = golden("kats")
+    kat = dict(zip(g['names'].tolist(), g['values'].tolist()))
+    assert O.sudakov_crit_fc(.01, .1, 2, 'quark')[0] == kat['q:critSudakov_fc_LL(.01,.1,2)']
+    assert O.sudakov_crit_fc(.01, .1, 2, 'gluon')[0] == kat['g:critSudakov_fc_LL(.01,.1,2)']
+    # and it IS the cdf of (z - z_c) theta^beta under critPDFAnalytic_fc_LL (vectorised MC on the oracle's samplers)
+    n = 1000000
+    s, jac, area = O.sample_critical('log', O.mt_uniforms(1, 2 * n).reshape(n, 2), .1, 1e-10)
+    w = O.pdf_crit_fc(s[:, 0], s[:, 1], .1, 'quark') * jac
+    edges = np.logspace(-8, np.log10(.5), 30)
+    r = O.integrate_hist((s[:, 0] - .1) * s[:, 1] ** 2., w, edges, area, last_bc=[1., 'minus'])
+    pull = (r['integral'][:-1] - O.sudakov_crit_fc(edges[:-1], .1, 2., 'quark')) / r['integral_err']
+    assert np.abs(pull).max() < 4.
+
+
 def test_function_vectors(golden):
     g = golden("functions")
     z, th, C, zpre, maxr = g['z'], g['theta'], g['C'], g['z_pre'], g['max_radius']
