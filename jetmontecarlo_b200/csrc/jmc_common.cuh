@@ -40,8 +40,8 @@ struct DeviceInfo {
 };
 int device_info(DeviceInfo* out);
 
-// small per-(thread, device) device scratch: poison flags, min/max staging, ...
-int scratch(size_t bytes, void** ptr);
+// small device scratch per (host thread, device, stream): poison flags, FP32 edges, staged batch parameters
+int scratch(size_t bytes, void** ptr, void* stream);
 
 // Derived constants of an integrand, computed once per launch on the host.
 struct RunParams {

@@ -532,7 +532,7 @@ extern "C" int jmc_hist(const double* d_obs, const double* d_weights, uint64_t n
     JMC_REQUIRE(d_obs != nullptr, "jmc_hist: obs is NULL");
     cudaStream_t st = (cudaStream_t)stream;
     int* d_poison;
-    rc = scratch(sizeof(int), (void**)&d_poison);
+    rc = scratch(sizeof(int), (void**)&d_poison, (void*)st);
     if (rc) return rc;
     JMC_CUDA(cudaMemsetAsync(d_poison, 0x7f, sizeof(int), st));   // 0x7f7f7f7f: "no poison"
     JMC_CUDA(cudaFuncSetAttribute(hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -782,7 +782,7 @@ int run_exact(const jmc_integrand* g, uint64_t n, uint64_t seed, uint64_t first_
     if (n == 0) return JMC_OK;
     cudaStream_t st = (cudaStream_t)stream;
     int* d_poison;
-    rc = scratch(sizeof(int), (void**)&d_poison);
+    rc = scratch(sizeof(int), (void**)&d_poison, (void*)st);
     if (rc) return rc;
     JMC_CUDA(cudaMemsetAsync(d_poison, 0x7f, sizeof(int), st));
 #define JMC_RUN(K) \
@@ -953,6 +953,7 @@ extern "C" int jmc_finalize(const double* d_sum_w, const double* d_sum_w2, const
                             double bc_value, double* d_density, double* d_density_err, double* d_integral,
                             double* d_integral_err, void* stream) {
     JMC_REQUIRE(n_edges >= 2, "jmc_finalize: need at least 2 edges");
+    JMC_REQUIRE(n_total > 0, "jmc_finalize: zero samples (the reference divides by len(observables) here)");
     JMC_REQUIRE(bc_kind >= JMC_BC_FIRST && bc_kind <= JMC_BC_LAST_MINUS, "jmc_finalize: invalid boundary condition");
     JMC_REQUIRE(d_sum_w && d_sum_w2 && d_count && d_edges, "jmc_finalize: NULL input");
     JMC_REQUIRE(d_density && d_density_err, "jmc_finalize: NULL output");

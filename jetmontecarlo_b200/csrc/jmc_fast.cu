@@ -435,7 +435,8 @@ fast_body(const FastParams& P_in, uint64_t n, uint64_t seed, uint64_t first, con
     // critical x subsequent integrand 0.3 % of the samples are active, i.e. 9 % of the warps would run the
     // ~330-instruction radiator code with one or two live lanes.  Instead the active draws are appended to a
     // per-warp shared-memory queue (ballot + popc, no atomics) and evaluated 32 at a time with every lane busy.
-    constexpr bool COMPACT = (KIND == JMC_KIND_CRIT_SUB) && !FIXED;
+    // (also the running-coupling critical integrand: 35 % of its samples are above the Landau scale)
+    constexpr bool COMPACT = (KIND == JMC_KIND_CRIT_SUB || KIND == JMC_KIND_CRIT) && !FIXED;
     const unsigned lane = threadIdx.x & 31u;
     float* q = (float*)(s_edges + ((ne + 3) & ~3)) + (threadIdx.x >> 5) * (kQueueFields * kQueueSlots);
     int qn = 0;                                          // warp-uniform queue length
@@ -443,8 +444,8 @@ fast_body(const FastParams& P_in, uint64_t n, uint64_t seed, uint64_t first, con
         Draw d;
         d.l2d = q[0 * kQueueSlots + slot];
         d.l2tc = q[1 * kQueueSlots + slot];
-        d.l2zs = q[2 * kQueueSlots + slot];
-        d.l2ts = q[3 * kQueueSlots + slot];
+        d.l2zs = KIND == JMC_KIND_CRIT ? 0.0f : q[2 * kQueueSlots + slot];
+        d.l2ts = KIND == JMC_KIND_CRIT ? 0.0f : q[3 * kQueueSlots + slot];
         const int bq = __float_as_int(q[4 * kQueueSlots + slot]);
         d.delta = ex2(d.l2d);
         d.z = P.zc + d.delta;
@@ -478,8 +479,10 @@ fast_body(const FastParams& P_in, uint64_t n, uint64_t seed, uint64_t first, con
                     const int slot = qn + __popc(m & ((1u << lane) - 1u));
                     q[0 * kQueueSlots + slot] = d.l2d;
                     q[1 * kQueueSlots + slot] = d.l2tc;
-                    q[2 * kQueueSlots + slot] = d.l2zs;
-                    q[3 * kQueueSlots + slot] = d.l2ts;
+                    if (KIND != JMC_KIND_CRIT) {
+                        q[2 * kQueueSlots + slot] = d.l2zs;
+                        q[3 * kQueueSlots + slot] = d.l2ts;
+                    }
                     q[4 * kQueueSlots + slot] = __int_as_float(bq_of());
                 }
                 qn += __popc(m);
@@ -844,7 +847,7 @@ int run_fast(const jmc_integrand* g, uint64_t n, uint64_t seed, uint64_t first_i
     if (rc) return rc;
     if (n == 0) return JMC_OK;
     char* scr;
-    rc = scratch(256 + sizeof(float) * (size_t)(n_edges > 0 ? n_edges : 1), (void**)&scr);
+    rc = scratch(256 + sizeof(float) * (size_t)(n_edges > 0 ? n_edges : 1), (void**)&scr, (void*)st);
     if (rc) return rc;
     int* d_poison = (int*)scr;
     float* d_edges_f = nullptr;
@@ -947,7 +950,7 @@ int run_fast_batch(const jmc_integrand* g, int n_points, uint64_t n, uint64_t se
     const size_t bytes_edges = sizeof(float) * edges_all.size();
     const size_t off_poison = (off_edges + bytes_edges + 255) & ~(size_t)255;
     char* scr;
-    int rc = scratch(off_poison + sizeof(int) * (size_t)n_points, (void**)&scr);
+    int rc = scratch(off_poison + sizeof(int) * (size_t)n_points, (void**)&scr, (void*)st);
     if (rc) return rc;
     FastParams* d_params = (FastParams*)scr;
     float* d_edges_f = h_edges ? (float*)(scr + off_edges) : nullptr;

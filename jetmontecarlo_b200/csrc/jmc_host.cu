@@ -48,16 +48,17 @@ int device_info(DeviceInfo* out) {
     return JMC_OK;
 }
 
-// one small scratch allocation per (thread, device); grows on demand
-int scratch(size_t bytes, void** ptr) {
-    struct Slot { int device; void* p; size_t cap; };
+// Small device scratch (poison flags, FP32 edges, staged batch parameters), one allocation per
+// (host thread, device, stream) so that launches queued on different streams never share it; grows on demand.
+int scratch(size_t bytes, void** ptr, void* stream) {
+    struct Slot { int device; void* stream; void* p; size_t cap; };
     static thread_local std::vector<Slot> slots;
     int dev = -1;
     JMC_CUDA(cudaGetDevice(&dev));
     for (auto& s : slots) {
-        if (s.device != dev) continue;
+        if (s.device != dev || s.stream != stream) continue;
         if (s.cap < bytes) {
-            JMC_CUDA(cudaFree(s.p));
+            JMC_CUDA(cudaFree(s.p));           // synchronises the device: nothing still reads the old block
             s.p = nullptr; s.cap = 0;
             JMC_CUDA(cudaMalloc(&s.p, bytes));
             s.cap = bytes;
@@ -65,7 +66,7 @@ int scratch(size_t bytes, void** ptr) {
         *ptr = s.p;
         return JMC_OK;
     }
-    Slot s{dev, nullptr, bytes < 256 ? 256 : bytes};
+    Slot s{dev, stream, nullptr, bytes < 256 ? 256 : bytes};
     JMC_CUDA(cudaMalloc(&s.p, s.cap));
     slots.push_back(s);
     *ptr = s.p;
@@ -249,9 +250,19 @@ extern "C" int jmc_run_batch(const jmc_integrand* g, int n_points, uint64_t n, u
     JMC_REQUIRE(g != nullptr && n_points >= 1, "jmc_run_batch: need at least one parameter point");
     JMC_REQUIRE(precision == JMC_F64 || precision == JMC_F32, "jmc_run_batch: precision must be JMC_F64 or JMC_F32");
     if (precision == JMC_F32 && g[0].kind != JMC_KIND_SHOWER && g[0].kind != JMC_KIND_PRE_CRIT_SUB
-        && g[0].kind != JMC_KIND_SIMPLE)
-        return run_fast_batch(g, n_points, n, seed, first_index, h_edges, n_edges, d_sum_w, d_sum_w2, d_count, d_minmax,
-                              stream);
+        && g[0].kind != JMC_KIND_SIMPLE) {
+        // a point may run in a single block whose bin counts are 32-bit: at most 2^31 samples per launch
+        const uint64_t kMaxPerLaunch = 1ull << 31;
+        do {
+            const uint64_t chunk = n < kMaxPerLaunch ? n : kMaxPerLaunch;
+            int rc = run_fast_batch(g, n_points, chunk, seed, first_index, h_edges, n_edges, d_sum_w, d_sum_w2, d_count,
+                                    d_minmax, stream);
+            if (rc) return rc;
+            n -= chunk;
+            first_index += chunk;
+        } while (n > 0);
+        return JMC_OK;
+    }
     // FP64 (and the kinds without a batched kernel): one launch per point on the same stream
     const size_t nb = n_edges > 0 ? (size_t)n_edges - 1 : 0;
     DevBufE edges;

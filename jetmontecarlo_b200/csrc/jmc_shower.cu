@@ -397,7 +397,7 @@ static int shower_launch(const jmc_integrand* g, uint64_t n, uint64_t seed, uint
         return set_error(JMC_ELIMIT, "jmc_run: %d edges exceed shared memory", n_edges);
     cudaStream_t st = (cudaStream_t)stream;
     char* scr;
-    rc = scratch(256 + sizeof(unsigned long long) * nb, (void**)&scr);
+    rc = scratch(256 + sizeof(unsigned long long) * nb, (void**)&scr, (void*)st);
     if (rc) return rc;
     int* d_err = (int*)scr;
     unsigned long long* d_before = (unsigned long long*)(scr + 256);

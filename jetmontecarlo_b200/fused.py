@@ -183,6 +183,9 @@ def integrate(integrand, num_samples, *, edges=None, numbins=None, binspacing='l
     if edges is not None:
         it.bins = np.asarray(edges, dtype=np.float64)
         it.binspacing = binspacing
+        with np.errstate(all='ignore'):
+            it.bin_midpoints = ((it.bins[1:] + it.bins[:-1]) / 2. if binspacing == 'lin'
+                                else np.exp((np.log(it.bins[1:]) + np.log(it.bins[:-1])) / 2.))
         it.hasBins = True
     else:
         # same arithmetic mode for both passes: the min/max pass must see the samples the histogram pass bins
