@@ -48,15 +48,18 @@ __global__ void __launch_bounds__(kThreads) eval_fn_kernel(int fn, jmc_fn_params
             case JMC_FN_PRE_RAD_FC: r = rad_pre_fc(x0, x1, p.z_cut, p.jet, x2); break;
             case JMC_FN_CRIT_RAD_RC: r = rad_crit_rc(x0, p.z_cut, p.jet); break;
             case JMC_FN_CRIT_RADPRIME_RC: r = radprime_crit_rc(x0, p.z_cut, p.jet); break;
-            case JMC_FN_CRIT_PDF_RC: r = pdf_crit_rc(x0, x1, p.z_cut, p.jet); break;
+            // (the *_surely_nan tests return early with the NaN the full evaluation would produce, see jmc_integrand.cuh)
+            case JMC_FN_CRIT_PDF_RC: r = crit_rc_surely_nan(x1, p.z_cut) ? qnan() : pdf_crit_rc(x0, x1, p.z_cut, p.jet); break;
             case JMC_FN_SUB_RAD_RC: r = rad_sub_rc(x0, p.beta, p.jet, x1); break;
             case JMC_FN_SUB_RADPRIME_RC: r = radprime_sub_rc(x0, p.beta, p.jet, x1); break;
-            case JMC_FN_SUB_PDF_RC: r = pdf_sub_rc(x0, p.beta, p.jet, x1); break;
+            case JMC_FN_SUB_PDF_RC: r = sub_rc_surely_nan(x0, p.beta, x1) ? qnan() : pdf_sub_rc(x0, p.beta, p.jet, x1); break;
             case JMC_FN_PRE_WEIGHT: r = weight_precritical(x0, x1, p.z_cut, p.jet); break;
             case JMC_FN_C_GROOMED: r = ecf_groomed(x0, x1, p.z_cut, p.beta, x2, x3, p.acc); break;
             case JMC_FN_C_UNGROOMED: r = ecf_ungroomed(x0, x1, p.beta, p.acc); break;
             case JMC_FN_TWO_EMISSION:
-                r = weight_two_emission(x0, x1, x2, x3, p.z_cut, p.beta, p.jet, p.fixed_coupling);
+                r = (!p.fixed_coupling && (crit_rc_surely_nan(x1, p.z_cut)
+                                           || sub_rc_surely_nan(csub_verbatim(x2, x3, p.beta), p.beta, x1)))
+                        ? qnan() : weight_two_emission(x0, x1, x2, x3, p.z_cut, p.beta, p.jet, p.fixed_coupling);
                 break;
             case JMC_FN_PRE_WEIGHT_ZEROBIN: r = weight_precritical_zerobin(x0, x1, p.z_cut, p.jet, p.epsilon); break;
             case JMC_FN_ALPHA_SPLITTING:
