@@ -6,6 +6,7 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <cstring>
 #include "../../include/jmc_b200.h"
 
 namespace jmc {
@@ -42,6 +43,12 @@ int device_info(DeviceInfo* out);
 
 // small device scratch per (host thread, device, stream): poison flags, FP32 edges, staged batch parameters
 int scratch(size_t bytes, void** ptr, void* stream);
+
+// Shared-memory accumulation of (sum w, sum w^2).  FP64 (and FP32) shared-memory atomic adds are compare-and-swap
+// loops on sm_100 (ATOMS.CAST.SPIN); only 32-bit integer ones are native.  Measured alternative: interleaving the
+// two sums and updating both with ONE 128-bit CAS (ATOMS.CAS.128 exists) is 3-4x SLOWER on 100-bin histograms
+// where every sample carries a weight (C1: 4.8e10 vs 2.1e11 samples/s; the wide CAS serialises harder under
+// contention), so the sums stay in two arrays with one 64-bit CAS loop each.
 
 // Derived constants of an integrand, computed once per launch on the host.
 struct RunParams {

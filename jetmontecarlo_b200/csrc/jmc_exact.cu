@@ -409,11 +409,11 @@ __device__ __forceinline__ void hist_flush(HistSmem& h, int n_edges, double* __r
     if (threadIdx.x == 0 && *s_poison != INT_MAX) atomicMin(g_poison, *s_poison);
 }
 
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(1024)
 hist_kernel(const double* __restrict__ obs, const double* __restrict__ w, uint64_t n,
             const double* __restrict__ edges, int n_edges, double* __restrict__ g_sum_w,
             double* __restrict__ g_sum_w2, unsigned long long* __restrict__ g_count, int* g_poison, BinGuess G) {
-    extern __shared__ double s_raw[];
+    extern __shared__ __align__(16) double s_raw[];
     __shared__ int s_poison;
     HistSmem h(s_raw, n_edges);
     if (threadIdx.x == 0) s_poison = INT_MAX;
@@ -539,10 +539,13 @@ extern "C" int jmc_hist(const double* d_obs, const double* d_weights, uint64_t n
     if (rc) return rc;
     JMC_CUDA(cudaMemsetAsync(d_poison, 0x7f, sizeof(int), st));   // 0x7f7f7f7f: "no poison"
     JMC_CUDA(cudaFuncSetAttribute(hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // big histograms (the reference's 5000 radiator bins take 140 KB) leave room for one block per SM: give that
+    // block 1024 threads so that 32 warps share the histogram instead of 8
+    const int threads = smem > 72 * 1024 ? 1024 : kThreads;
     int per_sm = 0;
-    JMC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hist_kernel, kThreads, smem));
+    JMC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hist_kernel, threads, smem));
     if (per_sm < 1) per_sm = 1;
-    const int grid = grid_for(n, kThreads, per_sm);
+    const int grid = grid_for(n, threads, per_sm);
     // Equally spaced edges (np.linspace / np.logspace, i.e. every setBins) get an affine first guess of the bin.
     // Reading the edges back costs one small synchronous copy; skipped for jobs too small to profit.
     BinGuess G{0, 0.f, 0.f};
@@ -559,8 +562,8 @@ extern "C" int jmc_hist(const double* d_obs, const double* d_weights, uint64_t n
             if (ok) G = BinGuess{mode, (float)b0, (float)(1.0 / d)};
         }
     }
-    hist_kernel<<<grid, kThreads, smem, st>>>(d_obs, d_weights, n, d_edges, n_edges, d_sum_w, d_sum_w2,
-                                               (unsigned long long*)d_count, d_poison, G);
+    hist_kernel<<<grid, threads, smem, st>>>(d_obs, d_weights, n, d_edges, n_edges, d_sum_w, d_sum_w2,
+                                              (unsigned long long*)d_count, d_poison, G);
     JMC_LAUNCHED("hist_kernel");
     if (d_weights) {
         poison_kernel<<<1, 256, 0, st>>>(d_poison, n_edges - 1, d_sum_w, d_sum_w2);
@@ -726,7 +729,7 @@ __global__ void __launch_bounds__(kThreads)
 run_exact_kernel(RunParams p, uint64_t n, uint64_t seed, uint64_t first, const double* __restrict__ edges,
                  int n_edges, double* __restrict__ g_sum_w, double* __restrict__ g_sum_w2,
                  unsigned long long* __restrict__ g_count, int* g_poison, double* __restrict__ d_minmax) {
-    extern __shared__ double s_raw[];
+    extern __shared__ __align__(16) double s_raw[];
     __shared__ int s_poison;
     HistSmem h(s_raw, n_edges > 0 ? n_edges : 1);
     const bool do_hist = edges != nullptr;

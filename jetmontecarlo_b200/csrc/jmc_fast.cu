@@ -583,7 +583,7 @@ __global__ void __launch_bounds__(BIG ? kFastThreadsBig : kFastThreads, BIG ? 1 
 run_fast_kernel(FastParams P, uint64_t n, uint64_t seed, uint64_t first, const float* __restrict__ g_edges,
                 double* __restrict__ g_sum_w, double* __restrict__ g_sum_w2,
                 unsigned long long* __restrict__ g_count, int* g_poison, double* __restrict__ d_minmax) {
-    extern __shared__ double s_dyn[];
+    extern __shared__ __align__(16) double s_dyn[];
     fast_body<KIND, FIXED, OBS_MLL, HOT>(P, n, seed, first, g_edges, g_sum_w, g_sum_w2, g_count, g_poison, d_minmax, s_dyn);
 }
 
@@ -597,7 +597,7 @@ run_fast_batch_kernel(const FastParams* __restrict__ params, uint64_t n, uint64_
                       const float* __restrict__ edges_all, int n_edges, double* __restrict__ sum_w_all,
                       double* __restrict__ sum_w2_all, unsigned long long* __restrict__ count_all, int* poison_all,
                       double* __restrict__ minmax_all) {
-    extern __shared__ double s_dyn[];
+    extern __shared__ __align__(16) double s_dyn[];
     __shared__ FastParams sP;
     const int point = blockIdx.y;
     const int words = (int)(sizeof(FastParams) / sizeof(int));
