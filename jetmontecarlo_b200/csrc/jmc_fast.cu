@@ -25,6 +25,7 @@
 // ref for the formulas: analytics/radiators/{fixedcoupling,running_coupling}.py,
 // numerics/{observables,weights}.py, numerics/radiators/samplers.py (file:line
 // next to each function below).
+#include <algorithm>
 #include <cfloat>
 #include <climits>
 #include <cmath>
@@ -74,6 +75,10 @@ struct FastParams {
     float omf_zcl;           // (1-f)*zcl
     float omf_zc;            // (1-f)*z_cut
     float l2_onorm;          // -2 log2(1 - z_cut)
+    float aK, c0K;           // (1 - z_cut)^-2 and c0 (1 - z_cut)^-2: the observable's normalisation folded into `a`
+    float bm0;               // 1 - z_cut - (1-f)*zcl : b = bm0 - delta (MLL observable)
+    float omb;               // 1 - beta
+    float act_c2, act_c3;    // thresholds of the "1 + Lambda(C, alpha(theta_c)) > 0" test in base-2 logs (see light())
     // fixed coupling
     float g;                 // 2 C_R alpha_fixed / pi
     float A;                 // ln(1/(2 z_cut)) * g         (theta exponent of critPDF_fc)
@@ -98,6 +103,7 @@ struct FastParams {
     float b0, inv_d;
     float mb0_inv_d;         // -b0 * inv_d
     float e_first, e_last;   // first / last edge in the compare domain
+    float nb_f;              // number of bins as a float
 };
 
 __device__ __forceinline__ float ex2(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
@@ -234,9 +240,10 @@ __device__ __forceinline__ float l2_sample(uint32_t w, float sL2, float l2w) {
 // non-zero.  Everything here is executed for every sample; it is straight-line code.
 // FIXED selects the coupling at compile time so that the other branch costs nothing.
 template <int KIND, bool FIXED, bool OBS_MLL>
-__device__ __forceinline__ bool light(const FastParams& P, uint64_t idx, const PhiloxKeys& keys, Draw& d, float& l2obs) {
+__device__ __forceinline__ bool light(const FastParams& P, uint32_t idx_lo, uint32_t idx_hi, const PhiloxKeys& keys,
+                                      Draw& d, float& l2obs) {
     uint32_t r[4];
-    philox4x32_10(idx, 0u, keys, r);
+    philox4x32_10(idx_lo, idx_hi, 0u, keys, r);
     if (KIND == JMC_KIND_RADIATOR) {
         // ungroomedSampler (samplers.py:204-226), C_ungroomed (observables.py:82-109)
         d.l2zs = l2_sample(r[0], P.sL2, -1.0f);
@@ -251,12 +258,12 @@ __device__ __forceinline__ bool light(const FastParams& P, uint64_t idx, const P
     d.l2tc = l2_sample(r[1], P.sL2, P.l2R);
     d.delta = ex2(d.l2d);
     d.z = P.zc + d.delta;
-    const float onorm = fmaf(P.beta, d.l2tc, P.l2_onorm);            // log2(theta_c^beta / (1 - z_cut)^2)
+    // C_groomed (observables.py:15-79) = a b theta_c^beta / (1 - z_cut)^2 with a = zmin - f (z_cut - z_pre) =
+    // delta + c0 and b = 1 - (1-f)(z_cut - z_pre) [- z at MLL] = bm0 - delta; the normalisation rides on `a`
+    const float aK = fmaf(d.delta, P.aK, P.c0K);
+    const float bb = OBS_MLL ? P.bm0 - d.delta : P.one_m;
     if (KIND == JMC_KIND_CRIT) {
-        // C_groomed (observables.py:15-79)
-        const float a = d.delta + P.c0;
-        const float b = OBS_MLL ? (1.0f - d.z) - P.omf_zcl : P.one_m;
-        l2obs = lg2(a * b) + onorm;
+        l2obs = fmaf(P.beta, d.l2tc, lg2(aK * bb));
         if (FIXED) return true;
         return fmaf(P.k, fmaf(JMC_LN2F, d.l2tc, P.lzc), 1.0f) > 0.0f && !P.crit_always_nan;   // 1 + Lambda(z_c theta) > 0
     }
@@ -265,25 +272,25 @@ __device__ __forceinline__ bool light(const FastParams& P, uint64_t idx, const P
     d.l2ts = l2_sample(r[3], P.sL2, P.l2R);
     if (KIND == JMC_KIND_CRIT_SUB) {
         // observable of twoEmissionWeight's integrand: max(C_groomed, csub), csub = z_s th_s^b th_s^b (weights.py:74)
-        const float a = d.delta + P.c0;
-        const float b = OBS_MLL ? (1.0f - d.z) - P.omf_zcl : P.one_m;
-        const float l2cc = lg2(a * b) + onorm;
+        const float l2cc = fmaf(P.beta, d.l2tc, lg2(aK * bb));
         const float l2cs = fmaf(2.0f * P.beta, d.l2ts, d.l2zs);
         l2obs = fmaxf(l2cc, l2cs);
         d.lcl2 = fmaf(-P.beta, d.l2tc, l2cs);                        // log2(csub / theta_c^beta)
         if (FIXED) return d.lcl2 < -1.0f;                            // subPDF_fc mask: C < theta_c^beta / 2
         // "the reference is not NaN": theta_c above both Landau thresholds (a constant), C < 1, and
         // 1 + Lambda(C, alpha(theta_c)) > 0, which after multiplying by alpha's positive denominator is linear
-        // in the logarithms:  1 + ca (max(ln P_T theta_c, 0) - ln M_Z + ln C) > 0
-        const float mu = fmaxf(fmaf(JMC_LN2F, d.l2tc, P.lnPT), 0.0f);
-        const float t = fmaf(JMC_LN2F, d.lcl2, mu - P.lnMZ);
-        return (d.l2tc > P.l2tc_min) & (d.lcl2 < 0.0f) & (fmaf(P.ca, t, 1.0f) > 0.0f);
+        // in the logarithms:  1 + ca (max(ln P_T theta_c, 0) - ln M_Z + ln C) > 0.  In base-2 logs, and with
+        // max(A, 0) + B = max(A + B, B):  log2 C > c2  or  log2 theta_c + log2 C > c3,
+        // c2 = (ln M_Z - 1/ca) / ln 2, c3 = c2 - log2 P_T; log2 theta_c + log2 C = (1 - beta) log2 theta_c + log2 csub.
+        const float x = fmaf(P.omb, d.l2tc, l2cs);
+        const bool landau_c = (x > P.act_c3) | (d.lcl2 > P.act_c2);
+        return landau_c & (d.l2tc > P.l2tc_min) & (d.lcl2 < 0.0f);
     }
     if (KIND == JMC_KIND_PRE_CRIT_SUB) {
         // all-emission integrand with the zero bin
         // (examples/tests/comparison_tests/comparison_utils_probabilistic.py:384-474)
         uint32_t r2[4];
-        philox4x32_10(idx, 1u, keys, r2);
+        philox4x32_10(idx_lo, idx_hi, 1u, keys, r2);
         d.l2zp = l2_sample(r2[0], P.sL2, P.l2zc);
         d.u5 = __uint2float_rn(r2[1]) * 2.3283064365386963e-10f;
         const float E2 = -P.g * d.l2tc;                              // E / ln2, E = 2 C_R a/pi ln(R0/theta_c)
@@ -295,7 +302,7 @@ __device__ __forceinline__ bool light(const FastParams& P, uint64_t idx, const P
         const float a = d.delta + P.omf_zc + P.f * zp;
         const float omf_zcl = (1.0f - P.f) * (P.zc - zp);
         const float b = OBS_MLL ? (1.0f - d.z) - omf_zcl : 1.0f - omf_zcl;
-        const float l2cc = lg2(a * b) + onorm;
+        const float l2cc = lg2(a * b) + fmaf(P.beta, d.l2tc, P.l2_onorm);
         const float l2cs = fmaf(P.beta, d.l2tc, d.l2zs);            // c_sub = z_s theta_c^beta
         l2obs = fmaxf(l2cc, l2cs);
         return true;
@@ -356,20 +363,14 @@ __device__ __forceinline__ float heavy(const FastParams& P, const Draw& d) {
 }
 
 // ---- binning ---------------------------------------------------------------
-// s_edges: edges in the compare domain (log2 or linear), FP32.  Returns -1 for a dropped sample.
-// UNILOG: edges known at compile time to be equally spaced in log2 (np.logspace bins, the common case).
-template <bool UNILOG>
+// s_edges: edges in the compare domain (log2 or linear), FP32.  Returns -1 for a dropped sample.  (The generic
+// form; np.logspace bins take the affine shortcut in fast_body.)
 __device__ __forceinline__ int bin_fast(const FastParams& P, float l2obs, const float* __restrict__ s_edges) {
-    const float v = (UNILOG || P.dom_log) ? l2obs : ex2(l2obs);
+    const float v = P.dom_log ? l2obs : ex2(l2obs);
     const int ne = P.n_edges;
     const bool in_range = (v >= P.e_first) & (v <= P.e_last);       // NaN fails both
     int idx;
-    if (UNILOG) {
-        // np.logspace bins: the bin is the floor of an affine map of log2(obs).  (The stored FP32 edges are that
-        // same map rounded; settling against them would cost ten more instructions per sample for samples within
-        // 1e-7 of an edge, which FP32 cannot place with respect to the FP64 edges anyway.)
-        idx = min(max(__float2int_rd(fmaf(v, P.inv_d, P.mb0_inv_d)), 0), ne - 2);
-    } else if (P.uniform) {
+    if (P.uniform) {
         // affine guess, then settle against the stored edges (FP32 rounding of the map can be off by one)
         idx = __float2int_rd(fmaf(v, P.inv_d, P.mb0_inv_d));
         idx = max(0, min(idx, ne - 2));
@@ -386,8 +387,8 @@ __device__ __forceinline__ int bin_fast(const FastParams& P, float l2obs, const 
     return in_range ? idx : -1;
 }
 
-// HOT: histogram only (no min/max tracking) into np.logspace-like bins -- the form every large job has; the
-// generic instantiation reads those choices from FastParams at run time.
+// HOT: histogram only (no min/max tracking) into np.logspace-like bins with nan_to_num weights -- the form every
+// large job has; the generic instantiation reads those choices from FastParams at run time.
 template <int KIND, bool FIXED, bool OBS_MLL, bool HOT>
 __device__ __forceinline__ void
 fast_body(const FastParams& P_in, uint64_t n, uint64_t seed, uint64_t first, const float* __restrict__ g_edges,
@@ -414,13 +415,20 @@ fast_body(const FastParams& P_in, uint64_t n, uint64_t seed, uint64_t first, con
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t stride = gridDim.x * blockDim.x;
     const uint32_t iters = n > tid ? (uint32_t)((n - tid + stride - 1) / stride) : 0u;
-    uint64_t idx = first + tid;
+    // The host never lets a launch cross a multiple of 2^32 in the global sample index, so the high half of the
+    // Philox counter is launch-uniform and the low half is plain 32-bit arithmetic.
+    const uint32_t idx_hi = (uint32_t)(first >> 32);
+    uint32_t idx = (uint32_t)first + tid;
+    // Kinds whose weight can be NaN by construction (running-coupling Landau region) run the hot instantiation
+    // only with nan_to_num set; for the others the flag is looked at only if a NaN ever shows up.
+    constexpr bool NAN_REGION = !FIXED && KIND != JMC_KIND_RADIATOR;
+    const bool nan_to_num = (HOT && NAN_REGION) || P.nan_to_num;
 
     // weight * jacobian of one sample into the block histogram (bq: bin, or -1 / -2 for a sample below /
     // above the binned range, which matters only for NumPy's NaN poisoning)
     auto accumulate = [&](float w, int bq) {
         if (w != w) {                                    // NaN: 0 under nan_to_num, else NumPy poisons bins >= bq
-            if (!P.nan_to_num) {
+            if (!nan_to_num) {
                 const int pb = bq >= 0 ? bq : (bq == -1 ? 0 : INT_MAX);
                 if (pb != INT_MAX) atomicMin(&s_poison, pb);
             }
@@ -452,27 +460,53 @@ fast_body(const FastParams& P_in, uint64_t n, uint64_t seed, uint64_t first, con
         d.lcl2 = fmaf(-P.beta, d.l2tc, fmaf(2.0f * P.beta, d.l2ts, d.l2zs));
         accumulate(heavy<KIND, FIXED>(P, d), bq);
     };
-    // everything after the draw for one sample: min/max, bin, count, weight (directly or through the queue)
-    auto handle = [&](const Draw& d, float l2obs, bool active, bool valid) {
-        // `valid` is a compile-time true in the main loop (see below) and a run-time flag only in the tail trip
+
+    // Bin of an observable: `ok` = inside the binned range, `b` = its bin (meaningful only when ok).
+    // HOT (np.logspace bins): the bin is the floor of an affine map of log2(obs), and the range test is made on the
+    // mapped value -- FFMA, two compares, F2I.  (The stored FP32 edges are that same map rounded; settling
+    // against them would cost ten more instructions per sample for samples within 1e-7 of an edge, which FP32
+    // cannot place with respect to the FP64 edges anyway.)
+    auto locate = [&](float l2obs, bool& ok, int& b) {
+        if (HOT) {
+            const float f = fmaf(l2obs, P.inv_d, P.mb0_inv_d);
+            ok = (f >= 0.0f) & (f < P.nb_f);             // NaN fails both
+            b = __float2int_rd(f);
+        } else {
+            b = bin_fast(P, l2obs, s_edges);
+            ok = b >= 0;
+        }
+    };
+    // bin for a weight, or -1 / -2 for a sample below / above the binned range (NaN poisoning only)
+    auto weight_bin = [&](float l2obs) {
+        bool ok;
+        int b;
+        locate(l2obs, ok, b);
+        if (ok) return b;
+        if (HOT) return -1;
+        const float v = P.dom_log ? l2obs : ex2(l2obs);
+        return v < P.e_first ? -1 : -2;
+    };
+    const int dummy_slot = nb + (int)lane;
+    // Every sample: min/max and the count histogram.  Dropped samples count into a per-lane dummy slot behind the
+    // bins: no branch around the atomic, and no same-address serialisation among the lanes that miss.
+    // `valid` is a compile-time true in the main loop and a run-time flag only in the ragged last trips.
+    auto tally = [&](float l2obs, bool valid) {
         if (do_minmax && valid) {
             mn = fminf(mn, l2obs);
             mx = fmaxf(mx, l2obs);
         }
         if (!do_hist) return;
-        int b = bin_fast<HOT>(P, l2obs, s_edges);
-        if (!valid) { b = -1; active = false; }
-        // dropped samples count into a per-lane dummy slot behind the bins: no branch around the atomic, and no
-        // same-address serialisation among the lanes that miss
-        atomicAdd(&s_count[b >= 0 ? b : nb + (int)lane], 1u);
-        // bin for the weight, or -1 / -2 for a sample below / above the binned range (NaN poisoning only); needed
-        // for the few samples that reach a weight, so it is formed inside those branches
-        auto bq_of = [&]() {
-            const float v = (HOT || P.dom_log) ? l2obs : ex2(l2obs);
-            return b >= 0 ? b : (v < P.e_first ? -1 : -2);
-        };
+        bool ok;
+        int b;
+        locate(l2obs, ok, b);
+        atomicAdd(&s_count[(ok && valid) ? b : dummy_slot], 1u);
+    };
+    // The weight of a sample, directly or through the queue.  Warp-collective when COMPACT.
+    auto weigh = [&](const Draw& d, float l2obs, bool active, bool valid) {
+        if (!do_hist) return;
+        if (!valid) active = false;
         if (COMPACT) {
-            if (!P.nan_to_num && !active && valid) accumulate(fnan(), bq_of());   // inactive = "the reference weight is NaN"
+            if (!nan_to_num && !active && valid) accumulate(fnan(), weight_bin(l2obs));   // inactive = "the reference weight is NaN"
             const unsigned m = __ballot_sync(0xffffffffu, active);
             if (m) {
                 if (active) {
@@ -483,7 +517,7 @@ fast_body(const FastParams& P_in, uint64_t n, uint64_t seed, uint64_t first, con
                         q[2 * kQueueSlots + slot] = d.l2zs;
                         q[3 * kQueueSlots + slot] = d.l2ts;
                     }
-                    q[4 * kQueueSlots + slot] = __int_as_float(bq_of());
+                    q[4 * kQueueSlots + slot] = __int_as_float(weight_bin(l2obs));
                 }
                 qn += __popc(m);
                 __syncwarp();
@@ -494,22 +528,23 @@ fast_body(const FastParams& P_in, uint64_t n, uint64_t seed, uint64_t first, con
                 }
             }
         } else if (active) {
-            accumulate(heavy<KIND, FIXED>(P, d), bq_of());
-        } else if (!FIXED && !P.nan_to_num && valid) {
-            accumulate(fnan(), bq_of());                 // inactive under running coupling = NaN weight
+            accumulate(heavy<KIND, FIXED>(P, d), weight_bin(l2obs));
+        } else if (!FIXED && !nan_to_num && valid) {
+            accumulate(fnan(), weight_bin(l2obs));       // inactive under running coupling = NaN weight
         }
     };
 
-    // Two samples per trip: their Philox chains are independent, so the scheduler interleaves them (the
-    // generator is a 10-deep dependent chain of IMAD.WIDE -> LOP3), and the warp-uniform work of a trip (round
-    // keys, constant loads, loop control) is paid once per two samples.  The ballots in handle() need every
-    // lane of the warp in every trip, so all lanes run to the warp's longest trip count.
+    // U samples per trip: their Philox chains are independent, so the scheduler interleaves them (the generator
+    // is a 10-deep dependent chain of IMAD.WIDE -> LOP3), and the warp-uniform work of a trip (constant loads, loop
+    // control, and for the compacted kinds ONE vote on "any lane has an active sample among its U") is paid once
+    // per U samples.  The ballots in weigh() need every lane of the warp in every trip, so all lanes run to the
+    // warp's longest trip count.
     PhiloxKeys keys(seed);
 #if JMC_FAST_PIN_KEYS
     keys.pin();
 #endif
     constexpr int U = JMC_FAST_UNROLL;
-    const uint64_t strideU = (uint64_t)U * stride;
+    const uint32_t strideU = (uint32_t)U * stride;
     // Main loop: trips in which every lane of the warp has all U samples (no validity tests); then at most two
     // checked trips for the ragged end.  Lanes of a warp differ by at most one sample (consecutive tid).
     const uint32_t full = __shfl_sync(0xffffffffu, iters, 31) / (uint32_t)U;
@@ -519,17 +554,31 @@ fast_body(const FastParams& P_in, uint64_t n, uint64_t seed, uint64_t first, con
         float o[U];
         bool a[U];
 #pragma unroll
-        for (int k = 0; k < U; ++k) a[k] = light<KIND, FIXED, OBS_MLL>(P, idx + (uint64_t)k * stride, keys, d[k], o[k]);
+        for (int k = 0; k < U; ++k) a[k] = light<KIND, FIXED, OBS_MLL>(P, idx + (uint32_t)k * stride, idx_hi, keys, d[k], o[k]);
 #pragma unroll
-        for (int k = 0; k < U; ++k) handle(d[k], o[k], a[k], true);
+        for (int k = 0; k < U; ++k) tally(o[k], true);
+        if (COMPACT) {
+            bool any = !nan_to_num;
+#pragma unroll
+            for (int k = 0; k < U; ++k) any |= a[k];
+            if (__any_sync(0xffffffffu, any)) {
+#pragma unroll
+                for (int k = 0; k < U; ++k) weigh(d[k], o[k], a[k], true);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < U; ++k) weigh(d[k], o[k], a[k], true);
+        }
     }
     for (uint32_t j = full; j < trips; ++j, idx += strideU) {
 #pragma unroll 1
         for (int k = 0; k < U; ++k) {
             Draw d;
             float o;
-            const bool a = light<KIND, FIXED, OBS_MLL>(P, idx + (uint64_t)k * stride, keys, d, o);
-            handle(d, o, a, (uint32_t)U * j + (uint32_t)k < iters);
+            const bool a = light<KIND, FIXED, OBS_MLL>(P, idx + (uint32_t)k * stride, idx_hi, keys, d, o);
+            const bool valid = (uint32_t)U * j + (uint32_t)k < iters;
+            tally(o, valid);
+            weigh(d, o, a, valid);
         }
     }
     if (COMPACT && do_hist) {
@@ -633,8 +682,10 @@ dump_fast_kernel(FastParams P, uint64_t n, uint64_t seed, uint64_t first, double
         d.u5 = 2.0f;
         float l2obs;
         const PhiloxKeys keys(seed);
-        const bool active = P.obs_mll ? light<KIND, FIXED, true>(P, first + i, keys, d, l2obs)
-                                      : light<KIND, FIXED, false>(P, first + i, keys, d, l2obs);
+        const uint64_t gi = first + i;
+        const uint32_t lo = (uint32_t)gi, hi = (uint32_t)(gi >> 32);
+        const bool active = P.obs_mll ? light<KIND, FIXED, true>(P, lo, hi, keys, d, l2obs)
+                                      : light<KIND, FIXED, false>(P, lo, hi, keys, d, l2obs);
         float w = active ? heavy<KIND, FIXED>(P, d) : (FIXED ? 0.0f : fnan());
         if (w != w && P.nan_to_num) w = 0.0f;
         if (samples) {
@@ -695,6 +746,17 @@ static int make_fast_params(const jmc_integrand* g, const double* h_edges, int n
     P.omf_zcl = (float)((1.0 - g->f_soft) * zcl);
     P.omf_zc = (float)((1.0 - g->f_soft) * g->z_cut);
     P.l2_onorm = (float)(-2.0 * std::log2(1.0 - g->z_cut));
+    {
+        const double K = 1.0 / ((1.0 - g->z_cut) * (1.0 - g->z_cut));
+        P.aK = (float)K;
+        P.c0K = (float)((g->z_cut - g->f_soft * zcl) * K);
+        P.bm0 = (float)(1.0 - g->z_cut - (1.0 - g->f_soft) * zcl);
+        P.omb = (float)(1.0 - g->beta);
+        const double ca = 2.0 * H_AMZ * H_BETA0;
+        const double c2 = (std::log(H_MZ) - 1.0 / ca) / ln2;
+        P.act_c2 = (float)c2;
+        P.act_c3 = (float)(c2 - std::log2(H_PT));
+    }
     const double gg = 2.0 * CR * H_ALPHA / H_PI;
     P.g = (float)gg;
     P.A = g->z_cut > 0 ? (float)(std::log(1.0 / (2.0 * g->z_cut)) * gg) : 0.f;
@@ -769,6 +831,7 @@ static int make_fast_params(const jmc_integrand* g, const double* h_edges, int n
         for (int k = 0; k < n_edges; ++k) (*edges_f)[k] = (float)dom[k];
         P.e_first = (*edges_f)[0];
         P.e_last = (*edges_f)[n_edges - 1];
+        P.nb_f = (float)(n_edges - 1);
         for (int k = 1; k < n_edges; ++k)
             if (!((*edges_f)[k] > (*edges_f)[k - 1]))
                 return set_error(JMC_ELIMIT, "jmc_run: bin edges %d and %d coincide in FP32; use JMC_F64 for bins this fine",
@@ -784,6 +847,9 @@ static size_t fast_smem_bytes(int n_edges, int threads = kFastThreads) {
     return sizeof(double) * 2 * nb + sizeof(unsigned int) * (nb + 32) + sizeof(float) * ne_pad
            + sizeof(float) * (threads / 32) * kQueueFields * kQueueSlots;
 }
+
+// samples from global index `first` up to the next multiple of 2^32
+static uint64_t fast_span(uint64_t first) { return 0x100000000ull - (first & 0xffffffffull); }
 
 template <int KIND, bool FIXED, bool OBS_MLL, bool HOT, bool BIG>
 static int launch_fast_t(const FastParams& P, uint64_t n, uint64_t seed, uint64_t first, const float* d_edges_f,
@@ -816,7 +882,8 @@ template <int KIND, bool FIXED>
 static int launch_fast(const FastParams& P, uint64_t n, uint64_t seed, uint64_t first, const float* d_edges_f,
                        double* d_sum_w, double* d_sum_w2, uint64_t* d_count, int* d_poison, double* d_minmax,
                        cudaStream_t st) {
-    const bool hot = d_edges_f != nullptr && d_minmax == nullptr && P.dom_log && P.uniform;
+    const bool hot = d_edges_f != nullptr && d_minmax == nullptr && P.dom_log && P.uniform
+                     && (P.nan_to_num || FIXED || KIND == JMC_KIND_RADIATOR);
     const bool big = hot && fast_smem_bytes(P.n_edges) > kBigSmemThreshold;
 #define JMC_GO(M, H, B) launch_fast_t<KIND, FIXED, M, H, B>(P, n, seed, first, d_edges_f, d_sum_w, d_sum_w2, d_count, d_poison, d_minmax, st)
     if (P.obs_mll) return hot ? (big ? JMC_GO(true, true, true) : JMC_GO(true, true, false)) : JMC_GO(true, false, false);
@@ -859,20 +926,26 @@ int run_fast(const jmc_integrand* g, uint64_t n, uint64_t seed, uint64_t first_i
     }
 #define JMC_RUNF(K)                                                                                                   \
     rc = g->fixed_coupling                                                                                            \
-             ? launch_fast<K, true>(P, n, seed, first_index, d_edges_f, d_sum_w, d_sum_w2, d_count, d_poison, d_minmax, st) \
-             : launch_fast<K, false>(P, n, seed, first_index, d_edges_f, d_sum_w, d_sum_w2, d_count, d_poison, d_minmax, st)
-    switch (g->kind) {
-        case JMC_KIND_RADIATOR: JMC_RUNF(JMC_KIND_RADIATOR); break;
-        case JMC_KIND_CRIT: JMC_RUNF(JMC_KIND_CRIT); break;
-        case JMC_KIND_CRIT_SUB: JMC_RUNF(JMC_KIND_CRIT_SUB); break;
-        case JMC_KIND_PRE_CRIT_SUB:
-            rc = launch_fast<JMC_KIND_PRE_CRIT_SUB, true>(P, n, seed, first_index, d_edges_f, d_sum_w, d_sum_w2, d_count,
-                                                          d_poison, d_minmax, st);
-            break;
-        default: return set_error(JMC_EINVAL, "jmc_run: kind %d has no FP32 form", g->kind);
+             ? launch_fast<K, true>(P, m, seed, first_index, d_edges_f, d_sum_w, d_sum_w2, d_count, d_poison, d_minmax, st) \
+             : launch_fast<K, false>(P, m, seed, first_index, d_edges_f, d_sum_w, d_sum_w2, d_count, d_poison, d_minmax, st)
+    // one launch per stretch of the sample stream that stays inside one multiple of 2^32 (fast_body's 32-bit index)
+    while (n) {
+        const uint64_t m = std::min<uint64_t>(n, fast_span(first_index));
+        switch (g->kind) {
+            case JMC_KIND_RADIATOR: JMC_RUNF(JMC_KIND_RADIATOR); break;
+            case JMC_KIND_CRIT: JMC_RUNF(JMC_KIND_CRIT); break;
+            case JMC_KIND_CRIT_SUB: JMC_RUNF(JMC_KIND_CRIT_SUB); break;
+            case JMC_KIND_PRE_CRIT_SUB:
+                rc = launch_fast<JMC_KIND_PRE_CRIT_SUB, true>(P, m, seed, first_index, d_edges_f, d_sum_w, d_sum_w2,
+                                                              d_count, d_poison, d_minmax, st);
+                break;
+            default: return set_error(JMC_EINVAL, "jmc_run: kind %d has no FP32 form", g->kind);
+        }
+        if (rc) return rc;
+        first_index += m;
+        n -= m;
     }
 #undef JMC_RUNF
-    if (rc) return rc;
     if (d_edges && !g->nan_to_num) {
         poison_fast_kernel<<<1, 256, 0, st>>>(d_poison, n_edges - 1, d_sum_w, d_sum_w2);
         JMC_LAUNCHED("poison_fast_kernel");
@@ -941,7 +1014,8 @@ int run_fast_batch(const jmc_integrand* g, int n_points, uint64_t n, uint64_t se
         int rc = make_fast_params(&g[i], h_edges ? h_edges + (size_t)i * n_edges : nullptr, n_edges, &params[i], &one);
         if (rc) return rc;
         if (h_edges) std::memcpy(&edges_all[(size_t)i * n_edges], one.data(), sizeof(float) * n_edges);
-        hot = hot && params[i].dom_log && params[i].uniform;
+        hot = hot && params[i].dom_log && params[i].uniform
+              && (params[i].nan_to_num || g[0].fixed_coupling || g[0].kind == JMC_KIND_RADIATOR);
         if (!h_edges) params[i].n_edges = 0;
     }
     if (n == 0) return JMC_OK;
@@ -973,15 +1047,22 @@ int run_fast_batch(const jmc_integrand* g, int n_points, uint64_t n, uint64_t se
         else { if (mll) { if (hot) JMC_B(K, false, true, true); else JMC_B(K, false, true, false); }         \
                else { if (hot) JMC_B(K, false, false, true); else JMC_B(K, false, false, false); } }          \
     } while (0)
-    switch (g[0].kind) {
-        case JMC_KIND_RADIATOR: JMC_BK(JMC_KIND_RADIATOR); break;
-        case JMC_KIND_CRIT: JMC_BK(JMC_KIND_CRIT); break;
-        case JMC_KIND_CRIT_SUB: JMC_BK(JMC_KIND_CRIT_SUB); break;
-        default: return set_error(JMC_EINVAL, "jmc_run_batch: kind %d is not batched", g[0].kind);
+    const uint64_t n_all = n;
+    while (n_all && n) {
+        const uint64_t n_left = n;
+        n = std::min<uint64_t>(n_left, fast_span(first_index));
+        switch (g[0].kind) {
+            case JMC_KIND_RADIATOR: JMC_BK(JMC_KIND_RADIATOR); break;
+            case JMC_KIND_CRIT: JMC_BK(JMC_KIND_CRIT); break;
+            case JMC_KIND_CRIT_SUB: JMC_BK(JMC_KIND_CRIT_SUB); break;
+            default: return set_error(JMC_EINVAL, "jmc_run_batch: kind %d is not batched", g[0].kind);
+        }
+        if (rc) return rc;
+        first_index += n;
+        n = n_left - n;
     }
 #undef JMC_BK
 #undef JMC_B
-    if (rc) return rc;
     bool any_nan_semantics = false;
     for (int i = 0; i < n_points; ++i) any_nan_semantics = any_nan_semantics || !g[i].nan_to_num;
     if (h_edges && any_nan_semantics) {

@@ -76,11 +76,17 @@ struct PhiloxKeys {
     }
 };
 
-__device__ __forceinline__ void philox4x32_10(uint64_t index, uint32_t block, const PhiloxKeys& K, uint32_t w[4]) {
-    uint32_t c0 = (uint32_t)index, c1 = (uint32_t)(index >> 32), c2 = block, c3 = 0u;
+// index given as its two halves: a launch that keeps the high half uniform (no 2^32 crossing inside it) gets the
+// first round's c1 ^ k0 and the second round's product of it for free (loop-invariant, hoisted by the compiler)
+__device__ __forceinline__ void philox4x32_10(uint32_t index_lo, uint32_t index_hi, uint32_t block,
+                                              const PhiloxKeys& K, uint32_t w[4]) {
+    uint32_t c0 = index_lo, c1 = index_hi, c2 = block, c3 = 0u;
 #pragma unroll
     for (int r = 0; r < 10; ++r) philox_round(c0, c1, c2, c3, K.k0[r], K.k1[r]);
     w[0] = c0; w[1] = c1; w[2] = c2; w[3] = c3;
+}
+__device__ __forceinline__ void philox4x32_10(uint64_t index, uint32_t block, const PhiloxKeys& K, uint32_t w[4]) {
+    philox4x32_10((uint32_t)index, (uint32_t)(index >> 32), block, K, w);
 }
 
 // two 53-bit uniforms in [0,1) from one block

@@ -155,15 +155,14 @@ def test_fast_histogram_equals_histogram_of_its_dump(cuda, kind, jet, fc, acc):
     r = H.run(ig, n, seed, edges, 'f32')
     cnt = r['count'].cpu().numpy()
     # restate the kernel's binning exactly: np.logspace edges -> bin = floor of an affine map of log2(obs) in
-    # FP32 (one FMA), clamped, with the range test against the FP32 log2 edges
+    # FP32 (one FMA); in range = mapped value in [0, number of bins)
     l2 = np.log2(obs).astype(np.float32)
     dom = np.log2(edges)
-    e32 = dom.astype(np.float32)
     d = (dom[-1] - dom[0]) / (len(edges) - 1)
     inv_d, mb0 = np.float32(1. / d), np.float32(-dom[0] / d)
     fma = (l2.astype(np.float64) * np.float64(inv_d) + np.float64(mb0)).astype(np.float32)
-    idx = np.clip(np.floor(fma).astype(np.int64), 0, len(edges) - 2)
-    keep = (l2 >= e32[0]) & (l2 <= e32[-1])
+    keep = (fma >= 0) & (fma < len(edges) - 1)
+    idx = np.floor(np.where(keep, fma, 0)).astype(np.int64)
     ref_cnt = np.bincount(idx[keep], minlength=len(edges) - 1)
     assert_array_equal(cnt, ref_cnt)
     assert abs(cnt - np.histogram(obs, edges)[0]).sum() <= 1e-4 * n     # and FP64 binning differs only at edge ties
@@ -220,6 +219,33 @@ def test_fast_same_stream_is_much_closer_than_statistics(cuda):
         acc = (rr['sum_w'], rr['sum_w2'], rr['count'])
     assert_array_equal(acc[2].cpu().numpy(), r1['count'].cpu().numpy())
     assert_allclose(acc[0].cpu().numpy(), r1['sum_w'].cpu().numpy(), rtol=1e-11)
+
+
+@pytest.mark.parametrize("kind,jet,fc,acc", [CASES[8], CASES[6], CASES[0]])
+def test_fast_index_range_across_2_to_the_32(cuda, kind, jet, fc, acc):
+    """the kernel's sample index is 32-bit arithmetic inside a launch; the host splits a job where the global
+    index crosses a multiple of 2^32.  A range straddling the boundary must equal the histogram of the dump of
+    the same 64-bit indices, and the sum of its two halves."""
+    import gpu_helpers as H
+    ig = _integrand(kind, jet, fc, acc)
+    edges = np.logspace(-11, np.log10(.5), 100)
+    first, n, seed = 2 ** 32 - 70_001, 200_000, 5
+    r = H.run(ig, n, seed, edges, 'f32', first=first)
+    _, obs, w = H.dump(ig, n, seed, 'f32', first=first)
+    cnt = r['count'].cpu().numpy()
+    assert abs(cnt - np.histogram(obs, edges)[0]).sum() <= 1e-4 * n
+    ref_sw = np.histogram(obs, edges, weights=w)[0]
+    assert_allclose(r['sum_w'].cpu().numpy(), ref_sw, rtol=1e-3, atol=1e-4 * np.abs(ref_sw).max())
+    acc_ = None
+    for f0, c in ((first, 70_001), (2 ** 32, n - 70_001)):
+        rr = H.run(ig, c, seed, edges, 'f32', first=f0, accumulate_into=acc_)
+        acc_ = (rr['sum_w'], rr['sum_w2'], rr['count'])
+    assert_array_equal(acc_[2].cpu().numpy(), cnt)
+    assert_allclose(acc_[0].cpu().numpy(), r['sum_w'].cpu().numpy(), rtol=1e-7)
+    # and the samples on both sides of the boundary are different samples (the high word enters the counter)
+    _, obs_lo, _ = H.dump(ig, 1000, seed, 'f32', first=0)
+    _, obs_hi, _ = H.dump(ig, 1000, seed, 'f32', first=2 ** 32)
+    assert not np.array_equal(obs_lo, obs_hi)
 
 
 def test_fast_nonuniform_and_linear_edges(cuda):
