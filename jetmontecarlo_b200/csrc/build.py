@@ -30,7 +30,7 @@ UNITS = {
     "jmc_exact.cu": ["--fmad=false"],
     "jmc_shower.cu": ["--fmad=false"],
     "jmc_fast.cu": ["--fmad=true"] + ["-D%s=%s" % (k, os.environ[k]) for k in
-                                      ("JMC_FAST_MIN_BLOCKS", "JMC_FAST_UNROLL", "JMC_FAST_PIN_KEYS") if os.environ.get(k)],
+                                      ("JMC_FAST_MIN_BLOCKS", "JMC_FAST_UNROLL", "JMC_FAST_PIN_KEYS", "JMC_PHILOX_SPLIT") if os.environ.get(k)],
     "jmc_host.cu": [],
 }
 
@@ -45,7 +45,7 @@ def _nvcc():
 def _digest():
     h = hashlib.sha256()
     names = sorted(f for f in os.listdir(HERE) if f.endswith((".cu", ".cuh", ".py")))
-    for k in ("JMC_FAST_MIN_BLOCKS", "JMC_FAST_UNROLL", "JMC_FAST_PIN_KEYS"):
+    for k in ("JMC_FAST_MIN_BLOCKS", "JMC_FAST_UNROLL", "JMC_FAST_PIN_KEYS", "JMC_PHILOX_SPLIT"):
         h.update(os.environ.get(k, "").encode())
     for name in names + [os.path.join(ROOT, "include", "jmc_b200.h")]:
         with open(os.path.join(HERE, name) if not os.path.isabs(name) else name, "rb") as f:

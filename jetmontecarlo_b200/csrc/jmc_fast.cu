@@ -39,13 +39,15 @@ namespace jmc {
 static constexpr int kFastThreads = 256, kFastThreadsBig = 1024;
 static constexpr size_t kBigSmemThreshold = 72 * 1024;     // block histograms above this use the 1024-thread kernels
 static constexpr int kQueueFields = 5, kQueueSlots = 64;   // per-warp compaction queue (see run_fast_kernel)
-// resident blocks per SM the register allocation must allow: 2 x 256 threads (<= 128 registers, 16-32 resident warps): measured fastest with pinned parameters and 4 samples per trip.
+// resident blocks per SM the register allocation must allow (3 x 256 threads: <= 85 registers) and samples per loop
+// trip; swept with scripts/try_variants.sh -- 3:2, 3:3 and 2:4 are within 2 % of each other, more samples per trip
+// or a fourth block lose to register pressure.
 // The rarely executed running-coupling radiator code may spill; the per-sample light path must not.
 #ifndef JMC_FAST_MIN_BLOCKS
-#define JMC_FAST_MIN_BLOCKS 2
+#define JMC_FAST_MIN_BLOCKS 3
 #endif
 #ifndef JMC_FAST_UNROLL
-#define JMC_FAST_UNROLL 4        // samples per loop trip
+#define JMC_FAST_UNROLL 2        // samples per loop trip
 #endif
 #ifndef JMC_FAST_PIN_KEYS
 #define JMC_FAST_PIN_KEYS 1      // keep the Philox round keys in registers across the loop
@@ -236,14 +238,47 @@ __device__ __forceinline__ float l2_sample(uint32_t w, float sL2, float l2w) {
     return fmaf(__uint2float_rn(w), sL2, l2w);
 }
 
+// Can the weight of this draw be non-zero?  (Running coupling: "the reference's weight is not NaN".)  A function of
+// the draw alone, so the hot loop only keeps the OR over a trip's samples and re-derives the per-sample answer in
+// the rare trips that have an active sample.
+template <int KIND, bool FIXED>
+__device__ __forceinline__ bool is_active(const FastParams& P, const Draw& d) {
+    if (KIND == JMC_KIND_CRIT) {
+        if (FIXED) return true;
+        return fmaf(P.k, fmaf(JMC_LN2F, d.l2tc, P.lzc), 1.0f) > 0.0f && !P.crit_always_nan;   // 1 + Lambda(z_c theta) > 0
+    }
+    if (KIND == JMC_KIND_CRIT_SUB) {
+        if (FIXED) return d.lcl2 < -1.0f;                            // subPDF_fc mask: C < theta_c^beta / 2
+        // theta_c above both Landau thresholds (a constant), C < 1, and 1 + Lambda(C, alpha(theta_c)) > 0, which
+        // after multiplying by alpha's positive denominator is linear in the logarithms:
+        //   1 + ca (max(ln P_T theta_c, 0) - ln M_Z + ln C) > 0.
+        // In base-2 logs, and with max(A, 0) + B = max(A + B, B):  log2 C > c2  or  log2 theta_c + log2 C > c3,
+        // c2 = (ln M_Z - 1/ca) / ln 2, c3 = c2 - log2 P_T;  log2 theta_c + log2 C = lcl2 + log2 theta_c.
+        const float x = d.l2tc + d.lcl2;
+        const bool landau_c = (x > P.act_c3) | (d.lcl2 > P.act_c2);
+        return landau_c & (d.l2tc > P.l2tc_min) & (d.lcl2 < 0.0f);
+    }
+    return true;
+}
+
 // Stage 1 ("light"): draw the sample, form log2(observable) and decide whether the weight can be
 // non-zero.  Everything here is executed for every sample; it is straight-line code.
 // FIXED selects the coupling at compile time so that the other branch costs nothing.
+// The random words of one sample: Philox block 0, and block 1 for the kind that needs six uniforms.
+template <int KIND>
+struct Words {
+    uint32_t a[4];
+    uint32_t b[KIND == JMC_KIND_PRE_CRIT_SUB ? 4 : 1];
+};
+template <int KIND>
+__device__ __forceinline__ void draw_words(uint32_t idx_lo, uint32_t idx_hi, const PhiloxKeys& keys, Words<KIND>& w) {
+    philox4x32_10(idx_lo, idx_hi, 0u, keys, w.a);
+    if (KIND == JMC_KIND_PRE_CRIT_SUB) philox4x32_10(idx_lo, idx_hi, 1u, keys, w.b);
+}
+
 template <int KIND, bool FIXED, bool OBS_MLL>
-__device__ __forceinline__ bool light(const FastParams& P, uint32_t idx_lo, uint32_t idx_hi, const PhiloxKeys& keys,
-                                      Draw& d, float& l2obs) {
-    uint32_t r[4];
-    philox4x32_10(idx_lo, idx_hi, 0u, keys, r);
+__device__ __forceinline__ bool light(const FastParams& P, const Words<KIND>& w, Draw& d, float& l2obs) {
+    const uint32_t* r = w.a;
     if (KIND == JMC_KIND_RADIATOR) {
         // ungroomedSampler (samplers.py:204-226), C_ungroomed (observables.py:82-109)
         d.l2zs = l2_sample(r[0], P.sL2, -1.0f);
@@ -264,8 +299,7 @@ __device__ __forceinline__ bool light(const FastParams& P, uint32_t idx_lo, uint
     const float bb = OBS_MLL ? P.bm0 - d.delta : P.one_m;
     if (KIND == JMC_KIND_CRIT) {
         l2obs = fmaf(P.beta, d.l2tc, lg2(aK * bb));
-        if (FIXED) return true;
-        return fmaf(P.k, fmaf(JMC_LN2F, d.l2tc, P.lzc), 1.0f) > 0.0f && !P.crit_always_nan;   // 1 + Lambda(z_c theta) > 0
+        return is_active<KIND, FIXED>(P, d);
     }
     // subsequent emission from the ungroomed sampler
     d.l2zs = l2_sample(r[2], P.sL2, -1.0f);
@@ -276,21 +310,12 @@ __device__ __forceinline__ bool light(const FastParams& P, uint32_t idx_lo, uint
         const float l2cs = fmaf(2.0f * P.beta, d.l2ts, d.l2zs);
         l2obs = fmaxf(l2cc, l2cs);
         d.lcl2 = fmaf(-P.beta, d.l2tc, l2cs);                        // log2(csub / theta_c^beta)
-        if (FIXED) return d.lcl2 < -1.0f;                            // subPDF_fc mask: C < theta_c^beta / 2
-        // "the reference is not NaN": theta_c above both Landau thresholds (a constant), C < 1, and
-        // 1 + Lambda(C, alpha(theta_c)) > 0, which after multiplying by alpha's positive denominator is linear
-        // in the logarithms:  1 + ca (max(ln P_T theta_c, 0) - ln M_Z + ln C) > 0.  In base-2 logs, and with
-        // max(A, 0) + B = max(A + B, B):  log2 C > c2  or  log2 theta_c + log2 C > c3,
-        // c2 = (ln M_Z - 1/ca) / ln 2, c3 = c2 - log2 P_T; log2 theta_c + log2 C = (1 - beta) log2 theta_c + log2 csub.
-        const float x = fmaf(P.omb, d.l2tc, l2cs);
-        const bool landau_c = (x > P.act_c3) | (d.lcl2 > P.act_c2);
-        return landau_c & (d.l2tc > P.l2tc_min) & (d.lcl2 < 0.0f);
+        return is_active<KIND, FIXED>(P, d);
     }
     if (KIND == JMC_KIND_PRE_CRIT_SUB) {
         // all-emission integrand with the zero bin
         // (examples/tests/comparison_tests/comparison_utils_probabilistic.py:384-474)
-        uint32_t r2[4];
-        philox4x32_10(idx_lo, idx_hi, 1u, keys, r2);
+        const uint32_t* r2 = w.b;
         d.l2zp = l2_sample(r2[0], P.sL2, P.l2zc);
         d.u5 = __uint2float_rn(r2[1]) * 2.3283064365386963e-10f;
         const float E2 = -P.g * d.l2tc;                              // E / ln2, E = 2 C_R a/pi ln(R0/theta_c)
@@ -463,13 +488,15 @@ fast_body(const FastParams& P_in, uint64_t n, uint64_t seed, uint64_t first, con
 
     // Bin of an observable: `ok` = inside the binned range, `b` = its bin (meaningful only when ok).
     // HOT (np.logspace bins): the bin is the floor of an affine map of log2(obs), and the range test is made on the
-    // mapped value -- FFMA, two compares, F2I.  (The stored FP32 edges are that same map rounded; settling
+    // mapped value -- FFMA, one compare, F2I.  (The stored FP32 edges are that same map rounded; settling
     // against them would cost ten more instructions per sample for samples within 1e-7 of an edge, which FP32
     // cannot place with respect to the FP64 edges anyway.)
     auto locate = [&](float l2obs, bool& ok, int& b) {
         if (HOT) {
             const float f = fmaf(l2obs, P.inv_d, P.mb0_inv_d);
-            ok = (f >= 0.0f) & (f < P.nb_f);             // NaN fails both
+            // 0 <= f < nb in ONE unsigned compare of the bit patterns: non-negative floats order like their bits,
+            // and a set sign bit or a NaN pattern is a huge unsigned number
+            ok = (unsigned)__float_as_int(f) < (unsigned)__float_as_int(P.nb_f);
             b = __float2int_rd(f);
         } else {
             b = bin_fast(P, l2obs, s_edges);
@@ -549,25 +576,24 @@ fast_body(const FastParams& P_in, uint64_t n, uint64_t seed, uint64_t first, con
     // checked trips for the ragged end.  Lanes of a warp differ by at most one sample (consecutive tid).
     const uint32_t full = __shfl_sync(0xffffffffu, iters, 31) / (uint32_t)U;
     const uint32_t trips = (__shfl_sync(0xffffffffu, iters, 0) + (uint32_t)(U - 1)) / (uint32_t)U;
+    // (Measured and dropped: software-pipelining the generator of trip j+1 against the evaluation of trip j, to
+    // mix FMA-heavy and ALU work inside each warp -- 16 more live registers cost more occupancy than the better
+    // mix gains: 2.4-2.7e11 samples/s against 2.8e11.)
     for (uint32_t j = 0; j < full; ++j, idx += strideU) {
         Draw d[U];
         float o[U];
-        bool a[U];
+        bool any = !nan_to_num;
 #pragma unroll
-        for (int k = 0; k < U; ++k) a[k] = light<KIND, FIXED, OBS_MLL>(P, idx + (uint32_t)k * stride, idx_hi, keys, d[k], o[k]);
+        for (int k = 0; k < U; ++k) {
+            Words<KIND> w;
+            draw_words<KIND>(idx + (uint32_t)k * stride, idx_hi, keys, w);
+            any |= light<KIND, FIXED, OBS_MLL>(P, w, d[k], o[k]);
+        }
 #pragma unroll
         for (int k = 0; k < U; ++k) tally(o[k], true);
-        if (COMPACT) {
-            bool any = !nan_to_num;
+        if (!COMPACT || __any_sync(0xffffffffu, any)) {
 #pragma unroll
-            for (int k = 0; k < U; ++k) any |= a[k];
-            if (__any_sync(0xffffffffu, any)) {
-#pragma unroll
-                for (int k = 0; k < U; ++k) weigh(d[k], o[k], a[k], true);
-            }
-        } else {
-#pragma unroll
-            for (int k = 0; k < U; ++k) weigh(d[k], o[k], a[k], true);
+            for (int k = 0; k < U; ++k) weigh(d[k], o[k], is_active<KIND, FIXED>(P, d[k]), true);
         }
     }
     for (uint32_t j = full; j < trips; ++j, idx += strideU) {
@@ -575,7 +601,9 @@ fast_body(const FastParams& P_in, uint64_t n, uint64_t seed, uint64_t first, con
         for (int k = 0; k < U; ++k) {
             Draw d;
             float o;
-            const bool a = light<KIND, FIXED, OBS_MLL>(P, idx + (uint32_t)k * stride, idx_hi, keys, d, o);
+            Words<KIND> wt;
+            draw_words<KIND>(idx + (uint32_t)k * stride, idx_hi, keys, wt);
+            const bool a = light<KIND, FIXED, OBS_MLL>(P, wt, d, o);
             const bool valid = (uint32_t)U * j + (uint32_t)k < iters;
             tally(o, valid);
             weigh(d, o, a, valid);
@@ -684,8 +712,10 @@ dump_fast_kernel(FastParams P, uint64_t n, uint64_t seed, uint64_t first, double
         const PhiloxKeys keys(seed);
         const uint64_t gi = first + i;
         const uint32_t lo = (uint32_t)gi, hi = (uint32_t)(gi >> 32);
-        const bool active = P.obs_mll ? light<KIND, FIXED, true>(P, lo, hi, keys, d, l2obs)
-                                      : light<KIND, FIXED, false>(P, lo, hi, keys, d, l2obs);
+        Words<KIND> wd;
+        draw_words<KIND>(lo, hi, keys, wd);
+        const bool active = P.obs_mll ? light<KIND, FIXED, true>(P, wd, d, l2obs)
+                                      : light<KIND, FIXED, false>(P, wd, d, l2obs);
         float w = active ? heavy<KIND, FIXED>(P, d) : (FIXED ? 0.0f : fnan());
         if (w != w && P.nan_to_num) w = 0.0f;
         if (samples) {

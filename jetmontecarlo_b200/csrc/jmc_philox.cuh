@@ -14,6 +14,9 @@
 //   f32: block b yields uniforms 4b..4b+3 = ((w[j]>>8) + 0.5) * 2^-24  in (0,1).
 #pragma once
 #include <cstdint>
+#ifndef JMC_PHILOX_SPLIT
+#define JMC_PHILOX_SPLIT 0       // 1: IMAD.HI + IMAD per product instead of one IMAD.WIDE (experiment switch)
+#endif
 
 namespace jmc {
 
@@ -21,7 +24,7 @@ struct PhiloxKey { uint32_t k0, k1; };
 
 __host__ __device__ __forceinline__ void philox_round(uint32_t& c0, uint32_t& c1, uint32_t& c2,
                                                       uint32_t& c3, uint32_t k0, uint32_t k1) {
-#ifdef __CUDA_ARCH__
+#if defined(__CUDA_ARCH__) && !JMC_PHILOX_SPLIT
     // one IMAD.WIDE.U32 per product (hi and lo together) instead of IMAD.HI + IMAD: halves the issue slots
     // of the generator, which is the largest single cost of a sample
     uint32_t hi0, lo0, hi1, lo1;
