@@ -404,6 +404,14 @@ def main():
             if args.precision == "f32" and args.variant == "c3_rc":
                 roofline["traffic"] = prof["dram_bytes_per_launch"]
                 roofline["ncu"] = prof
+                # the pipe that actually binds: the generator's 32x32->64 multiplies on the FMA-heavy pipe.  A
+                # kernel that only generates the Philox blocks takes generator_only_ms on this GPU; this kernel
+                # (generator + sampling + observable + Landau test + histogram) is measured against it.
+                floor_ms = prof.get("generator_only_ms_per_1e9_samples")
+                if floor_ms:
+                    roofline["generator_floor"] = {
+                        "ms_per_1e9_samples": floor_ms, "frac": floor_ms * (n / 1e9) / (kern_s * 1e3),
+                        "source": prof.get("generator_only_source")}
         except (OSError, KeyError, ValueError):
             pass
         line = {

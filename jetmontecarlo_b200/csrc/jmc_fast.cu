@@ -452,15 +452,13 @@ fast_body(const FastParams& P_in, uint64_t n, uint64_t seed, uint64_t first, con
     // weight * jacobian of one sample into the block histogram (bq: bin, or -1 / -2 for a sample below /
     // above the binned range, which matters only for NumPy's NaN poisoning)
     auto accumulate = [&](float w, int bq) {
-        if (w != w) {                                    // NaN: 0 under nan_to_num, else NumPy poisons bins >= bq
-            if (!nan_to_num) {
-                const int pb = bq >= 0 ? bq : (bq == -1 ? 0 : INT_MAX);
-                if (pb != INT_MAX) atomicMin(&s_poison, pb);
-            }
-        } else if (bq >= 0 && w != 0.0f) {
+        if (bq >= 0 && fabsf(w) > 0.0f) {                // the common case first: one compare rejects 0 and NaN
             const double wd = (double)w;
             atomicAdd(&s_sum_w[bq], wd);
             atomicAdd(&s_sum_w2[bq], wd * wd);
+        } else if (w != w && !nan_to_num) {              // NaN: 0 under nan_to_num, else NumPy poisons bins >= bq
+            const int pb = bq >= 0 ? bq : (bq == -1 ? 0 : INT_MAX);
+            if (pb != INT_MAX) atomicMin(&s_poison, pb);
         }
     };
 
