@@ -1,0 +1,47 @@
+"""Static checks of the built library (no GPU): the hot kernels were compiled for sm_100a only, keep their loops in
+registers, and carry the instruction forms DESIGN.md section 4.1 relies on."""
+import os
+import re
+import shutil
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB = os.path.join(ROOT, "jetmontecarlo_b200", "lib", "libjmc_b200.so")
+HEADLINE = "_ZN3jmc15run_fast_kernelILi2ELb0ELb1ELb1ELb0EEEvNS_10FastParamsEmmmPKfPdS4_PyPiS4_"   # CRIT_SUB rc MLL hot
+
+cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+pytestmark = pytest.mark.skipif(not os.path.exists(cuobjdump), reason="cuobjdump not installed")
+
+
+def _run(*args):
+    return subprocess.run([cuobjdump, *args, LIB], capture_output=True, text=True, check=True).stdout
+
+
+def test_only_sm_100a_code_is_embedded():
+    archs = set(re.findall(r"arch = (sm_\w+)", _run("-lelf") + _run("-sass", "-fun", HEADLINE)))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_fused_kernels_do_not_spill():
+    out = _run("-res-usage")
+    usage = re.findall(r"Function (\S+):\s*\n\s*REG:(\d+) STACK:(\d+)", out)
+    assert usage
+    fused = [(f, int(r), int(s)) for f, r, s in usage if "run_fast_kernel" in f or "run_fast_batch_kernel" in f]
+    assert len(fused) >= 48          # kind x coupling x observable accuracy x hot/generic (+ big-histogram variants)
+    for f, regs, stack in fused:
+        assert stack == 0, "%s spills %d B" % (f, stack)
+        assert regs <= 85, "%s needs %d registers: three 256-thread blocks per SM no longer fit" % (f, regs)
+    assert HEADLINE in [f for f, _, _ in fused]
+
+
+def test_headline_kernel_instruction_forms():
+    sass = _run("-sass", "-fun", HEADLINE)
+    ops = re.findall(r"^\s+/\*[0-9a-f]{4,5}\*/\s+(?:@!?U?P\d\s+)?([A-Z0-9_.]+)", sass, flags=re.M)
+    assert len(ops) > 1000
+    assert ops.count("IMAD.WIDE.U32") >= 36          # Philox products as one wide multiply each
+    assert "ATOMS.POPC.INC.32" in ops                # native shared-memory count atomic
+    assert any(o.startswith("ATOMS.CAST.SPIN") for o in ops)      # FP64 sums: compare-and-swap loop (no native form)
+    assert "MUFU.EX2" in ops and "MUFU.LG2" in ops   # base-2 log space
+    assert not any(o.startswith(("LDL", "STL")) for o in ops)     # no local memory
