@@ -241,7 +241,7 @@ def test_fast_index_range_across_2_to_the_32(cuda, kind, jet, fc, acc):
         rr = H.run(ig, c, seed, edges, 'f32', first=f0, accumulate_into=acc_)
         acc_ = (rr['sum_w'], rr['sum_w2'], rr['count'])
     assert_array_equal(acc_[2].cpu().numpy(), cnt)
-    assert_allclose(acc_[0].cpu().numpy(), r['sum_w'].cpu().numpy(), rtol=1e-7)
+    assert_allclose(acc_[0].cpu().numpy(), r['sum_w'].cpu().numpy(), rtol=1e-6)     # a sample that moves between the main loop and the ragged-end trips may change by an FP32 ulp
     # and the samples on both sides of the boundary are different samples (the high word enters the counter)
     _, obs_lo, _ = H.dump(ig, 1000, seed, 'f32', first=0)
     _, obs_hi, _ = H.dump(ig, 1000, seed, 'f32', first=2 ** 32)
