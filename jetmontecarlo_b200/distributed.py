@@ -48,15 +48,17 @@ def allreduce_histograms(sum_w, sum_w2, count, group=None):
 
 
 def allreduce_minmax(minmax, group=None):
-    """minmax = [min, max]: one MAX all-reduce of [-min, max]; NaN propagates."""
+    """minmax[..., 0] = min, minmax[..., 1] = max (one pair, or one pair per parameter point of a grid), merged
+    in place by ONE MAX all-reduce of [-min, max, has-NaN] rows; a NaN on any rank makes that pair NaN, as
+    np.min / np.max of the whole sample set would be."""
     if not is_distributed(group):
         return
-    buf = torch.stack([-minmax[0], minmax[1]])
-    has_nan = torch.isnan(buf).any().to(buf.dtype).reshape(1)
-    buf = torch.cat([torch.nan_to_num(buf, nan=float("-inf")), has_nan])
+    inf = float("inf")
+    mm = minmax.reshape(-1, 2)
+    buf = torch.stack([-mm[:, 0], mm[:, 1]], dim=1)
+    has_nan = torch.isnan(buf).any(dim=1, keepdim=True).to(buf.dtype)
+    buf = torch.cat([torch.nan_to_num(buf, nan=-inf, posinf=inf, neginf=-inf), has_nan], dim=1).contiguous()
     dist.all_reduce(buf, op=dist.ReduceOp.MAX, group=group)
-    if buf[2] > 0:
-        minmax.fill_(float("nan"))
-    else:
-        minmax[0] = -buf[0]
-        minmax[1] = buf[1]
+    out = torch.stack([-buf[:, 0], buf[:, 1]], dim=1)
+    out[buf[:, 2] > 0] = float("nan")
+    minmax.copy_(out.reshape(minmax.shape))

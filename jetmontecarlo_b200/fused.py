@@ -224,9 +224,7 @@ def integrate_batch(integrands, num_samples, *, edges=None, numbins=None, binspa
         mm[:, 0], mm[:, 1] = float('inf'), float('-inf')
         _lib.check(_lib.lib.jmc_run_batch(arr, npts, n_local, key, first, prec, None, 0, None, None, None, D.ptr(mm),
                                           D.stream()))
-        if dist_utils.is_distributed(group):
-            for i in range(npts):
-                dist_utils.allreduce_minmax(mm[i], group)
+        dist_utils.allreduce_minmax(mm, group)       # one collective for the whole grid
         mm = D.to_host(mm)
         mlb = np.full(npts, 1e-15) if min_log_bins is None else np.asarray(min_log_bins, dtype=float)
         rows = []

@@ -211,6 +211,19 @@ assert mm.tolist() == [0.5, 7.0]
 mm = torch.tensor([float("nan") if rank == 1 else 1., 2.], dtype=torch.float64)
 du.allreduce_minmax(mm)
 assert torch.isnan(mm).all()
+# a rank without samples contributes [inf, -inf]
+mm = torch.tensor([float("inf"), float("-inf")] if rank == 0 else [3., 4.], dtype=torch.float64)
+du.allreduce_minmax(mm)
+assert mm.tolist() == [3.0, 4.0]
+mm = torch.tensor([float("inf"), float("-inf")], dtype=torch.float64)
+du.allreduce_minmax(mm)
+assert mm.tolist() == [float("inf"), float("-inf")]
+# a whole parameter grid in one collective: rows are independent, NaN stays in its row
+grid = torch.tensor([[1. + rank, 5. + rank], [2. - rank, 9. - rank], [float("nan") if rank == 0 else 0., 1.],
+                     [-3., -2. * (rank + 1)]], dtype=torch.float64)
+du.allreduce_minmax(grid)
+assert grid[[0, 1, 3]].tolist() == [[1., 6.], [1., 9.], [-3., -2.]]
+assert torch.isnan(grid[2]).all()
 dist.barrier()
 dist.destroy_process_group()
 print("rank", rank, "ok")
