@@ -896,3 +896,49 @@ def ecf_from_chain_softdrop(chain, z_cut, beta, beta_sd=0., obs_acc=LL, n_emissi
         return c_list[0]
     rest = sorted(c_list[1:], reverse=True)
     return sum([c_list[0]] + rest[:int(n_emissions) - 1])
+
+
+def ecf_from_chain_rss(chain, z_cut, beta, f=1., obs_acc=LL, emission_type='precritsub', n_emissions=1,
+                       few_pres=True):
+    """Recursive-safe-subtraction grooming of one jet's (z, theta) chain: emissions softer than the remaining
+    z_cut are pre-critical (they eat into z_cut and, for f != 1, rescale the hard branch), the first one that
+    survives is critical, later ones are subsequent.  Returns None for a jet the reference drops (ecf < 0).
+    ``emission_type`` is matched by substring exactly as the reference does ('precrit' also contains 'crit').
+    ref: utils/partonshower_utils.py:501-674"""
+    if z_cut == 0:
+        return ecf_from_chain_ungroomed(chain, beta, obs_acc, n_emissions)
+    assert f > 1 / 3, "f = " + str(f) + " is less than 1/3"
+
+    def ecf(z, theta, zc):
+        if obs_acc == LL:
+            return (z - f * zc) * theta ** beta * (1. - (1. - f) * zc)
+        return (z - f * zc) * theta ** beta * (1. - z - (1. - f) * zc)
+
+    this_zcut, use_precrit = z_cut, True
+    c_crit, z_pres, c_subs = 1e-50, [1e-50], [1e-50]
+    for z, theta in chain:
+        # scalar types of the reference: z is a ratio of math.sqrt magnitudes (Python float), theta comes out of
+        # np.arccos (NumPy scalar, so theta**beta is NumPy's power, which squares exactly) -- bit-for-bit parity
+        # with the golden vectors depends on it in about one jet per hundred
+        z, theta = float(z), np.float64(theta)
+        if few_pres:
+            cutoff_zcut = this_zcut - max(z_pres)
+            hard_scale = 1 - (1 - f) * max(z_pres) / f
+        else:
+            cutoff_zcut = this_zcut - sum(z_pres)
+            hard_scale = np.prod([1 - (1 - f) * zp / f for zp in z_pres])
+        valid_precrit = (z < this_zcut) if few_pres else (z < cutoff_zcut)
+        if 'precrit' in emission_type and use_precrit and valid_precrit:
+            z_pres.append(z)
+        elif 'crit' in emission_type and z >= cutoff_zcut > 0.:
+            c_crit = ecf(z, theta, cutoff_zcut) * hard_scale ** 2.
+            this_zcut, use_precrit = 0., False
+        elif 'sub' in emission_type and this_zcut == 0.:
+            c_subs.append(ecf(z, theta, 0.) * hard_scale ** 2.)
+    c_list = c_subs + [c_crit]
+    if n_emissions == 'all':
+        total = sum(c_list)
+    else:
+        c_list.sort(reverse=True)
+        total = sum(c_list[:int(n_emissions)])
+    return total if total >= 0 else None

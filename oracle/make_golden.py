@@ -470,3 +470,38 @@ def callers():
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "callers":
     callers()
+
+
+# ------------------------------------------------------------------ round 1c: RSS grooming of shower chains ----
+RSS_CASES = [   # (f, obs_acc, emission_type, n_emissions, few_pres)
+    (1., 'LL', 'precritsub', 1, True), (1., 'LL', 'precritsub', 2, True), (1., 'MLL', 'precritsub', 'all', True),
+    (1., 'MLL', 'crit', 1, True), (1., 'LL', 'critsub', 2, True), (1., 'LL', 'sub', 1, True),
+    (1., 'MLL', 'precrit', 1, True), (.75, 'LL', 'precritsub', 1, True), (.75, 'MLL', 'precritsub', 'all', True),
+    (.75, 'LL', 'precritsub', 2, False), (.5, 'MLL', 'precritsub', 1, False), (1., 'LL', 'precritsub', 'all', False),
+]
+
+
+def shower_rss():
+    """getECFs_rss on the same jets as shower() (same seeds, so the chains must coincide with shower_*.npz)."""
+    case = 70
+    for jet in ('quark', 'gluon'):
+        for acc in ('LL', 'MLL'):
+            random.seed(SEED + case)
+            jets = PS.gen_jets(400, beta=2., jet_type=jet, radius=1., acc=acc, cutoff=Q.MU_NP, verbose=0)
+            lens = []
+            for jt in jets:
+                lens.append(sum(1 for m in jt.partons if m.daughter1 is not None and m.daughter2 is not None))
+            out = dict(seed=SEED + case, lens=np.array(lens))
+            for z_cut in (.1, .2):
+                for (f, oacc, etype, nem, few) in RSS_CASES:
+                    vals = PS.getECFs_rss(jets, z_cut, beta=2., f=f, obs_acc=oacc, emission_type=etype,
+                                          n_emissions=nem, few_pres=few)
+                    assert len(vals) == len(jets)        # no jet is dropped for these settings
+                    out[f'rss:{z_cut}:{f}:{oacc}:{etype}:{nem}:{int(few)}'] = np.array(vals)
+            out['rss_zcut0:LL:2'] = np.array(PS.getECFs_rss(jets, 0, beta=2., obs_acc='LL', n_emissions=2))
+            save(f"shower_rss_{jet}_{acc}", **out)
+            case += 1
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "rss":
+    shower_rss()

@@ -432,3 +432,26 @@ def test_sampler_argument_checks():
         O.sample_ungroomed('cubic', np.zeros((1, 2)))
     with pytest.raises(AssertionError):
         O.sample_ungroomed('lin', np.zeros((1, 2)), radius=0.)
+
+
+@pytest.mark.parametrize("jet,acc", [('quark', 'LL'), ('quark', 'MLL'), ('gluon', 'LL'), ('gluon', 'MLL')])
+def test_shower_rss_replay(golden, jet, acc):
+    """RSS grooming of the reference's own (z, theta) chains: bit for bit getECFs_rss (partonshower_utils.py:501-674)
+    for every setting in oracle/make_golden.py::RSS_CASES"""
+    chains_file, g = golden(f"shower_{jet}_{acc}"), golden(f"shower_rss_{jet}_{acc}")
+    assert_array_equal(chains_file['lens'], g['lens'])            # same seeds -> same jets
+    ends = np.cumsum(chains_file['lens'])
+    chains = [list(zip(chains_file['z'][e - n:e], chains_file['theta'][e - n:e])) for e, n in zip(ends, chains_file['lens'])]
+    keys = [k for k in g if k.startswith('rss:')]
+    assert len(keys) == 24
+    for k in keys:
+        _, z_cut, f, oacc, etype, nem, few = k.split(':')
+        nem = nem if nem == 'all' else int(nem)
+        got = [O.ecf_from_chain_rss(c, float(z_cut), 2., f=float(f), obs_acc=oacc, emission_type=etype,
+                                    n_emissions=nem, few_pres=bool(int(few))) for c in chains]
+        assert_array_equal(np.array(got), g[k], err_msg=k)
+    got = [O.ecf_from_chain_rss(c, 0, 2., obs_acc='LL', n_emissions=2) for c in chains]
+    assert_array_equal(np.array(got), g['rss_zcut0:LL:2'])
+    # the settings differ from one another (the vectors are not degenerate)
+    assert not np.array_equal(g['rss:0.1:1.0:LL:precritsub:1:1'], g['rss:0.1:0.75:LL:precritsub:1:1'])
+    assert not np.array_equal(g['rss:0.1:1.0:LL:precritsub:1:1'], g['rss:0.2:1.0:LL:precritsub:1:1'])
