@@ -1,7 +1,9 @@
 """Angularity-ordered parton shower -- host mirror of the part of
 jetmontecarlo/utils/partonshower_utils.py that is on the hot path:
 ``gen_jets`` (:294-328), ``getECFs_ungroomed`` (:445-499),
-``getECFs_softdrop`` (:676-790) and ``getECFs_rss`` (:501-674).
+``getECFs_softdrop`` (:676-790), ``getECFs_rss`` (:501-674), ``getangs``
+(:391-443), the ``getECFs`` dispatcher and ``save_shower_correlations``
+(:792-884, the production script's output file).
 
 The reference materialises every jet as a tree of Parton objects with
 3-vectors.  With ``split_soft=False`` (the only mode ``gen_jets`` uses) a jet
@@ -210,3 +212,61 @@ def getECFs_rss(jet_list, z_cut, beta=2., f=1., obs_acc='LL', emission_type='pre
                            emission_type=emission_type, n_emissions=n_emissions, few_pres=few_pres)
     ecfs = D.to_host(ecfs)
     return list(ecfs[ecfs >= 0])                # the reference keeps a jet only if its ecf >= 0
+
+
+def getangs(jet_list, beta=2., acc='LL', emission_type=None, verbose=1):
+    """List of angularities max_i z_i theta_i^beta, one per jet (1e-50 for a jet without emissions).
+    ref: utils/partonshower_utils.py:391-443 -- at 'LL' and 'MLL' alike the reference takes the largest single
+    emission of z theta^beta, which is the LL ungroomed ECF of the leading emission."""
+    assert emission_type is None, "the event record carries no emission types (the reference's jets from gen_jets do not either)"
+    assert acc in ['LL', 'MLL'], "the reference's 'ME' branch raises (sum of a float, :430); LL and MLL are supported"
+    return getECFs_ungroomed(jet_list, beta=beta, obs_acc='LL', n_emissions=1, verbose=0)
+
+
+def getECFs(jet_list, params, groomer=None):
+    """ref: utils/partonshower_utils.py:792-800"""
+    if groomer is None:
+        return getECFs_ungroomed(jet_list, **params)
+    elif groomer == 'RSS':
+        return getECFs_rss(jet_list, **params)
+    elif groomer in ['SoftDrop', 'SD', 'Soft Drop']:
+        return getECFs_softdrop(jet_list, **params)
+    else:
+        raise ValueError('Invalid groomer type ' + str(groomer) + '.')
+
+
+def save_shower_correlations(jet_list, file_path, z_cuts=[.05, .1, .2], beta=2., beta_sd=0., f_soft=1.,
+                             obs_acc='LL', few_pres=True, fixed_coupling=True, verbose=1):
+    """Writes the correlations file of the shower production script: same keys and array shapes as the
+    reference (ungroomed (1, N); RSS crit / critsub / precrit (n_zcut, N); RSS precritsub / two / all and the
+    Soft Drop ones (n_zcut, 1, N)).  ref: utils/partonshower_utils.py:802-884"""
+    n_emissions_list = [1, 2, 'all']
+    ungroomed = [[getECFs_ungroomed(jet_list, beta=beta, obs_acc=obs_acc, n_emissions=n, verbose=verbose)]
+                 for n in n_emissions_list]
+    rss = {k: [] for k in ('crit', 'critsub', 'precrit', 'precritsub', 'two', 'all')}
+    softdrop = {k: [] for k in ('crit', 'two', 'all')}
+    for z_cut in z_cuts:
+        params = dict(jet_list=jet_list, z_cut=z_cut, beta=beta, f=f_soft, obs_acc=obs_acc, few_pres=few_pres,
+                      verbose=verbose)
+        for etype in ('crit', 'precrit', 'critsub'):
+            rss[etype].append(getECFs_rss(**params, emission_type=etype))
+        for key, n in zip(('precritsub', 'two', 'all'), n_emissions_list):
+            rss[key].append([getECFs_rss(**params, emission_type='precritsub', n_emissions=n)])
+    for z_cut in z_cuts:
+        # (beta_sd = 0 whatever the argument says, as in the reference :853)
+        params = dict(jet_list=jet_list, z_cut=z_cut, beta=beta, beta_sd=0., obs_acc=obs_acc, verbose=verbose)
+        for key, n in zip(('crit', 'two', 'all'), n_emissions_list):
+            softdrop[key].append([getECFs_softdrop(**params, n_emissions=n)])
+    np.savez(file_path,
+             ungroomed_c1s=np.asarray(ungroomed[0]),
+             ungroomed_c1s_two=np.asarray(ungroomed[1]),
+             ungroomed_c1s_all=np.asarray(ungroomed[2]),
+             rss_c1s_crit=np.asarray(rss['crit']),
+             rss_c1s_critsub=np.asarray(rss['critsub']),
+             rss_c1s_precrit=np.asarray(rss['precrit']),
+             rss_c1s_precritsub=np.asarray(rss['precritsub']),
+             rss_c1s_two=np.asarray(rss['two']),
+             rss_c1s_all=np.asarray(rss['all']),
+             softdrop_c1s_crit=np.asarray(softdrop['crit']),
+             softdrop_c1s_two=np.asarray(softdrop['two']),
+             softdrop_c1s_all=np.asarray(softdrop['all']))

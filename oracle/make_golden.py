@@ -505,3 +505,20 @@ def shower_rss():
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "rss":
     shower_rss()
+
+
+def shower_correlations():
+    """The npz written by save_shower_correlations (the shower production script's output format,
+    partonshower_utils.py:802-884) for the quark MLL jets of shower()."""
+    random.seed(SEED + 71)
+    jets = PS.gen_jets(400, beta=2., jet_type='quark', radius=1., acc='MLL', cutoff=Q.MU_NP, verbose=0)
+    path = os.path.join(OUT, "shower_corr_quark_MLL.npz")
+    PS.save_shower_correlations(jets, path, z_cuts=[.05, .1, .2], beta=2., f_soft=1., obs_acc='MLL', few_pres=True,
+                                verbose=0)
+    z = dict(np.load(path))
+    np.savez_compressed(path, **z)
+    print("wrote", path, os.path.getsize(path), "bytes", {k: v.shape for k, v in z.items()})
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "corr":
+    shower_correlations()
