@@ -942,3 +942,62 @@ def ecf_from_chain_rss(chain, z_cut, beta, f=1., obs_acc=LL, emission_type='prec
         c_list.sort(reverse=True)
         total = sum(c_list[:int(n_emissions)])
     return total if total >= 0 else None
+
+
+# ---------------------------------------------------------------------------
+# Inverse-transform sampling from a cdf given as a function
+# ---------------------------------------------------------------------------
+def inverse_transform(cdf_vals, x_vals, r):
+    """x(r) by linear interpolation of the table (cdf -> x), extrapolating beyond it.
+    ref: utils/montecarlo_utils.py:377-399 (scipy interp1d, which sorts its abscissa, here the cdf values)"""
+    from scipy import interpolate
+    return interpolate.interp1d(cdf_vals, x_vals, fill_value='extrapolate')(r)
+
+
+def cdf_probe_points(domain):
+    """The 1000-odd points on which the reference inspects a cdf.  ref: utils/montecarlo_utils.py:147-154"""
+    if domain[0] < 0:
+        return np.linspace(domain[0], domain[1], 1000)
+    if domain[0] == 0:
+        return np.array([0, *lin_log_mixed_list(domain[0] + 1e-20, domain[1], 1000)])
+    return lin_log_mixed_list(domain[0], domain[1], 1000)
+
+
+def samples_from_cdf_tabulated(cdf, num_samples, domain, rand, catch_turnpoint=False, force_monotone=False):
+    """What samples_from_cdf does with a cdf that pynverse's ``inversefunc`` refuses (ValueError) -- the only part
+    of it that can be executed here, pynverse (0.1.4.4) being absent: tabulate the cdf on the probe points, then
+    in this order: monotone table -> inverse-transform samples of the table; cdf starting at 1 -> zero bin;
+    negligible (< 1e-20) up to a point and monotone after it -> retry on the rest of the domain; cdf reaching 1 and
+    turning back (``catch_turnpoint``) -> retry below the turning point; ``force_monotone`` -> drop the table
+    entries after which the cdf decreases; otherwise ValueError.  ``rand(n)`` supplies the uniforms
+    (np.random.rand in the reference).  Returns (samples, weights).
+    ref: utils/montecarlo_utils.py:93-375 (the ``except ValueError`` branch, :142-318)"""
+    pnts = cdf_probe_points(domain)
+    cdf_vals = np.nan_to_num(cdf(pnts))
+    monotone = cdf_vals[:-1] <= cdf_vals[1:]
+    if monotone.all():
+        samples = inverse_transform(cdf_vals, pnts, rand(num_samples))
+        return samples, np.ones_like(samples)
+    bad_low = pnts[:-1][~monotone]
+    bad_cdf_low = cdf(np.unique(bad_low))
+    if all(cdf_vals == 1.):
+        return np.zeros(num_samples), np.ones(num_samples)
+    if bad_low[0] == pnts[0] and bad_cdf_low[0] == 1:
+        return np.zeros(num_samples), np.ones(num_samples)
+    threshold = 1e-20
+    if all(cdf_vals < threshold):
+        samples = np.full(num_samples, domain[1])
+        return samples, np.ones_like(samples)
+    for i, (value, point) in enumerate(zip(cdf_vals, pnts)):
+        if value > threshold:
+            if not all(monotone[i:]):
+                break
+            return samples_from_cdf_tabulated(cdf, num_samples, [point, domain[1]], rand, catch_turnpoint,
+                                              force_monotone)
+    if bad_cdf_low[0] == 1 and catch_turnpoint:
+        return samples_from_cdf_tabulated(cdf, num_samples, [domain[0], bad_low[0]], rand, catch_turnpoint,
+                                          force_monotone)
+    if force_monotone:
+        samples = inverse_transform(cdf_vals[:-1][monotone], pnts[:-1][monotone], rand(num_samples))
+        return samples, np.ones_like(samples)
+    raise ValueError("cdf is not monotone on %s and neither catch_turnpoint nor force_monotone applies" % (list(domain),))

@@ -522,3 +522,50 @@ def shower_correlations():
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "corr":
     shower_correlations()
+
+
+# ------------------------------------------------------------------ round 1d: samples_from_cdf without pynverse ----
+def _refuse(*a, **k):
+    raise ValueError("inversefunc: refused (pynverse is not installed here; this drives samples_from_cdf into "
+                     "its own tabulated fall-backs)")
+
+
+CDF_CASES = {
+    # name: (cdf, domain, kwargs)
+    'square': (lambda x: np.clip(x, 0, 1) ** 2, [0, 1], {}),
+    'sudakov_pos_domain': (lambda x: np.exp(-np.log(1. / x) ** 2 * .3), [1e-8, 1.], {}),
+    'neg_domain': (lambda x: .5 * (1 + np.tanh(x)), [-4., 4.], {}),
+    'starts_at_one': (lambda x: np.where(x == 0, 1., .5 + .5 * x), [0, 1], {}),
+    'negligible_then_monotone': (lambda x: np.where(x < .01, 1e-30 * (1 + np.sin(1e4 * x)), (x - .01) / .99),
+                                 [0, 1], {}),
+    'turnpoint': (lambda x: np.where(x < .6, np.minimum(x / .4, 1.), 1. - (x - .6)), [1e-6, 1.],
+                  dict(catch_turnpoint=True)),
+    'wiggle_forced': (lambda x: np.clip(x + .02 * np.sin(60 * x), 0, 1), [0, 1], dict(force_monotone=True)),
+    'nan_head_forced': (lambda x: np.where(x < 1e-4, np.nan, np.clip(x + .05 * np.sin(25 * x), 0, 1)), [0, 1],
+                        dict(force_monotone=True)),
+}
+
+
+def cdf_sampling():
+    """samples_from_cdf with inversefunc refusing every cdf: the reference's own tabulated branches."""
+    import jetmontecarlo.utils.montecarlo_utils as MU
+    MU.inversefunc = _refuse
+    out = {}
+    for k, (name, (cdf, domain, kw)) in enumerate(CDF_CASES.items()):
+        np.random.seed(SEED + 300 + k)
+        samples, weights = MU.samples_from_cdf(cdf, 1500, domain=domain, verbose=0, **kw)
+        out[name + ':samples'], out[name + ':weights'] = np.asarray(samples, float), np.asarray(weights, float)
+        out[name + ':seed'] = SEED + 300 + k
+    for name in ('wiggle_forced', 'turnpoint'):        # without its flag the reference gives up
+        cdf, domain, _ = CDF_CASES[name]
+        try:
+            MU.samples_from_cdf(cdf, 10, domain=domain, verbose=0)
+            raised = False
+        except ValueError:
+            raised = True
+        out[name + ':raises_without_flag'] = raised
+    save("samples_from_cdf", **out)
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "cdf":
+    cdf_sampling()

@@ -156,29 +156,3 @@ def test_c2_veto_shower_against_integrated_radiator(cuda, jet):
     sigma = np.sqrt(cdf * (1 - cdf) / n_jets + (sud * dR) ** 2) + 2e-5
     assert np.abs((cdf - sud) / sigma).max() < 5., np.abs((cdf - sud) / sigma).max()
     assert np.abs(cdf - sud).max() < 1e-3
-
-
-@pytest.mark.parametrize("jet,acc", [('quark', 'MLL'), ('gluon', 'LL')])
-def test_shower_rss_on_device_chains(cuda, jet, acc):
-    """getECFs_rss (ref: partonshower_utils.py:501-674): chains regenerated on the GPU and groomed there, against the
-    oracle (pinned bit for bit to the reference's getECFs_rss) applied to the same chains"""
-    from jetmontecarlo_b200.utils import partonshower_utils as PS
-    n = 2000
-    jets = PS.gen_jets(n, beta=2., jet_type=jet, acc=acc, verbose=0, seed=77)
-    lens, zs, ths = jets.chains()
-    chains = [list(zip(zs[i, :lens[i]], ths[i, :lens[i]])) for i in range(n)]
-    for z_cut, kw in ((.1, dict()), (.1, dict(n_emissions=2, obs_acc='MLL')), (.2, dict(n_emissions='all', f=.75)),
-                      (.1, dict(f=.5, few_pres=False, n_emissions=2)), (.1, dict(emission_type='crit')),
-                      (.2, dict(emission_type='critsub', n_emissions=3, obs_acc='MLL'))):
-        args = dict(beta=2., f=1., obs_acc='LL', emission_type='precritsub', n_emissions=1, few_pres=True)
-        args.update(kw)
-        got = PS.getECFs_rss(jets, z_cut, **args)
-        beta = args.pop('beta')
-        ref = [O.ecf_from_chain_rss(c, z_cut, beta, **args) for c in chains]
-        assert len(got) == n
-        assert_allclose(got, ref, rtol=1e-12, err_msg=str(kw))
-    # grooming only removes radiation: the RSS-groomed leading ECF never exceeds the ungroomed one
-    ungroomed = np.array(PS.getECFs_ungroomed(jets, beta=2., obs_acc='LL', n_emissions=1))
-    groomed = np.array(PS.getECFs_rss(jets, .1, beta=2., obs_acc='LL', n_emissions=1))
-    assert np.all(groomed <= ungroomed * (1 + 1e-12)) and (groomed < ungroomed).mean() > .2
-    assert PS.getECFs_rss(jets, 0, beta=2., n_emissions=2) == PS.getECFs_ungroomed(jets, beta=2., n_emissions=2)

@@ -455,3 +455,40 @@ def test_shower_rss_replay(golden, jet, acc):
     # the settings differ from one another (the vectors are not degenerate)
     assert not np.array_equal(g['rss:0.1:1.0:LL:precritsub:1:1'], g['rss:0.1:0.75:LL:precritsub:1:1'])
     assert not np.array_equal(g['rss:0.1:1.0:LL:precritsub:1:1'], g['rss:0.2:1.0:LL:precritsub:1:1'])
+
+
+def _cdf_cases():
+    """the synthetic cdfs of oracle/make_golden.py::CDF_CASES, restated (the generator script imports the reference
+    and cannot be imported on the GPU box)"""
+    return {
+        'square': (lambda x: np.clip(x, 0, 1) ** 2, [0, 1], {}),
+        'sudakov_pos_domain': (lambda x: np.exp(-np.log(1. / x) ** 2 * .3), [1e-8, 1.], {}),
+        'neg_domain': (lambda x: .5 * (1 + np.tanh(x)), [-4., 4.], {}),
+        'starts_at_one': (lambda x: np.where(x == 0, 1., .5 + .5 * x), [0, 1], {}),
+        'negligible_then_monotone': (lambda x: np.where(x < .01, 1e-30 * (1 + np.sin(1e4 * x)), (x - .01) / .99),
+                                     [0, 1], {}),
+        'turnpoint': (lambda x: np.where(x < .6, np.minimum(x / .4, 1.), 1. - (x - .6)), [1e-6, 1.],
+                      dict(catch_turnpoint=True)),
+        'wiggle_forced': (lambda x: np.clip(x + .02 * np.sin(60 * x), 0, 1), [0, 1], dict(force_monotone=True)),
+        'nan_head_forced': (lambda x: np.where(x < 1e-4, np.nan, np.clip(x + .05 * np.sin(25 * x), 0, 1)), [0, 1],
+                            dict(force_monotone=True)),
+    }
+
+
+def test_samples_from_cdf_tabulated_branches(golden):
+    """samples_from_cdf (montecarlo_utils.py:93-375) with pynverse refusing the cdf: every tabulated fall-back of
+    the reference, bit for bit on the reference's np.random stream"""
+    g = golden("samples_from_cdf")
+    for name, (cdf, domain, kw) in _cdf_cases().items():
+        rs = np.random.RandomState(int(g[name + ':seed']))
+        with np.errstate(all='ignore'):
+            samples, weights = O.samples_from_cdf_tabulated(cdf, 1500, domain, rs.rand, **kw)
+        assert_array_equal(samples, g[name + ':samples'], err_msg=name)
+        assert_array_equal(weights, g[name + ':weights'], err_msg=name)
+    assert np.all(g['starts_at_one:samples'] == 0.)                      # zero bin
+    assert g['turnpoint:samples'].max() <= .6 and g['negligible_then_monotone:samples'].min() >= .01
+    for name in ('wiggle_forced', 'turnpoint'):
+        assert bool(g[name + ':raises_without_flag'])
+        cdf, domain, _ = _cdf_cases()[name]
+        with pytest.raises(ValueError):
+            O.samples_from_cdf_tabulated(cdf, 10, domain, np.random.RandomState(0).rand)
