@@ -569,3 +569,65 @@ def cdf_sampling():
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "cdf":
     cdf_sampling()
+
+
+# ------------------------------------------------------------------ round 1e: interpolation helpers ----
+def interpolation_helpers():
+    """get_1d_interpolation / monotonic_domain / get_2d_interpolation as the reference evaluates them
+    (utils/interpolation.py:43-273), on tables taken from the golden integrals and on a few analytic functions."""
+    from jetmontecarlo.utils import interpolation as I
+    out = {}
+    g = np.load(os.path.join(OUT, "c1_log0.npz"))
+    tables = {
+        'rad_log': (g['quark_fc_LL:edges'], g['quark_fc_LL:integral']),                  # decreasing, log-spaced
+        'lin_inc': (np.linspace(0., 2., 21), np.linspace(0., 2., 21) ** 2),               # increasing, lin-spaced
+        'wiggle': (np.linspace(0., 1., 41), np.linspace(0., 1., 41) + .05 * np.sin(20 * np.linspace(0., 1., 41))),
+    }
+    for name, (xs, fs) in tables.items():
+        probe = np.concatenate([[xs[0] - 1., xs[0], xs[1], xs[-1], xs[-1] + 1.], np.sqrt(np.abs(xs[1:] * xs[:-1])),
+                                (xs[1:] + xs[:-1]) / 2., xs])
+        out[f'{name}:xs'], out[f'{name}:fs'], out[f'{name}:probe'] = xs, fs, probe
+        if name != 'wiggle':
+            # (a fresh [None, None] every time: the reference's default is one mutable list that keeps the boundary
+            # values of the first table it ever saw, interpolation.py:188,229-232)
+            out[f'{name}:mono_default'] = I.get_1d_interpolation(xs, fs, monotonic=True,
+                                                                 bound_values=[None, None])(probe)
+            out[f'{name}:mono_bounds'] = I.get_1d_interpolation(xs, fs, monotonic=True, bounds=(xs[2], xs[-3]),
+                                                               bound_values=[None, None])(probe)
+        out[f'{name}:free_bounds'] = I.get_1d_interpolation(xs, fs, monotonic=False, bounds=(xs[0], xs[-1]),
+                                                           bound_values=[0., 0.])(probe)
+        out[f'{name}:free_cont'] = I.get_1d_interpolation(xs, fs, monotonic=False, bounds=(xs[1], xs[-2]),
+                                                         bound_values=None)(probe)
+        out[f'{name}:is_mono'] = np.array([I.is_monotonic_arr(fs), I.is_monotonic_arr(fs, 'increasing'),
+                                           I.is_monotonic_arr(fs, 'decreasing')])
+        out[f'{name}:where_inc'] = I.where_monotonic_arr(fs, 'increasing')
+        out[f'{name}:where_dec'] = I.where_monotonic_arr(fs, 'decreasing')
+    funcs = {'square': lambda x: x ** 2, 'sin': lambda x: np.sin(3. * x), 'cubic': lambda x: x ** 3 - x}
+    md = []
+    for fname, domain, point, check in [('square', [-10, 10], 1, 'increasing'), ('square', [0, 10], 1, 'increasing'),
+                                        ('square', [-10, 10], 1, 'decreasing'), ('square', [-10, 10], -1, 'decreasing'),
+                                        ('square', [-10, 10], -1, 'increasing'), ('sin', [0.1, 3.], 1.5, None),
+                                        ('sin', [-2., 2.], 0.1, 'increasing'), ('cubic', [-2., 2.], 0., None),
+                                        ('cubic', [.1, 2.], None, None), ('square', [1e-3, 4.], None, 'increasing')]:
+        res = I.monotonic_domain(funcs[fname], domain, point, check)
+        md.append([np.nan, np.nan] if res is None else [float(res[0]), float(res[1])])
+    out['monotonic_domain'] = np.array(md)
+    out['is_monotonic_func'] = np.array([I.is_monotonic_func(funcs['square'], [.1, 3.]),
+                                         I.is_monotonic_func(funcs['sin'], [.1, 3.]),
+                                         I.is_monotonic_func(funcs['sin'], [.1, .4], 'increasing'),
+                                         I.is_monotonic_func(funcs['square'], [.1, 3.], 'decreasing')])
+    # 2-D: rectangular grid (linear, extrapolating) and nearest neighbour
+    x, y = np.linspace(0., 1., 6), np.logspace(-3, 0, 5)
+    z = np.outer(x ** 2, np.log(1. / y) + 1.)
+    pts = np.array([[.1, .01], [.5, .5], [0., 1e-3], [1., 1.], [1.2, .5], [.33, 2.], [-.1, 1e-4]])
+    out['grid:x'], out['grid:y'], out['grid:z'], out['grid:pts'] = x, y, z, pts
+    out['grid:linear'] = I.get_2d_interpolation(x, y, z)(pts)
+    out['grid:nearest_method'] = I.get_2d_interpolation(x, y, z, method='nearest')(pts)
+    xx, yy = np.meshgrid(x, y, indexing='ij')
+    out['scatter:nearest'] = I.get_2d_interpolation(xx.flatten(), yy.flatten(), z.flatten(),
+                                                    interpolation_method='Nearest')(pts[:, 0], pts[:, 1])
+    save("interpolation", **out)
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "interp":
+    interpolation_helpers()

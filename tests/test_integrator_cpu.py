@@ -108,14 +108,24 @@ def test_file_formats_round_trip(tmp_path, golden):
 
 
 def test_interpolating_function_of_a_golden_integral(golden):
-    """makeInterpolatingFn on a reference result: exact at the edges, monotone between them, clamped outside"""
+    """makeInterpolatingFn on a reference result, as the radiator generators use it (setMonotone first,
+    generation.py:84,128); semantics of utils/interpolation.py, see tests/test_interpolation_cpu.py"""
+    from jetmontecarlo_b200.utils.interpolation import get_1d_interpolation
     g = golden("c1_log0")
     tag = "quark_fc_LL:"
     it = _integrator()
     it.bins, it.integral, it.hasMCIntegral = g[tag + 'edges'], list(g[tag + 'integral']), True
+    # without setMonotone and without bounds the reference refuses (interpolation.py:243-244)
+    with pytest.raises(AssertionError, match="Cannot assign boundary values"):
+        it.makeInterpolatingFn()
+    it.setMonotone()
     it.makeInterpolatingFn()
     assert it.hasInterpIntegral
-    assert_allclose(it.interpFn(it.bins), g[tag + 'integral'], rtol=1e-12, atol=1e-300)
+    probe = np.concatenate([it.bins, np.sqrt(it.bins[1:] * it.bins[:-1])])
+    assert_array_equal(it.interpFn(probe), get_1d_interpolation(it.bins, it.integral, monotonic=True)(probe))
+    # over the whole table: exact at the interior edges, between the neighbouring values inside a bin
+    it.makeInterpolatingFn(bounds=(it.bins[0], it.bins[-1]))
+    assert_allclose(it.interpFn(it.bins[1:-1]), g[tag + 'integral'][1:-1], rtol=1e-15)
     mid = np.sqrt(it.bins[1:] * it.bins[:-1])
     v = it.interpFn(mid)
     lo = np.minimum(g[tag + 'integral'][1:], g[tag + 'integral'][:-1])
