@@ -47,3 +47,54 @@ def vals_to_pdf(vals, num_bins, weights=None, bin_space='log', log_cutoff=None, 
     if bin_space == 'log':
         pdf = xs * pdf * np.log(10)
     return xs, pdf
+
+
+# ---- O(bins) post-processing of finished histograms (host, as in the reference) --------------------------------
+def histDerivative(hist, bins, giveHist=False, binInput='lin'):
+    """Second-order finite-difference derivative of a histogram with uniform (or, ``binInput='log'``, log-uniform)
+    bins: one-sided three-point stencils in the first and last bin, central differences between; for log bins the
+    derivative is with respect to the variable itself, not its logarithm.  Returns an extrapolating interpolant
+    over the bin centres (and the values there if ``giveHist``).  ref: utils/hist_utils.py:7-91"""
+    from scipy import interpolate
+    hist = np.asarray(hist)
+    if binInput == 'log':
+        bins = np.log(bins)
+    width = bins[-1] - bins[-2]
+    first = np.array([(-hist[2] + 4. * hist[1] - 3. * hist[0]) / (2. * width)])
+    bulk = (hist[2:] - hist[:-2]) / (2. * width)
+    last = np.array([(3. * hist[-1] - 4. * hist[-2] + hist[-3]) / (2. * width)])
+    if binInput == 'lin':
+        xs = (bins[1:] + bins[:-1]) / 2.
+        deriv = np.concatenate((first, bulk, last))
+    elif binInput == 'log':
+        xs = np.exp((bins[1:] + bins[:-1]) / 2.)
+        deriv = np.concatenate((first, bulk, last)) / xs
+    else:
+        raise AssertionError("The style of the input bins must be either 'lin' or 'log'.")
+    interp = interpolate.interp1d(x=xs, y=deriv, fill_value="extrapolate")
+    if giveHist:
+        return interp, deriv
+    return interp
+
+
+def nan_info(array, name):
+    """ref: utils/hist_utils.py:146-149"""
+    print(f'nan {name}')
+    print(int(np.isnan(np.asarray(array, dtype=float)).sum()))
+
+
+def notfinite_info(array, name):
+    """ref: utils/hist_utils.py:152-155"""
+    print(f'notfinite {name}')
+    print(int((~np.isfinite(np.asarray(array, dtype=float))).sum()))
+
+
+def smooth_data(x, y):
+    """Low-pass filter: real FFT coefficients whose square is below 5 % of the largest are dropped.
+    ref: utils/hist_utils.py:158-173"""
+    import scipy.fftpack
+    assert len(x) == len(y), "x and y must be the same length."
+    coeffs = scipy.fftpack.rfft(y)
+    power = coeffs ** 2
+    kept = np.where(power < power.max() * 5e-2, 0., coeffs)
+    return scipy.fftpack.irfft(kept)

@@ -631,3 +631,25 @@ def interpolation_helpers():
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "interp":
     interpolation_helpers()
+
+
+# ------------------------------------------------------------------ round 1f: histogram post-processing ----
+def hist_postprocessing():
+    """histDerivative / smooth_data (utils/hist_utils.py:7-91, 158-173) on a golden cumulative integral."""
+    from jetmontecarlo.utils.hist_utils import histDerivative, smooth_data
+    out = {}
+    for name in ('c1_log0', 'c1_lin1'):
+        g = np.load(os.path.join(OUT, name + ".npz"))
+        edges, integral = g['quark_fc_LL:edges'], g['quark_fc_LL:integral']
+        spacing = 'log' if 'log' in name else 'lin'
+        hist = integral[:-1]
+        interp, deriv = histDerivative(hist, edges, giveHist=True, binInput=spacing)
+        mids = np.exp((np.log(edges[1:]) + np.log(edges[:-1])) / 2.) if spacing == 'log' else (edges[1:] + edges[:-1]) / 2.
+        probe = np.concatenate([mids, edges[1:-1], [edges[0] * .5 if spacing == 'log' else -1., edges[-1] * 2.]])
+        out[f'{name}:deriv'], out[f'{name}:probe'], out[f'{name}:interp'] = deriv, probe, interp(probe)
+        out[f'{name}:smooth'] = smooth_data(mids, hist)
+    save("hist_postprocessing", **out)
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "histpost":
+    hist_postprocessing()

@@ -75,3 +75,23 @@ def test_2d_interpolants(golden):
         I.get_2d_interpolation(x, y, z, interpolation_method='spline')
     with pytest.raises(NotImplementedError, match="interp2d"):
         I.get_2d_interpolation(x, y, z, interpolation_method='Cubic')
+
+
+def test_hist_postprocessing(golden, capsys):
+    """histDerivative / smooth_data on a golden cumulative integral, bit for bit (ref: utils/hist_utils.py:7-91, 158-173)"""
+    from jetmontecarlo_b200.utils.hist_utils import histDerivative, nan_info, notfinite_info, smooth_data
+    g = golden("hist_postprocessing")
+    for name, spacing in (('c1_log0', 'log'), ('c1_lin1', 'lin')):
+        c1 = golden(name)
+        edges, hist = c1['quark_fc_LL:edges'], c1['quark_fc_LL:integral'][:-1]
+        interp, deriv = histDerivative(hist, edges, giveHist=True, binInput=spacing)
+        assert_array_equal(deriv, g[f'{name}:deriv'])
+        assert_array_equal(interp(g[f'{name}:probe']), g[f'{name}:interp'])
+        assert_array_equal(histDerivative(hist, edges, binInput=spacing)(g[f'{name}:probe']), g[f'{name}:interp'])
+        mids = np.exp((np.log(edges[1:]) + np.log(edges[:-1])) / 2.) if spacing == 'log' else (edges[1:] + edges[:-1]) / 2.
+        assert_array_equal(smooth_data(mids, hist), g[f'{name}:smooth'])
+    with pytest.raises(AssertionError, match="either 'lin' or 'log'"):
+        histDerivative(hist, edges, binInput='sqrt')
+    nan_info([1., np.nan, 2.], "w")
+    notfinite_info([1., np.nan, np.inf], "w")
+    assert capsys.readouterr().out.split() == ['nan', 'w', '1', 'notfinite', 'w', '2']
