@@ -246,3 +246,40 @@ def test_gloo_world_size_2():
         out, err = p.communicate(timeout=180)
         assert p.returncode == 0, err
         assert "ok" in out
+
+
+def test_c_abi_argument_errors_need_no_device():
+    """argument validation comes first: these calls fail with JMC_EINVAL and a message before any CUDA call, so they
+    behave the same with and without a GPU"""
+    from jetmontecarlo_b200 import _lib
+    from jetmontecarlo_b200.fused import Integrand
+    L = _lib.lib
+    s = Integrand.crit_sub('log', .1, 1e-10).c_struct()
+    buf = np.zeros(8)
+    P = lambda a: a.ctypes.data_as(C.c_void_p)
+    cases = [
+        (L.jmc_run(None, 10, 0, 0, 0, None, 0, None, None, None, None, None), b"integrand is NULL"),
+        (L.jmc_run(C.byref(s), 10, 0, 0, 7, None, 0, None, None, None, None, None), b"precision must be"),
+        (L.jmc_run_batch(C.byref(s), 0, 10, 0, 0, 1, None, 0, None, None, None, None, None), b"at least one parameter point"),
+        (L.jmc_dump(None, 10, 0, 0, 0, None, None, None, None), b"integrand is NULL"),
+        (L.jmc_set_density_host(P(buf), P(buf), 8, P(buf), 1, 1., 0, 0., None, None, None, None, None, None, None),
+         b"Need bins to produce density histogram."),
+        (L.jmc_set_density_host(None, None, 8, P(buf), 8, 1., 0, 0., None, None, None, None, None, None, None),
+         b"NULL input array"),
+        (L.jmc_integrate_host(C.byref(s), 10, 0, 0, 1, None, 0, 0, 0., None, None, None, None, None, None, None),
+         b"Need bins to produce density histogram."),
+        (L.jmc_sample_host(None, 4, 0, 0, P(buf), P(buf)), b"sampler is NULL"),
+        (L.jmc_sampler_area(None, None), b"NULL argument"),
+    ]
+    for rc, text in cases:
+        assert rc == -1, (rc, text)
+    # the message of the LAST failing call is the one kept (per thread)
+    assert b"NULL argument" in L.jmc_last_error()
+    bad = Integrand.crit_sub('log', .1, 1e-10).c_struct()
+    for field, value, text in (("kind", 99, b"unknown integrand kind"), ("method", 5, b"not a supported sample method"),
+                               ("jet", 3, b"not a supported jet type"), ("epsilon", 0., b"invalid for log sampling"),
+                               ("radius", 0., b"radius must be greater than zero"), ("obs_acc", 9, b"Accuracy must be LL or MLL")):
+        g = Integrand.crit_sub('log', .1, 1e-10).c_struct()
+        setattr(g, field, value)
+        assert L.jmc_run(C.byref(g), 10, 0, 0, 0, None, 0, None, None, None, None, None) == -1
+        assert text in L.jmc_last_error(), (field, L.jmc_last_error())
