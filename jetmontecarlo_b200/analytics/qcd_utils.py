@@ -102,3 +102,40 @@ def q_splitting_bar(z):
 
 def g_splitting_bar(z):
     return splitting_bar(z, 'gluon')
+
+
+# ---- small closed-form helpers (host; used by the analytic truth curves, never per Monte Carlo sample) ---------
+def W(x):
+    """W(x) = x ln x.  ref: analytics/qcd_utils.py:211-216"""
+    return x * np.log(x)
+
+
+def Lambda(x, alpha):
+    """ref: analytics/qcd_utils.py:218-221"""
+    return 2. * alpha * beta_0 * np.log(x)
+
+
+def b_q_bar(z_c):
+    """ref: analytics/qcd_utils.py:223-227"""
+    return CF * (-3. + 6. * z_c + 4. * np.log(2. - 2. * z_c)) / 2.
+
+
+def b_g_bar(z_c):
+    """ref: analytics/qcd_utils.py:229-236"""
+    return ((-1. + 2. * z_c) * (-4. * N_F * TF * (1. + (-1. + z_c) * z_c) + CA * (11. + 2. * (-1. + z_c) * z_c)) / 6.
+            + 2. * CA * np.log(2. - 2. * z_c))
+
+
+def _mpmath_vec(name, nin):
+    import mpmath
+    return np.frompyfunc(getattr(mpmath, name), nin, 1)
+
+
+def polylog_vec(*args):
+    """np-friendly mpmath.polylog.  ref: analytics/qcd_utils.py:239"""
+    return _mpmath_vec('polylog', 2)(*args)
+
+
+def hyp2f1_vec(*args):
+    """np-friendly mpmath.hyp2f1.  ref: analytics/qcd_utils.py:240"""
+    return _mpmath_vec('hyp2f1', 4)(*args)

@@ -653,3 +653,37 @@ def hist_postprocessing():
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "histpost":
     hist_postprocessing()
+
+
+# ------------------------------------------------------------------ round 1g: closed-form truth curves ----
+def closed_forms():
+    """critSudakov_fc_LL (analytics/sudakov_factors/fixedcoupling.py:11-51) and the Soft Drop closed forms
+    (analytics/radiators/soft_drop.py:15-194) on observable grids -- the curves the reference's tests plot their
+    Monte Carlo results against."""
+    import types
+    for name in ("jetmontecarlo.utils.plot_utils", "jetmontecarlo.utils.color_utils"):
+        if name not in sys.modules:                      # plotting helpers (matplotlib): not needed for the formulas
+            sys.modules[name] = types.ModuleType(name)
+    from jetmontecarlo.analytics.radiators import soft_drop as SD
+    out = {}
+    cs = np.logspace(-9, np.log10(.6), 60)
+    out['c'] = cs
+    for jet in ('quark', 'gluon'):
+        for z_c in (.05, .1, .2):
+            for beta in (1.5, 2., 3.):
+                for f in (1., .75):
+                    out[f'critSudakov:{jet}:{z_c}:{beta}:{f}'] = np.array(
+                        critSudakov_fc_LL(cs, z_c, beta, jet, f=f), dtype=float)
+                out[f'sd_rad_fc:{jet}:{z_c}:{beta}'] = SD.softdrop_rad_fc(cs, z_c, beta, jet_type=jet)
+                out[f'sd_radprime_fc:{jet}:{z_c}:{beta}'] = SD.softdrop_radprime_fc(cs, z_c, beta, jet_type=jet)
+                out[f'sd_sudakov_fc_LL:{jet}:{z_c}:{beta}'] = SD.softdrop_sudakov_fc(cs, z_c, beta, jet_type=jet)
+                out[f'sd_sudakov_fc_ME:{jet}:{z_c}:{beta}'] = SD.softdrop_sudakov_fc(cs, z_c, beta, jet_type=jet,
+                                                                                     acc='MLL')
+                for beta_sd in (0, 1.):
+                    out[f'sd_rad_rc:{jet}:{z_c}:{beta}:{beta_sd}'] = SD.softdrop_rad_rc(cs, z_c, beta, beta_sd=beta_sd,
+                                                                                        jet_type=jet)
+    save("closed_forms", **out)
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "closed":
+    closed_forms()
