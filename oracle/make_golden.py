@@ -687,3 +687,28 @@ def closed_forms():
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "closed":
     closed_forms()
+
+
+def closed_forms_fc():
+    """The fixed-coupling radiators beyond leading log (analytics/radiators/fixedcoupling.py:20-57, 110-160) and the
+    pre-critical radiator without frozen coupling (running_coupling.py:291-312)."""
+    out = {}
+    thetas = np.concatenate([[0.], np.logspace(-8, 0, 40)])
+    cs = np.concatenate([[0.], np.logspace(-9, np.log10(.499), 40)])
+    zps = np.logspace(-6, np.log10(.099), 30)
+    out['theta'], out['c'], out['z_pre'] = thetas, cs, zps
+    for jet in ('quark', 'gluon'):
+        for z_c in (.05, .1, .2):
+            out[f'critRadPrime_fc_LL:{jet}:{z_c}'] = FC.critRadPrimeAnalytic_fc_LL(thetas, z_c, jet)
+            out[f'critRad_fc:{jet}:{z_c}'] = FC.critRadAnalytic_fc(thetas, z_c, jet)
+            out[f'critRadPrime_fc:{jet}:{z_c}'] = FC.critRadPrimeAnalytic_fc(thetas, z_c, jet)
+            for th in (.3, 1e-2):
+                out[f'preRad_nofreeze:{jet}:{z_c}:{th}'] = RC.preRadAnalytic_nofreeze(zps * z_c / .1, th, z_c, jet_type=jet)
+        for beta in (1.5, 2., 3.):
+            out[f'subRad_fc:{jet}:{beta}'] = np.array(FC.subRadAnalytic_fc(cs, beta, jet), dtype=float)
+            out[f'subRadPrime_fc:{jet}:{beta}'] = FC.subRadPrimeAnalytic_fc(cs, beta, jet)
+    save("closed_forms_fc", **out)
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "closedfc":
+    closed_forms_fc()

@@ -61,3 +61,30 @@ def test_soft_drop_closed_forms(golden):
     assert np.all(np.diff(s) > 0) and s[-1] == 1.
     # (exactly at c = z_cut neither region's mask is set in the reference, :17-22: the radiator is 0 there)
     assert SD.softdrop_rad_fc(np.array([.1]), .1, 2.)[0] == 0.
+
+
+def test_fixed_coupling_radiators_beyond_ll(golden):
+    """ref: analytics/radiators/fixedcoupling.py:20-57, 110-160; running_coupling.py:298-312"""
+    from jetmontecarlo_b200.analytics.radiators import fixedcoupling as FC
+    from jetmontecarlo_b200.analytics.radiators import running_coupling as RC
+    g = golden("closed_forms_fc")
+    thetas, cs, zps = g['theta'], g['c'], g['z_pre']
+    n = 0
+    with np.errstate(all='ignore'):
+        for jet in ('quark', 'gluon'):
+            for z_c in (.05, .1, .2):
+                assert_array_equal(FC.critRadPrimeAnalytic_fc_LL(thetas, z_c, jet), g[f'critRadPrime_fc_LL:{jet}:{z_c}'])
+                assert_array_equal(FC.critRadAnalytic_fc(thetas, z_c, jet), g[f'critRad_fc:{jet}:{z_c}'])
+                assert_array_equal(FC.critRadPrimeAnalytic_fc(thetas, z_c, jet), g[f'critRadPrime_fc:{jet}:{z_c}'])
+                for th in (.3, 1e-2):
+                    got = RC.preRadAnalytic_nofreeze(zps * z_c / .1, th, z_c, jet_type=jet)
+                    assert_array_equal(got, g[f'preRad_nofreeze:{jet}:{z_c}:{th}'])
+                    n += 1
+            for beta in (1.5, 2., 3.):
+                assert_array_equal(np.array(FC.subRadAnalytic_fc(cs, beta, jet), dtype=float), g[f'subRad_fc:{jet}:{beta}'])
+                assert_array_equal(FC.subRadPrimeAnalytic_fc(cs, beta, jet), g[f'subRadPrime_fc:{jet}:{beta}'])
+    assert n == 12
+    # the reference's wrapper ignores its jet type: gluon == quark
+    assert_array_equal(g['preRad_nofreeze:gluon:0.1:0.3'], g['preRad_nofreeze:quark:0.1:0.3'])
+    with pytest.raises(AssertionError):
+        FC.critRadAnalytic_fc(thetas, .1, 'photon')
