@@ -220,6 +220,58 @@ class integrator():
                                                   bounds=(bins[0], bins[-1]), bound_values=(0., 0.))
         self.hasInterpDensity = True
 
+    def saveInterpolatingFn(self, fileName, save_integral=True):
+        """dill pickle of the interpolating function, as the reference writes it.  ref: integrator.py:241-247"""
+        import dill
+        assert self.hasInterpIntegral, \
+            "No interpolating function to save"
+        with open(fileName, 'wb') as file:
+            dill.dump(self.interpFn, file)
+
+    def loadInterpolatingFn(self, fileName):
+        """ref: integrator.py:249-254"""
+        import dill
+        with open(fileName, 'rb') as file:
+            self.interpFn = dill.load(file)
+        self.hasInterpIntegral = True
+
+    def saveInterpolatingDensity(self, fileName):
+        """ref: integrator.py:272-278"""
+        import dill
+        assert self.hasInterpDensity, \
+            "No interpolating function to save"
+        with open(fileName, 'wb') as file:
+            dill.dump(self.interpDensity, file)
+
+    def loadInterpolatingDensity(self, fileName):
+        """ref: integrator.py:280-285"""
+        import dill
+        with open(fileName, 'rb') as file:
+            self.interpDensity = dill.load(file)
+        self.hasInterpDensity = True
+
+    # ------------------
+    # Analytic results: hooks for subclasses (ref: integrator.py:290-315)
+    # ------------------
+    def findAnalyticIntegral(self):
+        """No analytic integral by default."""
+        self.hasAnalyticIntegral = False
+
+    def analyticIntegral(self, obs):
+        """Analytic integral at the observable ``obs``, if a subclass knows one."""
+        if not self.hasAnalyticIntegral:
+            return
+        pass
+
+    def setAnalyticDensity(self, binspacing):
+        """analyticDensity(observable): finite-difference derivative of the analytic integral at the bin midpoints."""
+        from ..utils.hist_utils import histDerivative
+        if not self.hasAnalyticIntegral:
+            return
+        self.analyticDensity = histDerivative(self.analyticIntegral(self.bin_midpoints), self.bins, giveHist=False,
+                                              binInput=binspacing)
+        self.hasAnalyticDensity = True
+
     # ------------------
     # csv save / load    (three files: values, errors, bin edges; ref: integrator.py:320-354)
     # ------------------
@@ -304,6 +356,15 @@ def integrate_1d(function, bounds, bin_space='lin', epsilon=1e-10, num_samples=1
 #######################################
 # 2 dimensional integrator
 #######################################
+def multidim_cumsum(a):
+    """Cumulative sum along every axis in turn, last axis first.  (Host helper kept for scripts that call it;
+    integrator_2d does this on the device, jmc_finalize2d.)  ref: montecarlo/integrator.py:463-467"""
+    out = a.cumsum(-1)
+    for i in range(2, a.ndim + 1):
+        np.cumsum(out, axis=-i, out=out)
+    return out
+
+
 class integrator_2d():
     """2-D version of ``integrator`` (ref: montecarlo/integrator.py:469-778; used by gen_pre_num_rad).
     np.histogram2d -> jmc_hist2d, normalisation and the double cumulative sum -> jmc_finalize2d.  The reference's

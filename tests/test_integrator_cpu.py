@@ -160,3 +160,52 @@ def test_sampler_file_format_and_descriptor(tmp_path, golden):
     assert (d.kind, d.method, d.radius, d.epsilon) == (_lib.SAMPLER_UNGROOMED, _lib.LOG, .4, 1e-5)
     d = simpleSampler('lin', bounds=[.25, .75])._descriptor()
     assert (d.kind, d.lo, d.hi) == (_lib.SAMPLER_SIMPLE, .25, .75)
+
+
+def test_pickled_interpolants_and_analytic_hooks(golden, tmp_path):
+    """dill files of the interpolating functions (integrator.py:241-285) and the analytic-integral hooks (:290-315)"""
+    from jetmontecarlo_b200.montecarlo.integrator import integrator, multidim_cumsum
+    g = golden("c1_lin1")
+    tag = "quark_fc_LL:"
+    it = _integrator()
+    with pytest.raises(AssertionError, match="No interpolating function to save"):
+        it.saveInterpolatingFn(str(tmp_path / "f.pkl"))
+    it.bins, it.bin_midpoints = g[tag + 'edges'], g[tag + 'midpoints']
+    it.integral, it.density = list(g[tag + 'integral']), g[tag + 'density']
+    it.hasBins = it.hasMCIntegral = it.hasMCDensity = True
+    it.makeInterpolatingFn(bounds=(it.bins[0], it.bins[-1]))
+    it.makeInterpolatingDensity('lin')
+    it.saveInterpolatingFn(str(tmp_path / "f.pkl"))
+    it.saveInterpolatingDensity(str(tmp_path / "d.pkl"))
+    other = _integrator()
+    other.loadInterpolatingFn(str(tmp_path / "f.pkl"))
+    other.loadInterpolatingDensity(str(tmp_path / "d.pkl"))
+    assert other.hasInterpIntegral and other.hasInterpDensity
+    x = np.linspace(it.bins[0], it.bins[-1], 57)
+    assert_array_equal(other.interpFn(x), it.interpFn(x))
+    assert_array_equal(other.interpDensity(x), it.interpDensity(x))
+    assert other.interpDensity(it.bins[0] - 1.) == 0. and other.interpDensity(it.bins[-1] + 1.) == 0.
+
+    # hooks: nothing by default; a subclass with an analytic integral gets its finite-difference density
+    it.findAnalyticIntegral()
+    assert it.hasAnalyticIntegral is False and it.analyticIntegral(.3) is None
+    it.setAnalyticDensity('lin')
+    assert it.hasAnalyticDensity is False
+
+    class cubic(integrator):
+        def findAnalyticIntegral(self):
+            self.hasAnalyticIntegral = True
+
+        def analyticIntegral(self, obs):
+            return np.asarray(obs) ** 3
+
+    c = cubic()
+    c.bins = np.linspace(0., 1., 101)
+    c.bin_midpoints = (c.bins[1:] + c.bins[:-1]) / 2.
+    c.findAnalyticIntegral()
+    c.setAnalyticDensity('lin')
+    assert c.hasAnalyticDensity
+    assert_allclose(c.analyticDensity(c.bin_midpoints[1:-1]), 3. * c.bin_midpoints[1:-1] ** 2, atol=2e-4)
+
+    a = np.arange(24.).reshape(2, 3, 4)
+    assert_array_equal(multidim_cumsum(a), a.cumsum(-1).cumsum(-2).cumsum(-3))
