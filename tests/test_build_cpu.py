@@ -45,3 +45,18 @@ def test_headline_kernel_instruction_forms():
     assert any(o.startswith("ATOMS.CAST.SPIN") for o in ops)      # FP64 sums: compare-and-swap loop (no native form)
     assert "MUFU.EX2" in ops and "MUFU.LG2" in ops   # base-2 log space
     assert not any(o.startswith(("LDL", "STL")) for o in ops)     # no local memory
+
+
+def test_bandwidth_and_shower_kernels_do_not_spill():
+    """the replay kernels (HBM-bound) and both shower instantiations keep their loops in registers"""
+    usage = dict((f, (int(r), int(s))) for f, r, s in
+                 re.findall(r"Function (\S+):\s*\n\s*REG:(\d+) STACK:(\d+)", _run("-res-usage")))
+    seen = 0
+    for name, (regs, stack) in usage.items():
+        if any(k in name for k in ("hist_kernelE", "minmax_kernelE", "inverse_transform_kernel", "shower_kernelI",
+                                   "hist2d_kernel", "sample_kernel", "uniforms_kernel")):
+            assert stack == 0, "%s spills %d B" % (name, stack)
+            seen += 1
+    assert seen >= 8
+    fp32_shower = [v for k, v in usage.items() if "shower_kernelILb0E" in k]
+    assert fp32_shower and fp32_shower[0][0] <= 64          # FP32 shower: at least 4 blocks of 256 threads per SM
