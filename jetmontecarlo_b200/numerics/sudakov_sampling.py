@@ -104,15 +104,15 @@ def conditional_samples_from_cdf(cdf, conds, domain_lo, domain_hi, uniforms, cat
             r = uniforms[rows]
             all_mono = mono.all(dim=1)
             # first place where the cdf decreases, and the (raw) cdf there
-            first_bad = torch.argmax((~mono).to(torch.int8), dim=1)
+            first_bad = torch.argmax((~mono).to(torch.int32), dim=1)
             raw_bad = torch.gather(raw, 1, first_bad[:, None]).squeeze(1)
             always_one = (vals == 1.).all(dim=1)
             starts_at_one = (first_bad == 0) & (raw_bad == 1.)
             negligible = (vals < _THRESHOLD).all(dim=1)
             # first point with a non-negligible cdf; is the table monotone from there on?
             above = vals > _THRESHOLD
-            first_above = torch.argmax(above.to(torch.int8), dim=1)
-            tail_mono = torch.flip(torch.cumprod(torch.flip(torch.cat([mono, ones], dim=1).to(torch.int8), [1]), 1), [1])
+            first_above = torch.argmax(above.to(torch.int32), dim=1)
+            tail_mono = torch.flip(torch.cumprod(torch.flip(torch.cat([mono, ones], dim=1).to(torch.int32), [1]), 1), [1])
             monotone_after = torch.gather(tail_mono, 1, first_above[:, None]).squeeze(1).bool() & above.any(dim=1)
             turning = (raw_bad == 1.) & bool(catch_turnpoint)
 
