@@ -13,8 +13,6 @@ exactly as the reference recurses.  ``tests/test_sudakov_sampling_cpu.py`` holds
 oracle (which is pinned to the reference's own tabulated branches) on CPU tensors; the same code runs on CUDA
 tensors in the product.
 """
-import ctypes as C
-
 import numpy as np
 import torch
 

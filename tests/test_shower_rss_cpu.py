@@ -4,7 +4,7 @@ ref: utils/partonshower_utils.py:501-674"""
 import numpy as np
 import pytest
 import torch
-from numpy.testing import assert_allclose, assert_array_equal
+from numpy.testing import assert_allclose
 
 from oracle import jmc_oracle as O
 
