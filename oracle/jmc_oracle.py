@@ -25,7 +25,12 @@ Third-party arithmetic the reference relies on and that is NOT under
 /root/reference: ``numpy`` (ufuncs, ``np.histogram``, ``np.cumsum``; reference
 pins numpy==1.23.1, this image has 2.3.x) and CPython's ``random`` (MT19937,
 53-bit doubles).  ``np.histogram`` is restated per sample in ``bin_index`` and
-checked against NumPy itself.
+checked against NumPy itself.  ``scipy.interpolate.interp1d`` (the installed
+SciPy) is used as is by ``inverse_transform``.  ``pynverse`` 0.1.4.4
+(``inversefunc``, utils/montecarlo_utils.py:6,141) is not installed: of
+``samples_from_cdf`` only the tabulated route the reference takes when
+``inversefunc`` refuses a cdf is restated (``samples_from_cdf_tabulated``) and
+pinned; its root-finding route is UNPINNED and not restated.
 """
 import math
 import random as _pyrandom
