@@ -283,3 +283,45 @@ def test_c_abi_argument_errors_need_no_device():
         setattr(g, field, value)
         assert L.jmc_run(C.byref(g), 10, 0, 0, 0, None, 0, None, None, None, None, None) == -1
         assert text in L.jmc_last_error(), (field, L.jmc_last_error())
+
+
+def test_header_is_c_and_library_is_callable_from_c(tmp_path):
+    """include/jmc_b200.h compiles as plain C99 and a C program can bind the library through it (what a non-Python
+    host of the reference's path would do)"""
+    import shutil
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not installed")
+    header = os.path.join(ROOT, "include", "jmc_b200.h")
+    res = subprocess.run([gcc, "-std=c99", "-pedantic", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", header],
+                         capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    src = tmp_path / "probe.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <dlfcn.h>
+#include "jmc_b200.h"
+int main(int argc, char** argv) {
+    void* h = dlopen(argv[1], RTLD_NOW);
+    if (!h) { printf("dlopen failed: %s\n", dlerror()); return 2; }
+    int (*ver)(void) = (int (*)(void))dlsym(h, "jmc_abi_version");
+    int (*area)(const jmc_sampler*, double*) = (int (*)(const jmc_sampler*, double*))dlsym(h, "jmc_sampler_area");
+    const char* (*err)(void) = (const char* (*)(void))dlsym(h, "jmc_last_error");
+    jmc_sampler s = {0};
+    double a = 0;
+    s.kind = JMC_SAMPLER_CRITICAL; s.method = JMC_LIN; s.zc = .1; s.radius = .8;
+    int rc = area(&s, &a);
+    printf("abi %d rc %d area %.17g\n", ver(), rc, a);
+    rc = area(0, 0);
+    printf("rc %d err %s\n", rc, err());
+    return 0;
+}
+''')
+    exe = tmp_path / "probe"
+    res = subprocess.run([gcc, "-std=c99", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src), "-ldl"],
+                         capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    lib = os.path.join(ROOT, "jetmontecarlo_b200", "lib", "libjmc_b200.so")
+    out = subprocess.run([str(exe), lib], capture_output=True, text=True).stdout.splitlines()
+    assert out[0] == "abi 1 rc 0 area %.17g" % ((1. / 2. - .1) * .8)
+    assert out[1] == "rc -1 err jmc_sampler_area: NULL argument"
