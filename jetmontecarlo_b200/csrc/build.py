@@ -47,8 +47,12 @@ def _digest():
     names = sorted(f for f in os.listdir(HERE) if f.endswith((".cu", ".cuh", ".py")))
     for k in ("JMC_FAST_MIN_BLOCKS", "JMC_FAST_UNROLL", "JMC_FAST_PIN_KEYS", "JMC_PHILOX_SPLIT"):
         h.update(os.environ.get(k, "").encode())
-    for name in names + [os.path.join(ROOT, "include", "jmc_b200.h")]:
-        with open(os.path.join(HERE, name) if not os.path.isabs(name) else name, "rb") as f:
+    # names are hashed relative to the repository so that the stamp survives a copy of the tree (the GPU box
+    # receives the built library with the snapshot and must load it as is)
+    files = [(name, os.path.join(HERE, name)) for name in names]
+    files.append(("include/jmc_b200.h", os.path.join(ROOT, "include", "jmc_b200.h")))
+    for name, path in files:
+        with open(path, "rb") as f:
             h.update(name.encode())
             h.update(f.read())
     return h.hexdigest()
