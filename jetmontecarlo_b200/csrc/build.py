@@ -26,11 +26,14 @@ LIB = os.path.join(LIB_DIR, "libjmc_b200.so")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
           "-I", os.path.join(ROOT, "include")]
+# compile-time experiment switches (scripts/try_variants.sh); unset = the defaults in the sources
+SWITCHES = ("JMC_FAST_MIN_BLOCKS", "JMC_FAST_UNROLL", "JMC_FAST_PIN_KEYS", "JMC_PHILOX_SPLIT", "JMC_ACC_MODE",
+            "JMC_HIST_MODE", "JMC_HIST_UNROLL", "JMC_SHOWER_MODE")
+_DEFS = ["-D%s=%s" % (k, os.environ[k]) for k in SWITCHES if os.environ.get(k)]
 UNITS = {
-    "jmc_exact.cu": ["--fmad=false"],
-    "jmc_shower.cu": ["--fmad=false"],
-    "jmc_fast.cu": ["--fmad=true"] + ["-D%s=%s" % (k, os.environ[k]) for k in
-                                      ("JMC_FAST_MIN_BLOCKS", "JMC_FAST_UNROLL", "JMC_FAST_PIN_KEYS", "JMC_PHILOX_SPLIT") if os.environ.get(k)],
+    "jmc_exact.cu": ["--fmad=false"] + _DEFS,
+    "jmc_shower.cu": ["--fmad=false"] + _DEFS,
+    "jmc_fast.cu": ["--fmad=true"] + _DEFS,
     "jmc_host.cu": [],
 }
 
@@ -45,7 +48,7 @@ def _nvcc():
 def _digest():
     h = hashlib.sha256()
     names = sorted(f for f in os.listdir(HERE) if f.endswith((".cu", ".cuh", ".py")))
-    for k in ("JMC_FAST_MIN_BLOCKS", "JMC_FAST_UNROLL", "JMC_FAST_PIN_KEYS", "JMC_PHILOX_SPLIT"):
+    for k in SWITCHES:
         h.update(os.environ.get(k, "").encode())
     # names are hashed relative to the repository so that the stamp survives a copy of the tree (the GPU box
     # receives the built library with the snapshot and must load it as is)

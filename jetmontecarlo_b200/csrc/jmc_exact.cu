@@ -340,34 +340,78 @@ __global__ void __launch_bounds__(kThreads) bin_index_kernel(const double* __res
 }
 
 // Shared-memory layout of a privatised histogram block:
-//   double edges[n_edges]; double sum_w[nb]; double sum_w2[nb]; uint32 count[nb]
+//   double edges[n_edges]; double sum_w[nb << shift]; double sum_w2[nb << shift]; uint32 count[nb]
+// The weighted sums exist in R = 2^shift lane-interleaved copies, slot [bin][lane & (R-1)]: FP64 shared-memory adds are
+// compare-and-swap loops on sm_100 (only 32-bit integer adds are native), and a loop runs one round per lane of the
+// warp on the same address.  With one copy per lane (R = 32; chosen by the host as large as shared memory allows) no
+// two lanes of a warp ever meet, so a round repeats only when another warp updates the same slot in between.
+#ifndef JMC_HIST_MODE
+#define JMC_HIST_MODE 1          // 1: lane-interleaved copies; 2: __match_any_sync pre-reduction; 0: one copy
+#endif
+#ifndef JMC_HIST_UNROLL
+#define JMC_HIST_UNROLL 4        // samples per thread per trip (their loads are issued together)
+#endif
 struct HistSmem {
     double* edges;
     double* sum_w;
     double* sum_w2;
     unsigned int* count;
-    __device__ HistSmem(void* base, int n_edges) {
+    int shift;
+    __device__ HistSmem(void* base, int n_edges, int shift_) : shift(shift_) {
         const int nb = n_edges - 1;
         edges = (double*)base;
         sum_w = edges + n_edges;
-        sum_w2 = sum_w + nb;
-        count = (unsigned int*)(sum_w2 + nb);
+        sum_w2 = sum_w + (nb << shift);
+        count = (unsigned int*)(sum_w2 + (nb << shift));
     }
 };
-static size_t hist_smem_bytes(int n_edges) {
+static size_t hist_smem_bytes(int n_edges, int shift = 0) {
     const size_t nb = (size_t)n_edges - 1;
-    return sizeof(double) * ((size_t)n_edges + 2 * nb) + sizeof(unsigned int) * nb;
+    return sizeof(double) * ((size_t)n_edges + 2 * (nb << shift)) + sizeof(unsigned int) * nb;
+}
+static int hist_spread_shift(int n_edges, size_t budget) {
+    if (JMC_HIST_MODE != 1) return 0;
+    int shift = 5;
+    while (shift > 0 && hist_smem_bytes(n_edges, shift) > budget) --shift;
+    return shift;
 }
 
 __device__ __forceinline__ void hist_init(HistSmem& h, const double* __restrict__ edges, int n_edges) {
     const int nb = n_edges - 1;
     for (int k = threadIdx.x; k < n_edges; k += blockDim.x) h.edges[k] = edges[k];
-    for (int k = threadIdx.x; k < nb; k += blockDim.x) {
+    for (int k = threadIdx.x; k < (nb << h.shift); k += blockDim.x) {
         h.sum_w[k] = 0.0;
         h.sum_w2[k] = 0.0;
-        h.count[k] = 0u;
     }
+    for (int k = threadIdx.x; k < nb; k += blockDim.x) h.count[k] = 0u;
     __syncthreads();
+}
+
+// (w, w^2) into bin b of the block histogram
+__device__ __forceinline__ void hist_add_weight(HistSmem& h, int b, double w) {
+    const unsigned lane = threadIdx.x & 31u;
+#if JMC_HIST_MODE == 2
+    const unsigned mask = __activemask();
+    const unsigned peers = __match_any_sync(mask, b);
+    const int leader = __ffs(peers) - 1;
+    unsigned others = peers & ~(1u << leader);
+    double aw = w, aw2 = w * w;
+    const double mw = aw, mw2 = aw2;
+    while (__any_sync(mask, others != 0u)) {
+        const int src = others ? __ffs(others) - 1 : (int)lane;
+        const double vw = __shfl_sync(mask, mw, src), vw2 = __shfl_sync(mask, mw2, src);
+        if (others) { aw += vw; aw2 += vw2; }
+        others &= others - 1u;
+    }
+    if ((int)lane == leader) {
+        atomicAdd(&h.sum_w[b], aw);
+        atomicAdd(&h.sum_w2[b], aw2);
+    }
+#else
+    const int slot = (b << h.shift) | (int)(lane & ((1u << h.shift) - 1u));
+    atomicAdd(&h.sum_w[slot], w);
+    atomicAdd(&h.sum_w2[slot], w * w);
+#endif
 }
 
 // One sample into the block histogram.  A NaN weight is not added; it lowers
@@ -386,10 +430,7 @@ __device__ __forceinline__ void hist_add(HistSmem& h, int n_edges, double obs, d
     }
     if (b < 0) return;
     atomicAdd(&h.count[b], 1u);
-    if (has_w && w != 0.0) {
-        atomicAdd(&h.sum_w[b], w);
-        atomicAdd(&h.sum_w2[b], w * w);
-    }
+    if (has_w && w != 0.0) hist_add_weight(h, b, w);
 }
 
 __device__ __forceinline__ void hist_flush(HistSmem& h, int n_edges, double* __restrict__ g_sum_w,
@@ -401,7 +442,11 @@ __device__ __forceinline__ void hist_flush(HistSmem& h, int n_edges, double* __r
         const unsigned int c = h.count[k];
         if (c) {
             atomicAdd(&g_count[k], (unsigned long long)c);
-            const double sw = h.sum_w[k], sw2 = h.sum_w2[k];
+            double sw = 0.0, sw2 = 0.0;
+            for (int r = 0; r < (1 << h.shift); ++r) {
+                sw += h.sum_w[(k << h.shift) + r];
+                sw2 += h.sum_w2[(k << h.shift) + r];
+            }
             if (g_sum_w && sw != 0.0) atomicAdd(&g_sum_w[k], sw);
             if (g_sum_w2 && sw2 != 0.0) atomicAdd(&g_sum_w2[k], sw2);
         }
@@ -409,19 +454,55 @@ __device__ __forceinline__ void hist_flush(HistSmem& h, int n_edges, double* __r
     if (threadIdx.x == 0 && *s_poison != INT_MAX) atomicMin(g_poison, *s_poison);
 }
 
+// Equally spaced edges (np.linspace / np.logspace, i.e. every setBins) get an affine first guess of the bin.  The
+// block derives it from the edges it has just staged (no host read-back of the edge array, no stream sync).
+__device__ __forceinline__ BinGuess derive_bin_guess(const double* s_edges, int n_edges) {
+    BinGuess G{0, 0.f, 0.f};
+    if (n_edges < 8) return G;                  // (uniform over the block: every thread takes the same path)
+    const double e0 = s_edges[0], e1 = s_edges[n_edges - 1];
+    {
+        const double d = (e1 - e0) / (n_edges - 1);
+        bool ok = d > 0.0 && isfinite(d) && isfinite(e0);
+        for (int k = threadIdx.x; ok && k < n_edges; k += blockDim.x) ok = fabs(s_edges[k] - (e0 + k * d)) < 0.25 * d;
+        if (__syncthreads_and(ok)) return BinGuess{1, (float)e0, (float)(1.0 / d)};
+    }
+    {
+        bool ok = e0 > 1e-30 && e1 < 1e30;      // the FP32 log2 guess must not underflow
+        const double l0 = ok ? log2(e0) : 0.0, d = ok ? (log2(e1) - l0) / (n_edges - 1) : 0.0;
+        ok = ok && d > 0.0 && isfinite(d);
+        for (int k = threadIdx.x; ok && k < n_edges; k += blockDim.x) ok = fabs(log2(s_edges[k]) - (l0 + k * d)) < 0.25 * d;
+        if (__syncthreads_and(ok)) return BinGuess{2, (float)l0, (float)(1.0 / d)};
+    }
+    return G;
+}
+
+// HBM-streaming: 16 B per sample (observable + weight).  Every thread issues the loads of JMC_HIST_UNROLL samples
+// before it bins the first one, so a resident grid keeps ~2048 x 16 B x UNROLL per SM in flight.
 __global__ void __launch_bounds__(1024)
 hist_kernel(const double* __restrict__ obs, const double* __restrict__ w, uint64_t n,
             const double* __restrict__ edges, int n_edges, double* __restrict__ g_sum_w,
-            double* __restrict__ g_sum_w2, unsigned long long* __restrict__ g_count, int* g_poison, BinGuess G) {
+            double* __restrict__ g_sum_w2, unsigned long long* __restrict__ g_count, int* g_poison, int shift) {
     extern __shared__ __align__(16) double s_raw[];
     __shared__ int s_poison;
-    HistSmem h(s_raw, n_edges);
+    HistSmem h(s_raw, n_edges, shift);
     if (threadIdx.x == 0) s_poison = INT_MAX;
     hist_init(h, edges, n_edges);
+    const BinGuess G = derive_bin_guess(h.edges, n_edges);
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     const bool has_w = w != nullptr;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-        hist_add(h, n_edges, obs[i], has_w ? w[i] : 1.0, has_w, &s_poison, G);
+    constexpr int U = JMC_HIST_UNROLL;
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + (U - 1) * stride < n; i += U * stride) {
+        double o[U], ww[U];
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            o[k] = __ldcs(obs + i + k * stride);
+            ww[k] = has_w ? __ldcs(w + i + k * stride) : 1.0;
+        }
+#pragma unroll
+        for (int k = 0; k < U; ++k) hist_add(h, n_edges, o[k], ww[k], has_w, &s_poison, G);
+    }
+    for (; i < n; i += stride) hist_add(h, n_edges, obs[i], has_w ? w[i] : 1.0, has_w, &s_poison, G);
     hist_flush(h, n_edges, g_sum_w, g_sum_w2, g_count, &s_poison, g_poison);
 }
 
@@ -538,32 +619,20 @@ extern "C" int jmc_hist(const double* d_obs, const double* d_weights, uint64_t n
     rc = scratch(sizeof(int), (void**)&d_poison, (void*)st);
     if (rc) return rc;
     JMC_CUDA(cudaMemsetAsync(d_poison, 0x7f, sizeof(int), st));   // 0x7f7f7f7f: "no poison"
-    JMC_CUDA(cudaFuncSetAttribute(hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // big histograms (the reference's 5000 radiator bins take 140 KB) leave room for one block per SM: give that
     // block 1024 threads so that 32 warps share the histogram instead of 8
     const int threads = smem > 72 * 1024 ? 1024 : kThreads;
+    DeviceInfo di;
+    if (device_info(&di)) return JMC_ENODEV;
+    const int shift = hist_spread_shift(n_edges, threads == 1024 ? (size_t)di.max_smem_optin - 1024 : 56 * 1024);
+    smem = hist_smem_bytes(n_edges, shift);
+    JMC_CUDA(cudaFuncSetAttribute(hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     JMC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hist_kernel, threads, smem));
     if (per_sm < 1) per_sm = 1;
     const int grid = grid_for(n, threads, per_sm);
-    // Equally spaced edges (np.linspace / np.logspace, i.e. every setBins) get an affine first guess of the bin.
-    // Reading the edges back costs one small synchronous copy; skipped for jobs too small to profit.
-    BinGuess G{0, 0.f, 0.f};
-    if (n >= (1u << 16) && n_edges >= 8 && n_edges <= 16384) {
-        std::vector<double> e(n_edges);
-        JMC_CUDA(cudaMemcpyAsync(e.data(), d_edges, sizeof(double) * n_edges, cudaMemcpyDeviceToHost, st));
-        JMC_CUDA(cudaStreamSynchronize(st));
-        for (int mode = 1; mode <= 2 && G.mode == 0; ++mode) {
-            if (mode == 2 && !(e[0] > 1e-30 && e[n_edges - 1] < 1e30)) break;   // FP32 log2 guess must not underflow
-            auto g = [&](double x) { return mode == 1 ? x : std::log2(x); };
-            const double b0 = g(e[0]), d = (g(e[n_edges - 1]) - b0) / (n_edges - 1);
-            bool ok = d > 0.0 && std::isfinite(d) && std::isfinite(b0);
-            for (int k = 0; ok && k < n_edges; ++k) ok = std::fabs(g(e[k]) - (b0 + k * d)) < 0.25 * d;
-            if (ok) G = BinGuess{mode, (float)b0, (float)(1.0 / d)};
-        }
-    }
     hist_kernel<<<grid, threads, smem, st>>>(d_obs, d_weights, n, d_edges, n_edges, d_sum_w, d_sum_w2,
-                                              (unsigned long long*)d_count, d_poison, G);
+                                              (unsigned long long*)d_count, d_poison, shift);
     JMC_LAUNCHED("hist_kernel");
     if (d_weights) {
         poison_kernel<<<1, 256, 0, st>>>(d_poison, n_edges - 1, d_sum_w, d_sum_w2);
@@ -728,10 +797,10 @@ template <int KIND>
 __global__ void __launch_bounds__(kThreads)
 run_exact_kernel(RunParams p, uint64_t n, uint64_t seed, uint64_t first, const double* __restrict__ edges,
                  int n_edges, double* __restrict__ g_sum_w, double* __restrict__ g_sum_w2,
-                 unsigned long long* __restrict__ g_count, int* g_poison, double* __restrict__ d_minmax) {
+                 unsigned long long* __restrict__ g_count, int* g_poison, double* __restrict__ d_minmax, int shift) {
     extern __shared__ __align__(16) double s_raw[];
     __shared__ int s_poison;
-    HistSmem h(s_raw, n_edges > 0 ? n_edges : 1);
+    HistSmem h(s_raw, n_edges > 0 ? n_edges : 1, shift);
     const bool do_hist = edges != nullptr;
     if (threadIdx.x == 0) s_poison = INT_MAX;
     if (do_hist) hist_init(h, edges, n_edges); else __syncthreads();
@@ -760,6 +829,8 @@ template <int KIND>
 static int launch_run_exact(const RunParams& p, uint64_t n, uint64_t seed, uint64_t first, const double* d_edges,
                             int n_edges, double* d_sum_w, double* d_sum_w2, uint64_t* d_count, int* d_poison,
                             double* d_minmax, size_t smem, cudaStream_t st) {
+    const int shift = (d_edges && smem <= 56 * 1024) ? hist_spread_shift(n_edges, 56 * 1024) : 0;
+    if (d_edges) smem = hist_smem_bytes(n_edges, shift);
     JMC_CUDA(cudaFuncSetAttribute(run_exact_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     JMC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, run_exact_kernel<KIND>, kThreads, smem));
@@ -767,7 +838,7 @@ static int launch_run_exact(const RunParams& p, uint64_t n, uint64_t seed, uint6
     const int grid = grid_for(n, kThreads, per_sm);
     if (grid < 0) return JMC_ENODEV;
     run_exact_kernel<KIND><<<grid, kThreads, smem, st>>>(p, n, seed, first, d_edges, n_edges, d_sum_w, d_sum_w2,
-                                                          (unsigned long long*)d_count, d_poison, d_minmax);
+                                                          (unsigned long long*)d_count, d_poison, d_minmax, shift);
     JMC_LAUNCHED("run_exact_kernel");
     return JMC_OK;
 }

@@ -52,6 +52,9 @@ static constexpr int kQueueFields = 5, kQueueSlots = 64;   // per-warp compactio
 #ifndef JMC_FAST_PIN_KEYS
 #define JMC_FAST_PIN_KEYS 1      // keep the Philox round keys in registers across the loop
 #endif
+#ifndef JMC_ACC_MODE
+#define JMC_ACC_MODE 1           // shared-memory accumulation of (sum w, sum w^2), see fast_body::accumulate
+#endif
 #define JMC_LN2F 0.69314718055994531f
 #define JMC_INV_LN2F 1.4426950408889634f
 
@@ -106,6 +109,7 @@ struct FastParams {
     float mb0_inv_d;         // -b0 * inv_d
     float e_first, e_last;   // first / last edge in the compare domain
     float nb_f;              // number of bins as a float
+    int spread_shift;        // log2 of the number of lane-interleaved copies of each bin's accumulator
 };
 
 __device__ __forceinline__ float ex2(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
@@ -425,14 +429,26 @@ fast_body(const FastParams& P_in, uint64_t n, uint64_t seed, uint64_t first, con
     // parameter loads; measured: no effect.)
     const FastParams& P = P_in;
     const int ne = P.n_edges, nb = ne > 0 ? ne - 1 : 0;
+    const int sh = P.spread_shift;
+    const int n_slots = nb << sh;
+#if JMC_ACC_MODE == 1
+    float2* s_acc = (float2*)s_raw;                               // (sum w, sum w^2) of slot [bin][lane & (R-1)]
+    unsigned int* s_count = (unsigned int*)(s_acc + n_slots);     // nb bins + 32 dummy slots for dropped samples
+#else
     double* s_sum_w = s_raw;
-    double* s_sum_w2 = s_sum_w + nb;
-    unsigned int* s_count = (unsigned int*)(s_sum_w2 + nb);       // nb bins + 32 dummy slots for dropped samples
+    double* s_sum_w2 = s_sum_w + n_slots;
+    unsigned int* s_count = (unsigned int*)(s_sum_w2 + n_slots);  // nb bins + 32 dummy slots for dropped samples
+#endif
     float* s_edges = (float*)(s_count + nb + 32);
     const bool do_hist = HOT || g_edges != nullptr;
     const bool do_minmax = !HOT && d_minmax != nullptr;
     if (threadIdx.x == 0) s_poison = INT_MAX;
-    for (int k = threadIdx.x; k < nb; k += blockDim.x) { s_sum_w[k] = 0.0; s_sum_w2[k] = 0.0; s_count[k] = 0u; }
+#if JMC_ACC_MODE == 1
+    for (int k = threadIdx.x; k < n_slots; k += blockDim.x) s_acc[k] = make_float2(0.0f, 0.0f);
+#else
+    for (int k = threadIdx.x; k < n_slots; k += blockDim.x) { s_sum_w[k] = 0.0; s_sum_w2[k] = 0.0; }
+#endif
+    for (int k = threadIdx.x; k < nb; k += blockDim.x) s_count[k] = 0u;
     if (threadIdx.x < 32) s_count[nb + threadIdx.x] = 0u;
     for (int k = threadIdx.x; k < ne; k += blockDim.x) s_edges[k] = g_edges[k];
     __syncthreads();
@@ -451,11 +467,50 @@ fast_body(const FastParams& P_in, uint64_t n, uint64_t seed, uint64_t first, con
 
     // weight * jacobian of one sample into the block histogram (bq: bin, or -1 / -2 for a sample below /
     // above the binned range, which matters only for NumPy's NaN poisoning)
+    // Back ends (JMC_ACC_MODE; shared-memory FP32/FP64/64-bit adds are compare-and-swap loops on sm_100, only 32-bit
+    // integer adds are native, so what costs is the number of CAS rounds = lanes of a warp on one address):
+    //  1 (default): R = 2^sh lane-interleaved copies of every bin, slot [bin][lane & (R-1)] holding (sum w, sum w^2)
+    //     as two floats updated by ONE 64-bit CAS.  With R = 32 no two lanes of a warp share a slot, so a round only
+    //     repeats when another warp hits the same slot in the same few cycles; the slots are summed in FP64 when the
+    //     block flushes.  A slot sees ~n_block / (nb R) adds of one sign: FP32 rounding ~ sqrt(adds) 2^-25 relative.
+    //  2: __match_any_sync on the bin, peers reduced by shuffles, one FP64 CAS pair per distinct bin per warp.
+    //  0 / 3: two FP64 CAS loops per sample on [bin] / on the lane-interleaved slot.
+    const unsigned lane_acc = threadIdx.x & 31u;
     auto accumulate = [&](float w, int bq) {
         if (bq >= 0 && fabsf(w) > 0.0f) {                // the common case first: one compare rejects 0 and NaN
+#if JMC_ACC_MODE == 1
+            unsigned long long* a = (unsigned long long*)&s_acc[(bq << sh) | (int)(lane_acc & ((1u << sh) - 1u))];
+            const float w2 = w * w;
+            unsigned long long old = *a, assumed;
+            do {
+                assumed = old;
+                const float x = __uint_as_float((unsigned)assumed) + w;
+                const float y = __uint_as_float((unsigned)(assumed >> 32)) + w2;
+                old = atomicCAS(a, assumed, ((unsigned long long)__float_as_uint(y) << 32) | __float_as_uint(x));
+            } while (old != assumed);
+#elif JMC_ACC_MODE == 2
+            const unsigned mask = __activemask();
+            const unsigned peers = __match_any_sync(mask, bq);
+            const int leader = __ffs(peers) - 1;
+            unsigned others = peers & ~(1u << leader);
+            float aw = w, aw2 = w * w;
+            const float mw = aw, mw2 = aw2;
+            while (__any_sync(mask, others != 0u)) {
+                const int src = others ? __ffs(others) - 1 : (int)lane_acc;
+                const float vw = __shfl_sync(mask, mw, src), vw2 = __shfl_sync(mask, mw2, src);
+                if (others) { aw += vw; aw2 += vw2; }
+                others &= others - 1u;
+            }
+            if ((int)lane_acc == leader) {
+                atomicAdd(&s_sum_w[bq], (double)aw);
+                atomicAdd(&s_sum_w2[bq], (double)aw2);
+            }
+#else
             const double wd = (double)w;
-            atomicAdd(&s_sum_w[bq], wd);
-            atomicAdd(&s_sum_w2[bq], wd * wd);
+            const int slot = (bq << sh) | (int)(lane_acc & ((1u << sh) - 1u));
+            atomicAdd(&s_sum_w[slot], wd);
+            atomicAdd(&s_sum_w2[slot], wd * wd);
+#endif
         } else if (w != w && !nan_to_num) {              // NaN: 0 under nan_to_num, else NumPy poisons bins >= bq
             const int pb = bq >= 0 ? bq : (bq == -1 ? 0 : INT_MAX);
             if (pb != INT_MAX) atomicMin(&s_poison, pb);
@@ -617,7 +672,15 @@ fast_body(const FastParams& P_in, uint64_t n, uint64_t seed, uint64_t first, con
             const unsigned int c = s_count[k];
             if (c) {
                 atomicAdd(&g_count[k], (unsigned long long)c);
-                const double sw = s_sum_w[k], sw2 = s_sum_w2[k];
+                double sw = 0.0, sw2 = 0.0;
+                for (int r = 0; r < (1 << sh); ++r) {
+#if JMC_ACC_MODE == 1
+                    const float2 v = s_acc[(k << sh) + r];
+                    sw += (double)v.x; sw2 += (double)v.y;
+#else
+                    sw += s_sum_w[(k << sh) + r]; sw2 += s_sum_w2[(k << sh) + r];
+#endif
+                }
                 if (sw != 0.0) atomicAdd(&g_sum_w[k], sw);
                 if (sw2 != 0.0) atomicAdd(&g_sum_w2[k], sw2);
             }
@@ -869,12 +932,21 @@ static int make_fast_params(const jmc_integrand* g, const double* h_edges, int n
     return JMC_OK;
 }
 
-static size_t fast_smem_bytes(int n_edges, int threads = kFastThreads) {
+static size_t fast_smem_bytes(int n_edges, int threads = kFastThreads, int shift = 0) {
     const size_t nb = n_edges > 0 ? (size_t)n_edges - 1 : 0;
     const size_t ne_pad = ((size_t)(n_edges > 0 ? n_edges : 0) + 3) & ~(size_t)3;
-    return sizeof(double) * 2 * nb + sizeof(unsigned int) * (nb + 32) + sizeof(float) * ne_pad
+    const size_t acc = (JMC_ACC_MODE == 1 ? sizeof(float2) : 2 * sizeof(double)) * (nb << shift);
+    return acc + sizeof(unsigned int) * (nb + 32) + sizeof(float) * ne_pad
            + sizeof(float) * (threads / 32) * kQueueFields * kQueueSlots;
 }
+// lane-interleaved accumulator copies: as many (up to one per lane) as keep the block under `budget` bytes
+static int fast_spread_shift(int n_edges, int threads, size_t budget) {
+    if (JMC_ACC_MODE == 0 || JMC_ACC_MODE == 2) return 0;
+    int shift = 5;
+    while (shift > 0 && fast_smem_bytes(n_edges, threads, shift) > budget) --shift;
+    return shift;
+}
+static constexpr size_t kSpreadBudget = 48 * 1024, kSpreadBudgetBig = 200 * 1024;
 
 // samples from global index `first` up to the next multiple of 2^32
 static uint64_t fast_span(uint64_t first) { return 0x100000000ull - (first & 0xffffffffull); }
@@ -886,7 +958,8 @@ static int launch_fast_t(const FastParams& P, uint64_t n, uint64_t seed, uint64_
     DeviceInfo di;
     if (device_info(&di)) return JMC_ENODEV;
     constexpr int threads = BIG ? kFastThreadsBig : kFastThreads;
-    const size_t smem = fast_smem_bytes(d_edges_f ? P.n_edges : 0, threads);
+    const int shift = fast_spread_shift(d_edges_f ? P.n_edges : 0, threads, BIG ? kSpreadBudgetBig : kSpreadBudget);
+    const size_t smem = fast_smem_bytes(d_edges_f ? P.n_edges : 0, threads, shift);
     if (smem > (size_t)di.max_smem_optin)
         return set_error(JMC_ELIMIT, "jmc_run: %d edges need %zu B of shared memory (limit %d B)", P.n_edges, smem,
                          di.max_smem_optin);
@@ -899,6 +972,7 @@ static int launch_fast_t(const FastParams& P, uint64_t n, uint64_t seed, uint64_
     const uint64_t cap = (uint64_t)di.sm_count * per_sm;      // persistent: one wave of resident blocks
     const int grid = (int)(want < cap ? want : cap);
     FastParams Q = P;
+    Q.spread_shift = shift;
     if (!d_edges_f) Q.n_edges = 0;
     kern<<<grid, threads, smem, st>>>(Q, n, seed, first, d_edges_f, d_sum_w, d_sum_w2, (unsigned long long*)d_count,
                                       d_poison, d_minmax);
@@ -994,11 +1068,11 @@ __global__ void poison_batch_kernel(const int* poison_all, int nb, double* sum_w
 template <int KIND, bool FIXED, bool OBS_MLL, bool HOT, bool BIG>
 static int launch_fast_batch_t(const FastParams* d_params, int n_points, int n_edges, uint64_t n, uint64_t seed,
                                uint64_t first, const float* d_edges_f, double* d_sum_w, double* d_sum_w2,
-                               uint64_t* d_count, int* d_poison, double* d_minmax, cudaStream_t st) {
+                               uint64_t* d_count, int* d_poison, double* d_minmax, int shift, cudaStream_t st) {
     DeviceInfo di;
     if (device_info(&di)) return JMC_ENODEV;
     constexpr int threads = BIG ? kFastThreadsBig : kFastThreads;
-    const size_t smem = fast_smem_bytes(d_edges_f ? n_edges : 0, threads);
+    const size_t smem = fast_smem_bytes(d_edges_f ? n_edges : 0, threads, d_edges_f ? shift : 0);
     if (smem > (size_t)di.max_smem_optin)
         return set_error(JMC_ELIMIT, "jmc_run_batch: %d edges need %zu B of shared memory (limit %d B)", n_edges, smem,
                          di.max_smem_optin);
@@ -1047,6 +1121,10 @@ int run_fast_batch(const jmc_integrand* g, int n_points, uint64_t n, uint64_t se
         if (!h_edges) params[i].n_edges = 0;
     }
     if (n == 0) return JMC_OK;
+    const bool big = hot && fast_smem_bytes(n_edges) > kBigSmemThreshold;
+    const int shift = h_edges ? fast_spread_shift(n_edges, big ? kFastThreadsBig : kFastThreads,
+                                                  big ? kSpreadBudgetBig : kSpreadBudget) : 0;
+    for (int i = 0; i < n_points; ++i) params[i].spread_shift = shift;
     const size_t bytes_params = sizeof(FastParams) * (size_t)n_points;
     const size_t off_edges = (bytes_params + 255) & ~(size_t)255;
     const size_t bytes_edges = sizeof(float) * edges_all.size();
@@ -1062,12 +1140,12 @@ int run_fast_batch(const jmc_integrand* g, int n_points, uint64_t n, uint64_t se
     JMC_CUDA(cudaMemsetAsync(d_poison, 0x7f, sizeof(int) * (size_t)n_points, st));
     JMC_CUDA(cudaStreamSynchronize(st));           // the staging vectors die at return
     const bool mll = g[0].obs_acc == JMC_ACC_MLL, fixed = g[0].fixed_coupling != 0;
-    const bool big = hot && fast_smem_bytes(n_edges) > kBigSmemThreshold;
 #define JMC_B(K, F, M, H)                                                                                              \
     rc = (H && big) ? launch_fast_batch_t<K, F, M, H, H>(d_params, n_points, n_edges, n, seed, first_index, d_edges_f, \
-                                                         d_sum_w, d_sum_w2, d_count, d_poison, d_minmax, st)             \
+                                                         d_sum_w, d_sum_w2, d_count, d_poison, d_minmax, shift, st)      \
                     : launch_fast_batch_t<K, F, M, H, false>(d_params, n_points, n_edges, n, seed, first_index,         \
-                                                             d_edges_f, d_sum_w, d_sum_w2, d_count, d_poison, d_minmax, st)
+                                                             d_edges_f, d_sum_w, d_sum_w2, d_count, d_poison, d_minmax, \
+                                                             shift, st)
 #define JMC_BK(K)                                                              \
     do {                                                                       \
         if (fixed) { if (mll) { if (hot) JMC_B(K, true, true, true); else JMC_B(K, true, true, false); }     \

@@ -42,7 +42,8 @@ def test_headline_kernel_instruction_forms():
     assert len(ops) > 1000
     assert ops.count("IMAD.WIDE.U32") >= 36          # Philox products as one wide multiply each
     assert "ATOMS.POPC.INC.32" in ops                # native shared-memory count atomic
-    assert any(o.startswith("ATOMS.CAST.SPIN") for o in ops)      # FP64 sums: compare-and-swap loop (no native form)
+    # (sum w, sum w^2) of a slot as one 64-bit compare-and-swap (no native shared-memory floating-point add on sm_100)
+    assert any(o.startswith("ATOMS.CAS") for o in ops)
     assert "MUFU.EX2" in ops and "MUFU.LG2" in ops   # base-2 log space
     assert not any(o.startswith(("LDL", "STL")) for o in ops)     # no local memory
 
