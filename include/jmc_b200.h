@@ -46,6 +46,13 @@ enum { JMC_QUARK = 0, JMC_GLUON = 1 };                     /* jet_type          
 enum { JMC_ACC_LL = 0, JMC_ACC_LL_NONSING = 1, JMC_ACC_MLL = 2 };
 enum { JMC_BC_FIRST = 0, JMC_BC_LAST_PLUS = 1, JMC_BC_LAST_MINUS = 2 };
 enum { JMC_F64 = 0, JMC_F32 = 1 };                         /* arithmetic of the fused path      */
+/* What d_count of the fused path holds.  JMC_COUNT_ALL: np.histogram's count (every sample inside the binned range),
+ * as integrator.setDensity computes it (montecarlo/integrator.py:101).  JMC_COUNT_WEIGHTED: only the samples whose
+ * weight is non-zero.  The reference uses the count solely to zero the density of empty bins (:123-124), and a bin
+ * without a weighted sample has sum w = 0, so density, error and integral are identical; the running-coupling
+ * integrands (weight NaN -> 0 below the Landau scale for up to 99.7 % of the samples) then skip observable, bin and
+ * count for those samples.  Honoured by JMC_F32 runs with nan_to_num set; everything else counts all. */
+enum { JMC_COUNT_ALL = 0, JMC_COUNT_WEIGHTED = 1 };
 
 /* Samplers.  ref: montecarlo/sampler.py:114-140 (simple),
  * numerics/radiators/samplers.py:23-119 (critical), :125-180 (precritical),
@@ -149,7 +156,7 @@ typedef struct jmc_integrand {
     int32_t nan_to_num;      /* 1: weights pass through np.nan_to_num          */
     int32_t shower_groomer;  /* SHOWER: 0 ungroomed, 1 Soft Drop               */
     int32_t shower_n_emissions; /* SHOWER: 1, 2, ... or 0 = 'all'              */
-    int32_t reserved;
+    int32_t counts;          /* JMC_COUNT_ALL / JMC_COUNT_WEIGHTED (fused FP32 path) */
     double  epsilon;         /* log-sampling cutoff                            */
     double  z_cut;           /* grooming parameter                             */
     double  radius;          /* jet radius                                     */
@@ -332,6 +339,33 @@ int jmc_integrate_host(const jmc_integrand* g, uint64_t n, uint64_t seed, uint64
                        double* h_density, double* h_density_err,
                        double* h_integral, double* h_integral_err,
                        double* h_sum_w, double* h_sum_w2, uint64_t* h_count);
+
+/* ---- handle: cached job description, device workspace and pinned staging ----
+ * The reference has no such object (it has no FFI); it exists so that a job issued from a host thread costs its
+ * kernels and nothing else.  A handle belongs to the device that was current at jmc_create and to one host thread /
+ * stream at a time.  It remembers the last (integrand, precision, edges) it saw together with everything derived
+ * from them (FP32 edges in the kernel's compare domain, kernel parameters, both edge arrays on the device), so a
+ * repeated or point-by-point job re-derives nothing, and it owns the device workspace and pinned staging of the
+ * host-buffer entry point.  jmc_integrate_host above uses one implicit handle per (host thread, device). */
+typedef struct jmc_handle jmc_handle;
+int jmc_create(jmc_handle** out);
+int jmc_destroy(jmc_handle* h);
+
+/* jmc_run with HOST edges (what a caller of integrator.setBins has anyway): no read-back, no synchronisation,
+ * asynchronous on `stream`.  Histograms accumulate into the caller's DEVICE buffers.  h_edges NULL + d_minmax: the
+ * min/max-only pass. */
+int jmc_handle_run(jmc_handle* h, const jmc_integrand* g, uint64_t n, uint64_t seed, uint64_t first_index,
+                   int precision, const double* h_edges, int n_edges,
+                   double* d_sum_w, double* d_sum_w2, uint64_t* d_count, double* d_minmax, void* stream);
+
+/* jmc_integrate_host on an explicit handle: at most one upload (edges, when they changed), the kernels, ONE
+ * device-to-host copy of histograms + results, ONE synchronisation; no allocation after the first call. */
+int jmc_handle_integrate_host(jmc_handle* h, const jmc_integrand* g, uint64_t n, uint64_t seed,
+                              uint64_t first_index, int precision, const double* h_edges, int n_edges,
+                              int bc_kind, double bc_value,
+                              double* h_density, double* h_density_err,
+                              double* h_integral, double* h_integral_err,
+                              double* h_sum_w, double* h_sum_w2, uint64_t* h_count);
 
 /* sampler.generateSamples into host arrays */
 int jmc_sample_host(const jmc_sampler* s, uint64_t n, uint64_t seed, uint64_t first_index,

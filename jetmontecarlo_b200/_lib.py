@@ -32,7 +32,7 @@ EXPORTS = (
     "jmc_sampler_area", "jmc_integrand_uniforms", "jmc_integrand_area", "jmc_sample", "jmc_uniforms", "jmc_inverse_transform",
     "jmc_eval_fn", "jmc_eval_integrand", "jmc_bin_index", "jmc_hist", "jmc_hist2d", "jmc_finalize2d", "jmc_minmax", "jmc_run", "jmc_run_batch", "jmc_finalize_batch", "jmc_dump", "jmc_shower_dump", "jmc_shower_chains",
     "jmc_finalize", "jmc_cumulative", "jmc_set_density_host", "jmc_integrate_host", "jmc_sample_host",
-    "jmc_eval_fn_host", "jmc_launch_count",
+    "jmc_eval_fn_host", "jmc_launch_count", "jmc_create", "jmc_destroy", "jmc_handle_run", "jmc_handle_integrate_host",
 )
 
 
@@ -53,7 +53,7 @@ class Integrand(C.Structure):
     _fields_ = [("kind", C.c_int32), ("method", C.c_int32), ("jet", C.c_int32),
                 ("fixed_coupling", C.c_int32), ("obs_acc", C.c_int32), ("split_acc", C.c_int32),
                 ("nan_to_num", C.c_int32), ("shower_groomer", C.c_int32),
-                ("shower_n_emissions", C.c_int32), ("reserved", C.c_int32),
+                ("shower_n_emissions", C.c_int32), ("counts", C.c_int32),
                 ("epsilon", C.c_double), ("z_cut", C.c_double), ("radius", C.c_double),
                 ("beta", C.c_double), ("f_soft", C.c_double), ("z_pre", C.c_double),
                 ("theta_scale", C.c_double), ("lo", C.c_double), ("hi", C.c_double),
@@ -105,6 +105,11 @@ def _load():
         "jmc_sample_host": (i32, [P(Sampler), u64, u64, u64, vp, vp]),
         "jmc_eval_fn_host": (i32, [i32, P(FnParams), u64, vp, i64, vp, i64, vp, i64, vp, i64, vp]),
         "jmc_launch_count": (u64, []),
+        "jmc_create": (i32, [P(vp)]),
+        "jmc_destroy": (i32, [vp]),
+        "jmc_handle_run": (i32, [vp, P(Integrand), u64, u64, u64, i32, vp, i32, vp, vp, vp, vp, vp]),
+        "jmc_handle_integrate_host": (i32, [vp, P(Integrand), u64, u64, u64, i32, vp, i32, i32, dbl,
+                                            vp, vp, vp, vp, vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)       # AttributeError if the symbol is not exported
@@ -128,3 +133,40 @@ def check(rc):
 
 def launch_count():
     return int(lib.jmc_launch_count())
+
+
+class Handle:
+    """``jmc_handle``: cached job description + device workspace + pinned staging (include/jmc_b200.h).  One per
+    (thread, device); ``default_handle()`` keeps them."""
+
+    def __init__(self):
+        self._h = C.c_void_p()
+        check(lib.jmc_create(C.byref(self._h)))
+
+    @property
+    def ptr(self):
+        return self._h
+
+    def close(self):
+        if self._h:
+            lib.jmc_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_handles = {}
+
+
+def default_handle(device_index):
+    """the calling thread's handle for a device"""
+    import threading
+    key = (threading.get_ident(), int(device_index))
+    h = _handles.get(key)
+    if h is None:
+        h = _handles[key] = Handle()
+    return h

@@ -62,4 +62,13 @@ struct RunParams {
 };
 int make_run_params(const jmc_integrand* g, RunParams* out);
 
+// An FP32 job prepared on the host (jmc_fast.cu): kernel parameters + FP32 edges in the compare domain.
+struct FastPlan;
+int fast_plan_make(const jmc_integrand* g, const double* h_edges, int n_edges, FastPlan** out);   // h_edges NULL: min/max pass
+void fast_plan_free(FastPlan* p);
+const float* fast_plan_edges(const FastPlan* p);                                                   // n_edges floats (host)
+int fast_plan_run(const FastPlan* plan, const float* d_edges_f, int* d_poison, uint64_t n, uint64_t seed,
+                  uint64_t first_index, double* d_sum_w, double* d_sum_w2, uint64_t* d_count, double* d_minmax,
+                  void* stream);
+
 }  // namespace jmc

@@ -39,15 +39,17 @@ namespace jmc {
 static constexpr int kFastThreads = 256, kFastThreadsBig = 1024;
 static constexpr size_t kBigSmemThreshold = 72 * 1024;     // block histograms above this use the 1024-thread kernels
 static constexpr int kQueueFields = 5, kQueueSlots = 64;   // per-warp compaction queue (see run_fast_kernel)
-// resident blocks per SM the register allocation must allow (3 x 256 threads: <= 85 registers) and samples per loop
-// trip; swept with scripts/try_variants.sh -- 3:2, 3:3 and 2:4 are within 2 % of each other, more samples per trip
-// or a fourth block lose to register pressure.
+// resident blocks per SM the register allocation must allow (3 x 256 threads: <= 85 registers) and sample pairs per
+// loop trip; swept with scripts/try_variants.sh.
 // The rarely executed running-coupling radiator code may spill; the per-sample light path must not.
 #ifndef JMC_FAST_MIN_BLOCKS
 #define JMC_FAST_MIN_BLOCKS 3
 #endif
-#ifndef JMC_FAST_UNROLL
-#define JMC_FAST_UNROLL 2        // samples per loop trip
+#ifndef JMC_FAST_PAIRS
+#define JMC_FAST_PAIRS 1         // sample pairs per loop trip, kinds with >= 4 uniforms per sample
+#endif
+#ifndef JMC_FAST_PAIRS_2W
+#define JMC_FAST_PAIRS_2W 2      // sample pairs per loop trip, kinds with 2 uniforms per sample (one Philox block per pair)
 #endif
 #ifndef JMC_FAST_PIN_KEYS
 #define JMC_FAST_PIN_KEYS 1      // keep the Philox round keys in registers across the loop
@@ -65,7 +67,7 @@ static constexpr double H_ALPHA = 0.0785101418528313, H_MU = 0.00033333333333333
 static constexpr double H_PI = 3.141592653589793;
 
 struct FastParams {
-    int kind, jet, fixed, obs_mll, split_acc, nan_to_num;
+    int kind, jet, fixed, obs_mll, split_acc, nan_to_num, count_weighted;
     // sampling, base-2 logs
     float L2;          // log2(eps)
     float sL2;         // 2^-32 log2(eps): maps a 32-bit word straight to u * log2(eps)
@@ -83,7 +85,8 @@ struct FastParams {
     float aK, c0K;           // (1 - z_cut)^-2 and c0 (1 - z_cut)^-2: the observable's normalisation folded into `a`
     float bm0;               // 1 - z_cut - (1-f)*zcl : b = bm0 - delta (MLL observable)
     float omb;               // 1 - beta
-    float act_c2, act_c3;    // thresholds of the "1 + Lambda(C, alpha(theta_c)) > 0" test in base-2 logs (see light())
+    float act_c2, act_c3;    // thresholds of the "1 + Lambda(C, alpha(theta_c)) > 0" test in base-2 logs
+    float wT1, wT2, wT3, wT4; // the same tests on float(random word), see active_from_words()
     // fixed coupling
     float g;                 // 2 C_R alpha_fixed / pi
     float A;                 // ln(1/(2 z_cut)) * g         (theta exponent of critPDF_fc)
@@ -224,10 +227,6 @@ __device__ __forceinline__ bool sub_rc(const FastParams& P, float lc, float Lc, 
     return true;
 }
 
-struct FastSample {            // what a dump shows for one sample
-    float z_c, th_c, z_s, th_s, z_pre, zb_u, delta;
-};
-
 // The draws of one sample, kept in registers between the two stages below.
 struct Draw {
     float l2d, l2tc, l2zs, l2ts, l2zp;   // base-2 logs of delta, theta_c, z_s, theta_s, z_pre
@@ -242,47 +241,77 @@ __device__ __forceinline__ float l2_sample(uint32_t w, float sL2, float l2w) {
     return fmaf(__uint2float_rn(w), sL2, l2w);
 }
 
-// Can the weight of this draw be non-zero?  (Running coupling: "the reference's weight is not NaN".)  A function of
-// the draw alone, so the hot loop only keeps the OR over a trip's samples and re-derives the per-sample answer in
-// the rare trips that have an active sample.
-template <int KIND, bool FIXED>
-__device__ __forceinline__ bool is_active(const FastParams& P, const Draw& d) {
-    if (KIND == JMC_KIND_CRIT) {
-        if (FIXED) return true;
-        return fmaf(P.k, fmaf(JMC_LN2F, d.l2tc, P.lzc), 1.0f) > 0.0f && !P.crit_always_nan;   // 1 + Lambda(z_c theta) > 0
+// ---- sample streams of the FP32 mode -------------------------------------------------------------------------
+// Pair p = (global sample index >> 1) owns the Philox blocks (counter = (p_lo, p_hi, slot, 0)); sample s = index & 1:
+//   2-uniform kinds (RADIATOR, CRIT):  slot 0, words 2s, 2s+1                       one block per TWO samples
+//   4-uniform kind (CRIT_SUB):         slot s, words 0..3
+//   6-uniform kind (PRE_CRIT_SUB):     slot s, words 0..3 + slot 2, words 2s, 2s+1   three blocks per two samples
+// A thread always evaluates both samples of a pair, so no generated word is thrown away.
+template <int KIND>
+struct PairWords {
+    static constexpr bool FOUR = KIND == JMC_KIND_CRIT_SUB || KIND == JMC_KIND_PRE_CRIT_SUB;
+    uint32_t a[4];
+    uint32_t b[FOUR ? 4 : 1];
+    uint32_t c[KIND == JMC_KIND_PRE_CRIT_SUB ? 4 : 1];
+};
+struct Words {
+    uint32_t r[4];       // critical (z, theta) then subsequent (z, theta); 2-uniform kinds use r[0], r[1]
+    uint32_t e[2];       // pre-critical z, zero-bin uniform
+};
+template <int KIND>
+__device__ __forceinline__ void draw_pair(uint32_t p_lo, uint32_t p_hi, const PhiloxKeys& keys, PairWords<KIND>& w) {
+    philox4x32_10(p_lo, p_hi, 0u, keys, w.a);
+    if (PairWords<KIND>::FOUR) philox4x32_10(p_lo, p_hi, 1u, keys, w.b);
+    if (KIND == JMC_KIND_PRE_CRIT_SUB) philox4x32_10(p_lo, p_hi, 2u, keys, w.c);
+}
+// words of sample s of the pair (s is a compile-time constant in the hot loop: no register indexing)
+template <int KIND>
+__device__ __forceinline__ Words sample_words(const PairWords<KIND>& pw, int s) {
+    Words w;
+    if (PairWords<KIND>::FOUR) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) w.r[k] = s ? pw.b[k] : pw.a[k];
+    } else {
+        w.r[0] = s ? pw.a[2] : pw.a[0];
+        w.r[1] = s ? pw.a[3] : pw.a[1];
+        w.r[2] = w.r[3] = 0u;
     }
-    if (KIND == JMC_KIND_CRIT_SUB) {
-        if (FIXED) return d.lcl2 < -1.0f;                            // subPDF_fc mask: C < theta_c^beta / 2
-        // theta_c above both Landau thresholds (a constant), C < 1, and 1 + Lambda(C, alpha(theta_c)) > 0, which
-        // after multiplying by alpha's positive denominator is linear in the logarithms:
-        //   1 + ca (max(ln P_T theta_c, 0) - ln M_Z + ln C) > 0.
-        // In base-2 logs, and with max(A, 0) + B = max(A + B, B):  log2 C > c2  or  log2 theta_c + log2 C > c3,
-        // c2 = (ln M_Z - 1/ca) / ln 2, c3 = c2 - log2 P_T;  log2 theta_c + log2 C = lcl2 + log2 theta_c.
-        const float x = d.l2tc + d.lcl2;
-        const bool landau_c = (x > P.act_c3) | (d.lcl2 > P.act_c2);
-        return landau_c & (d.l2tc > P.l2tc_min) & (d.lcl2 < 0.0f);
+    if (KIND == JMC_KIND_PRE_CRIT_SUB) {
+        w.e[0] = s ? pw.c[2] : pw.c[0];
+        w.e[1] = s ? pw.c[3] : pw.c[1];
+    } else {
+        w.e[0] = w.e[1] = 0u;
+    }
+    return w;
+}
+
+// Can the weight of this draw be non-zero?  For the running-coupling kinds: "the reference's weight is not NaN", a
+// function of the random words alone.  Every quantity of the test is affine in the words (log sampling), so it is made
+// on float(word) with the offsets and the factor 2^-32 log2(eps) < 0 folded into the thresholds (FastParams::wT*):
+//   CRIT:      1 + Lambda(z_c theta_c) > 0                                       <=>  f1 < wT1
+//   CRIT_SUB:  theta_c above both Landau thresholds (a constant)                 <=>  f1 < wT1
+//              C < 1 for log(2 - 2C) in b_bar(C), C = csub / theta_c^beta        <=>  lc > wT2
+//              1 + Lambda(C, alpha(theta_c)) > 0, which after multiplying by alpha's positive denominator is linear
+//              in the logs: 1 + ca (max(ln P_T theta_c, 0) - ln M_Z + ln C) > 0; with max(A, 0) + B = max(A + B, B):
+//              log2 C > c2  or  log2 theta_c + log2 C > c3                       <=>  lc < wT4  or  f1 + lc < wT3
+//   with lc = f2 + 2 beta f3 - beta f1  (log2 C = sL2 lc + const).  Three conversions, two FMAs, one add, four compares.
+template <int KIND, bool FIXED>
+__device__ __forceinline__ bool active_from_words(const FastParams& P, const uint32_t* r) {
+    if (!FIXED && KIND == JMC_KIND_CRIT) return (__uint2float_rn(r[1]) < P.wT1) & !P.crit_always_nan;
+    if (!FIXED && KIND == JMC_KIND_CRIT_SUB) {
+        const float f1 = __uint2float_rn(r[1]), f2 = __uint2float_rn(r[2]), f3 = __uint2float_rn(r[3]);
+        const float lc = fmaf(-P.beta, f1, fmaf(2.0f * P.beta, f3, f2));
+        const float x = lc + f1;
+        return (f1 < P.wT1) & (lc > P.wT2) & ((x < P.wT3) | (lc < P.wT4));
     }
     return true;
 }
 
-// Stage 1 ("light"): draw the sample, form log2(observable) and decide whether the weight can be
-// non-zero.  Everything here is executed for every sample; it is straight-line code.
+// Stage 1 ("light"): the sample from its words, log2(observable), and whether the weight can be non-zero.
 // FIXED selects the coupling at compile time so that the other branch costs nothing.
-// The random words of one sample: Philox block 0, and block 1 for the kind that needs six uniforms.
-template <int KIND>
-struct Words {
-    uint32_t a[4];
-    uint32_t b[KIND == JMC_KIND_PRE_CRIT_SUB ? 4 : 1];
-};
-template <int KIND>
-__device__ __forceinline__ void draw_words(uint32_t idx_lo, uint32_t idx_hi, const PhiloxKeys& keys, Words<KIND>& w) {
-    philox4x32_10(idx_lo, idx_hi, 0u, keys, w.a);
-    if (KIND == JMC_KIND_PRE_CRIT_SUB) philox4x32_10(idx_lo, idx_hi, 1u, keys, w.b);
-}
-
 template <int KIND, bool FIXED, bool OBS_MLL>
-__device__ __forceinline__ bool light(const FastParams& P, const Words<KIND>& w, Draw& d, float& l2obs) {
-    const uint32_t* r = w.a;
+__device__ __forceinline__ bool light(const FastParams& P, const Words& w, Draw& d, float& l2obs) {
+    const uint32_t* r = w.r;
     if (KIND == JMC_KIND_RADIATOR) {
         // ungroomedSampler (samplers.py:204-226), C_ungroomed (observables.py:82-109)
         d.l2zs = l2_sample(r[0], P.sL2, -1.0f);
@@ -303,7 +332,7 @@ __device__ __forceinline__ bool light(const FastParams& P, const Words<KIND>& w,
     const float bb = OBS_MLL ? P.bm0 - d.delta : P.one_m;
     if (KIND == JMC_KIND_CRIT) {
         l2obs = fmaf(P.beta, d.l2tc, lg2(aK * bb));
-        return is_active<KIND, FIXED>(P, d);
+        return active_from_words<KIND, FIXED>(P, r);
     }
     // subsequent emission from the ungroomed sampler
     d.l2zs = l2_sample(r[2], P.sL2, -1.0f);
@@ -314,14 +343,14 @@ __device__ __forceinline__ bool light(const FastParams& P, const Words<KIND>& w,
         const float l2cs = fmaf(2.0f * P.beta, d.l2ts, d.l2zs);
         l2obs = fmaxf(l2cc, l2cs);
         d.lcl2 = fmaf(-P.beta, d.l2tc, l2cs);                        // log2(csub / theta_c^beta)
-        return is_active<KIND, FIXED>(P, d);
+        if (FIXED) return d.lcl2 < -1.0f;                            // subPDF_fc mask: C < theta_c^beta / 2
+        return active_from_words<KIND, FIXED>(P, r);
     }
     if (KIND == JMC_KIND_PRE_CRIT_SUB) {
         // all-emission integrand with the zero bin
         // (examples/tests/comparison_tests/comparison_utils_probabilistic.py:384-474)
-        const uint32_t* r2 = w.b;
-        d.l2zp = l2_sample(r2[0], P.sL2, P.l2zc);
-        d.u5 = __uint2float_rn(r2[1]) * 2.3283064365386963e-10f;
+        d.l2zp = l2_sample(w.e[0], P.sL2, P.l2zc);
+        d.u5 = __uint2float_rn(w.e[1]) * 2.3283064365386963e-10f;
         const float E2 = -P.g * d.l2tc;                              // E / ln2, E = 2 C_R a/pi ln(R0/theta_c)
         d.cdf = ex2(-E2 * P.ln_zc_eps);                              // exp(-E ln(z_cut/eps))
         const bool zero_bin = d.u5 < d.cdf;
@@ -418,15 +447,20 @@ __device__ __forceinline__ int bin_fast(const FastParams& P, float l2obs, const 
 
 // HOT: histogram only (no min/max tracking) into np.logspace-like bins with nan_to_num weights -- the form every
 // large job has; the generic instantiation reads those choices from FastParams at run time.
-template <int KIND, bool FIXED, bool OBS_MLL, bool HOT>
+// COUNT_ALL: the per-bin count is np.histogram's (every sample inside the binned range).  With COUNT_ALL = false the
+// count is taken over the samples that carry a non-zero weight only.  The reference uses the count for one thing: to
+// zero the density of empty bins (integrator.py:101,123-124), and a bin without a weighted sample has sum w = 0
+// anyway, so density, error and integral are the same -- but the kinds whose weight is NaN -> 0 for most samples (the
+// running-coupling Landau region: 99.7 % of CRIT_SUB samples) then need neither observable nor bin nor count atomic
+// for those samples: the random words decide (active_from_words) and the rest is evaluated only for the survivors.
+template <int KIND, bool FIXED, bool OBS_MLL, bool HOT, bool COUNT_ALL>
 __device__ __forceinline__ void
 fast_body(const FastParams& P_in, uint64_t n, uint64_t seed, uint64_t first, const float* __restrict__ g_edges,
           double* __restrict__ g_sum_w, double* __restrict__ g_sum_w2, unsigned long long* __restrict__ g_count,
           int* g_poison, double* __restrict__ d_minmax, double* s_raw) {
     __shared__ int s_poison;
-    // (The ~17 per-sample parameters are re-read from the constant bank once per trip -- about 6 issue slots per
-    // sample.  Pinning them in registers through opaque inline asm does not survive ptxas, which rematerialises
-    // parameter loads; measured: no effect.)
+    // (The per-sample parameters are re-read from the constant bank once per trip.  Pinning them in registers
+    // through opaque inline asm does not survive ptxas, which rematerialises parameter loads; measured: no effect.)
     const FastParams& P = P_in;
     const int ne = P.n_edges, nb = ne > 0 ? ne - 1 : 0;
     const int sh = P.spread_shift;
@@ -453,20 +487,22 @@ fast_body(const FastParams& P_in, uint64_t n, uint64_t seed, uint64_t first, con
     for (int k = threadIdx.x; k < ne; k += blockDim.x) s_edges[k] = g_edges[k];
     __syncthreads();
     float mn = INFINITY, mx = -INFINITY;
-    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t stride = gridDim.x * blockDim.x;
-    const uint32_t iters = n > tid ? (uint32_t)((n - tid + stride - 1) / stride) : 0u;
-    // The host never lets a launch cross a multiple of 2^32 in the global sample index, so the high half of the
-    // Philox counter is launch-uniform and the low half is plain 32-bit arithmetic.
-    const uint32_t idx_hi = (uint32_t)(first >> 32);
-    uint32_t idx = (uint32_t)first + tid;
     // Kinds whose weight can be NaN by construction (running-coupling Landau region) run the hot instantiation
     // only with nan_to_num set; for the others the flag is looked at only if a NaN ever shows up.
     constexpr bool NAN_REGION = !FIXED && KIND != JMC_KIND_RADIATOR;
     const bool nan_to_num = (HOT && NAN_REGION) || P.nan_to_num;
+    // Warp-level compaction of the rare samples whose weight is not NaN -> 0.  In the running-coupling
+    // critical x subsequent integrand 0.3 % of the samples are active, i.e. 9 % of the warps would run the
+    // ~330-instruction radiator code with one or two live lanes.  Instead the words of the active samples are
+    // appended to a per-warp shared-memory queue (ballot + popc, no atomics) and evaluated 32 at a time with every
+    // lane busy.  (Also the running-coupling critical integrand: 35 % of its samples are above the Landau scale.)
+    constexpr bool COMPACT = (KIND == JMC_KIND_CRIT_SUB || KIND == JMC_KIND_CRIT) && !FIXED;
+    constexpr bool LAZY = COMPACT && HOT && !COUNT_ALL;     // observable and bin only for the samples in the queue
+    constexpr int QW = KIND == JMC_KIND_CRIT ? 2 : 4;       // words per queued sample
+    const unsigned lane = threadIdx.x & 31u;
 
     // weight * jacobian of one sample into the block histogram (bq: bin, or -1 / -2 for a sample below /
-    // above the binned range, which matters only for NumPy's NaN poisoning)
+    // above the binned range, which matters only for NumPy's NaN poisoning).
     // Back ends (JMC_ACC_MODE; shared-memory FP32/FP64/64-bit adds are compare-and-swap loops on sm_100, only 32-bit
     // integer adds are native, so what costs is the number of CAS rounds = lanes of a warp on one address):
     //  1 (default): R = 2^sh lane-interleaved copies of every bin, slot [bin][lane & (R-1)] holding (sum w, sum w^2)
@@ -475,11 +511,11 @@ fast_body(const FastParams& P_in, uint64_t n, uint64_t seed, uint64_t first, con
     //     block flushes.  A slot sees ~n_block / (nb R) adds of one sign: FP32 rounding ~ sqrt(adds) 2^-25 relative.
     //  2: __match_any_sync on the bin, peers reduced by shuffles, one FP64 CAS pair per distinct bin per warp.
     //  0 / 3: two FP64 CAS loops per sample on [bin] / on the lane-interleaved slot.
-    const unsigned lane_acc = threadIdx.x & 31u;
     auto accumulate = [&](float w, int bq) {
         if (bq >= 0 && fabsf(w) > 0.0f) {                // the common case first: one compare rejects 0 and NaN
+            if (LAZY) atomicAdd(&s_count[bq], 1u);
 #if JMC_ACC_MODE == 1
-            unsigned long long* a = (unsigned long long*)&s_acc[(bq << sh) | (int)(lane_acc & ((1u << sh) - 1u))];
+            unsigned long long* a = (unsigned long long*)&s_acc[(bq << sh) | (int)(lane & ((1u << sh) - 1u))];
             const float w2 = w * w;
             unsigned long long old = *a, assumed;
             do {
@@ -496,18 +532,18 @@ fast_body(const FastParams& P_in, uint64_t n, uint64_t seed, uint64_t first, con
             float aw = w, aw2 = w * w;
             const float mw = aw, mw2 = aw2;
             while (__any_sync(mask, others != 0u)) {
-                const int src = others ? __ffs(others) - 1 : (int)lane_acc;
+                const int src = others ? __ffs(others) - 1 : (int)lane;
                 const float vw = __shfl_sync(mask, mw, src), vw2 = __shfl_sync(mask, mw2, src);
                 if (others) { aw += vw; aw2 += vw2; }
                 others &= others - 1u;
             }
-            if ((int)lane_acc == leader) {
+            if ((int)lane == leader) {
                 atomicAdd(&s_sum_w[bq], (double)aw);
                 atomicAdd(&s_sum_w2[bq], (double)aw2);
             }
 #else
             const double wd = (double)w;
-            const int slot = (bq << sh) | (int)(lane_acc & ((1u << sh) - 1u));
+            const int slot = (bq << sh) | (int)(lane & ((1u << sh) - 1u));
             atomicAdd(&s_sum_w[slot], wd);
             atomicAdd(&s_sum_w2[slot], wd * wd);
 #endif
@@ -517,33 +553,11 @@ fast_body(const FastParams& P_in, uint64_t n, uint64_t seed, uint64_t first, con
         }
     };
 
-    // Warp-level compaction of the rare samples whose weight is not NaN -> 0.  In the running-coupling
-    // critical x subsequent integrand 0.3 % of the samples are active, i.e. 9 % of the warps would run the
-    // ~330-instruction radiator code with one or two live lanes.  Instead the active draws are appended to a
-    // per-warp shared-memory queue (ballot + popc, no atomics) and evaluated 32 at a time with every lane busy.
-    // (also the running-coupling critical integrand: 35 % of its samples are above the Landau scale)
-    constexpr bool COMPACT = (KIND == JMC_KIND_CRIT_SUB || KIND == JMC_KIND_CRIT) && !FIXED;
-    const unsigned lane = threadIdx.x & 31u;
-    float* q = (float*)(s_edges + ((ne + 3) & ~3)) + (threadIdx.x >> 5) * (kQueueFields * kQueueSlots);
-    int qn = 0;                                          // warp-uniform queue length
-    auto heavy_from_queue = [&](int slot) {
-        Draw d;
-        d.l2d = q[0 * kQueueSlots + slot];
-        d.l2tc = q[1 * kQueueSlots + slot];
-        d.l2zs = KIND == JMC_KIND_CRIT ? 0.0f : q[2 * kQueueSlots + slot];
-        d.l2ts = KIND == JMC_KIND_CRIT ? 0.0f : q[3 * kQueueSlots + slot];
-        const int bq = __float_as_int(q[4 * kQueueSlots + slot]);
-        d.delta = ex2(d.l2d);
-        d.z = P.zc + d.delta;
-        d.lcl2 = fmaf(-P.beta, d.l2tc, fmaf(2.0f * P.beta, d.l2ts, d.l2zs));
-        accumulate(heavy<KIND, FIXED>(P, d), bq);
-    };
-
     // Bin of an observable: `ok` = inside the binned range, `b` = its bin (meaningful only when ok).
     // HOT (np.logspace bins): the bin is the floor of an affine map of log2(obs), and the range test is made on the
-    // mapped value -- FFMA, one compare, F2I.  (The stored FP32 edges are that same map rounded; settling
-    // against them would cost ten more instructions per sample for samples within 1e-7 of an edge, which FP32
-    // cannot place with respect to the FP64 edges anyway.)
+    // mapped value -- FFMA, one compare, F2I.  The host shrinks the map by 2^-14 of a bin at either end
+    // (make_fast_params), so that an observable equal to the first or the last edge (the extreme sample, when the
+    // edges come from setBins) maps inside [0, nb) whatever the rounding of the FMA.
     auto locate = [&](float l2obs, bool& ok, int& b) {
         if (HOT) {
             const float f = fmaf(l2obs, P.inv_d, P.mb0_inv_d);
@@ -581,90 +595,146 @@ fast_body(const FastParams& P_in, uint64_t n, uint64_t seed, uint64_t first, con
         locate(l2obs, ok, b);
         atomicAdd(&s_count[(ok && valid) ? b : dummy_slot], 1u);
     };
-    // The weight of a sample, directly or through the queue.  Warp-collective when COMPACT.
-    auto weigh = [&](const Draw& d, float l2obs, bool active, bool valid) {
-        if (!do_hist) return;
-        if (!valid) active = false;
-        if (COMPACT) {
-            if (!nan_to_num && !active && valid) accumulate(fnan(), weight_bin(l2obs));   // inactive = "the reference weight is NaN"
-            const unsigned m = __ballot_sync(0xffffffffu, active);
-            if (m) {
-                if (active) {
-                    const int slot = qn + __popc(m & ((1u << lane) - 1u));
-                    q[0 * kQueueSlots + slot] = d.l2d;
-                    q[1 * kQueueSlots + slot] = d.l2tc;
-                    if (KIND != JMC_KIND_CRIT) {
-                        q[2 * kQueueSlots + slot] = d.l2zs;
-                        q[3 * kQueueSlots + slot] = d.l2ts;
-                    }
-                    q[4 * kQueueSlots + slot] = __int_as_float(weight_bin(l2obs));
-                }
-                qn += __popc(m);
-                __syncwarp();
-                if (qn >= 32) {
-                    qn -= 32;
-                    heavy_from_queue(qn + (int)lane);
-                    __syncwarp();
-                }
-            }
-        } else if (active) {
-            accumulate(heavy<KIND, FIXED>(P, d), weight_bin(l2obs));
-        } else if (!FIXED && !nan_to_num && valid) {
-            accumulate(fnan(), weight_bin(l2obs));       // inactive under running coupling = NaN weight
-        }
+    // a sample whose weight can be non-zero: everything from its words
+    auto weigh_words = [&](const Words& w) {
+        Draw d;
+        float o;
+        light<KIND, FIXED, OBS_MLL>(P, w, d, o);
+        accumulate(heavy<KIND, FIXED>(P, d), weight_bin(o));
     };
 
-    // U samples per trip: their Philox chains are independent, so the scheduler interleaves them (the generator
+    // per-warp queue of active samples: QW words per slot, 64 slots (at most 31 left over + 32 appended)
+    uint32_t* q = (uint32_t*)(s_edges + ((ne + 3) & ~3)) + (threadIdx.x >> 5) * (kQueueFields * kQueueSlots);
+    int qn = 0;                                          // warp-uniform queue length
+    auto drain = [&](int slot) {
+        Words w;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) w.r[k] = k < QW ? q[k * kQueueSlots + slot] : 0u;
+        w.e[0] = w.e[1] = 0u;
+        weigh_words(w);
+    };
+    // warp-collective: append the lanes whose sample is active, evaluate 32 queued samples when there are that many
+    auto enqueue = [&](const Words& w, bool active) {
+        const unsigned m = __ballot_sync(0xffffffffu, active);
+        if (!m) return;
+        if (active) {
+            const int slot = qn + __popc(m & ((1u << lane) - 1u));
+#pragma unroll
+            for (int k = 0; k < QW; ++k) q[k * kQueueSlots + slot] = w.r[k];
+        }
+        qn += __popc(m);
+        __syncwarp();
+        if (qn >= 32) {
+            qn -= 32;
+            drain(qn + (int)lane);
+            __syncwarp();
+        }
+    };
+    // One sample with every check (ragged trips, the half pairs at the ends of the index range, and the generic
+    // per-sample order of the kinds that are not compacted).  Warp-collective when COMPACT.
+    auto one = [&](const Words& w, bool valid) {
+        if (LAZY) {
+            enqueue(w, valid && active_from_words<KIND, FIXED>(P, w.r));
+            return;
+        }
+        Draw d;
+        float o;
+        const bool active = light<KIND, FIXED, OBS_MLL>(P, w, d, o) && valid;
+        tally(o, valid);
+        if (!do_hist) return;
+        if (!FIXED && !nan_to_num && !active && valid) accumulate(fnan(), weight_bin(o));   // inactive = NaN weight
+        if (COMPACT) enqueue(w, active);
+        else if (active) accumulate(heavy<KIND, FIXED>(P, d), weight_bin(o));
+    };
+
+    // ---- the index range in pairs.  Interior pairs [pa, pb) have both samples inside [first, first + n); an odd
+    // `first` / an odd end leave one half pair each, handled by warp 0 of block 0 after the loop.  The host never
+    // lets a launch cross a multiple of 2^32 in the sample index, so the high word of the pair counter is
+    // launch-uniform and the low word is plain 32-bit arithmetic (no wrap inside the launch).
+    const uint64_t end = first + n;
+    const uint64_t pa = (first + 1) >> 1, pb = end >> 1;
+    const uint32_t np = pb > pa ? (uint32_t)(pb - pa) : 0u;
+    const uint32_t p_hi = (uint32_t)(first >> 33);
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const uint32_t mine = np > tid ? (np - tid + stride - 1) / stride : 0u;      // pairs of this thread
+    uint32_t idx = (uint32_t)pa + tid;
+
+    // V pairs per trip: their Philox chains are independent, so the scheduler interleaves them (the generator
     // is a 10-deep dependent chain of IMAD.WIDE -> LOP3), and the warp-uniform work of a trip (constant loads, loop
-    // control, and for the compacted kinds ONE vote on "any lane has an active sample among its U") is paid once
-    // per U samples.  The ballots in weigh() need every lane of the warp in every trip, so all lanes run to the
-    // warp's longest trip count.
+    // control, and for the compacted kinds ONE vote on "any lane has an active sample") is paid once per 2V samples.
+    // The ballots need every lane of the warp in every trip, so all lanes run to the warp's longest trip count.
     PhiloxKeys keys(seed);
 #if JMC_FAST_PIN_KEYS
     keys.pin();
 #endif
-    constexpr int U = JMC_FAST_UNROLL;
-    const uint32_t strideU = (uint32_t)U * stride;
-    // Main loop: trips in which every lane of the warp has all U samples (no validity tests); then at most two
-    // checked trips for the ragged end.  Lanes of a warp differ by at most one sample (consecutive tid).
-    const uint32_t full = __shfl_sync(0xffffffffu, iters, 31) / (uint32_t)U;
-    const uint32_t trips = (__shfl_sync(0xffffffffu, iters, 0) + (uint32_t)(U - 1)) / (uint32_t)U;
-    // (Measured and dropped: software-pipelining the generator of trip j+1 against the evaluation of trip j, to
-    // mix FMA-heavy and ALU work inside each warp -- 16 more live registers cost more occupancy than the better
-    // mix gains: 2.4-2.7e11 samples/s against 2.8e11.)
-    for (uint32_t j = 0; j < full; ++j, idx += strideU) {
-        Draw d[U];
-        float o[U];
-        bool any = !nan_to_num;
+    constexpr int V = PairWords<KIND>::FOUR ? JMC_FAST_PAIRS : JMC_FAST_PAIRS_2W;
+    const uint32_t strideV = (uint32_t)V * stride;
+    // Main loop: trips in which every lane of the warp has all V pairs (no validity tests); then at most two
+    // checked trips for the ragged end.  Lanes of a warp differ by at most one pair (consecutive tid).
+    const uint32_t full = __shfl_sync(0xffffffffu, mine, 31) / (uint32_t)V;
+    const uint32_t trips = (__shfl_sync(0xffffffffu, mine, 0) + (uint32_t)(V - 1)) / (uint32_t)V;
+    for (uint32_t j = 0; j < full; ++j, idx += strideV) {
+        PairWords<KIND> pw[V];
 #pragma unroll
-        for (int k = 0; k < U; ++k) {
-            Words<KIND> w;
-            draw_words<KIND>(idx + (uint32_t)k * stride, idx_hi, keys, w);
-            any |= light<KIND, FIXED, OBS_MLL>(P, w, d[k], o[k]);
-        }
+        for (int v = 0; v < V; ++v) draw_pair<KIND>(idx + (uint32_t)v * stride, p_hi, keys, pw[v]);
+        if (COMPACT) {
+            bool act[2 * V];
+            bool any = false;
 #pragma unroll
-        for (int k = 0; k < U; ++k) tally(o[k], true);
-        if (!COMPACT || __any_sync(0xffffffffu, any)) {
+            for (int k = 0; k < 2 * V; ++k) {
+                const Words w = sample_words<KIND>(pw[k >> 1], k & 1);
+                if (LAZY) {
+                    act[k] = active_from_words<KIND, FIXED>(P, w.r);
+                } else {
+                    Draw d;
+                    float o;
+                    act[k] = light<KIND, FIXED, OBS_MLL>(P, w, d, o);
+                    tally(o, true);
+                    if (do_hist && !nan_to_num && !act[k]) accumulate(fnan(), weight_bin(o));
+                }
+                any |= act[k];
+            }
+            if (do_hist && __any_sync(0xffffffffu, any)) {
 #pragma unroll
-            for (int k = 0; k < U; ++k) weigh(d[k], o[k], is_active<KIND, FIXED>(P, d[k]), true);
+                for (int k = 0; k < 2 * V; ++k) enqueue(sample_words<KIND>(pw[k >> 1], k & 1), act[k]);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 2 * V; ++k) {
+                Draw d;
+                float o;
+                const bool active = light<KIND, FIXED, OBS_MLL>(P, sample_words<KIND>(pw[k >> 1], k & 1), d, o);
+                tally(o, true);
+                if (do_hist) {
+                    if (active) accumulate(heavy<KIND, FIXED>(P, d), weight_bin(o));
+                    else if (!FIXED && !nan_to_num) accumulate(fnan(), weight_bin(o));
+                }
+            }
         }
     }
-    for (uint32_t j = full; j < trips; ++j, idx += strideU) {
+    for (uint32_t j = full; j < trips; ++j, idx += strideV) {
 #pragma unroll 1
-        for (int k = 0; k < U; ++k) {
-            Draw d;
-            float o;
-            Words<KIND> wt;
-            draw_words<KIND>(idx + (uint32_t)k * stride, idx_hi, keys, wt);
-            const bool a = light<KIND, FIXED, OBS_MLL>(P, wt, d, o);
-            const bool valid = (uint32_t)U * j + (uint32_t)k < iters;
-            tally(o, valid);
-            weigh(d, o, a, valid);
+        for (int v = 0; v < V; ++v) {
+            PairWords<KIND> pw;
+            draw_pair<KIND>(idx + (uint32_t)v * stride, p_hi, keys, pw);
+            const bool valid = (uint32_t)V * j + (uint32_t)v < mine;
+            one(sample_words<KIND>(pw, 0), valid);
+            one(sample_words<KIND>(pw, 1), valid);
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x < 32) {
+        // half pairs: lane 0 takes sample `first` when it is odd, lane 1 takes sample end-1 when `end` is odd
+        const bool front = lane == 0 && (first & 1ull), back = lane == 1 && (end & 1ull);
+        if (__any_sync(0xffffffffu, front || back)) {
+            PairWords<KIND> pw;
+            draw_pair<KIND>((uint32_t)((back ? end : first) >> 1), p_hi, keys, pw);
+            one(sample_words<KIND>(pw, back ? 0 : 1), front || back);
         }
     }
     if (COMPACT && do_hist) {
         __syncwarp();
-        if ((int)lane < qn) heavy_from_queue((int)lane);
+        if ((int)lane < qn) drain((int)lane);
     }
     __syncthreads();
     if (do_hist) {
@@ -716,13 +786,14 @@ fast_body(const FastParams& P_in, uint64_t n, uint64_t seed, uint64_t first, con
 // one job: parameters in the constant bank
 // BIG: 1024-thread blocks, one per SM, for histograms that need most of an SM's shared memory (the reference's
 // default of 5000 radiator bins is 130 KB per block): 32 warps then share one histogram instead of 8.
-template <int KIND, bool FIXED, bool OBS_MLL, bool HOT, bool BIG>
+template <int KIND, bool FIXED, bool OBS_MLL, bool HOT, bool BIG, bool COUNT_ALL>
 __global__ void __launch_bounds__(BIG ? kFastThreadsBig : kFastThreads, BIG ? 1 : JMC_FAST_MIN_BLOCKS)
 run_fast_kernel(FastParams P, uint64_t n, uint64_t seed, uint64_t first, const float* __restrict__ g_edges,
                 double* __restrict__ g_sum_w, double* __restrict__ g_sum_w2,
                 unsigned long long* __restrict__ g_count, int* g_poison, double* __restrict__ d_minmax) {
     extern __shared__ __align__(16) double s_dyn[];
-    fast_body<KIND, FIXED, OBS_MLL, HOT>(P, n, seed, first, g_edges, g_sum_w, g_sum_w2, g_count, g_poison, d_minmax, s_dyn);
+    fast_body<KIND, FIXED, OBS_MLL, HOT, COUNT_ALL>(P, n, seed, first, g_edges, g_sum_w, g_sum_w2, g_count, g_poison,
+                                                    d_minmax, s_dyn);
 }
 
 // A grid of parameter points in one launch (BASELINE config 5: gen_crit_sub_num_rad's theta_crit loop,
@@ -742,17 +813,20 @@ run_fast_batch_kernel(const FastParams* __restrict__ params, uint64_t n, uint64_
     for (int k = threadIdx.x; k < words; k += blockDim.x) ((int*)&sP)[k] = ((const int*)&params[point])[k];
     __syncthreads();
     const size_t nb = n_edges > 0 ? (size_t)n_edges - 1 : 0;
-    fast_body<KIND, FIXED, OBS_MLL, HOT>(
+    fast_body<KIND, FIXED, OBS_MLL, HOT, true>(
         sP, n, seed, first, edges_all ? edges_all + (size_t)point * n_edges : nullptr,
         sum_w_all ? sum_w_all + point * nb : nullptr, sum_w2_all ? sum_w2_all + point * nb : nullptr,
         count_all ? count_all + point * nb : nullptr, poison_all + point,
         minmax_all ? minmax_all + 2 * (size_t)point : nullptr, s_dyn);
 }
 
-__global__ void poison_fast_kernel(const int* g_poison, int nb, double* g_sum_w, double* g_sum_w2) {
+// one block; leaves the flag re-armed ("no poison") for the next job that uses the same scratch
+__global__ void poison_fast_kernel(int* g_poison, int nb, double* g_sum_w, double* g_sum_w2) {
     const int pb = *g_poison;
+    __syncthreads();
+    if (threadIdx.x == 0) *g_poison = 0x7f7f7f7f;
     if (pb < 0 || pb >= nb) return;
-    for (int k = pb + blockIdx.x * blockDim.x + threadIdx.x; k < nb; k += gridDim.x * blockDim.x) {
+    for (int k = pb + threadIdx.x; k < nb; k += blockDim.x) {
         g_sum_w[k] = __longlong_as_double(0x7ff8000000000000LL);
         g_sum_w2[k] = __longlong_as_double(0x7ff8000000000000LL);
     }
@@ -771,10 +845,10 @@ dump_fast_kernel(FastParams P, uint64_t n, uint64_t seed, uint64_t first, double
         d.u5 = 2.0f;
         float l2obs;
         const PhiloxKeys keys(seed);
-        const uint64_t gi = first + i;
-        const uint32_t lo = (uint32_t)gi, hi = (uint32_t)(gi >> 32);
-        Words<KIND> wd;
-        draw_words<KIND>(lo, hi, keys, wd);
+        const uint64_t gi = first + i, pair = gi >> 1;
+        PairWords<KIND> pw;
+        draw_pair<KIND>((uint32_t)pair, (uint32_t)(pair >> 32), keys, pw);
+        const Words wd = sample_words<KIND>(pw, (int)(gi & 1ull));
         const bool active = P.obs_mll ? light<KIND, FIXED, true>(P, wd, d, l2obs)
                                       : light<KIND, FIXED, false>(P, wd, d, l2obs);
         float w = active ? heavy<KIND, FIXED>(P, d) : (FIXED ? 0.0f : fnan());
@@ -822,7 +896,7 @@ static int make_fast_params(const jmc_integrand* g, const double* h_edges, int n
     const double ln2 = std::log(2.0);
     const double CR = g->jet == JMC_QUARK ? H_CF : H_CA;
     P.kind = g->kind; P.jet = g->jet; P.fixed = g->fixed_coupling; P.obs_mll = g->obs_acc == JMC_ACC_MLL;
-    P.split_acc = g->split_acc; P.nan_to_num = g->nan_to_num;
+    P.split_acc = g->split_acc; P.nan_to_num = g->nan_to_num; P.count_weighted = g->counts == JMC_COUNT_WEIGHTED;
     P.L2 = (float)std::log2(g->epsilon);
     P.sL2 = (float)(std::log2(g->epsilon) * 2.3283064365386963e-10);
     P.l2w_cz = (float)std::log2(0.5 - g->z_cut);
@@ -899,6 +973,21 @@ static int make_fast_params(const jmc_integrand* g, const double* h_edges, int n
         const double ln_th_crit = g->z_cut > 0 ? -1.0 / k - std::log(g->z_cut) : -INFINITY;
         P.l2tc_min = (float)(std::fmax(ln_th_sub, ln_th_crit) / ln2);
     }
+    {
+        // the activity tests on float(word): l2x = sL2 * float(word) + offset with sL2 < 0, so "l2x > t" is
+        // "float(word) < (t - offset) / sL2" (active_from_words)
+        const double sL2 = std::log2(g->epsilon) * 2.3283064365386963e-10, l2R = std::log2(g->radius);
+        const double k0 = -1.0 + g->beta * l2R;             // log2 C = sL2 (f2 + 2 beta f3 - beta f1) + k0
+        if (g->kind == JMC_KIND_CRIT) {
+            const double k = 2.0 * H_ALPHA * H_BETA0;
+            P.wT1 = (float)(((-1.0 / k - std::log(g->z_cut)) / ln2 - l2R) / sL2);
+        } else {
+            P.wT1 = (float)(((double)P.l2tc_min - l2R) / sL2);
+        }
+        P.wT2 = (float)((0.0 - k0) / sL2);
+        P.wT4 = (float)(((double)P.act_c2 - k0) / sL2);
+        P.wT3 = (float)(((double)P.act_c3 - l2R - k0) / sL2);
+    }
     // ---- binning domain
     P.n_edges = n_edges;
     if (h_edges) {
@@ -917,12 +1006,22 @@ static int make_fast_params(const jmc_integrand* g, const double* h_edges, int n
         for (int k = 0; k < n_edges; ++k) uniform = uniform && std::fabs(dom[k] - (dom[0] + k * d)) <= 1e-9 * std::fabs(d) * n_edges + 1e-12;
         P.uniform = uniform;
         P.b0 = (float)dom[0];
-        P.inv_d = (float)(1.0 / d);
-        P.mb0_inv_d = (float)(-dom[0] / d);
         for (int k = 0; k < n_edges; ++k) (*edges_f)[k] = (float)dom[k];
         P.e_first = (*edges_f)[0];
         P.e_last = (*edges_f)[n_edges - 1];
         P.nb_f = (float)(n_edges - 1);
+        // The affine bin map f(x) = x * inv_d + mb0_inv_d, shrunk by a margin m of a bin at either end so that the
+        // FP32 images of the first and the last edge fall inside [0, nb): an observable equal to an end edge (the
+        // extreme sample, when the edges come from setBins) is then binned, as np.histogram's closed last bin does,
+        // whatever the rounding of the FMA.  m starts at 2^-14 of a bin (FP32 places log2(obs) no better than that).
+        const double nbd = (double)(n_edges - 1);
+        for (double m = std::ldexp(1.0, -14);; m *= 4.0) {
+            const double scale = (nbd - 2.0 * m) / nbd;
+            P.inv_d = (float)(scale / d);
+            P.mb0_inv_d = (float)(m - dom[0] * scale / d);
+            const float f_lo = std::fmaf(P.e_first, P.inv_d, P.mb0_inv_d), f_hi = std::fmaf(P.e_last, P.inv_d, P.mb0_inv_d);
+            if ((f_lo >= 0.0f && f_hi < P.nb_f) || m > 0.01) break;
+        }
         for (int k = 1; k < n_edges; ++k)
             if (!((*edges_f)[k] > (*edges_f)[k - 1]))
                 return set_error(JMC_ELIMIT, "jmc_run: bin edges %d and %d coincide in FP32; use JMC_F64 for bins this fine",
@@ -951,7 +1050,7 @@ static constexpr size_t kSpreadBudget = 48 * 1024, kSpreadBudgetBig = 200 * 1024
 // samples from global index `first` up to the next multiple of 2^32
 static uint64_t fast_span(uint64_t first) { return 0x100000000ull - (first & 0xffffffffull); }
 
-template <int KIND, bool FIXED, bool OBS_MLL, bool HOT, bool BIG>
+template <int KIND, bool FIXED, bool OBS_MLL, bool HOT, bool BIG, bool COUNT_ALL = true>
 static int launch_fast_t(const FastParams& P, uint64_t n, uint64_t seed, uint64_t first, const float* d_edges_f,
                        double* d_sum_w, double* d_sum_w2, uint64_t* d_count, int* d_poison, double* d_minmax,
                        cudaStream_t st) {
@@ -963,13 +1062,19 @@ static int launch_fast_t(const FastParams& P, uint64_t n, uint64_t seed, uint64_
     if (smem > (size_t)di.max_smem_optin)
         return set_error(JMC_ELIMIT, "jmc_run: %d edges need %zu B of shared memory (limit %d B)", P.n_edges, smem,
                          di.max_smem_optin);
-    auto kern = run_fast_kernel<KIND, FIXED, OBS_MLL, HOT, BIG>;
-    JMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    JMC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
-    if (per_sm < 1) per_sm = 1;
-    uint64_t want = (n + threads - 1) / threads;
-    const uint64_t cap = (uint64_t)di.sm_count * per_sm;      // persistent: one wave of resident blocks
+    auto kern = run_fast_kernel<KIND, FIXED, OBS_MLL, HOT, BIG, COUNT_ALL>;
+    // attribute + occupancy query once per (kernel, device, shared-memory size): small jobs are launch-bound
+    static thread_local struct { int device; size_t smem; int per_sm; } cfg = {-1, 0, 0};
+    if (cfg.device != di.device || cfg.smem != smem) {
+        JMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        JMC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
+        cfg = {di.device, smem, per_sm < 1 ? 1 : per_sm};
+    }
+    // persistent: at most one wave of resident blocks; small jobs get fewer blocks (>= 32 sample pairs per thread),
+    // so that zeroing and flushing the block histograms does not dominate them
+    const uint64_t want = (n / 64 + threads) / threads;
+    const uint64_t cap = (uint64_t)di.sm_count * cfg.per_sm;
     const int grid = (int)(want < cap ? want : cap);
     FastParams Q = P;
     Q.spread_shift = shift;
@@ -988,44 +1093,53 @@ static int launch_fast(const FastParams& P, uint64_t n, uint64_t seed, uint64_t 
                      && (P.nan_to_num || FIXED || KIND == JMC_KIND_RADIATOR);
     const bool big = hot && fast_smem_bytes(P.n_edges) > kBigSmemThreshold;
 #define JMC_GO(M, H, B) launch_fast_t<KIND, FIXED, M, H, B>(P, n, seed, first, d_edges_f, d_sum_w, d_sum_w2, d_count, d_poison, d_minmax, st)
+    // counts over the weighted samples only (jmc_integrand.counts): the kinds with a Landau region skip observable,
+    // bin and count atomic of the samples whose weight is NaN -> 0
+    constexpr bool CAN_LAZY = (KIND == JMC_KIND_CRIT_SUB || KIND == JMC_KIND_CRIT) && !FIXED;
+    if (CAN_LAZY && hot && !big && P.count_weighted) {
+        if (P.obs_mll)
+            return launch_fast_t<KIND, FIXED, true, true, false, !CAN_LAZY>(P, n, seed, first, d_edges_f, d_sum_w, d_sum_w2,
+                                                                            d_count, d_poison, d_minmax, st);
+        return launch_fast_t<KIND, FIXED, false, true, false, !CAN_LAZY>(P, n, seed, first, d_edges_f, d_sum_w, d_sum_w2,
+                                                                         d_count, d_poison, d_minmax, st);
+    }
     if (P.obs_mll) return hot ? (big ? JMC_GO(true, true, true) : JMC_GO(true, true, false)) : JMC_GO(true, false, false);
     return hot ? (big ? JMC_GO(false, true, true) : JMC_GO(false, true, false)) : JMC_GO(false, false, false);
 #undef JMC_GO
 }
 
-int run_fast(const jmc_integrand* g, uint64_t n, uint64_t seed, uint64_t first_index, const double* d_edges,
-             int n_edges, double* d_sum_w, double* d_sum_w2, uint64_t* d_count, double* d_minmax, void* stream) {
-    cudaStream_t st = (cudaStream_t)stream;
-    if (d_edges) {
-        JMC_REQUIRE(n_edges >= 2, "jmc_run: need at least 2 edges");
-        JMC_REQUIRE(d_sum_w && d_sum_w2 && d_count, "jmc_run: histogram outputs missing");
-    } else {
-        JMC_REQUIRE(d_minmax != nullptr, "jmc_run: neither edges nor minmax requested");
-    }
-    // The FP32 kernel bins against FP32 edges in its compare domain (log2 or linear); they are derived on the
-    // host from the caller's FP64 edges: one synchronous 8*n_edges byte read-back per launch.
-    std::vector<double> h_edges;
-    std::vector<float> edges_f;
-    if (d_edges) {
-        h_edges.resize(n_edges);
-        JMC_CUDA(cudaMemcpyAsync(h_edges.data(), d_edges, sizeof(double) * n_edges, cudaMemcpyDeviceToHost, st));
-        JMC_CUDA(cudaStreamSynchronize(st));
-    }
+// ---- a job prepared on the host: kernel parameters + FP32 edges in the compare domain ------------------------
+struct FastPlan {
+    jmc_integrand g;
     FastParams P;
-    int rc = make_fast_params(g, d_edges ? h_edges.data() : nullptr, d_edges ? n_edges : 0, &P, &edges_f);
-    if (rc) return rc;
-    if (n == 0) return JMC_OK;
-    char* scr;
-    rc = scratch(256 + sizeof(float) * (size_t)(n_edges > 0 ? n_edges : 1), (void**)&scr, (void*)st);
-    if (rc) return rc;
-    int* d_poison = (int*)scr;
-    float* d_edges_f = nullptr;
-    JMC_CUDA(cudaMemsetAsync(d_poison, 0x7f, sizeof(int), st));
-    if (d_edges) {
-        d_edges_f = (float*)(scr + 256);
-        JMC_CUDA(cudaMemcpyAsync(d_edges_f, edges_f.data(), sizeof(float) * n_edges, cudaMemcpyHostToDevice, st));
-        JMC_CUDA(cudaStreamSynchronize(st));     // edges_f goes out of scope at return
-    }
+    std::vector<float> edges_f;
+    int n_edges;
+};
+
+int fast_plan_make(const jmc_integrand* g, const double* h_edges, int n_edges, FastPlan** out) {
+    if (h_edges) JMC_REQUIRE(n_edges >= 2, "jmc_run: need at least 2 edges");
+    FastPlan* p = new FastPlan;
+    p->g = *g;
+    p->n_edges = h_edges ? n_edges : 0;
+    int rc = make_fast_params(g, h_edges, p->n_edges, &p->P, &p->edges_f);
+    if (rc) { delete p; return rc; }
+    *out = p;
+    return JMC_OK;
+}
+void fast_plan_free(FastPlan* p) { delete p; }
+const float* fast_plan_edges(const FastPlan* p) { return p->edges_f.data(); }
+
+// d_edges_f: the plan's FP32 edges on the device (NULL for a min/max-only pass); d_poison: one int preset to
+// 0x7f7f7f7f ("no poison"), left in that state.  Asynchronous on the stream, no host synchronisation.
+int fast_plan_run(const FastPlan* plan, const float* d_edges_f, int* d_poison, uint64_t n, uint64_t seed,
+                  uint64_t first_index, double* d_sum_w, double* d_sum_w2, uint64_t* d_count, double* d_minmax,
+                  void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    const jmc_integrand* g = &plan->g;
+    const FastParams& P = plan->P;
+    if (d_edges_f) JMC_REQUIRE(d_sum_w && d_sum_w2 && d_count, "jmc_run: histogram outputs missing");
+    else JMC_REQUIRE(d_minmax != nullptr, "jmc_run: neither edges nor minmax requested");
+    int rc = JMC_OK;
 #define JMC_RUNF(K)                                                                                                   \
     rc = g->fixed_coupling                                                                                            \
              ? launch_fast<K, true>(P, m, seed, first_index, d_edges_f, d_sum_w, d_sum_w2, d_count, d_poison, d_minmax, st) \
@@ -1048,11 +1162,50 @@ int run_fast(const jmc_integrand* g, uint64_t n, uint64_t seed, uint64_t first_i
         n -= m;
     }
 #undef JMC_RUNF
-    if (d_edges && !g->nan_to_num) {
-        poison_fast_kernel<<<1, 256, 0, st>>>(d_poison, n_edges - 1, d_sum_w, d_sum_w2);
+    if (d_edges_f && !g->nan_to_num) {
+        poison_fast_kernel<<<1, 256, 0, st>>>(d_poison, plan->n_edges - 1, d_sum_w, d_sum_w2);
         JMC_LAUNCHED("poison_fast_kernel");
     }
     return JMC_OK;
+}
+
+// jmc_run with DEVICE edges: the FP32 kernel bins against FP32 edges in its compare domain (log2 or linear), derived
+// on the host from the caller's FP64 edges -- one synchronous 8*n_edges byte read-back and one upload per call.
+// (jmc_handle_run takes host edges, caches the derived forms and never synchronises.)
+int run_fast(const jmc_integrand* g, uint64_t n, uint64_t seed, uint64_t first_index, const double* d_edges,
+             int n_edges, double* d_sum_w, double* d_sum_w2, uint64_t* d_count, double* d_minmax, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (d_edges) {
+        JMC_REQUIRE(n_edges >= 2, "jmc_run: need at least 2 edges");
+        JMC_REQUIRE(d_sum_w && d_sum_w2 && d_count, "jmc_run: histogram outputs missing");
+    } else {
+        JMC_REQUIRE(d_minmax != nullptr, "jmc_run: neither edges nor minmax requested");
+    }
+    std::vector<double> h_edges;
+    if (d_edges) {
+        h_edges.resize(n_edges);
+        JMC_CUDA(cudaMemcpyAsync(h_edges.data(), d_edges, sizeof(double) * n_edges, cudaMemcpyDeviceToHost, st));
+        JMC_CUDA(cudaStreamSynchronize(st));
+    }
+    FastPlan* plan = nullptr;
+    int rc = fast_plan_make(g, d_edges ? h_edges.data() : nullptr, n_edges, &plan);
+    if (rc) return rc;
+    if (n == 0) { fast_plan_free(plan); return JMC_OK; }
+    char* scr;
+    rc = scratch(256 + sizeof(float) * (size_t)(n_edges > 0 ? n_edges : 1), (void**)&scr, (void*)st);
+    if (rc) { fast_plan_free(plan); return rc; }
+    int* d_poison = (int*)scr;
+    float* d_edges_f = nullptr;
+    cudaError_t e = cudaMemsetAsync(d_poison, 0x7f, sizeof(int), st);
+    if (e == cudaSuccess && d_edges) {
+        d_edges_f = (float*)(scr + 256);
+        e = cudaMemcpyAsync(d_edges_f, plan->edges_f.data(), sizeof(float) * n_edges, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);     // the plan's host edges die at return
+    }
+    if (e != cudaSuccess) { fast_plan_free(plan); return cuda_fail(e, "jmc_run: staging the FP32 edges"); }
+    rc = fast_plan_run(plan, d_edges_f, d_poison, n, seed, first_index, d_sum_w, d_sum_w2, d_count, d_minmax, stream);
+    fast_plan_free(plan);
+    return rc;
 }
 
 __global__ void poison_batch_kernel(const int* poison_all, int nb, double* sum_w_all, double* sum_w2_all) {

@@ -362,26 +362,233 @@ extern "C" int jmc_set_density_host(const double* h_obs, const double* h_weights
                             h_integral, h_integral_err, h_sum_w, h_sum_w2, h_count);
 }
 
+// ---------------------------------------------------------------------------
+// handle: cached job description, device workspace and pinned staging, so that a job issued from host buffers costs
+// its kernels plus ONE device-to-host copy and ONE synchronisation (jmc_create / jmc_destroy)
+// ---------------------------------------------------------------------------
+struct jmc_handle {
+    int device = -1;
+    // cached job: integrand + edges as last seen, and what was derived from them
+    bool has_job = false;
+    int precision = -1;
+    jmc_integrand g;
+    std::vector<double> edges;
+    FastPlan* plan = nullptr;
+    // device workspace: [poison 256 B][edges f64][edges f32][sum_w, sum_w2, count][density, err, ierr, integral]
+    char* d_ws = nullptr;
+    size_t ws_cap = 0;
+    int ws_edges = 0;
+    // pinned host staging: [edges f64][edges f32][results]
+    char* h_pin = nullptr;
+    size_t pin_cap = 0;
+    cudaEvent_t staged = nullptr;      // last asynchronous copy that reads the pinned buffer
+    cudaStream_t stream = nullptr;     // stream of the host-buffer entry points
+};
+
+namespace {
+
+size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+struct WsLayout {
+    size_t off_e64, off_e32, off_hist, off_out, total;
+    explicit WsLayout(int n_edges) {
+        const size_t ne = (size_t)(n_edges > 0 ? n_edges : 1), nb = ne - 1;
+        off_e64 = 256;
+        off_e32 = off_e64 + align256(sizeof(double) * ne);
+        off_hist = off_e32 + align256(sizeof(float) * ne);
+        off_out = off_hist + sizeof(double) * 3 * nb;           // contiguous with the histograms: one copy back
+        total = align256(off_out + sizeof(double) * (4 * nb + 1));
+    }
+};
+
+int handle_reserve(jmc_handle* h, int n_edges) {
+    const WsLayout L(n_edges);
+    if (h->ws_cap < L.total) {
+        if (h->d_ws) JMC_CUDA(cudaFree(h->d_ws));           // synchronises: nothing still uses the old block
+        h->d_ws = nullptr; h->ws_cap = 0;
+        JMC_CUDA(cudaMalloc((void**)&h->d_ws, L.total));
+        h->ws_cap = L.total;
+        JMC_CUDA(cudaMemset(h->d_ws, 0x7f, 256));           // poison flag: "none"; the poison kernels re-arm it
+        h->has_job = false;
+    }
+    if (h->pin_cap < L.total) {
+        if (h->h_pin) JMC_CUDA(cudaFreeHost(h->h_pin));
+        h->h_pin = nullptr; h->pin_cap = 0;
+        JMC_CUDA(cudaMallocHost((void**)&h->h_pin, L.total));
+        h->pin_cap = L.total;
+    }
+    return JMC_OK;
+}
+
+// Make (g, edges, precision) the handle's current job: derive the FP32 plan and stage both edge arrays on the device,
+// asynchronously on `st`.  A job identical to the cached one costs two memcmp.
+int handle_set_job(jmc_handle* h, const jmc_integrand* g, int precision, const double* h_edges, int n_edges,
+                   cudaStream_t st) {
+    JMC_REQUIRE(h != nullptr && g != nullptr, "jmc_handle: NULL argument");
+    int dev = -1;
+    JMC_CUDA(cudaGetDevice(&dev));
+    JMC_REQUIRE(dev == h->device, "jmc_handle: created on device %d, used on device %d", h->device, dev);
+    if (!h_edges) n_edges = 0;
+    if (h->has_job && h->precision == precision && (int)h->edges.size() == n_edges
+        && std::memcmp(&h->g, g, sizeof(*g)) == 0
+        && (n_edges == 0 || std::memcmp(h->edges.data(), h_edges, sizeof(double) * n_edges) == 0))
+        return JMC_OK;
+    h->has_job = false;
+    if (h->plan) { fast_plan_free(h->plan); h->plan = nullptr; }
+    int rc = handle_reserve(h, n_edges);
+    if (rc) return rc;
+    const bool fast = precision == JMC_F32 && g->kind != JMC_KIND_SHOWER;
+    if (fast) {
+        rc = fast_plan_make(g, h_edges, n_edges, &h->plan);
+        if (rc) return rc;
+    }
+    if (n_edges > 0) {
+        const WsLayout L(n_edges);
+        JMC_CUDA(cudaEventSynchronize(h->staged));          // an earlier upload may still be reading the staging
+        std::memcpy(h->h_pin + L.off_e64, h_edges, sizeof(double) * n_edges);
+        const size_t bytes = fast ? L.off_e32 + sizeof(float) * n_edges - L.off_e64 : sizeof(double) * n_edges;
+        if (fast) std::memcpy(h->h_pin + L.off_e32, fast_plan_edges(h->plan), sizeof(float) * n_edges);
+        JMC_CUDA(cudaMemcpyAsync(h->d_ws + L.off_e64, h->h_pin + L.off_e64, bytes, cudaMemcpyHostToDevice, st));
+        JMC_CUDA(cudaEventRecord(h->staged, st));
+    }
+    h->g = *g;
+    h->precision = precision;
+    h->edges.assign(h_edges, h_edges + n_edges);
+    h->ws_edges = n_edges;
+    h->has_job = true;
+    return JMC_OK;
+}
+
+int handle_run(jmc_handle* h, const jmc_integrand* g, uint64_t n, uint64_t seed, uint64_t first_index, int precision,
+               double* d_sum_w, double* d_sum_w2, uint64_t* d_count, double* d_minmax, cudaStream_t st) {
+    const WsLayout L(h->ws_edges);
+    const int ne = h->ws_edges;
+    const double* d_e64 = ne ? (const double*)(h->d_ws + L.off_e64) : nullptr;
+    if (n == 0) return JMC_OK;
+    if (h->plan) {
+        // FP32 kernels take at most 2^38 samples per launch (32-bit per-block bin counts)
+        const uint64_t kMaxPerLaunch = 1ull << 38;
+        while (n) {
+            const uint64_t chunk = n < kMaxPerLaunch ? n : kMaxPerLaunch;
+            int rc = fast_plan_run(h->plan, ne ? (const float*)(h->d_ws + L.off_e32) : nullptr, (int*)h->d_ws, chunk,
+                                   seed, first_index, d_sum_w, d_sum_w2, d_count, d_minmax, (void*)st);
+            if (rc) return rc;
+            n -= chunk;
+            first_index += chunk;
+        }
+        return JMC_OK;
+    }
+    return jmc_run(g, n, seed, first_index, precision, d_e64, ne, d_sum_w, d_sum_w2, d_count, d_minmax, (void*)st);
+}
+
+}  // namespace
+
+extern "C" int jmc_create(jmc_handle** out) {
+    JMC_REQUIRE(out != nullptr, "jmc_create: NULL argument");
+    DeviceInfo di;
+    int rc = device_info(&di);
+    if (rc) return rc;
+    jmc_handle* h = new jmc_handle;
+    h->device = di.device;
+    cudaError_t e = cudaEventCreateWithFlags(&h->staged, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete h; return cuda_fail(e, "jmc_create"); }
+    *out = h;
+    return JMC_OK;
+}
+
+extern "C" int jmc_destroy(jmc_handle* h) {
+    if (!h) return JMC_OK;
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->plan) fast_plan_free(h->plan);
+    if (h->d_ws) cudaFree(h->d_ws);
+    if (h->h_pin) cudaFreeHost(h->h_pin);
+    if (h->staged) cudaEventDestroy(h->staged);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return JMC_OK;
+}
+
+extern "C" int jmc_handle_run(jmc_handle* h, const jmc_integrand* g, uint64_t n, uint64_t seed, uint64_t first_index,
+                              int precision, const double* h_edges, int n_edges, double* d_sum_w, double* d_sum_w2,
+                              uint64_t* d_count, double* d_minmax, void* stream) {
+    JMC_REQUIRE(precision == JMC_F64 || precision == JMC_F32, "jmc_handle_run: precision must be JMC_F64 or JMC_F32");
+    if (h_edges) {
+        JMC_REQUIRE(n_edges >= 2, "jmc_handle_run: need at least 2 edges");
+        JMC_REQUIRE(d_sum_w && d_sum_w2 && d_count, "jmc_handle_run: histogram outputs missing");
+    } else {
+        JMC_REQUIRE(d_minmax != nullptr, "jmc_handle_run: neither edges nor minmax requested");
+    }
+    int rc = handle_set_job(h, g, precision, h_edges, n_edges, (cudaStream_t)stream);
+    if (rc) return rc;
+    return handle_run(h, g, n, seed, first_index, precision, d_sum_w, d_sum_w2, d_count, d_minmax, (cudaStream_t)stream);
+}
+
+extern "C" int jmc_handle_integrate_host(jmc_handle* h, const jmc_integrand* g, uint64_t n, uint64_t seed,
+                                         uint64_t first_index, int precision, const double* h_edges, int n_edges,
+                                         int bc_kind, double bc_value, double* h_density, double* h_density_err,
+                                         double* h_integral, double* h_integral_err, double* h_sum_w,
+                                         double* h_sum_w2, uint64_t* h_count) {
+    JMC_REQUIRE(n_edges >= 2 && h_edges, "jmc_integrate_host: Need bins to produce density histogram.");
+    JMC_REQUIRE(precision == JMC_F64 || precision == JMC_F32, "jmc_integrate_host: precision must be JMC_F64 or JMC_F32");
+    JMC_REQUIRE(h != nullptr, "jmc_integrate_host: handle is NULL");
+    double area;
+    int rc = jmc_integrand_area(g, &area);
+    if (rc) return rc;
+    cudaStream_t st = h->stream;
+    rc = handle_set_job(h, g, precision, h_edges, n_edges, st);
+    if (rc) return rc;
+    const WsLayout L(n_edges);
+    const size_t nb = (size_t)n_edges - 1;
+    double* d_sum_w = (double*)(h->d_ws + L.off_hist);
+    double* d_sum_w2 = d_sum_w + nb;
+    uint64_t* d_count = (uint64_t*)(d_sum_w2 + nb);
+    double* d_density = (double*)(h->d_ws + L.off_out);
+    double* d_err = d_density + nb;
+    double* d_ierr = d_err + nb;
+    double* d_integral = d_ierr + nb;
+    JMC_CUDA(cudaMemsetAsync(d_sum_w, 0, sizeof(double) * 3 * nb, st));
+    rc = handle_run(h, g, n, seed, first_index, precision, d_sum_w, d_sum_w2, d_count, nullptr, st);
+    if (rc) return rc;
+    rc = jmc_finalize(d_sum_w, d_sum_w2, d_count, (const double*)(h->d_ws + L.off_e64), n_edges, area, n, bc_kind,
+                      bc_value, d_density, d_err, d_integral, d_ierr, (void*)st);
+    if (rc) return rc;
+    // histograms and results are contiguous: one copy into pinned memory, one synchronisation
+    const size_t bytes = sizeof(double) * (7 * nb + 1);
+    char* stage = h->h_pin + L.off_hist;
+    JMC_CUDA(cudaMemcpyAsync(stage, d_sum_w, bytes, cudaMemcpyDeviceToHost, st));
+    JMC_CUDA(cudaStreamSynchronize(st));
+    const double* r = (const double*)stage;
+    if (h_sum_w) std::memcpy(h_sum_w, r, sizeof(double) * nb);
+    if (h_sum_w2) std::memcpy(h_sum_w2, r + nb, sizeof(double) * nb);
+    if (h_count) std::memcpy(h_count, r + 2 * nb, sizeof(uint64_t) * nb);
+    if (h_density) std::memcpy(h_density, r + 3 * nb, sizeof(double) * nb);
+    if (h_density_err) std::memcpy(h_density_err, r + 4 * nb, sizeof(double) * nb);
+    if (h_integral_err) std::memcpy(h_integral_err, r + 5 * nb, sizeof(double) * nb);
+    if (h_integral) std::memcpy(h_integral, r + 6 * nb, sizeof(double) * (nb + 1));
+    return JMC_OK;
+}
+
+// the handle-less form keeps one handle per (host thread, device)
 extern "C" int jmc_integrate_host(const jmc_integrand* g, uint64_t n, uint64_t seed, uint64_t first_index,
                                   int precision, const double* h_edges, int n_edges, int bc_kind, double bc_value,
                                   double* h_density, double* h_density_err, double* h_integral,
                                   double* h_integral_err, double* h_sum_w, double* h_sum_w2, uint64_t* h_count) {
+    // argument validation comes before any CUDA call
     JMC_REQUIRE(n_edges >= 2 && h_edges, "jmc_integrate_host: Need bins to produce density histogram.");
-    double area;
-    int rc = jmc_integrand_area(g, &area);
-    if (rc) return rc;
-    const size_t nb = (size_t)n_edges - 1;
-    DevBuf edges, hist;
-    rc = edges.alloc(sizeof(double) * n_edges);
-    if (!rc) rc = hist.alloc(sizeof(double) * 3 * nb);
-    if (rc) return rc;
-    JMC_CUDA(cudaMemcpy(edges.p, h_edges, sizeof(double) * n_edges, cudaMemcpyHostToDevice));
-    JMC_CUDA(cudaMemset(hist.p, 0, sizeof(double) * 3 * nb));
-    rc = jmc_run(g, n, seed, first_index, precision, edges.as<double>(), n_edges, hist.as<double>(),
-                 hist.as<double>() + nb, (uint64_t*)(hist.as<double>() + 2 * nb), nullptr, nullptr);
-    if (rc) return rc;
-    return finalize_to_host(hist, n_edges, edges.as<double>(), area, n, bc_kind, bc_value, h_density, h_density_err,
-                            h_integral, h_integral_err, h_sum_w, h_sum_w2, h_count);
+    JMC_REQUIRE(g != nullptr, "jmc_integrate_host: integrand is NULL");
+    static thread_local std::vector<jmc_handle*> handles;
+    int dev = -1;
+    JMC_CUDA(cudaGetDevice(&dev));
+    jmc_handle* h = nullptr;
+    for (jmc_handle* c : handles) if (c->device == dev) h = c;
+    if (!h) {
+        int rc = jmc_create(&h);
+        if (rc) return rc;
+        handles.push_back(h);
+    }
+    return jmc_handle_integrate_host(h, g, n, seed, first_index, precision, h_edges, n_edges, bc_kind, bc_value,
+                                     h_density, h_density_err, h_integral, h_integral_err, h_sum_w, h_sum_w2, h_count);
 }
 
 extern "C" int jmc_sample_host(const jmc_sampler* s, uint64_t n, uint64_t seed, uint64_t first_index,

@@ -32,7 +32,7 @@ class Integrand:
     def __init__(self, kind, method, *, jet_type='quark', fixedcoupling=True, obs_acc='LL',
                  split_acc='LL', nan_to_num=False, epsilon=0., z_cut=0., radius=1., beta=2., f=1.,
                  z_pre=0., theta_scale=1., bounds=(0., 1.), groomer=0, n_emissions=1, beta_sd=0.,
-                 cutoff=0.):
+                 cutoff=0., counts='all'):
         assert method in ('lin', 'log'), str(method) + "is not a supported sample method."
         assert jet_type in ('quark', 'gluon'), str(jet_type) + "is not a supported jet type."
         assert obs_acc in ('LL', 'MLL'), "Accuracy must be LL or MLL"
@@ -49,6 +49,10 @@ class Integrand:
         self.bounds = (float(bounds[0]), float(bounds[1]))
         self.groomer, self.beta_sd, self.cutoff = int(groomer), float(beta_sd), float(cutoff)
         self.n_emissions = 0 if n_emissions == 'all' else int(n_emissions)
+        # 'all': per-bin counts as np.histogram gives them; 'weighted': only samples with a non-zero weight are
+        # counted (same density / integral; lets the FP32 path skip the samples whose weight is NaN -> 0)
+        assert counts in ('all', 'weighted'), "counts must be 'all' or 'weighted'"
+        self.counts = counts
 
     # ---- constructors ---------------------------------------------------------
     @classmethod
@@ -61,22 +65,22 @@ class Integrand:
 
     @classmethod
     def critical(cls, method, z_cut, epsilon=0., radius=1., beta=2., jet_type='quark', fixedcoupling=True,
-                 obs_acc='LL', z_pre=0., f=1., nan_to_num=None):
+                 obs_acc='LL', z_pre=0., f=1., nan_to_num=None, counts='all'):
         _check_zcut(z_cut)
         nan_to_num = (not fixedcoupling) if nan_to_num is None else nan_to_num
         return cls(_lib.KIND_CRIT, method, epsilon=epsilon, z_cut=z_cut, radius=radius, beta=beta,
                    jet_type=jet_type, fixedcoupling=fixedcoupling, obs_acc=obs_acc, z_pre=z_pre, f=f,
-                   nan_to_num=nan_to_num)
+                   nan_to_num=nan_to_num, counts=counts)
 
     @classmethod
     def crit_sub(cls, method, z_cut, epsilon=0., radius=1., beta=2., jet_type='quark', fixedcoupling=True,
-                 obs_acc='MLL', z_pre=None, f=0., nan_to_num=True):
+                 obs_acc='MLL', z_pre=None, f=0., nan_to_num=True, counts='all'):
         """Defaults are the Soft Drop / mMDT form ``z_pre=z_cut, f=0``
         (examples/sudakov_comparisons/sudakov_utils.py:481-486)."""
         _check_zcut(z_cut)
         return cls(_lib.KIND_CRIT_SUB, method, epsilon=epsilon, z_cut=z_cut, radius=radius, beta=beta,
                    jet_type=jet_type, fixedcoupling=fixedcoupling, obs_acc=obs_acc,
-                   z_pre=z_cut if z_pre is None else z_pre, f=f, nan_to_num=nan_to_num)
+                   z_pre=z_cut if z_pre is None else z_pre, f=f, nan_to_num=nan_to_num, counts=counts)
 
     @classmethod
     def pre_crit_sub(cls, method, z_cut, epsilon=0., radius=1., beta=2., jet_type='quark', fixedcoupling=True,
@@ -109,7 +113,7 @@ class Integrand:
             fixed_coupling=int(self.fixedcoupling), obs_acc=_lib.ACCS[self.obs_acc],
             split_acc=_lib.ACCS[self.split_acc], nan_to_num=int(self.nan_to_num),
             shower_groomer=self.groomer, shower_n_emissions=self.n_emissions,
-            epsilon=self.epsilon, z_cut=self.z_cut, radius=self.radius, beta=self.beta, f_soft=self.f,
+            counts=int(self.counts == 'weighted'), epsilon=self.epsilon, z_cut=self.z_cut, radius=self.radius, beta=self.beta, f_soft=self.f,
             z_pre=self.z_pre, theta_scale=self.theta_scale, lo=self.bounds[0], hi=self.bounds[1],
             beta_sd=self.beta_sd, shower_cutoff=self.cutoff)
 
@@ -142,19 +146,28 @@ def _check_zcut(zc):
 
 
 def accumulate(integrand, num_samples, seed, precision, edges_dev, sum_w, sum_w2, count, group=None,
-               minmax=None):
+               minmax=None, edges_host=None):
     """Run this rank's share of ``num_samples`` and (if distributed) all-reduce.
 
     The tensors are CUDA tensors: edges float64 [n_edges], sum_w / sum_w2
-    float64 [n_edges-1], count int64 [n_edges-1]; they are accumulated into."""
+    float64 [n_edges-1], count int64 [n_edges-1]; they are accumulated into.
+    With ``edges_host`` (the same edges as a NumPy array) the job goes through the calling thread's ``jmc_handle``:
+    nothing is read back, nothing synchronises, and a repeated job re-derives nothing."""
     D.require_cuda()
     num_samples = int(num_samples)
     first, n_local = dist_utils.shard(num_samples, group)
     s = integrand.c_struct()
     n_edges = 0 if edges_dev is None else int(edges_dev.numel())
-    _lib.check(_lib.lib.jmc_run(C.byref(s), n_local, int(seed) & 0xFFFFFFFFFFFFFFFF, first,
-                                PRECISIONS[precision], D.ptr(edges_dev), n_edges, D.ptr(sum_w), D.ptr(sum_w2),
-                                D.ptr(count), D.ptr(minmax), D.stream()))
+    key, prec = int(seed) & 0xFFFFFFFFFFFFFFFF, PRECISIONS[precision]
+    if edges_host is not None or edges_dev is None:
+        eh = None if edges_dev is None else np.ascontiguousarray(edges_host, dtype=np.float64)
+        handle = _lib.default_handle(torch.cuda.current_device())
+        _lib.check(_lib.lib.jmc_handle_run(handle.ptr, C.byref(s), n_local, key, first, prec,
+                                           None if eh is None else eh.ctypes.data_as(C.c_void_p), n_edges,
+                                           D.ptr(sum_w), D.ptr(sum_w2), D.ptr(count), D.ptr(minmax), D.stream()))
+    else:
+        _lib.check(_lib.lib.jmc_run(C.byref(s), n_local, key, first, prec, D.ptr(edges_dev), n_edges, D.ptr(sum_w),
+                                    D.ptr(sum_w2), D.ptr(count), D.ptr(minmax), D.stream()))
     if edges_dev is not None:
         dist_utils.allreduce_histograms(sum_w, sum_w2, count, group)
     if minmax is not None:

@@ -179,7 +179,7 @@ class integrator():
         assert self.hasBins, "Need bins to produce density histogram."
         self._alloc_hist()
         fused.accumulate(integrand, num_samples, seed, precision, self._edges_dev,
-                         self._sum_w, self._sum_w2, self._count, group)
+                         self._sum_w, self._sum_w2, self._count, group, edges_host=self.bins)
         self._density_from_hist(integrand.area, int(num_samples))
 
     # ------------------
