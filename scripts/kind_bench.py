@@ -12,13 +12,15 @@ cases = [
  ("    critical fc", Integrand.critical('log', .1, 1e-10, fixedcoupling=True)),
  ("    critical rc (65% NaN->0)", Integrand.critical('log', .1, 1e-10, fixedcoupling=False)),
  ("C3  crit x sub rc MLL (99.7% NaN->0)", Integrand.crit_sub('log', .1, 1e-10, fixedcoupling=False)),
+ ("C3  same, counts on request", Integrand.crit_sub('log', .1, 1e-10, fixedcoupling=False, counts='weighted')),
+ ("    critical rc, counts on request", Integrand.critical('log', .1, 1e-10, fixedcoupling=False, counts='weighted')),
  ("C3  crit x sub fc MLL", Integrand.crit_sub('log', .1, 1e-10, fixedcoupling=True)),
  ("C4  pre x crit x sub fc", Integrand.pre_crit_sub('log', .1, 1e-10)),
 ]
 for name, ig in cases:
     out = []
     for prec, n in (('f32', 10**9), ('f64', 10**8)):
-        H.run(ig, 10**6, 1, e, prec); torch.cuda.synchronize(); t = time.perf_counter()
+        H.run(ig, 10**6, 1, e, prec); H.run(ig, n, 3, e, prec); torch.cuda.synchronize(); t = time.perf_counter()
         H.run(ig, n, 2, e, prec); torch.cuda.synchronize(); dt = time.perf_counter() - t
         out.append(f"{prec} {n/dt:.3e}/s")
     print(f"{name:40s} " + "   ".join(out))

@@ -63,8 +63,8 @@ def test_two_ranks_equal_one(cuda, tmp_path):
     n = 20_000_001
     one = fused.integrate(ig, n, edges=edges, seed=3, precision='f32', last_bc=[1., 'minus'])
     np.testing.assert_array_equal(got['count'], one._count.cpu().numpy())
-    np.testing.assert_allclose(got['sum_w'], one._sum_w.cpu().numpy(), rtol=1e-9)
-    np.testing.assert_allclose(got['integral'], np.asarray(one.integral), rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(got['sum_w'], one._sum_w.cpu().numpy(), rtol=2e-6)
+    np.testing.assert_allclose(got['integral'], np.asarray(one.integral), rtol=2e-6, atol=1e-9)
     one2 = fused.integrate(ig, n, numbins=50, binspacing='log', seed=3, precision='f64', last_bc=[1., 'minus'])
     np.testing.assert_array_equal(got['bins2'], one2.bins)          # data-dependent edges via the min/max all-reduce
     np.testing.assert_array_equal(got['count2'], one2._count.cpu().numpy())
