@@ -9,6 +9,7 @@
 #include <cfloat>
 #include <climits>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 #include "jmc_common.cuh"
 #include "jmc_integrand.cuh"
@@ -371,7 +372,11 @@ static size_t hist_smem_bytes(int n_edges, int shift = 0) {
 }
 static int hist_spread_shift(int n_edges, size_t budget) {
     if (JMC_HIST_MODE != 1) return 0;
-    int shift = 5;
+    static const int max_shift = [] {                    // experiment switch (scripts/acc_shootout.sh)
+        const char* e = getenv("JMC_HIST_SPREAD_SHIFT");
+        return e ? atoi(e) : 5;
+    }();
+    int shift = max_shift;
     while (shift > 0 && hist_smem_bytes(n_edges, shift) > budget) --shift;
     return shift;
 }

@@ -29,6 +29,7 @@
 #include <cfloat>
 #include <climits>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 #include "jmc_common.cuh"
@@ -55,7 +56,18 @@ static constexpr int kQueueFields = 5, kQueueSlots = 64;   // per-warp compactio
 #define JMC_FAST_PIN_KEYS 1      // keep the Philox round keys in registers across the loop
 #endif
 #ifndef JMC_ACC_MODE
-#define JMC_ACC_MODE 1           // shared-memory accumulation of (sum w, sum w^2), see fast_body::accumulate
+#define JMC_ACC_MODE 3           // shared-memory accumulation of (sum w, sum w^2), see fast_body::accumulate
+#endif
+// accumulator types of the block histogram per mode: 0 / 2 / 3 FP64 both, 4 FP32 both, 5 FP64 sum w + FP32 sum w^2
+#if JMC_ACC_MODE == 4
+typedef float acc_w_t;
+typedef float acc_w2_t;
+#elif JMC_ACC_MODE == 5
+typedef double acc_w_t;
+typedef float acc_w2_t;
+#else
+typedef double acc_w_t;
+typedef double acc_w2_t;
 #endif
 #define JMC_LN2F 0.69314718055994531f
 #define JMC_INV_LN2F 1.4426950408889634f
@@ -465,23 +477,14 @@ fast_body(const FastParams& P_in, uint64_t n, uint64_t seed, uint64_t first, con
     const int ne = P.n_edges, nb = ne > 0 ? ne - 1 : 0;
     const int sh = P.spread_shift;
     const int n_slots = nb << sh;
-#if JMC_ACC_MODE == 1
-    float2* s_acc = (float2*)s_raw;                               // (sum w, sum w^2) of slot [bin][lane & (R-1)]
-    unsigned int* s_count = (unsigned int*)(s_acc + n_slots);     // nb bins + 32 dummy slots for dropped samples
-#else
-    double* s_sum_w = s_raw;
-    double* s_sum_w2 = s_sum_w + n_slots;
+    acc_w_t* s_sum_w = (acc_w_t*)s_raw;                           // slot [bin][lane & (R-1)]
+    acc_w2_t* s_sum_w2 = (acc_w2_t*)(s_sum_w + n_slots);
     unsigned int* s_count = (unsigned int*)(s_sum_w2 + n_slots);  // nb bins + 32 dummy slots for dropped samples
-#endif
     float* s_edges = (float*)(s_count + nb + 32);
     const bool do_hist = HOT || g_edges != nullptr;
     const bool do_minmax = !HOT && d_minmax != nullptr;
     if (threadIdx.x == 0) s_poison = INT_MAX;
-#if JMC_ACC_MODE == 1
-    for (int k = threadIdx.x; k < n_slots; k += blockDim.x) s_acc[k] = make_float2(0.0f, 0.0f);
-#else
-    for (int k = threadIdx.x; k < n_slots; k += blockDim.x) { s_sum_w[k] = 0.0; s_sum_w2[k] = 0.0; }
-#endif
+    for (int k = threadIdx.x; k < n_slots; k += blockDim.x) { s_sum_w[k] = 0; s_sum_w2[k] = 0; }
     for (int k = threadIdx.x; k < nb; k += blockDim.x) s_count[k] = 0u;
     if (threadIdx.x < 32) s_count[nb + threadIdx.x] = 0u;
     for (int k = threadIdx.x; k < ne; k += blockDim.x) s_edges[k] = g_edges[k];
@@ -503,28 +506,23 @@ fast_body(const FastParams& P_in, uint64_t n, uint64_t seed, uint64_t first, con
 
     // weight * jacobian of one sample into the block histogram (bq: bin, or -1 / -2 for a sample below /
     // above the binned range, which matters only for NumPy's NaN poisoning).
-    // Back ends (JMC_ACC_MODE; shared-memory FP32/FP64/64-bit adds are compare-and-swap loops on sm_100, only 32-bit
-    // integer adds are native, so what costs is the number of CAS rounds = lanes of a warp on one address):
-    //  1 (default): R = 2^sh lane-interleaved copies of every bin, slot [bin][lane & (R-1)] holding (sum w, sum w^2)
-    //     as two floats updated by ONE 64-bit CAS.  With R = 32 no two lanes of a warp share a slot, so a round only
-    //     repeats when another warp hits the same slot in the same few cycles; the slots are summed in FP64 when the
-    //     block flushes.  A slot sees ~n_block / (nb R) adds of one sign: FP32 rounding ~ sqrt(adds) 2^-25 relative.
-    //  2: __match_any_sync on the bin, peers reduced by shuffles, one FP64 CAS pair per distinct bin per warp.
-    //  0 / 3: two FP64 CAS loops per sample on [bin] / on the lane-interleaved slot.
+    // Back ends (JMC_ACC_MODE).  Shared-memory floating-point adds are compare-and-swap loops on sm_100 (LDS, add,
+    // ATOMS.CAST.SPIN, branch; only 32-bit integer adds are native), and a loop runs one round per lane of the warp
+    // on the same address -- with 99 log bins that is 3-6 rounds for most warps.  Measured on B200 (C1 / C3 fc / C4,
+    // 1e9 samples, profiles/r02b_shootout.log):
+    //  0: two FP64 loops on [bin]                                              2.64e11 / 1.78e11 / 1.43e11
+    //  3 (default): R = 2^sh lane-interleaved copies of every bin, slot [bin][lane & (R-1)]: lanes of a warp that hit
+    //     the same bin no longer share an address, so a loop almost never repeats; the copies are summed when the
+    //     block flushes                                                         2.97e11 / 1.87e11 / 1.54e11
+    //  2: __match_any_sync on the bin, peers reduced by shuffles, one loop pair per distinct bin per warp: the
+    //     match + shuffle rounds cost more than the retries they save          2.15e11 / 1.38e11 / 1.20e11
+    //  (dropped: both sums as two floats in one slot updated by an explicit 64-bit atomicCAS -- ATOMS.CAS.64 returns
+    //   the old value and is served lane by lane, ~64 cycles per warp: 0.98e11 / 1.49e11 / 1.38e11)
+    //  4 / 5: mode 3 with FP32 slots for both sums / for sum w^2 only (summed in FP64 at the flush)
     auto accumulate = [&](float w, int bq) {
         if (bq >= 0 && fabsf(w) > 0.0f) {                // the common case first: one compare rejects 0 and NaN
             if (LAZY) atomicAdd(&s_count[bq], 1u);
-#if JMC_ACC_MODE == 1
-            unsigned long long* a = (unsigned long long*)&s_acc[(bq << sh) | (int)(lane & ((1u << sh) - 1u))];
-            const float w2 = w * w;
-            unsigned long long old = *a, assumed;
-            do {
-                assumed = old;
-                const float x = __uint_as_float((unsigned)assumed) + w;
-                const float y = __uint_as_float((unsigned)(assumed >> 32)) + w2;
-                old = atomicCAS(a, assumed, ((unsigned long long)__float_as_uint(y) << 32) | __float_as_uint(x));
-            } while (old != assumed);
-#elif JMC_ACC_MODE == 2
+#if JMC_ACC_MODE == 2
             const unsigned mask = __activemask();
             const unsigned peers = __match_any_sync(mask, bq);
             const int leader = __ffs(peers) - 1;
@@ -542,10 +540,10 @@ fast_body(const FastParams& P_in, uint64_t n, uint64_t seed, uint64_t first, con
                 atomicAdd(&s_sum_w2[bq], (double)aw2);
             }
 #else
-            const double wd = (double)w;
             const int slot = (bq << sh) | (int)(lane & ((1u << sh) - 1u));
+            const acc_w_t wd = (acc_w_t)w;
             atomicAdd(&s_sum_w[slot], wd);
-            atomicAdd(&s_sum_w2[slot], wd * wd);
+            atomicAdd(&s_sum_w2[slot], (acc_w2_t)(wd * wd));
 #endif
         } else if (w != w && !nan_to_num) {              // NaN: 0 under nan_to_num, else NumPy poisons bins >= bq
             const int pb = bq >= 0 ? bq : (bq == -1 ? 0 : INT_MAX);
@@ -744,12 +742,8 @@ fast_body(const FastParams& P_in, uint64_t n, uint64_t seed, uint64_t first, con
                 atomicAdd(&g_count[k], (unsigned long long)c);
                 double sw = 0.0, sw2 = 0.0;
                 for (int r = 0; r < (1 << sh); ++r) {
-#if JMC_ACC_MODE == 1
-                    const float2 v = s_acc[(k << sh) + r];
-                    sw += (double)v.x; sw2 += (double)v.y;
-#else
-                    sw += s_sum_w[(k << sh) + r]; sw2 += s_sum_w2[(k << sh) + r];
-#endif
+                    sw += (double)s_sum_w[(k << sh) + r];
+                    sw2 += (double)s_sum_w2[(k << sh) + r];
                 }
                 if (sw != 0.0) atomicAdd(&g_sum_w[k], sw);
                 if (sw2 != 0.0) atomicAdd(&g_sum_w2[k], sw2);
@@ -1034,18 +1028,22 @@ static int make_fast_params(const jmc_integrand* g, const double* h_edges, int n
 static size_t fast_smem_bytes(int n_edges, int threads = kFastThreads, int shift = 0) {
     const size_t nb = n_edges > 0 ? (size_t)n_edges - 1 : 0;
     const size_t ne_pad = ((size_t)(n_edges > 0 ? n_edges : 0) + 3) & ~(size_t)3;
-    const size_t acc = (JMC_ACC_MODE == 1 ? sizeof(float2) : 2 * sizeof(double)) * (nb << shift);
+    const size_t acc = (sizeof(acc_w_t) + sizeof(acc_w2_t)) * (nb << shift);
     return acc + sizeof(unsigned int) * (nb + 32) + sizeof(float) * ne_pad
            + sizeof(float) * (threads / 32) * kQueueFields * kQueueSlots;
 }
 // lane-interleaved accumulator copies: as many (up to one per lane) as keep the block under `budget` bytes
 static int fast_spread_shift(int n_edges, int threads, size_t budget) {
     if (JMC_ACC_MODE == 0 || JMC_ACC_MODE == 2) return 0;
-    int shift = 5;
+    static const int max_shift = [] {                    // experiment switch (scripts/acc_shootout.sh)
+        const char* e = getenv("JMC_FAST_SPREAD_SHIFT");
+        return e ? atoi(e) : 5;
+    }();
+    int shift = max_shift;
     while (shift > 0 && fast_smem_bytes(n_edges, threads, shift) > budget) --shift;
     return shift;
 }
-static constexpr size_t kSpreadBudget = 48 * 1024, kSpreadBudgetBig = 200 * 1024;
+static constexpr size_t kSpreadBudget = 56 * 1024, kSpreadBudgetBig = 200 * 1024;
 
 // samples from global index `first` up to the next multiple of 2^32
 static uint64_t fast_span(uint64_t first) { return 0x100000000ull - (first & 0xffffffffull); }

@@ -45,8 +45,8 @@ def test_headline_kernel_instruction_forms():
     assert ops.count("IMAD.WIDE.U32") >= 36          # Philox products as one wide multiply each
     assert "ATOMS.POPC.INC.32" in ops                # native shared-memory count atomic
     assert "ATOMS.POPC.INC.32" in re.findall(r"(ATOMS[A-Z0-9_.]+)", _run("-sass", "-fun", HEADLINE_COUNT_ALL))
-    # (sum w, sum w^2) of a slot as one 64-bit compare-and-swap (no native shared-memory floating-point add on sm_100)
-    assert any(o.startswith("ATOMS.CAS") for o in ops)
+    # FP64 sums: compare-and-swap loops (sm_100 has no native shared-memory floating-point add)
+    assert any(o.startswith("ATOMS.CAST.SPIN") for o in ops)
     assert "MUFU.EX2" in ops and "MUFU.LG2" in ops   # base-2 log space
     assert not any(o.startswith(("LDL", "STL")) for o in ops)     # no local memory
 
