@@ -31,47 +31,69 @@ __device__ __forceinline__ double fn_arg(const FnArgs& A, int k, uint64_t i) {
     return A.a[k] ? A.a[k][i * A.stride[k]] : A.scalar[k];
 }
 
-__global__ void __launch_bounds__(kThreads) eval_fn_kernel(int fn, jmc_fn_params p, FnArgs A, uint64_t n,
+// One instantiation per function id: the register allocation of the simple functions (products, observables,
+// fixed-coupling forms) is no longer that of the running-coupling radiators (the single switch kernel of round 1
+// needed 226 registers for all 23 of them), and the dead branches are gone.
+template <int FN>
+__device__ __forceinline__ double eval_one(const jmc_fn_params& p, double x0, double x1, double x2, double x3) {
+    switch (FN) {
+        case JMC_FN_ALPHA_S: return alpha_running(x0, x1);
+        case JMC_FN_SPLITTING: return splitting(x0, p.jet, p.acc);
+        case JMC_FN_RADIATOR_WEIGHT: return weight_radiator(x0, x1, p.jet, p.fixed_coupling, p.acc);
+        case JMC_FN_CRIT_PDF_FC: return pdf_crit_fc(x0, x1, p.z_cut, p.jet);
+        case JMC_FN_CRIT_RAD_FC: return rad_crit_fc(x0, p.z_cut, p.jet);
+        case JMC_FN_SUB_RAD_FC: return rad_sub_fc(x0, p.beta, p.jet, x1);
+        case JMC_FN_SUB_RADPRIME_FC: return radprime_sub_fc(x0, p.beta, p.jet, x1);
+        case JMC_FN_SUB_PDF_FC: return pdf_sub_fc(x0, p.beta, p.jet, x1);
+        case JMC_FN_PRE_RAD_FC: return rad_pre_fc(x0, x1, p.z_cut, p.jet, x2);
+        case JMC_FN_CRIT_RAD_RC: return rad_crit_rc(x0, p.z_cut, p.jet);
+        case JMC_FN_CRIT_RADPRIME_RC: return radprime_crit_rc(x0, p.z_cut, p.jet);
+        // (the *_surely_nan tests return early with the NaN the full evaluation would produce, see jmc_integrand.cuh)
+        case JMC_FN_CRIT_PDF_RC: return crit_rc_surely_nan(x1, p.z_cut) ? qnan() : pdf_crit_rc(x0, x1, p.z_cut, p.jet);
+        case JMC_FN_SUB_RAD_RC: return rad_sub_rc(x0, p.beta, p.jet, x1);
+        case JMC_FN_SUB_RADPRIME_RC: return radprime_sub_rc(x0, p.beta, p.jet, x1);
+        case JMC_FN_SUB_PDF_RC: return sub_rc_surely_nan(x0, p.beta, x1) ? qnan() : pdf_sub_rc(x0, p.beta, p.jet, x1);
+        case JMC_FN_PRE_WEIGHT: return weight_precritical(x0, x1, p.z_cut, p.jet);
+        case JMC_FN_C_GROOMED: return ecf_groomed(x0, x1, p.z_cut, p.beta, x2, x3, p.acc);
+        case JMC_FN_C_UNGROOMED: return ecf_ungroomed(x0, x1, p.beta, p.acc);
+        case JMC_FN_TWO_EMISSION:
+            return (!p.fixed_coupling && (crit_rc_surely_nan(x1, p.z_cut)
+                                          || sub_rc_surely_nan(csub_verbatim(x2, x3, p.beta), p.beta, x1)))
+                       ? qnan() : weight_two_emission(x0, x1, x2, x3, p.z_cut, p.beta, p.jet, p.fixed_coupling);
+        case JMC_FN_PRE_WEIGHT_ZEROBIN: return weight_precritical_zerobin(x0, x1, p.z_cut, p.jet, p.epsilon);
+        case JMC_FN_ALPHA_SPLITTING:
+            return (p.fixed_coupling ? JMC_ALPHA_FIXED : alpha_running(x0, x1)) * splitting(x0, p.jet, p.acc);
+        case JMC_FN_MUL: return x0 * x1;
+        case JMC_FN_MASK_FINITE: return (isfinite(x0) && isfinite(x1)) ? x0 : 0.0;
+        default: return qnan();
+    }
+}
+// number of arguments a function reads (the others are never loaded)
+template <int FN>
+struct FnArity {
+    static constexpr int value =
+        (FN == JMC_FN_SPLITTING || FN == JMC_FN_CRIT_RAD_FC || FN == JMC_FN_CRIT_RAD_RC || FN == JMC_FN_CRIT_RADPRIME_RC) ? 1
+        : (FN == JMC_FN_PRE_RAD_FC) ? 3
+        : (FN == JMC_FN_C_GROOMED || FN == JMC_FN_TWO_EMISSION) ? 4 : 2;
+};
+
+template <int FN>
+__global__ void __launch_bounds__(kThreads) eval_fn_kernel(jmc_fn_params p, FnArgs A, uint64_t n,
                                                             double* __restrict__ out) {
+    constexpr int NA = FnArity<FN>::value;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const double x0 = fn_arg(A, 0, i), x1 = fn_arg(A, 1, i), x2 = fn_arg(A, 2, i), x3 = fn_arg(A, 3, i);
-        double r;
-        switch (fn) {
-            case JMC_FN_ALPHA_S: r = alpha_running(x0, x1); break;
-            case JMC_FN_SPLITTING: r = splitting(x0, p.jet, p.acc); break;
-            case JMC_FN_RADIATOR_WEIGHT: r = weight_radiator(x0, x1, p.jet, p.fixed_coupling, p.acc); break;
-            case JMC_FN_CRIT_PDF_FC: r = pdf_crit_fc(x0, x1, p.z_cut, p.jet); break;
-            case JMC_FN_CRIT_RAD_FC: r = rad_crit_fc(x0, p.z_cut, p.jet); break;
-            case JMC_FN_SUB_RAD_FC: r = rad_sub_fc(x0, p.beta, p.jet, x1); break;
-            case JMC_FN_SUB_RADPRIME_FC: r = radprime_sub_fc(x0, p.beta, p.jet, x1); break;
-            case JMC_FN_SUB_PDF_FC: r = pdf_sub_fc(x0, p.beta, p.jet, x1); break;
-            case JMC_FN_PRE_RAD_FC: r = rad_pre_fc(x0, x1, p.z_cut, p.jet, x2); break;
-            case JMC_FN_CRIT_RAD_RC: r = rad_crit_rc(x0, p.z_cut, p.jet); break;
-            case JMC_FN_CRIT_RADPRIME_RC: r = radprime_crit_rc(x0, p.z_cut, p.jet); break;
-            // (the *_surely_nan tests return early with the NaN the full evaluation would produce, see jmc_integrand.cuh)
-            case JMC_FN_CRIT_PDF_RC: r = crit_rc_surely_nan(x1, p.z_cut) ? qnan() : pdf_crit_rc(x0, x1, p.z_cut, p.jet); break;
-            case JMC_FN_SUB_RAD_RC: r = rad_sub_rc(x0, p.beta, p.jet, x1); break;
-            case JMC_FN_SUB_RADPRIME_RC: r = radprime_sub_rc(x0, p.beta, p.jet, x1); break;
-            case JMC_FN_SUB_PDF_RC: r = sub_rc_surely_nan(x0, p.beta, x1) ? qnan() : pdf_sub_rc(x0, p.beta, p.jet, x1); break;
-            case JMC_FN_PRE_WEIGHT: r = weight_precritical(x0, x1, p.z_cut, p.jet); break;
-            case JMC_FN_C_GROOMED: r = ecf_groomed(x0, x1, p.z_cut, p.beta, x2, x3, p.acc); break;
-            case JMC_FN_C_UNGROOMED: r = ecf_ungroomed(x0, x1, p.beta, p.acc); break;
-            case JMC_FN_TWO_EMISSION:
-                r = (!p.fixed_coupling && (crit_rc_surely_nan(x1, p.z_cut)
-                                           || sub_rc_surely_nan(csub_verbatim(x2, x3, p.beta), p.beta, x1)))
-                        ? qnan() : weight_two_emission(x0, x1, x2, x3, p.z_cut, p.beta, p.jet, p.fixed_coupling);
-                break;
-            case JMC_FN_PRE_WEIGHT_ZEROBIN: r = weight_precritical_zerobin(x0, x1, p.z_cut, p.jet, p.epsilon); break;
-            case JMC_FN_ALPHA_SPLITTING:
-                r = (p.fixed_coupling ? JMC_ALPHA_FIXED : alpha_running(x0, x1)) * splitting(x0, p.jet, p.acc);
-                break;
-            case JMC_FN_MUL: r = x0 * x1; break;
-            case JMC_FN_MASK_FINITE: r = (isfinite(x0) && isfinite(x1)) ? x0 : 0.0; break;
-            default: r = qnan();
-        }
-        out[i] = r;
+        const double x0 = fn_arg(A, 0, i), x1 = NA > 1 ? fn_arg(A, 1, i) : 0.0, x2 = NA > 2 ? fn_arg(A, 2, i) : 0.0,
+                     x3 = NA > 3 ? fn_arg(A, 3, i) : 0.0;
+        out[i] = eval_one<FN>(p, x0, x1, x2, x3);
     }
+}
+
+template <int FN>
+static void launch_eval_fn(int fn, const jmc_fn_params& p, const FnArgs& A, uint64_t n, double* out, int grid,
+                           cudaStream_t st) {
+    if (fn == FN) eval_fn_kernel<FN><<<grid, kThreads, 0, st>>>(p, A, n, out);
+    else if constexpr (FN + 1 < JMC_FN_COUNT) launch_eval_fn<FN + 1>(fn, p, A, n, out, grid, st);
 }
 
 static int grid_for(uint64_t n, int threads, int blocks_per_sm = 8) {
@@ -106,7 +128,7 @@ extern "C" int jmc_eval_fn(int fn, const jmc_fn_params* p, uint64_t n, const dou
     if (fn == JMC_FN_C_GROOMED) { A.scalar[2] = p->z_pre; A.scalar[3] = p->f_soft; }
     const int grid = grid_for(n, kThreads);
     if (grid < 0) return JMC_ENODEV;
-    eval_fn_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(fn, *p, A, n, d_out);
+    launch_eval_fn<0>(fn, *p, A, n, d_out, grid, (cudaStream_t)stream);
     JMC_LAUNCHED("eval_fn_kernel");
     return JMC_OK;
 }
