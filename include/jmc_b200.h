@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define JMC_ABI_VERSION 1
+#define JMC_ABI_VERSION 2
 
 /* error codes */
 #define JMC_OK 0
@@ -53,6 +53,8 @@ enum { JMC_F64 = 0, JMC_F32 = 1 };                         /* arithmetic of the 
  * integrands (weight NaN -> 0 below the Landau scale for up to 99.7 % of the samples) then skip observable, bin and
  * count for those samples.  Honoured by JMC_F32 runs with nan_to_num set; everything else counts all. */
 enum { JMC_COUNT_ALL = 0, JMC_COUNT_WEIGHTED = 1 };
+/* recursive safe subtraction (getECFs_rss, utils/partonshower_utils.py:501-674) */
+enum { JMC_RSS_PRECRIT = 1, JMC_RSS_CRIT = 2, JMC_RSS_SUB = 4, JMC_RSS_FEW_PRES = 8 };
 
 /* Samplers.  ref: montecarlo/sampler.py:114-140 (simple),
  * numerics/radiators/samplers.py:23-119 (critical), :125-180 (precritical),
@@ -140,8 +142,8 @@ enum {
      * on the host).  ref: montecarlo/integrator.py:390-457. */
     JMC_KIND_SIMPLE = 4,
     /* Angularity shower with the MLL veto algorithm; one "sample" = one jet,
-     * weight 1.  obs = ungroomed or Soft Drop ECF of the emission chain.
-     * ref: utils/partonshower_utils.py:130-328, 445-499, 676-790. */
+     * weight 1.  obs = ungroomed, Soft Drop or RSS-groomed ECF of the emission chain.
+     * ref: utils/partonshower_utils.py:130-328, 445-499, 501-674, 676-790. */
     JMC_KIND_SHOWER = 5,
     JMC_KIND_COUNT = 6
 };
@@ -154,7 +156,7 @@ typedef struct jmc_integrand {
     int32_t obs_acc;         /* JMC_ACC_LL / JMC_ACC_MLL                       */
     int32_t split_acc;       /* JMC_ACC_* (radiatorWeight; shower: LL or MLL)  */
     int32_t nan_to_num;      /* 1: weights pass through np.nan_to_num          */
-    int32_t shower_groomer;  /* SHOWER: 0 ungroomed, 1 Soft Drop               */
+    int32_t shower_groomer;  /* SHOWER: 0 ungroomed, 1 Soft Drop, 2 recursive safe subtraction (f_soft, z_cut) */
     int32_t shower_n_emissions; /* SHOWER: 1, 2, ... or 0 = 'all'              */
     int32_t counts;          /* JMC_COUNT_ALL / JMC_COUNT_WEIGHTED (fused FP32 path) */
     double  epsilon;         /* log-sampling cutoff                            */
@@ -167,6 +169,9 @@ typedef struct jmc_integrand {
     double  lo, hi;          /* SIMPLE: bounds                                 */
     double  beta_sd;         /* SHOWER: Soft Drop angular exponent             */
     double  shower_cutoff;   /* SHOWER: continue while z*theta > cutoff        */
+    int32_t shower_rss_flags;/* SHOWER, groomer 2: JMC_RSS_* (emission types kept: the reference matches its
+                                emission_type string by substring, partonshower_utils.py:588-640; few_pres) */
+    int32_t reserved;
 } jmc_integrand;
 
 /* ---- library ---------------------------------------------------------- */
@@ -302,6 +307,14 @@ int jmc_shower_dump(const jmc_integrand* g, uint64_t n, uint64_t seed, uint64_t 
  * the reference's Parton tree and 3-vectors are functions of it.  ref: utils/partonshower_utils.py:224-328 */
 int jmc_shower_chains(const jmc_integrand* g, uint64_t n, uint64_t seed, uint64_t first_index, int precision,
                       int max_emissions, double* d_chains, int32_t* d_n_emissions, void* stream);
+
+/* The ECF pickers on a stored event record: d_chains [n, max_emissions, 2] = (z, theta) in emission order, d_n_emissions
+ * [n] (lengths; longer than max_emissions = truncated record) -> d_obs [n], with the groomer, accuracy, z_cut, f_soft,
+ * n_emissions and RSS flags of `g`: ungroomed, Soft Drop or recursive safe subtraction, FP64 in the reference's
+ * operation order (the same accumulator the shower kernel carries per jet).
+ * ref: utils/partonshower_utils.py:445-499 (getECFs_ungroomed), :676-790 (getECFs_softdrop), :501-674 (getECFs_rss) */
+int jmc_chain_ecf(const jmc_integrand* g, const int32_t* d_n_emissions, const double* d_chains, uint64_t n,
+                  int max_emissions, double* d_obs, void* stream);
 
 /* density, error, cumulative integral (+ error) from the histograms.
  * ref: montecarlo/integrator.py:113-124 (density), :129-202 (integrate).

@@ -10,12 +10,15 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libjmc_b200.so")
 
+ABI_VERSION = 2
+
 # ---- enums (include/jmc_b200.h) ---------------------------------------------
 LIN, LOG = 0, 1
 QUARK, GLUON = 0, 1
 ACC_LL, ACC_LL_NONSING, ACC_MLL = 0, 1, 2
 BC_FIRST, BC_LAST_PLUS, BC_LAST_MINUS = 0, 1, 2
 F64, F32 = 0, 1
+RSS_PRECRIT, RSS_CRIT, RSS_SUB, RSS_FEW_PRES = 1, 2, 4, 8
 SAMPLER_SIMPLE, SAMPLER_CRITICAL, SAMPLER_PRECRITICAL, SAMPLER_UNGROOMED = 0, 1, 2, 3
 (FN_ALPHA_S, FN_SPLITTING, FN_RADIATOR_WEIGHT, FN_CRIT_PDF_FC, FN_CRIT_RAD_FC, FN_SUB_RAD_FC,
  FN_SUB_RADPRIME_FC, FN_SUB_PDF_FC, FN_PRE_RAD_FC, FN_CRIT_RAD_RC, FN_CRIT_RADPRIME_RC,
@@ -33,6 +36,7 @@ EXPORTS = (
     "jmc_eval_fn", "jmc_eval_integrand", "jmc_bin_index", "jmc_hist", "jmc_hist2d", "jmc_finalize2d", "jmc_minmax", "jmc_run", "jmc_run_batch", "jmc_finalize_batch", "jmc_dump", "jmc_shower_dump", "jmc_shower_chains",
     "jmc_finalize", "jmc_cumulative", "jmc_set_density_host", "jmc_integrate_host", "jmc_sample_host",
     "jmc_eval_fn_host", "jmc_launch_count", "jmc_create", "jmc_destroy", "jmc_handle_run", "jmc_handle_integrate_host",
+    "jmc_chain_ecf",
 )
 
 
@@ -57,7 +61,8 @@ class Integrand(C.Structure):
                 ("epsilon", C.c_double), ("z_cut", C.c_double), ("radius", C.c_double),
                 ("beta", C.c_double), ("f_soft", C.c_double), ("z_pre", C.c_double),
                 ("theta_scale", C.c_double), ("lo", C.c_double), ("hi", C.c_double),
-                ("beta_sd", C.c_double), ("shower_cutoff", C.c_double)]
+                ("beta_sd", C.c_double), ("shower_cutoff", C.c_double),
+                ("shower_rss_flags", C.c_int32), ("reserved", C.c_int32)]
 
 
 class JmcError(RuntimeError):
@@ -105,6 +110,7 @@ def _load():
         "jmc_sample_host": (i32, [P(Sampler), u64, u64, u64, vp, vp]),
         "jmc_eval_fn_host": (i32, [i32, P(FnParams), u64, vp, i64, vp, i64, vp, i64, vp, i64, vp]),
         "jmc_launch_count": (u64, []),
+        "jmc_chain_ecf": (i32, [P(Integrand), vp, vp, u64, i32, vp, vp]),
         "jmc_create": (i32, [P(vp)]),
         "jmc_destroy": (i32, [vp]),
         "jmc_handle_run": (i32, [vp, P(Integrand), u64, u64, u64, i32, vp, i32, vp, vp, vp, vp, vp]),
@@ -115,8 +121,8 @@ def _load():
         fn = getattr(lib, name)       # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.jmc_abi_version() != 1:
-        raise ImportError("libjmc_b200.so ABI version %d, expected 1" % lib.jmc_abi_version())
+    if lib.jmc_abi_version() != ABI_VERSION:
+        raise ImportError("libjmc_b200.so ABI version %d, expected %d" % (lib.jmc_abi_version(), ABI_VERSION))
     return lib
 
 

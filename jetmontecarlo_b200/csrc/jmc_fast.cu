@@ -553,9 +553,9 @@ fast_body(const FastParams& P_in, uint64_t n, uint64_t seed, uint64_t first, con
 
     // Bin of an observable: `ok` = inside the binned range, `b` = its bin (meaningful only when ok).
     // HOT (np.logspace bins): the bin is the floor of an affine map of log2(obs), and the range test is made on the
-    // mapped value -- FFMA, one compare, F2I.  The host shrinks the map by 2^-14 of a bin at either end
-    // (make_fast_params), so that an observable equal to the first or the last edge (the extreme sample, when the
-    // edges come from setBins) maps inside [0, nb) whatever the rounding of the FMA.
+    // mapped value -- FFMA, one compare, F2I.  The host nudges the two constants of the map by single ulps
+    // (make_fast_params) until the first and the last edge themselves (the extreme samples, when the edges come from
+    // setBins) map inside [0, nb) whatever the rounding of the FMA.
     auto locate = [&](float l2obs, bool& ok, int& b) {
         if (HOT) {
             const float f = fmaf(l2obs, P.inv_d, P.mb0_inv_d);
@@ -1004,17 +1004,31 @@ static int make_fast_params(const jmc_integrand* g, const double* h_edges, int n
         P.e_first = (*edges_f)[0];
         P.e_last = (*edges_f)[n_edges - 1];
         P.nb_f = (float)(n_edges - 1);
-        // The affine bin map f(x) = x * inv_d + mb0_inv_d, shrunk by a margin m of a bin at either end so that the
-        // FP32 images of the first and the last edge fall inside [0, nb): an observable equal to an end edge (the
-        // extreme sample, when the edges come from setBins) is then binned, as np.histogram's closed last bin does,
-        // whatever the rounding of the FMA.  m starts at 2^-14 of a bin (FP32 places log2(obs) no better than that).
+        // The affine bin map f(x) = fmaf(x, inv_d, mb0_inv_d), nudged until the FP32 images of the first and the last
+        // edge fall inside [0, nb): an observable equal to an end edge (the extreme sample, when the edges come from
+        // setBins) is then binned, as np.histogram's closed last bin does, whatever the rounding of the FMA.  The
+        // nudges are single ulps of the two constants (the distortion stays at the level FP32 places log2(obs) anyway);
+        // should they not converge, the map is shrunk about its ends by a growing margin instead.
+        P.inv_d = (float)(1.0 / d);
+        P.mb0_inv_d = (float)(-dom[0] / d);
+        bool ok = false;
+        for (int it = 0; it < 512 && !ok; ++it) {
+            const float f_lo = std::fmaf(P.e_first, P.inv_d, P.mb0_inv_d), f_hi = std::fmaf(P.e_last, P.inv_d, P.mb0_inv_d);
+            ok = f_lo >= 0.0f && f_hi < P.nb_f;
+            if (ok) break;
+            if (f_hi >= P.nb_f) {
+                if (P.e_last > 0.0f) P.inv_d = std::nextafterf(P.inv_d, 0.0f);
+                else if (P.e_last < 0.0f) P.inv_d = std::nextafterf(P.inv_d, INFINITY);
+                else P.mb0_inv_d = std::nextafterf(P.mb0_inv_d, -INFINITY);
+            }
+            if (std::fmaf(P.e_first, P.inv_d, P.mb0_inv_d) < 0.0f) P.mb0_inv_d = std::nextafterf(P.mb0_inv_d, INFINITY);
+        }
         const double nbd = (double)(n_edges - 1);
-        for (double m = std::ldexp(1.0, -14);; m *= 4.0) {
+        for (double m = std::ldexp(1.0, -14); !ok && m < 0.01; m *= 2.0) {
             const double scale = (nbd - 2.0 * m) / nbd;
             P.inv_d = (float)(scale / d);
             P.mb0_inv_d = (float)(m - dom[0] * scale / d);
-            const float f_lo = std::fmaf(P.e_first, P.inv_d, P.mb0_inv_d), f_hi = std::fmaf(P.e_last, P.inv_d, P.mb0_inv_d);
-            if ((f_lo >= 0.0f && f_hi < P.nb_f) || m > 0.01) break;
+            ok = std::fmaf(P.e_first, P.inv_d, P.mb0_inv_d) >= 0.0f && std::fmaf(P.e_last, P.inv_d, P.mb0_inv_d) < P.nb_f;
         }
         for (int k = 1; k < n_edges; ++k)
             if (!((*edges_f)[k] > (*edges_f)[k - 1]))

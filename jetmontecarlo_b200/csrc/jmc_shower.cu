@@ -36,9 +36,17 @@ static constexpr int kShowerThreads = 128;
 static constexpr int kMaxEmissions = 64;     // as the oracle; the reference recurses until the cutoff
 static constexpr int kTopN = 4;              // n_emissions up to 4 (+ 'all')
 
+// lanes of a warp that have finished their jet wait until this many are ready, then bin their observables and
+// refill together (see shower_kernel)
+#ifndef JMC_SHOWER_GROUP
+#define JMC_SHOWER_GROUP 8
+#endif
+
 struct ShowerParams {
     int jet, mll_shower, obs_mll, groomer, n_emissions;
+    int rss_pre, rss_crit, rss_sub, rss_few_pres;     // RSS: emission types kept, and the few-precriticals approximation
     double beta, radius, cutoff, z_cut, beta_sd;
+    double f_soft;         // RSS: energy fraction groomed from the softer branch
     double alpha;          // alpha_fixed (LL) or the veto overestimate 1.5 (MLL)
     double kfac;           // pi beta / (C_R alpha)
     double cr;
@@ -71,18 +79,23 @@ template <typename T>
 struct EcfAcc {
     T top[kTopN];        // largest values seen, descending (ungroomed: all; soft drop: the ones after the first kept)
     T sum_all;           // running sum in chain order
-    T first;             // soft drop: the critical emission's value
-    bool dropping;       // soft drop: still below the grooming condition
+    T first;             // soft drop: the critical emission's value; RSS: c_crit
+    bool dropping;       // soft drop: still below the grooming condition; RSS: pre-critical emissions still allowed
+    T this_zcut, max_zpre, sum_zpre, prod_scale;      // RSS state (partonshower_utils.py:501-674)
     static __device__ __forceinline__ T tiny() { return sizeof(T) == 8 ? (T)1e-50 : (T)0; }
     static __device__ __forceinline__ double wide(T v) { return (sizeof(T) == 4 && v == (T)0) ? 1e-50 : (double)v; }
-    __device__ __forceinline__ void reset(int groomer) {
+    __device__ __forceinline__ void reset(int groomer, double z_cut = 0.0) {
 #pragma unroll
         for (int k = 0; k < kTopN; ++k) top[k] = (T)-1;
-        // getECFs_ungroomed starts its list with 1e-50 (:459); soft drop appends its two 1e-50 at the end
-        sum_all = groomer ? (T)0 : tiny();
-        first = (T)-1;
+        // getECFs_ungroomed starts its list with 1e-50 (:459); soft drop appends its two 1e-50 at the end;
+        // RSS: c_subs = [1e-50], c_crit = 1e-50, z_pres = [1e-50] (:560-563)
+        sum_all = groomer == 1 ? (T)0 : tiny();
+        first = groomer == 2 ? tiny() : (T)-1;
         dropping = true;
-        if (!groomer) insert(tiny());
+        if (groomer != 1) insert(tiny());
+        this_zcut = (T)z_cut;
+        max_zpre = sum_zpre = tiny();
+        prod_scale = (T)1;
     }
     // branch-free insertion into the descending top-N (a bubble of max/min pairs)
     __device__ __forceinline__ void insert(T c) {
@@ -111,7 +124,54 @@ struct EcfAcc {
         insert(c);
         sum_all += c;
     }
+    // Recursive safe subtraction: emissions softer than what is left of z_cut are pre-critical (they use z_cut up
+    // and, for f != 1, rescale the hard branch), the first survivor is critical, later ones are subsequent.
+    // thb = theta^beta.  Operation order of the reference (:575-640) -- in FP64 the result is the oracle's bit for bit.
+    __device__ __forceinline__ void add_rss(T z, T thb, const ShowerParams& p) {
+        const T f = (T)p.f_soft;
+        T cutoff, scale;
+        bool valid_pre;
+        if (p.rss_few_pres) {
+            cutoff = this_zcut - max_zpre;
+            scale = (T)1 - ((T)1 - f) * max_zpre / f;
+            valid_pre = z < this_zcut;
+        } else {
+            cutoff = this_zcut - sum_zpre;
+            scale = prod_scale;
+            valid_pre = z < cutoff;
+        }
+        if (p.rss_pre && dropping && valid_pre) {
+            max_zpre = z > max_zpre ? z : max_zpre;
+            sum_zpre += z;
+            prod_scale *= (T)1 - ((T)1 - f) * z / f;
+            return;
+        }
+        const bool is_crit = p.rss_crit && z >= cutoff && cutoff > (T)0;
+        const bool is_sub = !is_crit && p.rss_sub && this_zcut == (T)0;
+        if (!is_crit && !is_sub) return;
+        const T zc = is_crit ? cutoff : (T)0;
+        const T tail = p.obs_mll ? (T)1 - z - ((T)1 - f) * zc : (T)1 - ((T)1 - f) * zc;
+        const T c = (z - f * zc) * thb * tail * (scale * scale);
+        if (is_crit) {
+            first = c;
+            this_zcut = (T)0;
+            dropping = false;
+        } else {
+            sum_all += c;
+            insert(c);
+        }
+    }
     __device__ __forceinline__ double result(const ShowerParams& p) {
+        if (p.groomer == 2) {
+            // c_list = c_subs + [c_crit]: the sum of all, or of the n largest (:655-668)
+            if (p.n_emissions == 0) return (double)sum_all + wide(first) + (sizeof(T) == 4 ? 1e-50 : 0.0);
+            insert(first);
+            double s = 0.0;
+            bool any = false;
+            for (int k = 0; k < kTopN && k < p.n_emissions; ++k)
+                if (top[k] >= (T)0) { s = any ? s + wide(top[k]) : wide(top[k]); any = true; }
+            return s;
+        }
         if (!p.groomer) {
             if (p.n_emissions == 0) return (double)sum_all + (sizeof(T) == 4 ? 1e-50 : 0.0);
             double s = 0.0;                    // sum(cs[:n]) over the descending list
@@ -189,7 +249,7 @@ shower_kernel(ShowerParams p, uint64_t n, uint64_t seed, uint64_t first, const d
     bool alive = j < n;
     auto start_jet = [&]() {
         us.reset(first + j, seed);
-        acc.reset(p.groomer);
+        acc.reset(p.groomer, p.z_cut);
         ang = p.ang_init;                       // ang_init = R^beta / 2, z_init = 1/2, theta_init = R (:316-321)
         lf = p.lf_init;
         z = 0.5;
@@ -204,13 +264,23 @@ shower_kernel(ShowerParams p, uint64_t n, uint64_t seed, uint64_t first, const d
     };
     if (alive) start_jet();
 
-    while (__any_sync(0xffffffffu, alive)) {
-        if (!alive) continue;
+    while (true) {
         // does the chain continue?  (angularity_shower: recurse while z theta > cutoff, :262-279).  The cutoff is
         // tested on ACCEPTED emissions only: inside angularity_split the veto loop keeps trying without it (:188-209)
-        bool finished;
-        if (EXACT) finished = in_veto_loop ? false : (!(z * theta > p.cutoff) || n_em >= kMaxEmissions);
-        else finished = in_veto_loop ? false : (!(lnz + lnth > ln_cut_f) || n_em >= kMaxEmissions);
+        bool finished = false;
+        if (alive && !in_veto_loop) {
+            if (EXACT) finished = !(z * theta > p.cutoff) || n_em >= kMaxEmissions;
+            else finished = !(lnz + lnth > ln_cut_f) || n_em >= kMaxEmissions;
+        }
+        // Finishing a jet (observable, bin, histogram atomic, refill) is ~100 instructions that only the finished
+        // lanes execute; with ~30 trials per jet some lane of a warp finishes in two iterations out of three, and
+        // the other lanes would idle through it every time.  Finished lanes therefore wait until JMC_SHOWER_GROUP
+        // of them are ready (or until no lane of the warp has a trial left to do) and finish together.
+        const unsigned alive_mask = __ballot_sync(0xffffffffu, alive);
+        if (!alive_mask) break;
+        const unsigned fin_mask = __ballot_sync(0xffffffffu, finished);
+        const bool flush = __popc(fin_mask) >= JMC_SHOWER_GROUP || fin_mask == alive_mask;
+        if (!alive || (finished && !flush)) continue;
         if (!finished) {
             bool accepted;
             ++n_trials;
@@ -241,7 +311,7 @@ shower_kernel(ShowerParams p, uint64_t n, uint64_t seed, uint64_t first, const d
                         zp = pz + zf * p1;
                     }
                     const float cut = alpha * zp * veto_norm_f;
-                    if (cut > 1.0f) *error_flag = 1;
+                    if (cut > 1.0f) atomicOr(error_flag, 1);
                     accepted = r3 < cut;
                 }
             }
@@ -253,7 +323,11 @@ shower_kernel(ShowerParams p, uint64_t n, uint64_t seed, uint64_t first, const d
                     c[1] = EXACT ? theta : (double)__expf(lnth);
                 }
                 ++n_em;
-                if (EXACT) {
+                if (n_em >= kMaxEmissions && error_flag) atomicOr(error_flag, 2);     // the record is cut here
+                if (p.groomer == 2) {
+                    if (EXACT) acc.add_rss(z, np_pow(theta, p.beta), p);
+                    else acc.add_rss(zf, __expf(beta_f * lnth), p);
+                } else if (EXACT) {
                     acc.add(ecf_ungroomed(z, theta, p.beta, p.obs_mll ? JMC_ACC_MLL : JMC_ACC_LL),
                             z > p.z_cut * np_pow(theta, p.beta_sd), p.groomer);
                 } else {
@@ -314,6 +388,48 @@ shower_kernel(ShowerParams p, uint64_t n, uint64_t seed, uint64_t first, const d
     }
 }
 
+// ECF of stored event records (replay form of the pickers): one jet per thread walks its (z, theta) chain through the
+// same accumulator the shower kernel carries per lane, in FP64 and the reference's operation order.
+// chains: [n, cap, 2]; a warp stages 32 jets x 8 emissions at a time through shared memory so that the reads of a
+// record are 128-byte rows rather than one 16-byte element per lane.
+__global__ void __launch_bounds__(kShowerThreads)
+chain_ecf_kernel(ShowerParams p, const int* __restrict__ lens, const double* __restrict__ chains, uint64_t n, int cap,
+                 double* __restrict__ out) {
+    __shared__ double2 s_tile[kShowerThreads / 32][32][9];      // [warp][jet][emission], padded against bank conflicts
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t rounds = (n + stride - 1) / stride;
+    for (uint64_t r = 0; r < rounds; ++r) {
+        const uint64_t base = r * stride + (uint64_t)blockIdx.x * blockDim.x + warp * 32;   // first jet of this warp
+        const uint64_t j = base + lane;
+        const int len = j < n ? min(lens[j], cap) : 0;
+        int longest = len;
+        for (int o = 16; o > 0; o >>= 1) longest = max(longest, __shfl_xor_sync(0xffffffffu, longest, o));
+        EcfAcc<double> acc;
+        acc.reset(p.groomer, p.z_cut);
+        for (int e0 = 0; e0 < longest; e0 += 8) {
+            // 8 lanes read the 8 emissions (128 B) of one jet: 4 jets per load instruction, 8 instructions per tile
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const unsigned jet = q * 4 + (lane >> 3), em = lane & 7u;
+                const uint64_t gj = base + jet;
+                double2 v = make_double2(0.0, 0.0);
+                if (gj < n && e0 + (int)em < cap) v = *(const double2*)(chains + ((size_t)gj * cap + e0 + em) * 2);
+                s_tile[warp][jet][em] = v;
+            }
+            __syncwarp();
+            for (int e = 0; e < 8 && e0 + e < len; ++e) {
+                const double2 zt = s_tile[warp][lane][e];
+                if (p.groomer == 2) acc.add_rss(zt.x, np_pow(zt.y, p.beta), p);
+                else acc.add(ecf_ungroomed(zt.x, zt.y, p.beta, p.obs_mll ? JMC_ACC_MLL : JMC_ACC_LL),
+                             zt.x > p.z_cut * np_pow(zt.y, p.beta_sd), p.groomer);
+            }
+            __syncwarp();
+        }
+        if (j < n) out[j] = acc.result(p);
+    }
+}
+
 // weight 1 per jet: sum w = sum w^2 = count
 __global__ void shower_sums_kernel(const unsigned long long* __restrict__ before, const unsigned long long* __restrict__ after,
                                    int nb, double* __restrict__ sum_w, double* __restrict__ sum_w2) {
@@ -339,6 +455,15 @@ static int make_shower_params(const jmc_integrand* g, ShowerParams* out) {
     p.mll_shower = g->split_acc == JMC_ACC_MLL;
     p.obs_mll = g->obs_acc == JMC_ACC_MLL;
     p.groomer = g->shower_groomer;
+    JMC_REQUIRE(p.groomer >= 0 && p.groomer <= 2, "shower: groomer must be 0 (none), 1 (Soft Drop) or 2 (RSS)");
+    p.rss_pre = (g->shower_rss_flags & JMC_RSS_PRECRIT) != 0;
+    p.rss_crit = (g->shower_rss_flags & JMC_RSS_CRIT) != 0;
+    p.rss_sub = (g->shower_rss_flags & JMC_RSS_SUB) != 0;
+    p.rss_few_pres = (g->shower_rss_flags & JMC_RSS_FEW_PRES) != 0;
+    p.f_soft = g->f_soft;
+    if (p.groomer == 2)
+        JMC_REQUIRE(g->f_soft > 1.0 / 3.0, "f = %g is less than 1/3, and the grooming may groom away harder branches first.",
+                    g->f_soft);
     p.n_emissions = g->shower_n_emissions;
     p.beta = g->beta; p.radius = g->radius; p.cutoff = g->shower_cutoff; p.z_cut = g->z_cut; p.beta_sd = g->beta_sd;
     p.cr = g->jet == JMC_QUARK ? JMC_CF : JMC_CA;
@@ -427,7 +552,12 @@ static int shower_launch(const jmc_integrand* g, uint64_t n, uint64_t seed, uint
     int h_err = 0;
     JMC_CUDA(cudaMemcpyAsync(&h_err, d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
     JMC_CUDA(cudaStreamSynchronize(st));
-    if (h_err) return set_error(JMC_EDOMAIN, "The pdf must be everywhere less than the proposed pdf!");
+    if (h_err & 1) return set_error(JMC_EDOMAIN, "The pdf must be everywhere less than the proposed pdf!");
+    // the reference recurses until z theta <= cutoff; the device keeps at most kMaxEmissions per jet.  A jet that
+    // reaches the cap is reported instead of being returned truncated.
+    if (h_err & 2)
+        return set_error(JMC_ELIMIT, "shower: a jet reached the cap of %d emissions (cutoff %g too low for the device "
+                                     "record)", kMaxEmissions, g->shower_cutoff);
     return JMC_OK;
 }
 
@@ -448,6 +578,24 @@ extern "C" int jmc_shower_dump(const jmc_integrand* g, uint64_t n, uint64_t seed
     // the output arrays are indexed by the local jet number 0..n-1; jet i is stream index first_index + i
     return jmc::shower_launch(g, n, seed, first_index, precision, nullptr, 0, nullptr, nullptr, nullptr, nullptr, d_obs,
                               d_n_emissions, d_n_trials, stream);
+}
+
+extern "C" int jmc_chain_ecf(const jmc_integrand* g, const int32_t* d_n_emissions, const double* d_chains, uint64_t n,
+                             int max_emissions, double* d_obs, void* stream) {
+    JMC_REQUIRE(g != nullptr && g->kind == JMC_KIND_SHOWER, "jmc_chain_ecf: integrand must be a shower");
+    jmc::ShowerParams p;
+    int rc = jmc::make_shower_params(g, &p);
+    if (rc) return rc;
+    JMC_REQUIRE(max_emissions >= 1, "jmc_chain_ecf: need room for at least one emission");
+    if (n == 0) return JMC_OK;
+    JMC_REQUIRE(d_n_emissions && d_chains && d_obs, "jmc_chain_ecf: NULL array");
+    jmc::DeviceInfo di;
+    if (jmc::device_info(&di)) return JMC_ENODEV;
+    const uint64_t want = (n + jmc::kShowerThreads - 1) / jmc::kShowerThreads, cap = (uint64_t)di.sm_count * 8;
+    jmc::chain_ecf_kernel<<<(int)(want < cap ? want : cap), jmc::kShowerThreads, 0, (cudaStream_t)stream>>>(
+        p, d_n_emissions, d_chains, n, max_emissions, d_obs);
+    JMC_LAUNCHED("chain_ecf_kernel");
+    return JMC_OK;
 }
 
 extern "C" int jmc_shower_chains(const jmc_integrand* g, uint64_t n, uint64_t seed, uint64_t first_index, int precision,

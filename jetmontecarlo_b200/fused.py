@@ -49,6 +49,7 @@ class Integrand:
         self.bounds = (float(bounds[0]), float(bounds[1]))
         self.groomer, self.beta_sd, self.cutoff = int(groomer), float(beta_sd), float(cutoff)
         self.n_emissions = 0 if n_emissions == 'all' else int(n_emissions)
+        self.rss_flags = 0
         # 'all': per-bin counts as np.histogram gives them; 'weighted': only samples with a non-zero weight are
         # counted (same density / integral; lets the FP32 path skip the samples whose weight is NaN -> 0)
         assert counts in ('all', 'weighted'), "counts must be 'all' or 'weighted'"
@@ -98,13 +99,21 @@ class Integrand:
 
     @classmethod
     def shower(cls, beta=2., jet_type='quark', acc='MLL', radius=1., cutoff=None, groomer='ungroomed',
-               z_cut=0., beta_sd=0., obs_acc='LL', n_emissions=1):
+               z_cut=0., beta_sd=0., obs_acc='LL', n_emissions=1, f=1., emission_type='precritsub', few_pres=True):
+        """``groomer``: 'ungroomed', 'softdrop' (z_cut, beta_sd) or 'rss' (recursive safe subtraction: z_cut, f,
+        emission_type matched by substring as the reference does, few_pres; utils/partonshower_utils.py:501-674)."""
         from .analytics.qcd_utils import MU_NP
         assert acc in ('LL', 'MLL'), "Invalid accuracy."
-        assert groomer in ('ungroomed', 'softdrop')
-        return cls(_lib.KIND_SHOWER, 'lin', radius=radius, beta=beta, jet_type=jet_type, split_acc=acc,
-                   obs_acc=obs_acc, z_cut=z_cut, groomer=int(groomer == 'softdrop'), n_emissions=n_emissions,
-                   beta_sd=beta_sd, cutoff=MU_NP if cutoff is None else cutoff)
+        assert groomer in ('ungroomed', 'softdrop', 'rss')
+        if groomer == 'rss':
+            assert f > 1 / 3, "f = " + str(f) + " is less than 1/3, and the grooming may groom away harder branches first."
+        ig = cls(_lib.KIND_SHOWER, 'lin', radius=radius, beta=beta, jet_type=jet_type, split_acc=acc,
+                 obs_acc=obs_acc, z_cut=z_cut, groomer={'ungroomed': 0, 'softdrop': 1, 'rss': 2}[groomer],
+                 n_emissions=n_emissions, beta_sd=beta_sd, cutoff=MU_NP if cutoff is None else cutoff, f=f)
+        ig.rss_flags = ((_lib.RSS_PRECRIT if 'precrit' in emission_type else 0)
+                        | (_lib.RSS_CRIT if 'crit' in emission_type else 0)
+                        | (_lib.RSS_SUB if 'sub' in emission_type else 0) | (_lib.RSS_FEW_PRES if few_pres else 0))
+        return ig
 
     # ---- C struct and derived quantities ---------------------------------------
     def c_struct(self):
@@ -115,7 +124,7 @@ class Integrand:
             shower_groomer=self.groomer, shower_n_emissions=self.n_emissions,
             counts=int(self.counts == 'weighted'), epsilon=self.epsilon, z_cut=self.z_cut, radius=self.radius, beta=self.beta, f_soft=self.f,
             z_pre=self.z_pre, theta_scale=self.theta_scale, lo=self.bounds[0], hi=self.bounds[1],
-            beta_sd=self.beta_sd, shower_cutoff=self.cutoff)
+            beta_sd=self.beta_sd, shower_cutoff=self.cutoff, shower_rss_flags=self.rss_flags)
 
     @property
     def area(self):

@@ -12,9 +12,9 @@ function of (seed, jet index) through the counter RNG -- so ``gen_jets`` here
 returns a light ``JetList`` *description* and the ECF extractors regenerate
 the chains on the GPU (jmc_shower_dump), writing only the per-jet observable.
 For pdfs of very many jets use ``jetmontecarlo_b200.fused.Integrand.shower``,
-which bins on the fly.  RSS grooming works on the event record
-(``JetList.chains_device``): one vectorised pass over the emission index with
-per-jet state, on the device the chains were generated on.
+which bins on the fly.  RSS grooming runs inside the shower kernel as well
+(per-lane state of the jet being generated); the event record
+(``JetList.chains_device``) is written only on request.
 """
 import ctypes as C
 
@@ -125,93 +125,47 @@ def getECFs_softdrop(jet_list, z_cut, beta=2., beta_sd=0., obs_acc='LL', n_emiss
 
 
 
-def rss_from_chains(lens, z, theta, z_cut, beta=2., f=1., obs_acc='LL', emission_type='precritsub', n_emissions=1,
-                    few_pres=True):
-    """Recursive-safe-subtraction grooming of ordered emission chains, all jets at once: torch tensors ``lens``
-    [n], ``z`` and ``theta`` [n, L] on any device (the shower's chains never leave the GPU); one pass over the
-    emission index with per-jet state vectors.  Emissions softer than what is left of z_cut are pre-critical (they
-    use z_cut up and, for f != 1, rescale the hard branch), the first survivor is critical, later ones are
-    subsequent; the ECF is the sum of the ``n_emissions`` largest contributions (or of all).  ``emission_type`` is
-    matched by substring, as the reference does.  ref: utils/partonshower_utils.py:501-674"""
-    assert obs_acc in ['LL', 'MLL'], "Accuracy must be LL or MLL"
-    assert f > 1 / 3, "f = " + str(f) + " is less than 1/3, and the grooming may groom away harder branches first."
-    assert n_emissions == 'all' or int(n_emissions) >= 1
-    n = lens.numel()
-    dev, f64 = z.device, torch.float64
-    full = lambda v, dt=f64: torch.full((n,), v, dtype=dt, device=dev)
-    this_zcut, use_pre = full(float(z_cut)), full(True, torch.bool)
-    max_zpre, sum_zpre, prod_scale = full(1e-50), full(1e-50), full(1.)
-    c_crit, sum_subs = full(1e-50), full(1e-50)
-    k = 0 if n_emissions == 'all' else int(n_emissions)
-    top = [full(0.) for _ in range(k)]            # the k largest contributions, descending (all are >= 0)
-
-    def insert(values, mask):
-        v = torch.where(mask, values, full(0.))
-        for i in range(k):
-            hi, lo = torch.maximum(top[i], v), torch.minimum(top[i], v)
-            top[i], v = hi, lo
-
-    def ecf(zz, th, zc):
-        tail = (1. - (1. - f) * zc) if obs_acc == 'LL' else (1. - zz - (1. - f) * zc)
-        return (zz - f * zc) * th ** beta * tail
-
-    has_pre, has_crit, has_sub = ('precrit' in emission_type), ('crit' in emission_type), ('sub' in emission_type)
-    if k:
-        insert(full(1e-50), full(True, torch.bool))          # the 1e-50 floor of the reference's c_subs list
-    steps = int(lens.max().item()) if n else 0
-    assert steps <= z.shape[1], "emission chains were truncated: raise max_emissions"
-    for j in range(steps):
-        zz, th = z[:, j], theta[:, j]
-        live = lens > j
-        if few_pres:
-            cutoff = this_zcut - max_zpre
-            scale = 1 - (1 - f) * max_zpre / f
-            valid_pre = zz < this_zcut
-        else:
-            cutoff = this_zcut - sum_zpre
-            scale = prod_scale
-            valid_pre = zz < cutoff
-        is_pre = live & use_pre & valid_pre if has_pre else torch.zeros_like(live)
-        is_crit = live & ~is_pre & (zz >= cutoff) & (cutoff > 0.) if has_crit else torch.zeros_like(live)
-        is_sub = live & ~is_pre & ~is_crit & (this_zcut == 0.) if has_sub else torch.zeros_like(live)
-        # critical / subsequent contributions with the hard-branch rescaling in force at this emission
-        c_new = ecf(zz, th, torch.where(is_crit, cutoff, full(0.))) * scale ** 2.
-        c_crit = torch.where(is_crit, c_new, c_crit)
-        sum_subs = torch.where(is_sub, sum_subs + c_new, sum_subs)
-        if k:
-            insert(c_new, is_sub)
-        # pre-critical emissions use z_cut up
-        max_zpre = torch.where(is_pre, torch.maximum(max_zpre, zz), max_zpre)
-        sum_zpre = torch.where(is_pre, sum_zpre + zz, sum_zpre)
-        prod_scale = torch.where(is_pre, prod_scale * (1 - (1 - f) * zz / f), prod_scale)
-        this_zcut = torch.where(is_crit, full(0.), this_zcut)
-        use_pre = use_pre & ~is_crit
-    if not k:
-        return sum_subs + c_crit
-    insert(c_crit, full(True, torch.bool))
-    total = top[0]
-    for i in range(1, k):
-        total = total + top[i]
-    return total
-
-
 def getECFs_rss(jet_list, z_cut, beta=2., f=1., obs_acc='LL', emission_type='precritsub', n_emissions=1,
                 few_pres=True, rescale_hard=True, verbose=0):
-    """List of RSS-groomed ECFs, one per jet, from *ungroomed* jets.  The chains are regenerated on the GPU
-    (jmc_shower_chains) and groomed there by ``rss_from_chains``; only the per-jet observable comes back.
-    ref: utils/partonshower_utils.py:501-674"""
+    """List of RSS-groomed ECFs, one per jet, from *ungroomed* jets.  Recursive safe subtraction runs inside the shower
+    kernel, on the per-lane state of the jet being generated (``EcfAcc::add_rss``, csrc/jmc_shower.cu): emissions
+    softer than what is left of z_cut are pre-critical (they use z_cut up and, for f != 1, rescale the hard branch),
+    the first survivor is critical, later ones are subsequent; the ECF is the sum of the ``n_emissions`` largest
+    contributions (or of all).  ``emission_type`` is matched by substring, as the reference does.  Only the per-jet
+    observable comes back.  ref: utils/partonshower_utils.py:501-674"""
     if z_cut == 0:
         return getECFs_ungroomed(jet_list, beta=beta, obs_acc=obs_acc, n_emissions=n_emissions, verbose=verbose)
-    max_emissions = CHAIN_RECORD
-    while True:
-        lens, chains = jet_list.chains_device(max_emissions)
-        if len(jet_list) == 0 or int(lens.max().item()) <= max_emissions:
-            break
-        max_emissions *= 2                      # a longer chain than the record: regenerate with room for it
-    ecfs = rss_from_chains(lens, chains[:, :, 0], chains[:, :, 1], z_cut, beta=beta, f=f, obs_acc=obs_acc,
-                           emission_type=emission_type, n_emissions=n_emissions, few_pres=few_pres)
-    ecfs = D.to_host(ecfs)
+    assert obs_acc in ['LL', 'MLL'], "Accuracy must be LL or MLL"
+    assert f > 1 / 3, "f = " + str(f) + " is less than 1/3, and the grooming may groom away harder branches first."
+    _check_n_emissions(n_emissions)
+    assert beta == jet_list.beta, "the accelerated path bins the shower's own angularity exponent"
+    ig = jet_list._integrand(obs_acc=obs_acc, n_emissions=n_emissions, groomer='rss', z_cut=z_cut, f=f,
+                             emission_type=emission_type, few_pres=few_pres)
+    obs, _, _ = jet_list._dump(ig)
+    ecfs = D.to_host(obs)
     return list(ecfs[ecfs >= 0])                # the reference keeps a jet only if its ecf >= 0
+
+
+def ecfs_from_chains(lens, chains, beta=2., obs_acc='LL', n_emissions=1, groomer='ungroomed', z_cut=0., beta_sd=0.,
+                     f=1., emission_type='precritsub', few_pres=True):
+    """The ECF pickers on a stored event record (``JetList.chains_device`` or any (z, theta) chains): CUDA tensors
+    ``lens`` [n] int32 and ``chains`` [n, L, 2] -> tensor [n] of observables, evaluated by ``jmc_chain_ecf`` with the
+    accumulator of the shower kernel (FP64, the reference's operation order).
+    ref: utils/partonshower_utils.py:445-499, 501-674, 676-790"""
+    D.require_cuda()
+    _check_n_emissions(n_emissions)
+    ig = Integrand.shower(beta=beta, obs_acc=obs_acc, n_emissions=n_emissions, groomer=groomer, z_cut=z_cut,
+                          beta_sd=beta_sd, f=f, emission_type=emission_type, few_pres=few_pres)
+    lens = lens.to(device=D.device(), dtype=torch.int32).contiguous()
+    chains = chains.to(device=D.device(), dtype=torch.float64).contiguous()
+    assert chains.dim() == 3 and chains.shape[0] == lens.numel() and chains.shape[2] == 2
+    assert lens.numel() == 0 or int(lens.max().item()) <= chains.shape[1], \
+        "emission chains were truncated: raise max_emissions"
+    out = D.empty((lens.numel(),))
+    s = ig.c_struct()
+    _lib.check(_lib.lib.jmc_chain_ecf(C.byref(s), D.ptr(lens), D.ptr(chains), lens.numel(), int(chains.shape[1]),
+                                      D.ptr(out), D.stream()))
+    return out
 
 
 def getangs(jet_list, beta=2., acc='LL', emission_type=None, verbose=1):

@@ -159,10 +159,17 @@ def test_fast_histogram_equals_histogram_of_its_dump(cuda, kind, jet, fc, acc):
     l2 = np.log2(obs).astype(np.float32)
     dom = np.log2(edges)
     d = (dom[-1] - dom[0]) / (len(edges) - 1)
-    # (the host shrinks the map by 2^-14 of a bin at either end so that the end edges themselves map inside)
-    nb, m = len(edges) - 1, 2. ** -14
-    scale = (nb - 2. * m) / nb
-    inv_d, mb0 = np.float32(scale / d), np.float32(m - dom[0] * scale / d)
+    inv_d, mb0 = np.float32(1. / d), np.float32(-dom[0] / d)
+    # (the host nudges the two constants by single ulps until both end edges map inside [0, nb), make_fast_params)
+    f32 = lambda x: np.float32(np.float64(np.float32(x)) * np.float64(inv_d) + np.float64(mb0))
+    nb_f, e_lo, e_hi = np.float32(len(edges) - 1), np.float32(dom[0]), np.float32(dom[-1])
+    for _ in range(512):
+        if f32(e_lo) >= 0 and f32(e_hi) < nb_f:
+            break
+        if f32(e_hi) >= nb_f:
+            inv_d = np.nextafter(inv_d, np.float32(0 if e_hi > 0 else np.inf))
+        if f32(e_lo) < 0:
+            mb0 = np.nextafter(mb0, np.float32(np.inf))
     fma = (l2.astype(np.float64) * np.float64(inv_d) + np.float64(mb0)).astype(np.float32)
     keep = (fma >= 0) & (fma < len(edges) - 1)
     idx = np.floor(np.where(keep, fma, 0)).astype(np.int64)

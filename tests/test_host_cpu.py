@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
     for name in names:
         assert hasattr(_lib.lib, name), name + " is declared in include/jmc_b200.h but not exported"
     assert sorted(_lib.EXPORTS) == names
-    assert _lib.lib.jmc_abi_version() == 1
+    assert _lib.lib.jmc_abi_version() == _lib.ABI_VERSION == 2
 
 
 def test_struct_layout_matches_header():
@@ -323,5 +323,5 @@ int main(int argc, char** argv) {
     assert res.returncode == 0, res.stderr
     lib = os.path.join(ROOT, "jetmontecarlo_b200", "lib", "libjmc_b200.so")
     out = subprocess.run([str(exe), lib], capture_output=True, text=True).stdout.splitlines()
-    assert out[0] == "abi 1 rc 0 area %.17g" % ((1. / 2. - .1) * .8)
+    assert out[0] == "abi 2 rc 0 area %.17g" % ((1. / 2. - .1) * .8)
     assert out[1] == "rc -1 err jmc_sampler_area: NULL argument"
