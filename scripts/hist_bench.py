@@ -25,6 +25,10 @@ for label, w in (("all weights non-zero", torch.rand(n, dtype=torch.float64, dev
         ms = ev[0].elapsed_time(ev[1])
         uni = "uniform-log" if np.allclose(np.diff(np.log(edges)), np.diff(np.log(edges))[0]) else "irregular"
         print(f"jmc_hist  {label:28s} {ne:5d} {uni:11s} edges: {ms:7.3f} ms  {16*n/ms/1e6:7.0f} GB/s = {16*n/ms/1e6/peak:.2f} of measured HBM peak  ({n/ms*1e3:.3e} samples/s)")
+ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+for rep in range(3):
+    ev[0].record(); tot = obs.sum(); ev[1].record(); torch.cuda.synchronize()
+ms = ev[0].elapsed_time(ev[1]); print(f"yardstick: torch sum of the same array {ms:7.3f} ms  {8*n/ms/1e6:7.0f} GB/s = {8*n/ms/1e6/peak:.2f} of measured HBM peak")
 mm = D.empty((2,))
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
 for rep in range(3):
