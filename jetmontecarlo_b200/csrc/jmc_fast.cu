@@ -479,14 +479,13 @@ fast_body(const FastParams& P_in, uint64_t n, uint64_t seed, uint64_t first, con
     const int n_slots = nb << sh;
     acc_w_t* s_sum_w = (acc_w_t*)s_raw;                           // slot [bin][lane & (R-1)]
     acc_w2_t* s_sum_w2 = (acc_w2_t*)(s_sum_w + n_slots);
-    unsigned int* s_count = (unsigned int*)(s_sum_w2 + n_slots);  // nb bins + 32 dummy slots for dropped samples
-    float* s_edges = (float*)(s_count + nb + 32);
+    unsigned int* s_count = (unsigned int*)(s_sum_w2 + n_slots);  // the same slots + 32 dummy slots for dropped samples
+    float* s_edges = (float*)(s_count + n_slots + 32);
     const bool do_hist = HOT || g_edges != nullptr;
     const bool do_minmax = !HOT && d_minmax != nullptr;
     if (threadIdx.x == 0) s_poison = INT_MAX;
-    for (int k = threadIdx.x; k < n_slots; k += blockDim.x) { s_sum_w[k] = 0; s_sum_w2[k] = 0; }
-    for (int k = threadIdx.x; k < nb; k += blockDim.x) s_count[k] = 0u;
-    if (threadIdx.x < 32) s_count[nb + threadIdx.x] = 0u;
+    for (int k = threadIdx.x; k < n_slots; k += blockDim.x) { s_sum_w[k] = 0; s_sum_w2[k] = 0; s_count[k] = 0u; }
+    if (threadIdx.x < 32) s_count[n_slots + threadIdx.x] = 0u;
     for (int k = threadIdx.x; k < ne; k += blockDim.x) s_edges[k] = g_edges[k];
     __syncthreads();
     float mn = INFINITY, mx = -INFINITY;
@@ -521,7 +520,7 @@ fast_body(const FastParams& P_in, uint64_t n, uint64_t seed, uint64_t first, con
     //  4 / 5: mode 3 with FP32 slots for both sums / for sum w^2 only (summed in FP64 at the flush)
     auto accumulate = [&](float w, int bq) {
         if (bq >= 0 && fabsf(w) > 0.0f) {                // the common case first: one compare rejects 0 and NaN
-            if (LAZY) atomicAdd(&s_count[bq], 1u);
+            if (LAZY) atomicAdd(&s_count[(bq << sh) | (int)(lane & ((1u << sh) - 1u))], 1u);
 #if JMC_ACC_MODE == 2
             const unsigned mask = __activemask();
             const unsigned peers = __match_any_sync(mask, bq);
@@ -553,9 +552,9 @@ fast_body(const FastParams& P_in, uint64_t n, uint64_t seed, uint64_t first, con
 
     // Bin of an observable: `ok` = inside the binned range, `b` = its bin (meaningful only when ok).
     // HOT (np.logspace bins): the bin is the floor of an affine map of log2(obs), and the range test is made on the
-    // mapped value -- FFMA, one compare, F2I.  The host nudges the two constants of the map by single ulps
-    // (make_fast_params) until the first and the last edge themselves (the extreme samples, when the edges come from
-    // setBins) map inside [0, nb) whatever the rounding of the FMA.
+    // mapped value -- FFMA, one compare, F2I.  The host anchors the map at the first edge and lowers its slope by
+    // single ulps (make_fast_params) until the first and the last edge themselves (the extreme samples, when the edges
+    // come from setBins) map inside [0, nb) whatever the rounding of the FMA.
     auto locate = [&](float l2obs, bool& ok, int& b) {
         if (HOT) {
             const float f = fmaf(l2obs, P.inv_d, P.mb0_inv_d);
@@ -578,9 +577,11 @@ fast_body(const FastParams& P_in, uint64_t n, uint64_t seed, uint64_t first, con
         const float v = P.dom_log ? l2obs : ex2(l2obs);
         return v < P.e_first ? -1 : -2;
     };
-    const int dummy_slot = nb + (int)lane;
-    // Every sample: min/max and the count histogram.  Dropped samples count into a per-lane dummy slot behind the
-    // bins: no branch around the atomic, and no same-address serialisation among the lanes that miss.
+    const int dummy_slot = n_slots + (int)lane;
+    const int lane_copy = (int)(lane & ((1u << sh) - 1u));
+    // Every sample: min/max and the count histogram (native 32-bit shared atomics on the lane-interleaved copy of the
+    // bin: with 16-32 copies the lanes of a warp fall on distinct banks).  Dropped samples count into a per-lane
+    // dummy slot behind the bins: no branch around the atomic, no same-address serialisation among the lanes that miss.
     // `valid` is a compile-time true in the main loop and a run-time flag only in the ragged last trips.
     auto tally = [&](float l2obs, bool valid) {
         if (do_minmax && valid) {
@@ -591,7 +592,7 @@ fast_body(const FastParams& P_in, uint64_t n, uint64_t seed, uint64_t first, con
         bool ok;
         int b;
         locate(l2obs, ok, b);
-        atomicAdd(&s_count[(ok && valid) ? b : dummy_slot], 1u);
+        atomicAdd(&s_count[(ok && valid) ? ((b << sh) | lane_copy) : dummy_slot], 1u);
     };
     // a sample whose weight can be non-zero: everything from its words
     auto weigh_words = [&](const Words& w) {
@@ -698,16 +699,23 @@ fast_body(const FastParams& P_in, uint64_t n, uint64_t seed, uint64_t first, con
                 for (int k = 0; k < 2 * V; ++k) enqueue(sample_words<KIND>(pw[k >> 1], k & 1), act[k]);
             }
         } else {
+            // all arithmetic of the trip first (independent chains the scheduler can interleave), then its shared-
+            // memory atomics back to back: an atomic in the middle would order the samples' instruction streams
+            float o[2 * V], wt[2 * V];
 #pragma unroll
             for (int k = 0; k < 2 * V; ++k) {
                 Draw d;
-                float o;
-                const bool active = light<KIND, FIXED, OBS_MLL>(P, sample_words<KIND>(pw[k >> 1], k & 1), d, o);
-                tally(o, true);
+                const bool active = light<KIND, FIXED, OBS_MLL>(P, sample_words<KIND>(pw[k >> 1], k & 1), d, o[k]);
+                wt[k] = 0.0f;
                 if (do_hist) {
-                    if (active) accumulate(heavy<KIND, FIXED>(P, d), weight_bin(o));
-                    else if (!FIXED && !nan_to_num) accumulate(fnan(), weight_bin(o));
+                    if (active) wt[k] = heavy<KIND, FIXED>(P, d);
+                    else if (!FIXED && !nan_to_num) wt[k] = fnan();
                 }
+            }
+#pragma unroll
+            for (int k = 0; k < 2 * V; ++k) {
+                tally(o[k], true);
+                if (do_hist) accumulate(wt[k], weight_bin(o[k]));
             }
         }
     }
@@ -737,7 +745,8 @@ fast_body(const FastParams& P_in, uint64_t n, uint64_t seed, uint64_t first, con
     __syncthreads();
     if (do_hist) {
         for (int k = threadIdx.x; k < nb; k += blockDim.x) {
-            const unsigned int c = s_count[k];
+            unsigned int c = 0u;
+            for (int r = 0; r < (1 << sh); ++r) c += s_count[(k << sh) + r];
             if (c) {
                 atomicAdd(&g_count[k], (unsigned long long)c);
                 double sw = 0.0, sw2 = 0.0;
@@ -1004,31 +1013,17 @@ static int make_fast_params(const jmc_integrand* g, const double* h_edges, int n
         P.e_first = (*edges_f)[0];
         P.e_last = (*edges_f)[n_edges - 1];
         P.nb_f = (float)(n_edges - 1);
-        // The affine bin map f(x) = fmaf(x, inv_d, mb0_inv_d), nudged until the FP32 images of the first and the last
-        // edge fall inside [0, nb): an observable equal to an end edge (the extreme sample, when the edges come from
-        // setBins) is then binned, as np.histogram's closed last bin does, whatever the rounding of the FMA.  The
-        // nudges are single ulps of the two constants (the distortion stays at the level FP32 places log2(obs) anyway);
-        // should they not converge, the map is shrunk about its ends by a growing margin instead.
+        // The affine bin map f(x) = fmaf(x, inv_d, mb0_inv_d), anchored at the first edge: mb0_inv_d is the smallest
+        // float that maps the FP32 first edge to f >= 0, and the slope inv_d is lowered ulp by ulp (each costs < 1e-5
+        // of a bin at the far end) until the FP32 last edge maps below nb.  An observable equal to an end edge (the
+        // extreme sample, when the edges come from setBins) is then binned, as np.histogram's closed last bin does,
+        // whatever the rounding of the FMA.
         P.inv_d = (float)(1.0 / d);
-        P.mb0_inv_d = (float)(-dom[0] / d);
-        bool ok = false;
-        for (int it = 0; it < 512 && !ok; ++it) {
-            const float f_lo = std::fmaf(P.e_first, P.inv_d, P.mb0_inv_d), f_hi = std::fmaf(P.e_last, P.inv_d, P.mb0_inv_d);
-            ok = f_lo >= 0.0f && f_hi < P.nb_f;
-            if (ok) break;
-            if (f_hi >= P.nb_f) {
-                if (P.e_last > 0.0f) P.inv_d = std::nextafterf(P.inv_d, 0.0f);
-                else if (P.e_last < 0.0f) P.inv_d = std::nextafterf(P.inv_d, INFINITY);
-                else P.mb0_inv_d = std::nextafterf(P.mb0_inv_d, -INFINITY);
-            }
-            if (std::fmaf(P.e_first, P.inv_d, P.mb0_inv_d) < 0.0f) P.mb0_inv_d = std::nextafterf(P.mb0_inv_d, INFINITY);
-        }
-        const double nbd = (double)(n_edges - 1);
-        for (double m = std::ldexp(1.0, -14); !ok && m < 0.01; m *= 2.0) {
-            const double scale = (nbd - 2.0 * m) / nbd;
-            P.inv_d = (float)(scale / d);
-            P.mb0_inv_d = (float)(m - dom[0] * scale / d);
-            ok = std::fmaf(P.e_first, P.inv_d, P.mb0_inv_d) >= 0.0f && std::fmaf(P.e_last, P.inv_d, P.mb0_inv_d) < P.nb_f;
+        for (int it = 0; it < 4096; ++it) {
+            P.mb0_inv_d = (float)(-(double)P.e_first * (double)P.inv_d);
+            while (std::fmaf(P.e_first, P.inv_d, P.mb0_inv_d) < 0.0f) P.mb0_inv_d = std::nextafterf(P.mb0_inv_d, INFINITY);
+            if (std::fmaf(P.e_last, P.inv_d, P.mb0_inv_d) < P.nb_f) break;
+            P.inv_d = std::nextafterf(P.inv_d, 0.0f);
         }
         for (int k = 1; k < n_edges; ++k)
             if (!((*edges_f)[k] > (*edges_f)[k - 1]))
@@ -1043,7 +1038,7 @@ static size_t fast_smem_bytes(int n_edges, int threads = kFastThreads, int shift
     const size_t nb = n_edges > 0 ? (size_t)n_edges - 1 : 0;
     const size_t ne_pad = ((size_t)(n_edges > 0 ? n_edges : 0) + 3) & ~(size_t)3;
     const size_t acc = (sizeof(acc_w_t) + sizeof(acc_w2_t)) * (nb << shift);
-    return acc + sizeof(unsigned int) * (nb + 32) + sizeof(float) * ne_pad
+    return acc + sizeof(unsigned int) * ((nb << shift) + 32) + sizeof(float) * ne_pad
            + sizeof(float) * (threads / 32) * kQueueFields * kQueueSlots;
 }
 // lane-interleaved accumulator copies: as many (up to one per lane) as keep the block under `budget` bytes

@@ -1006,3 +1006,124 @@ def samples_from_cdf_tabulated(cdf, num_samples, domain, rand, catch_turnpoint=F
         samples = inverse_transform(cdf_vals[:-1][monotone], pnts[:-1][monotone], rand(num_samples))
         return samples, np.ones_like(samples)
     raise ValueError("cdf is not monotone on %s and neither catch_turnpoint nor force_monotone applies" % (list(domain),))
+
+
+# ---------------------------------------------------------------------------
+# Generic MonteCarloProcess (hit-or-miss box sampling) and the e+e- -> hadrons (LO) client with its EWOCs
+# ---------------------------------------------------------------------------
+def alpha_em_one_loop(mu):
+    """ref: analytics/qcd_utils.py:108-112"""
+    alpha_em_zmass = 1. / 127
+    beta0_em = 1. / (3 * np.pi)
+    return alpha_em_zmass / (1 + 2 * alpha_em_zmass * beta0_em * np.log(mu / M_Z))
+
+
+def sum_square_quark_charges(energy):
+    """ref: analytics/qcd_utils.py:72-96 (u, d above 0.01 GeV; s above 0.05; c above 2.5; b above 10; no top)"""
+    total = 0
+    if energy > 0.01:
+        total += (1 / 3) ** 2
+        total += (2 / 3) ** 2
+    if energy > 0.05:
+        total += (-1 / 3) ** 2
+    if energy > 2.5:
+        total += (2 / 3) ** 2
+    if energy > 10.0:
+        total += (-1 / 3) ** 2
+    return total
+
+
+def ee2hadrons_lo_prefactor(energy):
+    """ref: analytics/ewocs/eec.py:9-19"""
+    return 8 * energy ** 2. * alpha_one_loop(energy) * alpha_em_one_loop(energy) ** 2. * sum_square_quark_charges(energy)
+
+
+def ee2h_in_phasespace(a, b):
+    """0 < x_i < 1 for x_1 = 1 - a, x_2 = 1 - b, x_3 = 2 - x_1 - x_2.
+    ref: examples/processes/ee2hadrons_LO.py:17-21"""
+    x_1, x_2 = 1 - a, 1 - b
+    x_3 = 2 - x_1 - x_2
+    return (0 < x_1) & (x_1 < 1) & (0 < x_2) & (x_2 < 1) & (0 < x_3) & (x_3 < 1)
+
+
+def ee2h_differential_xsec(a, b, prefactor):
+    """The reference's expression VERBATIM: its second variable is the kinematic variable 1 - x_2 itself (the
+    "1 -" is missing at examples/processes/ee2hadrons_LO.py:28), a deterministic quirk that is reproduced."""
+    x_1, x_2 = 1 - a, b
+    return prefactor * (x_1 ** 2. + x_2 ** 2.) / ((1. - x_1) * (1. - x_2))
+
+
+def process_hit_or_miss(uniforms, num_samples, method, epsilon, bounds, in_phasespace, xsec):
+    """MonteCarloProcess.addSample in a loop: draw every kinematic variable in its box, keep the point if it lies
+    in the phase space (weight = jacobian * differential cross section), else count a rejection and try again.
+    ``uniforms``: the sequence random.random() would produce.  Returns samples [N, d], weights [N], rejected.
+    ref: montecarlo/process.py:117-143"""
+    samples, weights, rejected, k = [], [], 0, 0
+    log_eps = np.log(epsilon) if method == 'log' else None
+    while len(samples) < num_samples:
+        point, jac = [], 1.
+        for lo, hi in bounds:
+            u = uniforms[k]
+            k += 1
+            if method == 'lin':
+                point.append(lo + u * (hi - lo))
+            else:
+                point.append(lo + np.exp(log_eps * u + np.log(hi - lo)))
+                jac *= point[-1]
+        if in_phasespace(*point):
+            samples.append(point)
+            weights.append(jac * xsec(*point))
+        else:
+            rejected += 1
+    return np.array(samples), np.array(weights), rejected
+
+
+def process_area(bounds, num_samples, rejected):
+    """ref: montecarlo/process.py:154-175"""
+    max_area = 1.
+    for lo, hi in bounds:
+        max_area *= hi - lo
+    return max_area * (num_samples / (num_samples + rejected))
+
+
+def ee2h_pair_observable(samples, which, kappa=None):
+    """The pairwise observable of the three parton pairs (1,2), (2,3), (3,1), concatenated pair by pair as
+    ee2hLO_PairwiseObservable.update does.  ref: examples/processes/ee2hadrons_LO.py:75-150"""
+    x_1, x_2 = 1 - samples[:, 0], 1 - samples[:, 1]
+    x_3 = 2 - x_1 - x_2
+    out = []
+    with np.errstate(all='ignore'):
+        for x_i, x_j in ((x_1, x_2), (x_2, x_3), (x_3, x_1)):
+            cos = 2. / (x_i * x_j) - 2. / x_i - 2. / x_j + 1
+            if which == 'costheta':
+                out.append(cos)
+            elif which == 'theta':
+                out.append(np.arccos(cos))
+            elif which == 'm2':
+                out.append(-(1 - x_i - x_j))
+            elif which == 'gecf':
+                out.append(2 ** (kappa / 2 - 2) * x_i * x_j * (1 - cos) ** (kappa / 2))
+            elif which == 'z_i':
+                out.append(x_i / 2)
+            elif which == 'z_j':
+                out.append(x_j / 2)
+            else:
+                raise ValueError(which)
+    return np.concatenate(out)
+
+
+def ewoc_weights(z1, z2, weights, energy_weights=(1, 1)):
+    """ref: montecarlo/ewoc.py:23-27"""
+    w1, w2 = energy_weights
+    return z1 ** w1 * z2 ** w2 * weights
+
+
+def ewoc_bins(observables, numbins, binspacing, minval=None, maxval=None):
+    """generate_ewoc's bins: integrator.setBins on the observables with the optional end points joined.
+    ref: montecarlo/ewoc.py:41-50"""
+    obs = np.asarray(observables)
+    if minval is not None:
+        obs = np.concatenate([[minval], obs])
+    if maxval is not None:
+        obs = np.concatenate([obs, [maxval]])
+    return make_edges(numbins, obs, binspacing)

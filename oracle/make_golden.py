@@ -712,3 +712,64 @@ def closed_forms_fc():
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "closedfc":
     closed_forms_fc()
+
+
+def process_ewoc():
+    """The generic MonteCarloProcess (hit-or-miss box sampling with an efficiency-scaled area, montecarlo/process.py:
+    109-191) through its one client, e+e- -> hadrons at LO (examples/processes/ee2hadrons_LO.py), the pairwise
+    observables and the energy-weighted correlator built on it (montecarlo/ewoc.py:11-75;
+    examples/ewocs/ee2hadrons_LO/eec.py, mass-squared_ewoc.py)."""
+    import types
+    if "matplotlib" not in sys.modules:                  # ewoc.py imports pyplot for plot_ewoc only
+        mpl, plt = types.ModuleType("matplotlib"), types.ModuleType("matplotlib.pyplot")
+        mpl.pyplot = plt
+        sys.modules["matplotlib"], sys.modules["matplotlib.pyplot"] = mpl, plt
+    from jetmontecarlo.montecarlo.ewoc import Npoint_MonteCarloEWOC
+    from jetmontecarlo.analytics.ewocs.eec import ee2hadrons_LO_prefactor
+    from examples.processes import ee2hadrons_LO as E
+    for case, method in enumerate(('log', 'lin')):
+        out = {}
+        random.seed(SEED + 900 + case)
+        # the uniforms the sampling loop will consume (2 per trial), for the oracle's replay
+        state = random.getstate()
+        n = 3000
+        process = E.ee2hadrons_LO(energy=1000., num_samples=n, sampleMethod=method)
+        n_trials = n + process.num_rejected_samples
+        random.setstate(state)
+        out['uniforms'] = np.array([random.random() for _ in range(2 * n_trials)])
+        out['samples'] = np.array(process.samples)
+        out['jacobians'] = np.array(process.jacobians)
+        out['num_rejected'] = np.array(process.num_rejected_samples)
+        out['area'] = np.array(process.area)
+        out['prefactor'] = np.array(ee2hadrons_LO_prefactor(1000.))
+        named = process.named_samples()
+        out['x_1'], out['x_2'], out['x_3'] = (np.array(named[k]) for k in ('x_1', 'x_2', 'x_3'))
+        for name, fn in (('costheta', E.costheta_ij), ('m2', E.m2_ij), ('theta', E.theta_ij), ('z_i', E.z_i), ('z_j', E.z_j)):
+            ob = E.ee2hLO_PairwiseObservable(process, fn, name)
+            out[f'obs:{name}'] = np.array(ob.observables)
+            out[f'obs:{name}:weights'] = np.array(ob.weights)
+        out['obs:gecf1.5'] = np.array(E.ee2hLO_PairwiseObservable(process, lambda a, b: E.gecf_ij(a, b, 1.5), 'g').observables)
+        zi = E.ee2hLO_PairwiseObservable(process, E.z_i, 'z_i')
+        zj = E.ee2hLO_PairwiseObservable(process, E.z_j, 'z_j')
+        for name, fn, spacing, ew in (('costheta', E.costheta_ij, 'lin', (1, 1)), ('m2', E.m2_ij, 'lin', (1, 1)),
+                                      ('m2', E.m2_ij, 'log', (2, 1)), ('theta', E.theta_ij, 'log', (1, 1))):
+            ob = E.ee2hLO_PairwiseObservable(process, fn, name)
+            ewoc = Npoint_MonteCarloEWOC(process, ob, energy_weights=ew)
+            ewoc.set_weights(zi, zj)
+            ewoc.generate_ewoc(numbins=40, binspacing=spacing)
+            tag = f'ewoc:{name}:{spacing}:{ew[0]}{ew[1]}'
+            out[tag + ':weights'] = np.array(ewoc.weights)
+            out[tag + ':bins'] = np.array(ewoc.bins)
+            out[tag + ':density'] = np.array(ewoc.density)
+            out[tag + ':density_err'] = np.array(ewoc.densityErr)
+        # explicit range end points
+        ob = E.ee2hLO_PairwiseObservable(process, E.costheta_ij, 'c')
+        ewoc = Npoint_MonteCarloEWOC(process, ob)
+        ewoc.set_weights(zi, zj)
+        ewoc.generate_ewoc(numbins=25, binspacing='lin', minval=-1., maxval=1.)
+        out['ewoc:range:bins'], out['ewoc:range:density'] = np.array(ewoc.bins), np.array(ewoc.density)
+        save(f"process_ee2h_{method}", **out)
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "process":
+    process_ewoc()

@@ -159,17 +159,18 @@ def test_fast_histogram_equals_histogram_of_its_dump(cuda, kind, jet, fc, acc):
     l2 = np.log2(obs).astype(np.float32)
     dom = np.log2(edges)
     d = (dom[-1] - dom[0]) / (len(edges) - 1)
-    inv_d, mb0 = np.float32(1. / d), np.float32(-dom[0] / d)
-    # (the host nudges the two constants by single ulps until both end edges map inside [0, nb), make_fast_params)
-    f32 = lambda x: np.float32(np.float64(np.float32(x)) * np.float64(inv_d) + np.float64(mb0))
+    # the host anchors the map at the FP32 first edge and lowers the slope ulp by ulp until the FP32 last edge maps
+    # below the number of bins (make_fast_params)
     nb_f, e_lo, e_hi = np.float32(len(edges) - 1), np.float32(dom[0]), np.float32(dom[-1])
-    for _ in range(512):
-        if f32(e_lo) >= 0 and f32(e_hi) < nb_f:
-            break
-        if f32(e_hi) >= nb_f:
-            inv_d = np.nextafter(inv_d, np.float32(0 if e_hi > 0 else np.inf))
-        if f32(e_lo) < 0:
+    fmaf = lambda x, a, c: np.float32(np.float64(x) * np.float64(a) + np.float64(c))
+    inv_d = np.float32(1. / d)
+    for _ in range(4096):
+        mb0 = np.float32(-np.float64(e_lo) * np.float64(inv_d))
+        while fmaf(e_lo, inv_d, mb0) < 0:
             mb0 = np.nextafter(mb0, np.float32(np.inf))
+        if fmaf(e_hi, inv_d, mb0) < nb_f:
+            break
+        inv_d = np.nextafter(inv_d, np.float32(0))
     fma = (l2.astype(np.float64) * np.float64(inv_d) + np.float64(mb0)).astype(np.float32)
     keep = (fma >= 0) & (fma < len(edges) - 1)
     idx = np.floor(np.where(keep, fma, 0)).astype(np.int64)

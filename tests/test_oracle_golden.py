@@ -492,3 +492,44 @@ def test_samples_from_cdf_tabulated_branches(golden):
         cdf, domain, _ = _cdf_cases()[name]
         with pytest.raises(ValueError):
             O.samples_from_cdf_tabulated(cdf, 10, domain, np.random.RandomState(0).rand)
+
+
+@pytest.mark.parametrize("method", ['log', 'lin'])
+def test_process_and_ewoc_replay(golden, method):
+    """MonteCarloProcess (hit-or-miss box sampling, efficiency-scaled area), the e+e- -> hadrons LO client, its
+    pairwise observables and the EWOC built on them: the oracle on the reference's own uniform sequence, bit for bit.
+    ref: montecarlo/process.py:109-191, montecarlo/ewoc.py:11-75, examples/processes/ee2hadrons_LO.py"""
+    g = golden(f"process_ee2h_{method}")
+    pre = O.ee2hadrons_lo_prefactor(1000.)
+    assert pre == float(g['prefactor'])
+    bounds = [(0, 1), (0, 1)]
+    samples, weights, rejected = O.process_hit_or_miss(
+        g['uniforms'], 3000, method, 1e-8, bounds, O.ee2h_in_phasespace,
+        lambda a, b: O.ee2h_differential_xsec(a, b, pre))
+    assert_array_equal(samples, g['samples'])
+    assert_array_equal(weights, g['jacobians'])
+    assert rejected == int(g['num_rejected']) and 2 * (3000 + rejected) == len(g['uniforms'])
+    assert O.process_area(bounds, 3000, rejected) == float(g['area'])
+    for name in ('costheta', 'm2', 'theta', 'z_i', 'z_j'):
+        assert_array_equal(O.ee2h_pair_observable(samples, name), g[f'obs:{name}'], err_msg=name)
+        assert_array_equal(np.tile(weights, 3), g[f'obs:{name}:weights'])
+    assert_array_equal(O.ee2h_pair_observable(samples, 'gecf', kappa=1.5), g['obs:gecf1.5'])
+    zi, zj = O.ee2h_pair_observable(samples, 'z_i'), O.ee2h_pair_observable(samples, 'z_j')
+    area = float(g['area'])
+    for name, spacing, ew in (('costheta', 'lin', (1, 1)), ('m2', 'lin', (1, 1)), ('m2', 'log', (2, 1)),
+                              ('theta', 'log', (1, 1))):
+        tag = f'ewoc:{name}:{spacing}:{ew[0]}{ew[1]}'
+        obs = O.ee2h_pair_observable(samples, name)
+        w = O.ewoc_weights(zi, zj, np.tile(weights, 3), ew)
+        assert_array_equal(w, g[tag + ':weights'])
+        edges = O.ewoc_bins(obs, 40, spacing)
+        assert_array_equal(edges, g[tag + ':bins'])
+        h, h2, c = O.histograms(obs, w, edges)
+        dens, err = O.density_from_hist(h, h2, c, edges, area, len(obs))
+        assert_array_equal(dens, g[tag + ':density'])
+        assert_array_equal(err, g[tag + ':density_err'])
+    obs = O.ee2h_pair_observable(samples, 'costheta')
+    edges = O.ewoc_bins(obs, 25, 'lin', minval=-1., maxval=1.)
+    assert_array_equal(edges, g['ewoc:range:bins'])
+    h, h2, c = O.histograms(obs, O.ewoc_weights(zi, zj, np.tile(weights, 3)), edges)
+    assert_array_equal(O.density_from_hist(h, h2, c, edges, area, len(obs))[0], g['ewoc:range:density'])
