@@ -1126,4 +1126,4 @@ def ewoc_bins(observables, numbins, binspacing, minval=None, maxval=None):
         obs = np.concatenate([[minval], obs])
     if maxval is not None:
         obs = np.concatenate([obs, [maxval]])
-    return make_edges(numbins, obs, binspacing)
+    return make_edges(numbins, obs, binspacing)[0]
