@@ -42,5 +42,16 @@ for name, ig, bc in (("C1 radiator fc (nan_to_num off: poison pass)", Integrand.
         for k in range(200):
             _lib.check(L.jmc_handle_run(h.ptr, C.byref(s), n, 1, k * n, _lib.F32, P(e1), nb + 1, D.ptr(sw), D.ptr(sw2), D.ptr(cnt), None, st))
         ev1.record(); torch.cuda.synchronize()
+        # device time of ONE run (events enqueued right around it; the stream is idle before)
+        dts = []
+        for k in range(30):
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            _lib.check(L.jmc_handle_run(h.ptr, C.byref(s), n, 1, k * n, _lib.F32, P(e1), nb + 1, D.ptr(sw), D.ptr(sw2), D.ptr(cnt), None, st))
+            b.record(); torch.cuda.synchronize()
+            dts.append(a.elapsed_time(b) * 1e3)
+        dts.sort()
+        print(f"    device time of one run (event to event, median of 30): {dts[15]:.1f} us  (spread shift env: {os.environ.get('JMC_FAST_SPREAD_SHIFT', 'default')})")
         print(f"{name:45s} n={n:.0e}: jmc_integrate_host {whole:7.1f} us | run+sync {t_run:6.1f}  finalize+sync {t_fin:6.1f}  "
               f"torch memset+sync {t_ms:6.1f}  bare sync {t_sync:5.1f} | run back-to-back (GPU time per job) {ev0.elapsed_time(ev1) * 5:6.1f} us")
