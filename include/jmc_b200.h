@@ -100,7 +100,8 @@ enum {
     JMC_FN_ALPHA_SPLITTING = 20, /* a0=z a1=theta: alpha * splittingFn(z)   numerics/splitting.py:34-39,52-58 */
     JMC_FN_MUL = 21,             /* a0 * a1 (weights * jacobians, e.g. montecarlo/integrator.py:447)        */
     JMC_FN_MASK_FINITE = 22,     /* a0=w a1=v: w if both finite else 0 (make_finite of utils/hist_utils.py:103-108) */
-    JMC_FN_COUNT = 23
+    JMC_FN_EWOC_WEIGHT = 23,     /* a0=z1 a1=z2 a2=w, s3=w1, beta=w2: z1**w1 * z2**w2 * w   montecarlo/ewoc.py:23-27 */
+    JMC_FN_COUNT = 24
 };
 
 typedef struct jmc_fn_params {
@@ -352,6 +353,42 @@ int jmc_integrate_host(const jmc_integrand* g, uint64_t n, uint64_t seed, uint64
                        double* h_density, double* h_density_err,
                        double* h_integral, double* h_integral_err,
                        double* h_sum_w, double* h_sum_w2, uint64_t* h_count);
+
+/* ---- generic Monte Carlo process + pairwise observables + energy-weighted correlators -------------------------
+ * MonteCarloProcess (montecarlo/process.py:109-191): hit-or-miss sampling of a box of kinematic variables under a
+ * phase-space constraint, weight = jacobian x differential cross section, area = box volume x acceptance.  The
+ * constraint and the cross section are code, so a process is one of the kinds implemented on the device; the
+ * reference has exactly one, e+ e- -> hadrons at LO (examples/processes/ee2hadrons_LO.py: variables 1 - x_1, 1 - x_2
+ * in (0,1)^2, 0 < x_i < 1). */
+enum { JMC_PROCESS_EE2HADRONS_LO = 0 };
+/* pairwise observables of two partons with energy fractions (x_i, x_j), examples/processes/ee2hadrons_LO.py:95-150 */
+enum { JMC_PAIR_COSTHETA = 0, JMC_PAIR_THETA = 1, JMC_PAIR_M2 = 2, JMC_PAIR_GECF = 3, JMC_PAIR_Z_I = 4, JMC_PAIR_Z_J = 5 };
+
+typedef struct jmc_process {
+    int32_t kind;            /* JMC_PROCESS_*                                   */
+    int32_t method;          /* JMC_LIN / JMC_LOG                               */
+    double  epsilon;         /* log-sampling cutoff                             */
+    double  lo[4], hi[4];    /* kinematic_bounds (the first two are used)       */
+    double  energy;          /* GeV                                             */
+    double  prefactor;       /* of the differential cross section (analytics/ewocs/eec.py:9-19), from the host */
+} jmc_process;
+
+/* generateSamples: sample i is the first accepted trial of Philox stream first_index + i (trial t = block t).
+ * d_samples [n,2] and d_weights [n] (= jacobian * differential cross section) may be NULL; *d_rejected (device
+ * scalar) is incremented by the number of rejected trials (num_rejected_samples, process.py:142).  Synchronises
+ * (a process whose box holds no accepted point is reported as JMC_EDOMAIN). */
+int jmc_process_sample(const jmc_process* p, uint64_t n, uint64_t seed, uint64_t first_index,
+                       double* d_samples, double* d_weights, uint64_t* d_rejected, void* stream);
+/* ee2hLO_PairwiseObservable.update: d_obs [3n], pair-major ((1,2) of all events, then (2,3), then (3,1)). */
+int jmc_process_pairs(const jmc_process* p, const double* d_samples, uint64_t n, int obs_id, double kappa,
+                      double* d_obs, void* stream);
+/* Fused Npoint_MonteCarloEWOC (montecarlo/ewoc.py:11-75): generate -> three pairs per event -> observable obs_id,
+ * weight z_i^w1 z_j^w2 * event weight -> histograms over d_edges (accumulated; 3n entries), and / or min, max of the
+ * observable in d_minmax (caller initialises to +inf, -inf; d_edges may then be NULL).  Nothing per event is stored. */
+int jmc_process_ewoc(const jmc_process* p, uint64_t n, uint64_t seed, uint64_t first_index, int obs_id, double kappa,
+                     double w1, double w2, const double* d_edges, int n_edges,
+                     double* d_sum_w, double* d_sum_w2, uint64_t* d_count, double* d_minmax,
+                     uint64_t* d_rejected, void* stream);
 
 /* ---- handle: cached job description, device workspace and pinned staging ----
  * The reference has no such object (it has no FFI); it exists so that a job issued from a host thread costs its

@@ -23,7 +23,8 @@ SAMPLER_SIMPLE, SAMPLER_CRITICAL, SAMPLER_PRECRITICAL, SAMPLER_UNGROOMED = 0, 1,
 (FN_ALPHA_S, FN_SPLITTING, FN_RADIATOR_WEIGHT, FN_CRIT_PDF_FC, FN_CRIT_RAD_FC, FN_SUB_RAD_FC,
  FN_SUB_RADPRIME_FC, FN_SUB_PDF_FC, FN_PRE_RAD_FC, FN_CRIT_RAD_RC, FN_CRIT_RADPRIME_RC,
  FN_CRIT_PDF_RC, FN_SUB_RAD_RC, FN_SUB_RADPRIME_RC, FN_SUB_PDF_RC, FN_PRE_WEIGHT, FN_C_GROOMED,
- FN_C_UNGROOMED, FN_TWO_EMISSION, FN_PRE_WEIGHT_ZEROBIN, FN_ALPHA_SPLITTING, FN_MUL, FN_MASK_FINITE) = range(23)
+ FN_C_UNGROOMED, FN_TWO_EMISSION, FN_PRE_WEIGHT_ZEROBIN, FN_ALPHA_SPLITTING, FN_MUL, FN_MASK_FINITE,
+ FN_EWOC_WEIGHT) = range(24)
 KIND_RADIATOR, KIND_CRIT, KIND_CRIT_SUB, KIND_PRE_CRIT_SUB, KIND_SIMPLE, KIND_SHOWER = range(6)
 
 METHODS = {'lin': LIN, 'log': LOG}
@@ -36,7 +37,7 @@ EXPORTS = (
     "jmc_eval_fn", "jmc_eval_integrand", "jmc_bin_index", "jmc_hist", "jmc_hist2d", "jmc_finalize2d", "jmc_minmax", "jmc_run", "jmc_run_batch", "jmc_finalize_batch", "jmc_dump", "jmc_shower_dump", "jmc_shower_chains",
     "jmc_finalize", "jmc_cumulative", "jmc_set_density_host", "jmc_integrate_host", "jmc_sample_host",
     "jmc_eval_fn_host", "jmc_launch_count", "jmc_create", "jmc_destroy", "jmc_handle_run", "jmc_handle_integrate_host",
-    "jmc_chain_ecf",
+    "jmc_chain_ecf", "jmc_process_sample", "jmc_process_pairs", "jmc_process_ewoc",
 )
 
 
@@ -63,6 +64,15 @@ class Integrand(C.Structure):
                 ("theta_scale", C.c_double), ("lo", C.c_double), ("hi", C.c_double),
                 ("beta_sd", C.c_double), ("shower_cutoff", C.c_double),
                 ("shower_rss_flags", C.c_int32), ("reserved", C.c_int32)]
+
+
+class Process(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("method", C.c_int32), ("epsilon", C.c_double),
+                ("lo", C.c_double * 4), ("hi", C.c_double * 4), ("energy", C.c_double), ("prefactor", C.c_double)]
+
+
+PROCESS_EE2HADRONS_LO = 0
+PAIR_COSTHETA, PAIR_THETA, PAIR_M2, PAIR_GECF, PAIR_Z_I, PAIR_Z_J = range(6)
 
 
 class JmcError(RuntimeError):
@@ -111,6 +121,9 @@ def _load():
         "jmc_eval_fn_host": (i32, [i32, P(FnParams), u64, vp, i64, vp, i64, vp, i64, vp, i64, vp]),
         "jmc_launch_count": (u64, []),
         "jmc_chain_ecf": (i32, [P(Integrand), vp, vp, u64, i32, vp, vp]),
+        "jmc_process_sample": (i32, [P(Process), u64, u64, u64, vp, vp, vp, vp]),
+        "jmc_process_pairs": (i32, [P(Process), vp, u64, i32, dbl, vp, vp]),
+        "jmc_process_ewoc": (i32, [P(Process), u64, u64, u64, i32, dbl, dbl, dbl, vp, i32, vp, vp, vp, vp, vp, vp]),
         "jmc_create": (i32, [P(vp)]),
         "jmc_destroy": (i32, [vp]),
         "jmc_handle_run": (i32, [vp, P(Integrand), u64, u64, u64, i32, vp, i32, vp, vp, vp, vp, vp]),

@@ -52,6 +52,24 @@ def alpha1loop(mu):
     return alpha_s_zmass / (1 + 2 * alpha_s_zmass * beta_0 * np.log(mu / M_Z))
 
 
+def alpha_em_1loop(mu):
+    """One-loop electromagnetic coupling at mu [GeV].  ref: analytics/qcd_utils.py:108-112"""
+    alpha_em_zmass = 1. / 127
+    beta0_em = 1. / (3 * np.pi)
+    return alpha_em_zmass / (1 + 2 * alpha_em_zmass * beta0_em * np.log(mu / M_Z))
+
+
+def sum_square_quark_charges(energy):
+    """Sum of the squared charges of the quarks that can be produced at ``energy`` [GeV], in units of e (u, d above
+    10 MeV; s above 50 MeV; c above 2.5 GeV; b above 10 GeV; no top).  ref: analytics/qcd_utils.py:72-96"""
+    thresholds = ((0.01, 1 / 3), (0.01, 2 / 3), (0.05, -1 / 3), (2.5, 2 / 3), (10.0, -1 / 3))
+    square_charges = 0
+    for threshold, charge in thresholds:
+        if energy > threshold:
+            square_charges += charge ** 2
+    return square_charges
+
+
 R0 = 1.
 alpha_fixed = alpha1loop(P_T * R0)      # ref: qcd_utils.py:196
 MU_NP = 1. / (P_T * R0)

@@ -6,6 +6,7 @@ Each translation unit has its own floating-point contract:
   jmc_exact.cu   --fmad=false   FP64 in NumPy operation order (replay parity, bit-exact bins)
   jmc_fast.cu    FMA + fast intrinsics: the FP32 log-space throughput path
   jmc_shower.cu  --fmad=false   veto-algorithm shower (FP64 chain, checkable against the oracle)
+  jmc_process.cu --fmad=false   hit-or-miss process sampling, pairwise observables, EWOC histograms
   jmc_host.cu    host plumbing and the host-buffer entry points
 The objects are linked into jetmontecarlo_b200/lib/libjmc_b200.so, which
 travels to the GPU box with the repository snapshot (it is git-ignored).
@@ -33,6 +34,7 @@ _DEFS = ["-D%s=%s" % (k, os.environ[k]) for k in SWITCHES if os.environ.get(k)]
 UNITS = {
     "jmc_exact.cu": ["--fmad=false"] + _DEFS,
     "jmc_shower.cu": ["--fmad=false"] + _DEFS,
+    "jmc_process.cu": ["--fmad=false"] + _DEFS,
     "jmc_fast.cu": ["--fmad=true"] + _DEFS,
     "jmc_host.cu": [],
 }

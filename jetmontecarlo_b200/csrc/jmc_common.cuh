@@ -69,6 +69,10 @@ void fast_plan_free(FastPlan* p);
 const float* fast_plan_edges(const FastPlan* p);                                                   // n_edges floats (host)
 int fast_plan_run(const FastPlan* plan, const float* d_edges_f, int* d_poison, uint64_t n, uint64_t seed,
                   uint64_t first_index, double* d_sum_w, double* d_sum_w2, uint64_t* d_count, double* d_minmax,
-                  void* stream);
+                  void* stream, bool defer_poison = false);
+// jmc_finalize that also applies (and re-arms) the NaN flag a fused run left in *d_poison (jmc_exact.cu)
+int finalize_poisoned(double* d_sum_w, double* d_sum_w2, const uint64_t* d_count, const double* d_edges, int n_edges,
+                      double area, uint64_t n_total, int bc_kind, double bc_value, double* d_density,
+                      double* d_density_err, double* d_integral, double* d_integral_err, int* d_poison, void* stream);
 
 }  // namespace jmc

@@ -67,6 +67,10 @@ __device__ __forceinline__ double eval_one(const jmc_fn_params& p, double x0, do
             return (p.fixed_coupling ? JMC_ALPHA_FIXED : alpha_running(x0, x1)) * splitting(x0, p.jet, p.acc);
         case JMC_FN_MUL: return x0 * x1;
         case JMC_FN_MASK_FINITE: return (isfinite(x0) && isfinite(x1)) ? x0 : 0.0;
+        case JMC_FN_EWOC_WEIGHT: {       // NumPy order: (z1**w1 * z2**w2) * w; small integer powers as np.power forms them
+            auto pw = [](double x, double e) { return e == 1.0 ? x : (e == 2.0 ? x * x : (e == 0.0 ? 1.0 : pow(x, e))); };
+            return pw(x0, x3) * pw(x1, p.beta) * x2;
+        }
         default: return qnan();
     }
 }
@@ -76,7 +80,7 @@ struct FnArity {
     static constexpr int value =
         (FN == JMC_FN_SPLITTING || FN == JMC_FN_CRIT_RAD_FC || FN == JMC_FN_CRIT_RAD_RC || FN == JMC_FN_CRIT_RADPRIME_RC) ? 1
         : (FN == JMC_FN_PRE_RAD_FC) ? 3
-        : (FN == JMC_FN_C_GROOMED || FN == JMC_FN_TWO_EMISSION) ? 4 : 2;
+        : (FN == JMC_FN_C_GROOMED || FN == JMC_FN_TWO_EMISSION || FN == JMC_FN_EWOC_WEIGHT) ? 4 : 2;
 };
 
 template <int FN>
@@ -491,18 +495,6 @@ extern "C" int jmc_bin_index(const double* d_obs, uint64_t n, const double* d_ed
     return JMC_OK;
 }
 
-static int check_hist_args(const char* who, const double* d_edges, int n_edges, size_t* smem) {
-    JMC_REQUIRE(n_edges >= 2, "%s: need at least 2 edges", who);
-    JMC_REQUIRE(d_edges != nullptr, "%s: edges is NULL", who);
-    DeviceInfo di;
-    if (device_info(&di)) return JMC_ENODEV;
-    *smem = hist_smem_bytes(n_edges);
-    if (*smem > (size_t)di.max_smem_optin)
-        return set_error(JMC_ELIMIT, "%s: %d edges need %zu B of shared memory (limit %d B, about 8100 edges)", who,
-                         n_edges, *smem, di.max_smem_optin);
-    return JMC_OK;
-}
-
 extern "C" int jmc_hist(const double* d_obs, const double* d_weights, uint64_t n, const double* d_edges, int n_edges,
                         double* d_sum_w, double* d_sum_w2, uint64_t* d_count, void* stream) {
     size_t smem;
@@ -523,7 +515,7 @@ extern "C" int jmc_hist(const double* d_obs, const double* d_weights, uint64_t n
     if (device_info(&di)) return JMC_ENODEV;
     // (measured, 99 log bins, every weight non-zero: 16 copies 3.6 TB/s, 32 copies 3.1 TB/s -- the 50 KB per block of
     // the latter halve the resident threads and with them the loads in flight -- 8 copies 2.9, 4 copies 2.5, 1 copy 2.0)
-    const int shift = hist_spread_shift(n_edges, threads == 1024 ? (size_t)di.max_smem_optin - 1024 : 28 * 1024);
+    const int shift = hist_spread_shift(n_edges, threads == 1024 ? (size_t)di.max_smem_optin - 1024 : 33 * 1024);
     smem = hist_smem_bytes(n_edges, shift);
     const bool vec = (((uintptr_t)d_obs | (uintptr_t)d_weights) & 15u) == 0;      // (a NULL weight array is aligned)
     auto kern = vec ? hist_kernel<true> : hist_kernel<false>;
@@ -704,7 +696,13 @@ run_exact_kernel(RunParams p, uint64_t n, uint64_t seed, uint64_t first, const d
     HistSmem h(s_raw, n_edges > 0 ? n_edges : 1, shift);
     const bool do_hist = edges != nullptr;
     if (threadIdx.x == 0) s_poison = INT_MAX;
-    if (do_hist) hist_init(h, edges, n_edges); else __syncthreads();
+    BinGuess G{0, 0.f, 0.f, 0.f};
+    if (do_hist) {
+        hist_init(h, edges, n_edges);
+        G = derive_bin_guess(h.edges, n_edges);
+    } else {
+        __syncthreads();
+    }
     double mn = INFINITY, mx = -INFINITY;
     bool has_nan = false;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
@@ -715,7 +713,7 @@ run_exact_kernel(RunParams p, uint64_t n, uint64_t seed, uint64_t first, const d
         draw_exact<KIND>(p, first + i, seed, s);
         double jac, obs, wj;
         integrand_eval<KIND>(p, s, jac, obs, wj);
-        if (do_hist) hist_add(h, n_edges, obs, wj, true, &s_poison);
+        if (do_hist) hist_add(h, n_edges, obs, wj, true, &s_poison, G);
         if (d_minmax) {
             has_nan |= (obs != obs);
             mn = fmin(mn, obs);
@@ -730,7 +728,7 @@ template <int KIND>
 static int launch_run_exact(const RunParams& p, uint64_t n, uint64_t seed, uint64_t first, const double* d_edges,
                             int n_edges, double* d_sum_w, double* d_sum_w2, uint64_t* d_count, int* d_poison,
                             double* d_minmax, size_t smem, cudaStream_t st) {
-    const int shift = (d_edges && smem <= 56 * 1024) ? hist_spread_shift(n_edges, 56 * 1024) : 0;
+    const int shift = (d_edges && smem <= 64 * 1024) ? hist_spread_shift(n_edges, 64 * 1024) : 0;
     if (d_edges) smem = hist_smem_bytes(n_edges, shift);
     JMC_CUDA(cudaFuncSetAttribute(run_exact_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
@@ -863,15 +861,29 @@ __device__ __forceinline__ void block_exclusive_scan2(double& a, double& b, doub
 // boundary condition, reversed for a last-bin one (integrator.py:162-192).
 // FROM_HIST: density and its error are first derived from the histograms
 // (integrator.py:113-124); otherwise they are inputs (integrate() alone).
+// poison (single job only): the fused kernels' NaN flag -- bins at or above *poison hold NaN sums, as NumPy's
+// cumsum-based weighted histogram would (applied here instead of by a kernel of its own; the flag is re-armed)
 template <bool FROM_HIST>
 __global__ void __launch_bounds__(kScanThreads)
 finalize_kernel(const double* __restrict__ sum_w, const double* __restrict__ sum_w2,
                 const unsigned long long* __restrict__ count, const double* __restrict__ edges, int n_edges,
                 double area, const double* __restrict__ area_per_job, double n_total, int bc_kind, double bc_value,
                 double* __restrict__ density, double* __restrict__ density_err, double* __restrict__ integral,
-                double* __restrict__ integral_err) {
+                double* __restrict__ integral_err, int* poison = nullptr) {
     __shared__ double s_a[32], s_b[32];
     const int nb = n_edges - 1;
+    if (FROM_HIST && poison) {
+        const int pb = *poison;
+        __syncthreads();
+        if (threadIdx.x == 0) *poison = 0x7f7f7f7f;
+        if (pb >= 0 && pb < nb) {
+            for (int k = pb + threadIdx.x; k < nb; k += blockDim.x) {
+                const_cast<double*>(sum_w)[k] = qnan();
+                const_cast<double*>(sum_w2)[k] = qnan();
+            }
+            __syncthreads();
+        }
+    }
     // blockIdx.x = job of a batch (jmc_finalize_batch); a single job is a batch of one
     {
         const size_t job = blockIdx.x;
@@ -942,6 +954,21 @@ extern "C" int jmc_finalize(const double* d_sum_w, const double* d_sum_w2, const
     JMC_LAUNCHED("finalize_kernel");
     return JMC_OK;
 }
+
+namespace jmc {
+// jmc_finalize that also applies (and re-arms) the NaN flag of a fused run: one launch less per job
+int finalize_poisoned(double* d_sum_w, double* d_sum_w2, const uint64_t* d_count, const double* d_edges, int n_edges,
+                      double area, uint64_t n_total, int bc_kind, double bc_value, double* d_density,
+                      double* d_density_err, double* d_integral, double* d_integral_err, int* d_poison, void* stream) {
+    JMC_REQUIRE(n_total > 0, "jmc_finalize: zero samples (the reference divides by len(observables) here)");
+    JMC_REQUIRE(bc_kind >= JMC_BC_FIRST && bc_kind <= JMC_BC_LAST_MINUS, "jmc_finalize: invalid boundary condition");
+    finalize_kernel<true><<<1, kScanThreads, 0, (cudaStream_t)stream>>>(
+        d_sum_w, d_sum_w2, (const unsigned long long*)d_count, d_edges, n_edges, area, nullptr, (double)n_total, bc_kind,
+        bc_value, d_density, d_density_err, d_integral, d_integral_err, d_poison);
+    JMC_LAUNCHED("finalize_kernel");
+    return JMC_OK;
+}
+}  // namespace jmc
 
 extern "C" int jmc_finalize_batch(int n_jobs, const double* d_sum_w, const double* d_sum_w2, const uint64_t* d_count,
                                   const double* d_edges, int n_edges, const double* d_area, uint64_t n_total,

@@ -671,7 +671,9 @@ fast_body(const FastParams& P_in, uint64_t n, uint64_t seed, uint64_t first, con
     const uint32_t strideV = (uint32_t)V * stride;
     // Main loop: trips in which every lane of the warp has all V pairs (no validity tests); then at most two
     // checked trips for the ragged end.  Lanes of a warp differ by at most one pair (consecutive tid).
-    const uint32_t full = __shfl_sync(0xffffffffu, mine, 31) / (uint32_t)V;
+    // (small jobs take the checked loop only: every stretch of code a block runs through once is fetched cold, and
+    // below ~1e6 samples that fetch, not the arithmetic, is the kernel's duration)
+    const uint32_t full = n < (1ull << 21) ? 0u : __shfl_sync(0xffffffffu, mine, 31) / (uint32_t)V;
     const uint32_t trips = (__shfl_sync(0xffffffffu, mine, 0) + (uint32_t)(V - 1)) / (uint32_t)V;
     for (uint32_t j = 0; j < full; ++j, idx += strideV) {
         PairWords<KIND> pw[V];
@@ -1140,7 +1142,7 @@ const float* fast_plan_edges(const FastPlan* p) { return p->edges_f.data(); }
 // 0x7f7f7f7f ("no poison"), left in that state.  Asynchronous on the stream, no host synchronisation.
 int fast_plan_run(const FastPlan* plan, const float* d_edges_f, int* d_poison, uint64_t n, uint64_t seed,
                   uint64_t first_index, double* d_sum_w, double* d_sum_w2, uint64_t* d_count, double* d_minmax,
-                  void* stream) {
+                  void* stream, bool defer_poison) {
     cudaStream_t st = (cudaStream_t)stream;
     const jmc_integrand* g = &plan->g;
     const FastParams& P = plan->P;
@@ -1169,7 +1171,7 @@ int fast_plan_run(const FastPlan* plan, const float* d_edges_f, int* d_poison, u
         n -= m;
     }
 #undef JMC_RUNF
-    if (d_edges_f && !g->nan_to_num) {
+    if (d_edges_f && !g->nan_to_num && !defer_poison) {
         poison_fast_kernel<<<1, 256, 0, st>>>(d_poison, plan->n_edges - 1, d_sum_w, d_sum_w2);
         JMC_LAUNCHED("poison_fast_kernel");
     }

@@ -90,7 +90,7 @@ __device__ __forceinline__ void hist_add_weight(HistSmem& h, int b, double w) {
 // One sample into the block histogram.  A NaN weight is not added; it lowers
 // the poison bin instead (NumPy: NaN in a cumsum reaches every later bin).
 __device__ __forceinline__ void hist_add(HistSmem& h, int n_edges, double obs, double w, bool has_w,
-                                         int* s_poison, const BinGuess& G = BinGuess{0, 0.f, 0.f}) {
+                                         int* s_poison, const BinGuess& G = BinGuess{0, 0.f, 0.f, 0.f}) {
     const int b = bin_index_guided(obs, h.edges, n_edges, G);
     if (has_w && w != w) {
         // obs below the first edge sorts before every bin -> poisons them all;
@@ -133,21 +133,44 @@ __device__ __forceinline__ void hist_flush(HistSmem& h, int n_edges, double* __r
 // Equally spaced edges (np.linspace / np.logspace, i.e. every setBins) get an affine first guess of the bin.  The
 // block derives it from the edges it has just staged (no host read-back of the edge array, no stream sync).
 __device__ __forceinline__ BinGuess derive_bin_guess(const double* s_edges, int n_edges) {
-    BinGuess G{0, 0.f, 0.f};
+    BinGuess G{0, 0.f, 0.f, 0.f};
     if (n_edges < 8) return G;                  // (uniform over the block: every thread takes the same path)
     const double e0 = s_edges[0], e1 = s_edges[n_edges - 1];
+    const double nb = (double)(n_edges - 1);
+    // `tight`: every edge within 1e-6 of a bin of the uniform model -- then the FP32 map decides alone wherever its
+    // value is further than eps from an integer; eps = twice the sum of the error bounds of the map
     {
-        const double d = (e1 - e0) / (n_edges - 1);
-        bool ok = d > 0.0 && isfinite(d) && isfinite(e0);
-        for (int k = threadIdx.x; ok && k < n_edges; k += blockDim.x) ok = fabs(s_edges[k] - (e0 + k * d)) < 0.25 * d;
-        if (__syncthreads_and(ok)) return BinGuess{1, (float)e0, (float)(1.0 / d)};
+        const double d = (e1 - e0) / nb;
+        bool ok = d > 0.0 && isfinite(d) && isfinite(e0), tight = true;
+        for (int k = threadIdx.x; ok && k < n_edges; k += blockDim.x) {
+            const double dev = fabs(s_edges[k] - (e0 + k * d));
+            ok = dev < 0.25 * d;
+            tight = tight && dev < 1e-6 * d;
+        }
+        const int all_tight = __syncthreads_and(tight);
+        if (__syncthreads_and(ok)) {
+            // (float)x and (float)e0: 2^-24 relative each; the product: 2^-24 relative of a value below nb
+            const double eps = 2.0 * (1.2e-7 * fmax(fabs(e0), fabs(e1)) / d + 1.2e-7 * nb + 1e-6);
+            return BinGuess{1, (float)e0, (float)(1.0 / d), (all_tight && eps < 0.2) ? (float)eps : 0.f};
+        }
     }
     {
-        bool ok = e0 > 1e-30 && e1 < 1e30;      // the FP32 log2 guess must not underflow
-        const double l0 = ok ? log2(e0) : 0.0, d = ok ? (log2(e1) - l0) / (n_edges - 1) : 0.0;
+        bool ok = e0 > 1e-30 && e1 < 1e30, tight = true;      // the FP32 log2 guess must not underflow
+        const double l0 = ok ? log2(e0) : 0.0, d = ok ? (log2(e1) - l0) / nb : 0.0;
         ok = ok && d > 0.0 && isfinite(d);
-        for (int k = threadIdx.x; ok && k < n_edges; k += blockDim.x) ok = fabs(log2(s_edges[k]) - (l0 + k * d)) < 0.25 * d;
-        if (__syncthreads_and(ok)) return BinGuess{2, (float)l0, (float)(1.0 / d)};
+        for (int k = threadIdx.x; ok && k < n_edges; k += blockDim.x) {
+            const double dev = fabs(log2(s_edges[k]) - (l0 + k * d));
+            ok = dev < 0.25 * d;
+            tight = tight && dev < 1e-6 * d;
+        }
+        const int all_tight = __syncthreads_and(tight);
+        if (__syncthreads_and(ok)) {
+            // __log2f: 2 ulp of the result outside [0.5, 2] (CUDA math API) -> 2 * 2^-23 * |log2 x|, at least 2^-21.4;
+            // (float)x: 2^-24 / ln 2; (float)l0: 2^-24 |l0|; the product: 2^-24 relative of a value below nb
+            const double span = fmax(fmax(fabs(l0), fabs(log2(e1))), 1.0);
+            const double eps = 2.0 * ((2.4e-7 * span + 4e-7 + 1e-7 + 6e-8 * span) / d + 1.2e-7 * nb + 1e-6);
+            return BinGuess{2, (float)l0, (float)(1.0 / d), (all_tight && eps < 0.2) ? (float)eps : 0.f};
+        }
     }
     return G;
 }
@@ -189,6 +212,20 @@ __device__ __forceinline__ void minmax_merge(double mn, double mx, bool has_nan,
             atomic_max_double(&d_minmax[1], mx);
         }
     }
+}
+
+
+// host: argument checks shared by the histogram entry points; *smem = bytes of one accumulator copy per bin
+static inline int check_hist_args(const char* who, const double* d_edges, int n_edges, size_t* smem) {
+    JMC_REQUIRE(n_edges >= 2, "%s: need at least 2 edges", who);
+    JMC_REQUIRE(d_edges != nullptr, "%s: edges is NULL", who);
+    DeviceInfo di;
+    if (device_info(&di)) return JMC_ENODEV;
+    *smem = hist_smem_bytes(n_edges);
+    if (*smem > (size_t)di.max_smem_optin)
+        return set_error(JMC_ELIMIT, "%s: %d edges need %zu B of shared memory (limit %d B, about 8100 edges)", who,
+                         n_edges, *smem, di.max_smem_optin);
+    return JMC_OK;
 }
 
 

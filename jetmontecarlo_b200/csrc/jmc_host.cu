@@ -460,7 +460,8 @@ int handle_set_job(jmc_handle* h, const jmc_integrand* g, int precision, const d
 }
 
 int handle_run(jmc_handle* h, const jmc_integrand* g, uint64_t n, uint64_t seed, uint64_t first_index, int precision,
-               double* d_sum_w, double* d_sum_w2, uint64_t* d_count, double* d_minmax, cudaStream_t st) {
+               double* d_sum_w, double* d_sum_w2, uint64_t* d_count, double* d_minmax, cudaStream_t st,
+               bool defer_poison = false) {
     const WsLayout L(h->ws_edges);
     const int ne = h->ws_edges;
     const double* d_e64 = ne ? (const double*)(h->d_ws + L.off_e64) : nullptr;
@@ -471,7 +472,7 @@ int handle_run(jmc_handle* h, const jmc_integrand* g, uint64_t n, uint64_t seed,
         while (n) {
             const uint64_t chunk = n < kMaxPerLaunch ? n : kMaxPerLaunch;
             int rc = fast_plan_run(h->plan, ne ? (const float*)(h->d_ws + L.off_e32) : nullptr, (int*)h->d_ws, chunk,
-                                   seed, first_index, d_sum_w, d_sum_w2, d_count, d_minmax, (void*)st);
+                                   seed, first_index, d_sum_w, d_sum_w2, d_count, d_minmax, (void*)st, defer_poison);
             if (rc) return rc;
             n -= chunk;
             first_index += chunk;
@@ -548,10 +549,16 @@ extern "C" int jmc_handle_integrate_host(jmc_handle* h, const jmc_integrand* g, 
     double* d_ierr = d_err + nb;
     double* d_integral = d_ierr + nb;
     JMC_CUDA(cudaMemsetAsync(d_sum_w, 0, sizeof(double) * 3 * nb, st));
-    rc = handle_run(h, g, n, seed, first_index, precision, d_sum_w, d_sum_w2, d_count, nullptr, st);
+    // FP32 plans leave their NaN flag in the handle's scratch: the finalize kernel applies it (no kernel of its own)
+    const bool deferred = h->plan != nullptr;
+    rc = handle_run(h, g, n, seed, first_index, precision, d_sum_w, d_sum_w2, d_count, nullptr, st, deferred);
     if (rc) return rc;
-    rc = jmc_finalize(d_sum_w, d_sum_w2, d_count, (const double*)(h->d_ws + L.off_e64), n_edges, area, n, bc_kind,
-                      bc_value, d_density, d_err, d_integral, d_ierr, (void*)st);
+    JMC_REQUIRE(n > 0, "jmc_integrate_host: zero samples (the reference divides by len(observables) here)");
+    rc = deferred ? finalize_poisoned(d_sum_w, d_sum_w2, d_count, (const double*)(h->d_ws + L.off_e64), n_edges, area, n,
+                                      bc_kind, bc_value, d_density, d_err, d_integral, d_ierr,
+                                      g->nan_to_num ? nullptr : (int*)h->d_ws, (void*)st)
+                  : jmc_finalize(d_sum_w, d_sum_w2, d_count, (const double*)(h->d_ws + L.off_e64), n_edges, area, n,
+                                 bc_kind, bc_value, d_density, d_err, d_integral, d_ierr, (void*)st);
     if (rc) return rc;
     // histograms and results are contiguous: one copy into pinned memory, one synchronisation
     const size_t bytes = sizeof(double) * (7 * nb + 1);

@@ -373,6 +373,8 @@ __device__ __forceinline__ int bin_index(double x, const double* __restrict__ ed
 struct BinGuess {
     int mode;
     float b0, inv_d;       // guess = floor((g(x) - b0) * inv_d), g = identity or log2
+    float eps;             // > 0: the guess is CERTAIN when the fractional part of the mapped value lies in
+                           // (eps, 1 - eps) -- eps bounds every rounding error of the FP32 map (derive_bin_guess)
 };
 __device__ __forceinline__ int bin_index_guided(double x, const double* __restrict__ edges, int n_edges,
                                                 const BinGuess& G) {
@@ -380,7 +382,12 @@ __device__ __forceinline__ int bin_index_guided(double x, const double* __restri
     if (!(x >= edges[0]) || !(x <= edges[n_edges - 1])) return -1;
     const float xf = (float)x;
     const float g = G.mode == 1 ? xf : __log2f(xf);
-    int idx = __float2int_rd((g - G.b0) * G.inv_d);
+    const float f = (g - G.b0) * G.inv_d;
+    const float fl = floorf(f);
+    int idx = (int)fl;
+    // Away from the edges the FP32 map cannot be off by a bin: no look at the stored edges at all (two shared-memory
+    // loads with scattered addresses less per sample).  Within eps of an edge the exact walk below decides.
+    if (G.eps > 0.0f && f - fl > G.eps && f - fl < 1.0f - G.eps && idx >= 0 && idx <= n_edges - 2) return idx;
     idx = max(0, min(idx, n_edges - 2));
     while (idx > 0 && x < edges[idx]) --idx;
     while (idx < n_edges - 2 && x >= edges[idx + 1]) ++idx;

@@ -46,14 +46,9 @@ class integrator():
     # Integration Tools:
     # ------------------
     def _device_obs(self, observables):
-        """Device copy of an observable array, cached between setBins and
-        setDensity so a host array crosses PCIe once."""
-        cached = getattr(self, '_obs_cache', None)
-        if cached is not None and cached[0] is observables:
-            return cached[1]
-        dev = D.to_device(observables).reshape(-1)
-        self._obs_cache = (observables, dev)
-        return dev
+        """The observable array on the device (CUDA tensors are used in place; a host array is uploaded every time it
+        is passed: the caller may have changed it in place between setBins and setDensity, and nothing is pinned)."""
+        return D.to_device(observables).reshape(-1)
 
     def _min_max(self, observables):
         dev = self._device_obs(observables)
@@ -132,7 +127,6 @@ class integrator():
         _lib.check(_lib.lib.jmc_hist(D.ptr(obs), D.ptr(w), obs.numel(), D.ptr(self._edges_dev), nb + 1,
                                      D.ptr(self._sum_w), D.ptr(self._sum_w2), D.ptr(self._count), D.stream()))
         self._density_from_hist(area, obs.numel())
-        self._obs_cache = None
 
     def integrate(self):
         """Cumulative integral of the density from the boundary condition.
@@ -313,7 +307,6 @@ class integrator():
         for flag in self._FLAGS:
             setattr(self, flag, False)
         self.firstBinBndCond = self.lastBinBndCond = None
-        self._obs_cache = None
         self.checkValidAttributes()
 
 

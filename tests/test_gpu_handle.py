@@ -109,7 +109,7 @@ def test_counts_on_request(cuda, which):
     assert np.all(cw <= ca) and cw.sum() < (1. if which == 1 else .01) * ca.sum()
     _, obs, wt = H.dump(mk('all'), n, seed, 'f32', first=3)
     ref = np.histogram(obs[wt != 0], EDGES)[0]
-    assert abs(cw - ref).sum() <= 3                   # FP32 edge ties
+    assert abs(cw - ref).sum() <= 3 + 2e-5 * ref.sum()          # FP32 edge ties (the dump is another instantiation)
     assert np.all((cw > 0) == (w['sum_w2'].cpu().numpy() > 0))
     ia = fused.integrate(mk('all'), n, edges=EDGES, seed=seed, precision='f32', last_bc=[1., 'minus'])
     iw = fused.integrate(mk('weighted'), n, edges=EDGES, seed=seed, precision='f32', last_bc=[1., 'minus'])
