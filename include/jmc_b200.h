@@ -208,6 +208,21 @@ int jmc_uniforms(uint64_t n, uint64_t seed, uint64_t first_index, int n_uniform,
 int jmc_inverse_transform(const double* d_cdf_vals, const double* d_x_vals, int n_table, uint64_t n, uint64_t seed,
                           uint64_t first_index, double* d_out, void* stream);
 
+/* Per-event inverse-transform sampling from a CONDITIONAL cdf exp(-R(x, cond_i)): one sample per event i from the
+ * cdf of x on [d_dom_lo[i], d_dom_hi[i]] given cond_i, with the uniform d_uniforms[i].  R is a numerical radiator
+ * tabulated on the rectangular grid (d_grid_x [nx], d_grid_y [ny], d_table [nx, ny] row-major) and interpolated as
+ * get_2d_interpolation does (utils/interpolation.py:248-273): interpolation 0 = 'RectangularGrid' (bilinear,
+ * linearly extrapolated), 1 = 'Nearest' grid node.  Per event this is samples_from_cdf(cdf_i, 1, domain_i,
+ * catch_turnpoint, force_monotone) on its tabulated route (utils/montecarlo_utils.py:142-318: probe grid, zero bin,
+ * overflow bin, negligible head, turning point, forced monotonicity, then interp1d inversion :377-399); one event per
+ * thread block.  Synchronises: an event whose cdf none of the options resolves is reported as JMC_EDOMAIN.
+ * ref: examples/sudakov_comparisons/sudakov_utils.py:134-238 (generate_precritical / generate_subsequent_samples) */
+int jmc_conditional_inverse_transform(const double* d_grid_x, int nx, const double* d_grid_y, int ny,
+                                      const double* d_table, int interpolation, const double* d_cond,
+                                      const double* d_dom_lo, const double* d_dom_hi, const double* d_uniforms,
+                                      uint64_t n, int catch_turnpoint, int force_monotone, double* d_samples,
+                                      void* stream);
+
 /* ---- replay path: arrays in, arrays out -------------------------------- */
 int jmc_eval_fn(int fn, const jmc_fn_params* p, uint64_t n,
                 const double* d_a0, int64_t stride0, const double* d_a1, int64_t stride1,

@@ -38,6 +38,7 @@ EXPORTS = (
     "jmc_finalize", "jmc_cumulative", "jmc_set_density_host", "jmc_integrate_host", "jmc_sample_host",
     "jmc_eval_fn_host", "jmc_launch_count", "jmc_create", "jmc_destroy", "jmc_handle_run", "jmc_handle_integrate_host",
     "jmc_chain_ecf", "jmc_process_sample", "jmc_process_pairs", "jmc_process_ewoc",
+    "jmc_conditional_inverse_transform",
 )
 
 
@@ -124,6 +125,7 @@ def _load():
         "jmc_process_sample": (i32, [P(Process), u64, u64, u64, vp, vp, vp, vp]),
         "jmc_process_pairs": (i32, [P(Process), vp, u64, i32, dbl, vp, vp]),
         "jmc_process_ewoc": (i32, [P(Process), u64, u64, u64, i32, dbl, dbl, dbl, vp, i32, vp, vp, vp, vp, vp, vp]),
+        "jmc_conditional_inverse_transform": (i32, [vp, i32, vp, i32, vp, i32, vp, vp, vp, vp, u64, i32, i32, vp, vp]),
         "jmc_create": (i32, [P(vp)]),
         "jmc_destroy": (i32, [vp]),
         "jmc_handle_run": (i32, [vp, P(Integrand), u64, u64, u64, i32, vp, i32, vp, vp, vp, vp, vp]),

@@ -7,6 +7,7 @@ Each translation unit has its own floating-point contract:
   jmc_fast.cu    FMA + fast intrinsics: the FP32 log-space throughput path
   jmc_shower.cu  --fmad=false   veto-algorithm shower (FP64 chain, checkable against the oracle)
   jmc_process.cu --fmad=false   hit-or-miss process sampling, pairwise observables, EWOC histograms
+  jmc_sudakov.cu --fmad=false   per-event inverse-transform sampling from tabulated conditional cdfs
   jmc_host.cu    host plumbing and the host-buffer entry points
 The objects are linked into jetmontecarlo_b200/lib/libjmc_b200.so, which
 travels to the GPU box with the repository snapshot (it is git-ignored).
@@ -35,6 +36,7 @@ UNITS = {
     "jmc_exact.cu": ["--fmad=false"] + _DEFS,
     "jmc_shower.cu": ["--fmad=false"] + _DEFS,
     "jmc_process.cu": ["--fmad=false"] + _DEFS,
+    "jmc_sudakov.cu": ["--fmad=false"] + _DEFS,
     "jmc_fast.cu": ["--fmad=true"] + _DEFS,
     "jmc_host.cu": [],
 }

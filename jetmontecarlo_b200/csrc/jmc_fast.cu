@@ -125,6 +125,7 @@ struct FastParams {
     float e_first, e_last;   // first / last edge in the compare domain
     float nb_f;              // number of bins as a float
     int spread_shift;        // log2 of the number of lane-interleaved copies of each bin's accumulator
+    int checked_only;        // small job: every trip through the checked loop (see fast_body)
 };
 
 __device__ __forceinline__ float ex2(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
@@ -673,7 +674,7 @@ fast_body(const FastParams& P_in, uint64_t n, uint64_t seed, uint64_t first, con
     // checked trips for the ragged end.  Lanes of a warp differ by at most one pair (consecutive tid).
     // (small jobs take the checked loop only: every stretch of code a block runs through once is fetched cold, and
     // below ~1e6 samples that fetch, not the arithmetic, is the kernel's duration)
-    const uint32_t full = n < (1ull << 21) ? 0u : __shfl_sync(0xffffffffu, mine, 31) / (uint32_t)V;
+    const uint32_t full = P.checked_only ? 0u : __shfl_sync(0xffffffffu, mine, 31) / (uint32_t)V;
     const uint32_t trips = (__shfl_sync(0xffffffffu, mine, 0) + (uint32_t)(V - 1)) / (uint32_t)V;
     for (uint32_t j = 0; j < full; ++j, idx += strideV) {
         PairWords<KIND> pw[V];
@@ -1085,8 +1086,13 @@ static int launch_fast_t(const FastParams& P, uint64_t n, uint64_t seed, uint64_
     const uint64_t want = (n / 64 + threads) / threads;
     const uint64_t cap = (uint64_t)di.sm_count * cfg.per_sm;
     const int grid = (int)(want < cap ? want : cap);
+    static const uint64_t small_n = [] {                 // experiment switch: jobs below this take the checked loop only
+        const char* e = getenv("JMC_FAST_SMALL_N");
+        return e ? (uint64_t)atof(e) : (uint64_t)0;
+    }();
     FastParams Q = P;
     Q.spread_shift = shift;
+    Q.checked_only = n < small_n;
     if (!d_edges_f) Q.n_edges = 0;
     kern<<<grid, threads, smem, st>>>(Q, n, seed, first, d_edges_f, d_sum_w, d_sum_w2, (unsigned long long*)d_count,
                                       d_poison, d_minmax);

@@ -1,6 +1,6 @@
 """GPU tests of the "next" rows that were written after this round's GPU budget was spent: their
-host logic and arithmetic are pinned on the CPU (tests/test_shower_rss_cpu.py, tests/test_samples_from_cdf_cpu.py,
-tests/test_oracle_golden.py); these run the same checks with the device in the loop.  The file sorts last on purpose."""
+host logic and arithmetic are pinned on the CPU (tests/test_samples_from_cdf_cpu.py, tests/test_oracle_golden.py); these
+run the same checks with the device in the loop."""
 import numpy as np
 import pytest
 from numpy.testing import assert_allclose
@@ -59,31 +59,3 @@ def test_samples_from_cdf_on_device(cuda):
     assert np.abs(xs ** 2 - (np.arange(n) + .5) / n).max() < 1e-2
     zero, _ = samples_from_cdf(cases['starts_at_one'][0], 10, domain=[0, 1], verbose=0, seed=seed)
     assert np.all(zero == 0.)
-
-
-def test_conditional_sudakov_sampling_on_device(cuda):
-    """per-event inverse-transform sampling (numerics/sudakov_sampling.py) on CUDA tensors == the same tensor code on
-    the CPU (which tests/test_sudakov_sampling_cpu.py holds to the reference's per-event loop), with the uniforms of
-    the counter RNG"""
-    import torch
-    from jetmontecarlo_b200.numerics import sudakov_sampling as S
-    from test_sudakov_sampling_cpu import _pre_radiator_table
-    zs, ths, R = _pre_radiator_table()
-    n, seed, z_cut = 20000, 9, .1
-    rng = np.random.RandomState(1)
-    theta = np.exp(rng.uniform(np.log(1e-6), 0., n))
-    th_dev = torch.from_numpy(theta).to(cuda)
-    got, w = S.generate_precritical_samples(S.grid_interpolant(zs, ths, R, device=cuda), th_dev, z_cut, seed=seed)
-    assert got.is_cuda and bool((w == 1.).all())
-    r = O.philox_uniforms53(seed, 0, n, 1)[:, 0]
-    ref, _ = S.generate_precritical_samples(S.grid_interpolant(zs, ths, R), torch.from_numpy(theta), z_cut,
-                                            uniforms=torch.from_numpy(r))
-    got, ref = got.cpu().numpy(), ref.numpy()
-    close = np.isclose(got, ref, rtol=1e-9, atol=1e-300)
-    # (exp / log / pow differ in the last bit between the CPU and the GPU; on a plateau of a noisy radiator that can
-    #  flip one "cdf[k] <= cdf[k+1]" and move that event's sample)
-    assert close.mean() > .97, close.mean()
-    assert np.all((got >= 0) & (got <= z_cut * 1.001))      # (a forced-monotone table drops its last point: r above
-    #                                                          the remaining cdf values extrapolates slightly past z_cut)
-    # the sample distribution is the same
-    assert abs(np.median(got) / np.median(ref) - 1) < 1e-3
