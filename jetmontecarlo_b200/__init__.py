@@ -12,6 +12,27 @@ there is no CPU fallback -- importing the package without the built library
 raises ImportError and calling into it without a CUDA device raises
 RuntimeError.
 """
+import importlib
+import pkgutil
+import sys
+
 from . import _lib  # noqa: F401  (fails loudly when the CUDA library is missing)
 
-__version__ = "0.1.0"
+__version__ = "0.2.0"
+
+
+def install_as(name="jetmontecarlo"):
+    """Make ``import <name>.<module>`` resolve to this package's mirror of that module, so that a script written
+    against the reference (``from jetmontecarlo.montecarlo.integrator import *`` ...) runs on the GPU path unchanged.
+    Modules of the reference that are not on the hot path (plotting, file catalog, ...) are not provided: importing
+    them fails as it would without the reference installed.  Returns the list of aliased module names."""
+    me = sys.modules[__name__]
+    aliased = []
+    sys.modules[name] = me
+    for info in pkgutil.walk_packages(me.__path__, prefix=__name__ + "."):
+        short = info.name[len(__name__) + 1:]
+        if short.startswith("_") or short.startswith("csrc") or short in ("fused", "distributed"):
+            continue
+        sys.modules[name + "." + short] = importlib.import_module(info.name)
+        aliased.append(name + "." + short)
+    return aliased

@@ -1081,9 +1081,9 @@ static int launch_fast_t(const FastParams& P, uint64_t n, uint64_t seed, uint64_
         JMC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
         cfg = {di.device, smem, per_sm < 1 ? 1 : per_sm};
     }
-    // persistent: at most one wave of resident blocks; small jobs get fewer blocks (>= 32 sample pairs per thread),
+    // persistent: at most one wave of resident blocks; small jobs get fewer blocks (>= 8 sample pairs per thread),
     // so that zeroing and flushing the block histograms does not dominate them
-    const uint64_t want = (n / 64 + threads) / threads;
+    const uint64_t want = (n / 16 + threads) / threads;
     const uint64_t cap = (uint64_t)di.sm_count * cfg.per_sm;
     const int grid = (int)(want < cap ? want : cap);
     static const uint64_t small_n = [] {                 // experiment switch: jobs below this take the checked loop only

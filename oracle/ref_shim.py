@@ -54,6 +54,9 @@ def install():
         try:
             import matplotlib  # noqa: F401
         except Exception:
-            pass
+            # montecarlo/ewoc.py imports pyplot for its plot method only: an empty stand-in lets the module import
+            mpl, plt = types.ModuleType("matplotlib"), types.ModuleType("matplotlib.pyplot")
+            mpl.pyplot = plt
+            sys.modules["matplotlib"], sys.modules["matplotlib.pyplot"] = mpl, plt
     if REFERENCE_ROOT not in sys.path:
         sys.path.insert(0, REFERENCE_ROOT)

@@ -143,9 +143,11 @@ def test_every_branch_of_the_shape_list(cuda):
         ref = _loop(_table_cdf(xs, ys, R), ys, lo, hi, rr, **kw)
         return got.cpu().numpy(), ref
 
-    # zero bin: a cdf that is 1 at the lower end of the domain and lower right after it
-    xs, ys, R = _one_d_table(lambda x, c: np.where(x == 0, 1., .5 + .4 * x / 2.), 0., 2., conds)
-    got, ref = run(xs, ys, R, np.zeros(2), np.full(2, 2.), np.array([.3, .6]))
+    # zero bin: a cdf that is 1 at the lower end of the domain and lower right after it (a radiator table that jumps
+    # from 0 at x = 0 to a finite value one tiny grid step later, then falls back to 0 at the end of the domain)
+    xs = np.concatenate([[0., 1e-12], np.logspace(-9, np.log10(2.), 50)])
+    R = np.stack([np.concatenate([[0., 5.], np.linspace(5., 0., 50)])] * 2, axis=1)
+    got, ref = run(xs, conds, R, np.zeros(2), np.full(2, 2.), np.array([.3, .6]))
     assert_array_equal(got, ref)
     assert np.all(ref == 0.)
     # overflow bin: negligible everywhere (with a dip, so that the table is not trivially monotone)
