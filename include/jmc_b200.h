@@ -101,7 +101,12 @@ enum {
     JMC_FN_MUL = 21,             /* a0 * a1 (weights * jacobians, e.g. montecarlo/integrator.py:447)        */
     JMC_FN_MASK_FINITE = 22,     /* a0=w a1=v: w if both finite else 0 (make_finite of utils/hist_utils.py:103-108) */
     JMC_FN_EWOC_WEIGHT = 23,     /* a0=z1 a1=z2 a2=w, s3=w1, beta=w2: z1**w1 * z2**w2 * w   montecarlo/ewoc.py:23-27 */
-    JMC_FN_COUNT = 24
+    /* the pieces of the running-coupling radiators (soft-collinear regions 1-3, hard-collinear 1-2), a0 = C or theta,
+     * a1 = alpha (NULL: s1); the reference's analytic MLL curves are assembled from them
+     * (analytics/radiators/running_coupling.py:11-117 and :157-258) */
+    JMC_FN_SUB_SC1 = 24, JMC_FN_SUB_SC2 = 25, JMC_FN_SUB_SC3 = 26, JMC_FN_SUB_HC1 = 27, JMC_FN_SUB_HC2 = 28,
+    JMC_FN_CRIT_SC1 = 29, JMC_FN_CRIT_SC2 = 30, JMC_FN_CRIT_SC3 = 31, JMC_FN_CRIT_HC1 = 32, JMC_FN_CRIT_HC2 = 33,
+    JMC_FN_COUNT = 34
 };
 
 typedef struct jmc_fn_params {

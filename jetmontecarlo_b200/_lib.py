@@ -24,7 +24,8 @@ SAMPLER_SIMPLE, SAMPLER_CRITICAL, SAMPLER_PRECRITICAL, SAMPLER_UNGROOMED = 0, 1,
  FN_SUB_RADPRIME_FC, FN_SUB_PDF_FC, FN_PRE_RAD_FC, FN_CRIT_RAD_RC, FN_CRIT_RADPRIME_RC,
  FN_CRIT_PDF_RC, FN_SUB_RAD_RC, FN_SUB_RADPRIME_RC, FN_SUB_PDF_RC, FN_PRE_WEIGHT, FN_C_GROOMED,
  FN_C_UNGROOMED, FN_TWO_EMISSION, FN_PRE_WEIGHT_ZEROBIN, FN_ALPHA_SPLITTING, FN_MUL, FN_MASK_FINITE,
- FN_EWOC_WEIGHT) = range(24)
+ FN_EWOC_WEIGHT, FN_SUB_SC1, FN_SUB_SC2, FN_SUB_SC3, FN_SUB_HC1, FN_SUB_HC2, FN_CRIT_SC1, FN_CRIT_SC2, FN_CRIT_SC3,
+ FN_CRIT_HC1, FN_CRIT_HC2) = range(34)
 KIND_RADIATOR, KIND_CRIT, KIND_CRIT_SUB, KIND_PRE_CRIT_SUB, KIND_SIMPLE, KIND_SHOWER = range(6)
 
 METHODS = {'lin': LIN, 'log': LOG}

@@ -6,6 +6,7 @@ import numpy as np
 
 from ... import _lib
 from ..._arrayfn import eval_fn
+from ..qcd_utils import *  # noqa: F401,F403  (re-exported as the reference's module does)
 from ..qcd_utils import _jet
 
 _MAXR = {1: "max_radius"}

@@ -7,6 +7,7 @@ import numpy as np
 
 from ... import _lib
 from ..._arrayfn import eval_fn
+from ..qcd_utils import *  # noqa: F401,F403  (the reference's module re-exports the QCD constants the same way)
 from ..qcd_utils import _jet, alpha_fixed
 
 _MAXR = {1: "max_radius"}
@@ -47,6 +48,61 @@ def subRadPrimeAnalytic(c, beta=2., jet_type='quark', maxRadius=1.):
 def subPDFAnalytic(c, beta=2., jet_type='quark', maxRadius=1.):
     """ref: analytics/radiators/running_coupling.py:409-422"""
     return eval_fn(_lib.FN_SUB_PDF_RC, [c, maxRadius], jet=_jet(jet_type), beta=beta, scalar_fields=_MAXR)
+
+
+# ---- the regions the radiators are assembled from (the reference's analytic MLL curves use them piecewise) --------
+def _piece(fn, x, alpha, jet_type, **kw):
+    return eval_fn(fn, [x, alpha], jet=_jet(jet_type), **kw)
+
+
+def subSC1(C, beta=2, jet_type='quark', alpha=alpha_fixed):
+    """ref: analytics/radiators/running_coupling.py:11-29"""
+    return _piece(_lib.FN_SUB_SC1, C, alpha, jet_type, beta=beta)
+
+
+def subSC2(C, beta=2, jet_type='quark', alpha=alpha_fixed):
+    """ref: analytics/radiators/running_coupling.py:30-56"""
+    return _piece(_lib.FN_SUB_SC2, C, alpha, jet_type, beta=beta)
+
+
+def subSC3(C, beta=2, jet_type='quark', alpha=alpha_fixed):
+    """ref: analytics/radiators/running_coupling.py:57-72"""
+    return _piece(_lib.FN_SUB_SC3, C, alpha, jet_type, beta=beta)
+
+
+def subHC1(C, beta=2, jet_type='quark', alpha=alpha_fixed):
+    """ref: analytics/radiators/running_coupling.py:77-95"""
+    return _piece(_lib.FN_SUB_HC1, C, alpha, jet_type, beta=beta)
+
+
+def subHC2(C, beta=2, jet_type='quark', alpha=alpha_fixed):
+    """ref: analytics/radiators/running_coupling.py:97-117"""
+    return _piece(_lib.FN_SUB_HC2, C, alpha, jet_type, beta=beta)
+
+
+def critSC1(theta, z_c, jet_type='quark', alpha=alpha_fixed):
+    """ref: analytics/radiators/running_coupling.py:157-175"""
+    return _piece(_lib.FN_CRIT_SC1, theta, alpha, jet_type, z_cut=z_c)
+
+
+def critSC2(theta, z_c, jet_type='quark', alpha=alpha_fixed):
+    """ref: analytics/radiators/running_coupling.py:177-199"""
+    return _piece(_lib.FN_CRIT_SC2, theta, alpha, jet_type, z_cut=z_c)
+
+
+def critSC3(theta, z_c, jet_type='quark', alpha=alpha_fixed):
+    """ref: analytics/radiators/running_coupling.py:201-219"""
+    return _piece(_lib.FN_CRIT_SC3, theta, alpha, jet_type, z_cut=z_c)
+
+
+def critHC1(theta, z_c, jet_type='quark', alpha=alpha_fixed):
+    """ref: analytics/radiators/running_coupling.py:224-240"""
+    return _piece(_lib.FN_CRIT_HC1, theta, alpha, jet_type, z_cut=z_c)
+
+
+def critHC2(theta, z_c, jet_type='quark', alpha=alpha_fixed):
+    """ref: analytics/radiators/running_coupling.py:242-258"""
+    return _piece(_lib.FN_CRIT_HC2, theta, alpha, jet_type, z_cut=z_c)
 
 
 # ---- pre-critical radiator without frozen coupling (host closed form) ---------------------------------------------

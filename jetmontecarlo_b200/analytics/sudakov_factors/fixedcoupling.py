@@ -6,6 +6,7 @@ import warnings
 
 import numpy as np
 
+from ..qcd_utils import *  # noqa: F401,F403  (re-exported as the reference's module does)
 from ..qcd_utils import CR, alpha_fc, hyp2f1_vec
 
 

@@ -71,6 +71,16 @@ __device__ __forceinline__ double eval_one(const jmc_fn_params& p, double x0, do
             auto pw = [](double x, double e) { return e == 1.0 ? x : (e == 2.0 ? x * x : (e == 0.0 ? 1.0 : pow(x, e))); };
             return pw(x0, x3) * pw(x1, p.beta) * x2;
         }
+        case JMC_FN_SUB_SC1: return sub_sc1(x0, p.beta, p.jet, x1);
+        case JMC_FN_SUB_SC2: return sub_sc2(x0, p.beta, p.jet, x1);
+        case JMC_FN_SUB_SC3: return sub_sc3(x0, p.beta, p.jet, x1);
+        case JMC_FN_SUB_HC1: return sub_hc1(x0, p.beta, p.jet, x1);
+        case JMC_FN_SUB_HC2: return sub_hc2(x0, p.beta, p.jet, x1);
+        case JMC_FN_CRIT_SC1: return crit_sc1(x0, p.z_cut, p.jet, x1);
+        case JMC_FN_CRIT_SC2: return crit_sc2(x0, p.z_cut, p.jet, x1);
+        case JMC_FN_CRIT_SC3: return crit_sc3(x0, p.z_cut, p.jet, x1);
+        case JMC_FN_CRIT_HC1: return crit_hc1(x0, p.z_cut, p.jet, x1);
+        case JMC_FN_CRIT_HC2: return crit_hc2(x0, p.z_cut, p.jet, x1);
         default: return qnan();
     }
 }

@@ -161,21 +161,25 @@ struct EcfAcc {
             insert(c);
         }
     }
+    template <int G = -1>
     __device__ __forceinline__ double result(const ShowerParams& p) {
-        if (p.groomer == 2) {
+        const int groomer = G < 0 ? p.groomer : G;
+        if (groomer == 2) {
             // c_list = c_subs + [c_crit]: the sum of all, or of the n largest (:655-668)
             if (p.n_emissions == 0) return (double)sum_all + wide(first) + (sizeof(T) == 4 ? 1e-50 : 0.0);
             insert(first);
             double s = 0.0;
             bool any = false;
-            for (int k = 0; k < kTopN && k < p.n_emissions; ++k)
-                if (top[k] >= (T)0) { s = any ? s + wide(top[k]) : wide(top[k]); any = true; }
+#pragma unroll
+            for (int k = 0; k < kTopN; ++k)
+                if (k < p.n_emissions && top[k] >= (T)0) { s = any ? s + wide(top[k]) : wide(top[k]); any = true; }
             return s;
         }
-        if (!p.groomer) {
+        if (!groomer) {
             if (p.n_emissions == 0) return (double)sum_all + (sizeof(T) == 4 ? 1e-50 : 0.0);
             double s = 0.0;                    // sum(cs[:n]) over the descending list
-            for (int k = 0; k < kTopN && k < p.n_emissions; ++k) if (top[k] >= (T)0) s += wide(top[k]);
+#pragma unroll
+            for (int k = 0; k < kTopN; ++k) if (k < p.n_emissions && top[k] >= (T)0) s += wide(top[k]);
             return s;
         }
         // c_list += [1e-50, 1e-50]
@@ -191,13 +195,15 @@ struct EcfAcc {
         insert(tiny());
         insert(tiny());
         double s = (double)first;              // sum([c0] + rest[:n-1])
-        for (int k = 0; k < kTopN && k < p.n_emissions - 1; ++k) if (top[k] >= (T)0) s += wide(top[k]);
+#pragma unroll
+        for (int k = 0; k < kTopN; ++k) if (k < p.n_emissions - 1 && top[k] >= (T)0) s += wide(top[k]);
         return s;
     }
 };
 
 // One veto trial in the reference's FP64 operation order.  Returns true if the emission is accepted.
 // ref: partonshower_utils.py:168-209
+template <bool MLL, bool QUARK>
 __device__ __forceinline__ bool trial_exact(const ShowerParams& p, UStream& us, double& ang, double& z, double& theta,
                                             int* error_flag) {
     const double r1 = us.next(), r2 = us.next();
@@ -206,13 +212,16 @@ __device__ __forceinline__ bool trial_exact(const ShowerParams& p, UStream& us, 
     z = pow(2.0 * ang_f, r2) / 2.0;
     theta = pow(2.0 * ang_f, (1 - r2) / p.beta);
     ang = ang_f;
-    if (!p.mll_shower) return true;
-    const double cut = alpha_running(z, theta) * splitting(z, p.jet, JMC_ACC_MLL) / (2.0 * p.cr * p.alpha / z);
+    if (!MLL) return true;
+    const double cut = alpha_running(z, theta) * splitting(z, QUARK ? JMC_QUARK : JMC_GLUON, JMC_ACC_MLL)
+                       / (2.0 * p.cr * p.alpha / z);
     if (cut > 1.0) *error_flag = 1;            // the reference raises ValueError here
     return us.next() < cut;
 }
 
-template <bool EXACT>
+// Launch-uniform choices are template parameters (shower accuracy, groomer, jet type, whether anything per jet is
+// written out): the veto loop runs ~30 times per jet and every uniform branch in it costs issue slots on all of them.
+template <bool EXACT, bool MLL, int GROOMER, bool QUARK, bool RECORD>
 __global__ void __launch_bounds__(kShowerThreads)
 shower_kernel(ShowerParams p, uint64_t n, uint64_t seed, uint64_t first, const double* __restrict__ edges,
               int n_edges, unsigned long long* __restrict__ g_count, double* __restrict__ d_minmax,
@@ -249,7 +258,7 @@ shower_kernel(ShowerParams p, uint64_t n, uint64_t seed, uint64_t first, const d
     bool alive = j < n;
     auto start_jet = [&]() {
         us.reset(first + j, seed);
-        acc.reset(p.groomer, p.z_cut);
+        acc.reset(GROOMER, p.z_cut);
         ang = p.ang_init;                       // ang_init = R^beta / 2, z_init = 1/2, theta_init = R (:316-321)
         lf = p.lf_init;
         z = 0.5;
@@ -285,7 +294,7 @@ shower_kernel(ShowerParams p, uint64_t n, uint64_t seed, uint64_t first, const d
             bool accepted;
             ++n_trials;
             if (EXACT) {
-                accepted = trial_exact(p, us, ang, z, theta, error_flag);
+                accepted = trial_exact<MLL, QUARK>(p, us, ang, z, theta, error_flag);
             } else {
                 // FP32: l' = -sqrt(l^2 - K ln r1); ln z = r2 l' - ln 2; ln theta = (1 - r2) l' / beta
                 uint32_t r[4];
@@ -297,11 +306,11 @@ shower_kernel(ShowerParams p, uint64_t n, uint64_t seed, uint64_t first, const d
                 lf = lp;
                 zf = __expf(lnz);
                 accepted = true;
-                if (p.mll_shower) {
+                if (MLL) {
                     const float alpha = 0.118f / (1.0f + ca_f * (fmaxf(lnPT_f + lnz + lnth, 0.0f) - lnMZ_f));
                     const float omz = 1.0f - zf;
                     float zp;                    // z * (P(z) + P(1-z))
-                    if (p.jet == JMC_QUARK) {
+                    if (QUARK) {
                         zp = (float)JMC_CF * ((1.0f + omz * omz) + zf * (1.0f + zf * zf) / omz);
                     } else {
                         const float pz = (float)JMC_CA * (2.0f * omz + zf * zf * omz)
@@ -317,33 +326,33 @@ shower_kernel(ShowerParams p, uint64_t n, uint64_t seed, uint64_t first, const d
             }
             in_veto_loop = !accepted;
             if (accepted) {
-                if (dump_chain && n_em < chain_cap) {        // event record on request: (z, theta) of emission n_em
+                if (RECORD && dump_chain && n_em < chain_cap) {        // event record on request: (z, theta) of emission n_em
                     double* c = dump_chain + ((size_t)j * chain_cap + n_em) * 2;
                     c[0] = EXACT ? z : (double)zf;
                     c[1] = EXACT ? theta : (double)__expf(lnth);
                 }
                 ++n_em;
                 if (n_em >= kMaxEmissions && error_flag) atomicOr(error_flag, 2);     // the record is cut here
-                if (p.groomer == 2) {
+                if (GROOMER == 2) {
                     if (EXACT) acc.add_rss(z, np_pow(theta, p.beta), p);
                     else acc.add_rss(zf, __expf(beta_f * lnth), p);
                 } else if (EXACT) {
                     acc.add(ecf_ungroomed(z, theta, p.beta, p.obs_mll ? JMC_ACC_MLL : JMC_ACC_LL),
-                            z > p.z_cut * np_pow(theta, p.beta_sd), p.groomer);
+                            z > p.z_cut * np_pow(theta, p.beta_sd), GROOMER);
                 } else {
                     // C = z theta^beta [(1 - z)], grooming condition ln z > ln z_cut + beta_sd ln theta
                     float c = __expf(fmaf(beta_f, lnth, lnz));
                     if (p.obs_mll) c *= 1.0f - zf;
-                    acc.add(c, lnz > fmaf(beta_sd_f, lnth, ln_zcut_f), p.groomer);
+                    acc.add(c, lnz > fmaf(beta_sd_f, lnth, ln_zcut_f), GROOMER);
                 }
             }
             continue;
         }
         // jet finished: observable -> histogram, then take the next jet
-        const double obs = acc.result(p);
-        if (dump_obs) dump_obs[j] = obs;
-        if (dump_n) dump_n[j] = n_em;
-        if (dump_trials) dump_trials[j] = n_trials;
+        const double obs = acc.template result<GROOMER>(p);
+        if (RECORD && dump_obs) dump_obs[j] = obs;
+        if (RECORD && dump_n) dump_n[j] = n_em;
+        if (RECORD && dump_trials) dump_trials[j] = n_trials;
         if (n_edges > 0) {
             // the jets' bins: np.logspace edges, usually behind one zero-bin edge (plot_comparisons.py:296-298)
             int b;
@@ -531,17 +540,26 @@ static int shower_launch(const jmc_integrand* g, uint64_t n, uint64_t seed, uint
     uint64_t want = (n + kShowerThreads - 1) / kShowerThreads;
     const uint64_t cap = (uint64_t)di.sm_count * 8;
     const int grid = (int)(want < cap ? want : cap);
-    if (precision == JMC_F64) {
-        JMC_CUDA(cudaFuncSetAttribute(shower_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        shower_kernel<true><<<grid, kShowerThreads, smem, st>>>(p, n, seed, first_index, d_edges, n_edges,
-                                                                 (unsigned long long*)d_count, d_minmax, d_obs, d_n_em,
-                                                                 d_trials, d_chain, chain_cap, d_err);
-    } else {
-        JMC_CUDA(cudaFuncSetAttribute(shower_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        shower_kernel<false><<<grid, kShowerThreads, smem, st>>>(p, n, seed, first_index, d_edges, n_edges,
-                                                                  (unsigned long long*)d_count, d_minmax, d_obs, d_n_em,
-                                                                  d_trials, d_chain, chain_cap, d_err);
-    }
+    const bool record = d_obs || d_n_em || d_trials || d_chain;
+    // instantiation for (precision, shower accuracy, groomer, jet type, record)
+    auto launch = [&](auto kern) -> cudaError_t {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        kern<<<grid, kShowerThreads, smem, st>>>(p, n, seed, first_index, d_edges, n_edges, (unsigned long long*)d_count,
+                                                 d_minmax, d_obs, d_n_em, d_trials, d_chain, chain_cap, d_err);
+        return cudaSuccess;
+    };
+#define JMC_SH5(E, M, G, Q, R) launch(shower_kernel<E, M, G, Q, R>)
+#define JMC_SH4(E, M, G, Q) (record ? JMC_SH5(E, M, G, Q, true) : JMC_SH5(E, M, G, Q, false))
+#define JMC_SH3(E, M, G) (p.jet == JMC_QUARK ? JMC_SH4(E, M, G, true) : JMC_SH4(E, M, G, false))
+#define JMC_SH2(E, M) (p.groomer == 0 ? JMC_SH3(E, M, 0) : (p.groomer == 1 ? JMC_SH3(E, M, 1) : JMC_SH3(E, M, 2)))
+#define JMC_SH1(E) (p.mll_shower ? JMC_SH2(E, true) : JMC_SH2(E, false))
+    JMC_CUDA(precision == JMC_F64 ? JMC_SH1(true) : JMC_SH1(false));
+#undef JMC_SH1
+#undef JMC_SH2
+#undef JMC_SH3
+#undef JMC_SH4
+#undef JMC_SH5
     JMC_LAUNCHED("shower_kernel");
     if (nb) {
         shower_sums_kernel<<<(int)((nb + 255) / 256), 256, 0, st>>>(d_before, (const unsigned long long*)d_count, (int)nb,

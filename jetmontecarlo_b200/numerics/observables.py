@@ -4,7 +4,7 @@ from .. import _lib
 from .._arrayfn import eval_fn
 
 
-def C_groomed(z_crit, theta_crit, z_cut, beta, z_pre=0., f=1., acc='LL'):
+def C_groomed(z_crit, theta_crit, z_cut, beta, z_pre=0., f=1., acc='LL', verbose=0):
     """Groomed ECF of a critical emission; Soft Drop / mMDT is
     ``z_pre=z_cut, f=0``.  ref: numerics/observables.py:15-79"""
     assert acc in ['LL', 'MLL'], "Accuracy must be LL or MLL!"

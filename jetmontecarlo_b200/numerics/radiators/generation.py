@@ -12,6 +12,7 @@ from ...utils.interpolation import get_2d_interpolation, lin_log_mixed_list
 from ..observables import C_ungroomed, C_ungroomed_max
 from ..weights import radiatorWeight
 from ..._arrayfn import eval_fn
+from ...analytics.qcd_utils import *  # noqa: F401,F403  (re-exported as the reference's module does)
 from ... import _lib
 
 local_verbose = 0

@@ -23,12 +23,148 @@ import torch
 
 from .. import _device as D
 from .. import _lib
+from ..analytics.qcd_utils import *  # noqa: F401,F403  (re-exported as the reference's module does)
 from ..analytics.qcd_utils import MU_NP, check_jet_type
 from ..fused import PRECISIONS, Integrand
 from ..montecarlo.sampler import next_key
 
 
 CHAIN_RECORD = 64        # emissions per jet in a first event record (MLL gluon jets average about 20)
+
+
+# ---- the event record as objects, on request ------------------------------------------------------------------------
+# With split_soft=False (the only mode gen_jets uses, :321) a jet IS its ordered (z, theta) chain: every splitting
+# takes the hard daughter of the previous one.  The device produces chains; the classes below rebuild the reference's
+# tree of Parton objects with momenta from a chain, for the scripts that walk it (shower visualisation, custom
+# groomers).  ref: utils/partonshower_utils.py:13-112, utils/vector_utils.py:22-137
+class Vector:
+    """A three-vector with the few operations the shower record needs (magnitude, rotation about an axis)."""
+
+    def __init__(self, vector):
+        self.vector = np.array(vector, dtype=float)
+
+    def dim(self):
+        return len(self.vector)
+
+    def mag(self):
+        return float(np.sqrt(np.dot(self.vector, self.vector)))
+
+    def unit(self):
+        return Vector(self.vector / self.mag())
+
+    def rotate_around(self, axis, angle):
+        """Rodrigues rotation of this vector about ``axis`` by ``angle``"""
+        k = axis.vector / axis.mag()
+        v = self.vector
+        return Vector(v * np.cos(angle) + np.cross(k, v) * np.sin(angle) + k * np.dot(k, v) * (1. - np.cos(angle)))
+
+
+def angle(vec1, vec2):
+    """opening angle of two vectors"""
+    cos = np.dot(vec1.vector, vec2.vector) / (vec1.mag() * vec2.mag())
+    return float(np.arccos(np.clip(cos, -1., 1.)))
+
+
+def rand_perp_vector(vector, rng=None):
+    """a unit vector perpendicular to ``vector`` with a uniformly random azimuth"""
+    rng = np.random if rng is None else rng
+    v = vector.vector / vector.mag()
+    helper = np.array([1., 0., 0.]) if abs(v[0]) < .9 else np.array([0., 1., 0.])
+    e1 = np.cross(v, helper)
+    e1 /= np.sqrt(np.dot(e1, e1))
+    e2 = np.cross(v, e1)
+    phi = rng.uniform(0., 2. * np.pi)
+    return Vector(np.cos(phi) * e1 + np.sin(phi) * e2)
+
+
+def split_momentum(mom_vector, z, theta, rng=None):
+    """(soft, hard) momenta of a splitting with momentum fraction z and opening angle theta"""
+    assert mom_vector.dim() == 3, "Currently only splitting 3D vectors!"
+    assert mom_vector.mag() > 0, "Cannot split zero momentum."
+    perp = rand_perp_vector(mom_vector, rng)
+    q = Vector(mom_vector.vector * z).rotate_around(perp, theta / 2)
+    k = Vector(mom_vector.vector * (1 - z)).rotate_around(perp, -theta / 2)
+    return q, k
+
+
+class Parton():
+    """Momentum, mother / daughters and identifiers of one parton of the shower record."""
+
+    def __init__(self, momentum):
+        self.momentum = momentum
+        self.mass = None
+        self.mother = None
+        self.daughter1 = None
+        self.daughter2 = None
+        self.pid = None
+        self.isFinalState = True
+        self.type = None
+
+    def split(self, z, theta, rng=None):
+        q, k = split_momentum(self.momentum, z, theta, rng)
+        self.daughter1, self.daughter2 = Parton(q), Parton(k)
+        self.daughter1.mother = self.daughter2.mother = self
+        self.isFinalState = False
+
+
+class Jet:
+    """A list of partons built up by a shower."""
+
+    def __init__(self, momentum, radius, partons=None):
+        assert momentum.mag() > 0, "Unphysical transverse momentum."
+        assert radius > 0, "Unphysical jet radius."
+        self.momentum = momentum
+        self.R = radius
+        self.partons = [Parton(momentum)] if partons is None else list(partons)
+        self.has_showered = False
+
+    @classmethod
+    def from_chain(cls, chain, radius=1., rng=None):
+        """The record the reference's recursive shower leaves behind for the emission chain [(z, theta), ...]:
+        mother, then for every emission its soft and hard daughters, the hard one splitting next."""
+        from ..analytics.qcd_utils import P_T
+        jet = cls(Vector([0, P_T, 0]), radius)
+        parton = jet.partons[0]
+        parton.type = 'mother'
+        for z, theta in chain:
+            parton.split(float(z), float(theta), rng)
+            parton.daughter1.type, parton.daughter2.type = 'soft', 'hard'
+            jet.partons.append(parton.daughter1)
+            jet.partons.append(parton.daughter2)
+            parton = parton.daughter2
+        jet.has_showered = True
+        return jet
+
+    def chain(self):
+        """the (z, theta) chain back from the tree: z = |soft| / |mother|, theta = angle between the daughters"""
+        out, parton = [], self.partons[0]
+        while parton.daughter1 is not None:
+            out.append((parton.daughter1.momentum.mag() / parton.momentum.mag(),
+                        angle(parton.daughter1.momentum, parton.daughter2.momentum)))
+            parton = parton.daughter2
+        return out
+
+
+def angularity_shower(parton, ang_init, z_init, theta_init, beta, jet_type, jet, acc='LL', split_soft=True,
+                      cutoff=MU_NP, seed=None):
+    """Showers ``parton`` inside ``jet`` (both are modified in place, as in the reference): the chain is generated on
+    the device starting from angularity ``ang_init`` and attached to the record.  Only the hard daughter splits
+    further (``split_soft=False``, what gen_jets uses); a shower of both daughters is a tree the device kernel does
+    not generate.  ref: utils/partonshower_utils.py:224-285"""
+    if split_soft:
+        raise NotImplementedError("angularity_shower: split_soft=True is not on the accelerated path "
+                                  "(gen_jets uses split_soft=False)")
+    if not z_init * theta_init > cutoff:
+        return
+    radius = (2. * ang_init) ** (1. / beta)            # the chain of a jet of this radius starts at ang_init
+    lens, z, theta = JetList(1, beta, jet_type, radius, acc, cutoff,
+                             next_key() if seed is None else int(seed)).chains(CHAIN_RECORD)
+    for k in range(int(lens[0])):
+        parton.split(float(z[0, k]), float(theta[0, k]))
+        parton.daughter1.type, parton.daughter2.type = 'soft', 'hard'
+        jet.partons.append(parton.daughter1)
+        jet.partons.append(parton.daughter2)
+        parton = parton.daughter2
 
 
 class JetList:
@@ -76,6 +212,19 @@ class JetList:
         lens, chains = self.chains_device(max_emissions, precision)
         c = D.to_host(chains)
         return D.to_host(lens), c[:, :, 0], c[:, :, 1]
+
+    def jets(self, max_emissions=CHAIN_RECORD, rng=None):
+        """The jets as ``Jet`` objects (Parton trees with momenta), rebuilt on the host from the device's event record:
+        for scripts that walk the tree.  The observables never need this."""
+        lens, z, theta = self.chains(max_emissions)
+        assert len(lens) == 0 or int(lens.max()) <= max_emissions, "emission chains were truncated: raise max_emissions"
+        return [Jet.from_chain(zip(z[i, :lens[i]], theta[i, :lens[i]]), self.radius, rng) for i in range(len(lens))]
+
+    def __iter__(self):
+        return iter(self.jets())
+
+    def __getitem__(self, i):
+        return self.jets()[i]
 
     def emission_counts(self):
         """(accepted emissions, veto trials) per jet"""

@@ -57,7 +57,7 @@ def test_bandwidth_and_shower_kernels_do_not_spill():
                  re.findall(r"Function (\S+):\s*\n\s*REG:(\d+) STACK:(\d+)", _run("-res-usage")))
     seen = 0
     for name, (regs, stack) in usage.items():
-        if any(k in name for k in ("hist_kernelI", "minmax_kernelE", "chain_ecf_kernel", "inverse_transform_kernel", "shower_kernelI",
+        if any(k in name for k in ("hist_kernelI", "minmax_kernelE", "inverse_transform_kernel", "shower_kernelI",
                                    "hist2d_kernel", "sample_kernel", "uniforms_kernel")):
             assert stack == 0, "%s spills %d B" % (name, stack)
             seen += 1

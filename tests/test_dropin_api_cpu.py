@@ -29,7 +29,8 @@ MIRRORED = ["montecarlo.sampler", "montecarlo.integrator", "montecarlo.process",
 NOT_ON_THE_PATH = {
     "np", "plt", "random", "math", "warnings", "interpolate", "scipy", "derivative", "inversefunc", "dill", "os", "sys",
     "ABC", "abstractmethod", "dataclass", "Callable", "Path", "time", "cm", "mpl", "matplotlib", "polylog", "hyp2f1",
-    "gamma", "gaussian_filter1d", "mpmath", "fsolve", "reduce", "TwoParticleJetAlgorithm",
+    "gamma", "gaussian_filter1d", "mpmath", "fsolve", "reduce", "TwoParticleJetAlgorithm", "spence", "beta",
+    "eec",       # the analytic EEC curve: a plot-side truth curve (out of scope)
 }
 
 
