@@ -62,3 +62,18 @@ def allreduce_minmax(minmax, group=None):
     out = torch.stack([-buf[:, 0], buf[:, 1]], dim=1)
     out[buf[:, 2] > 0] = float("nan")
     minmax.copy_(out.reshape(minmax.shape))
+
+
+def gather_rows(rows, n_total, world, group=None):
+    """Concatenate the ranks' row blocks (sizes from ``shard_bounds``: they differ by at most one row) into the full
+    [n_total, ...] array on every rank: ONE all-gather of equally padded blocks, no reduction."""
+    per = -(-int(n_total) // int(world))
+    pad = torch.zeros((per,) + tuple(rows.shape[1:]), dtype=rows.dtype, device=rows.device)
+    pad[:rows.shape[0]] = rows
+    out = torch.empty((world * per,) + tuple(rows.shape[1:]), dtype=rows.dtype, device=rows.device)
+    dist.all_gather_into_tensor(out, pad.contiguous(), group=group)
+    pieces = []
+    for r in range(world):
+        _, count = shard_bounds(n_total, r, world)
+        pieces.append(out[r * per:r * per + count])
+    return torch.cat(pieces, dim=0)

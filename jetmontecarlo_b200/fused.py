@@ -233,45 +233,58 @@ def integrate_batch(integrands, num_samples, *, edges=None, numbins=None, binspa
     theta_crit of gen_crit_sub_num_rad).  Every point sees the same sample stream.  ``edges``: array
     [n_points, n_edges]; or ``numbins`` + ``binspacing`` (+ per-point ``min_log_bins``) for the reference's
     data-dependent bins, found by a batched min/max pass.  Returns a dict of arrays with a leading n_points axis:
-    bins, density, densityErr, integral, integralErr (same conventions as ``integrator``)."""
+    bins, density, densityErr, integral, integralErr (same conventions as ``integrator``).
+
+    With ``torch.distributed`` initialised the GRID is sharded, not the samples: every rank integrates its own
+    contiguous block of parameter points over the whole sample stream, so nothing has to be reduced -- the ranks'
+    finished rows are gathered ("shard the parameter grid instead of samples")."""
     from .montecarlo.integrator import _bc_args
     D.require_cuda()
-    npts = len(integrands)
-    arr = _as_struct_array(integrands)
+    npts_all = len(integrands)
+    world = torch.distributed.get_world_size(group) if dist_utils.is_distributed(group) else 1
+    rank = torch.distributed.get_rank(group) if world > 1 else 0
+    p0, p_count = dist_utils.shard_bounds(npts_all, rank, world)
+    mine = list(integrands[p0:p0 + p_count])
+    npts = len(mine)
     num_samples = int(num_samples)
-    first, n_local = dist_utils.shard(num_samples, group)
     prec, key = PRECISIONS[precision], int(seed) & 0xFFFFFFFFFFFFFFFF
-    if edges is None:
+    if edges is not None:
+        edges = np.ascontiguousarray(edges, dtype=np.float64)[p0:p0 + p_count]
+    elif npts:
+        arr = _as_struct_array(mine)
         mm = torch.empty((npts, 2), dtype=torch.float64, device=D.device())
         mm[:, 0], mm[:, 1] = float('inf'), float('-inf')
-        _lib.check(_lib.lib.jmc_run_batch(arr, npts, n_local, key, first, prec, None, 0, None, None, None, D.ptr(mm),
+        _lib.check(_lib.lib.jmc_run_batch(arr, npts, num_samples, key, 0, prec, None, 0, None, None, None, D.ptr(mm),
                                           D.stream()))
-        dist_utils.allreduce_minmax(mm, group)       # one collective for the whole grid
         mm = D.to_host(mm)
-        mlb = np.full(npts, 1e-15) if min_log_bins is None else np.asarray(min_log_bins, dtype=float)
+        mlb = np.full(npts_all, 1e-15) if min_log_bins is None else np.asarray(min_log_bins, dtype=float)
         rows = []
         for i in range(npts):                       # integrator.setBins, one row per point (host, O(bins))
             lo, hi = mm[i]
             if binspacing == 'lin':
                 rows.append(np.linspace(min(0, lo), hi, numbins))
             else:
-                rows.append(np.logspace(np.log10(max(lo, mlb[i])), np.log10(hi), numbins))
+                rows.append(np.logspace(np.log10(max(lo, mlb[p0 + i])), np.log10(hi), numbins))
         edges = np.array(rows)
-    edges = np.ascontiguousarray(edges, dtype=np.float64)
-    ne = edges.shape[1]
+    ne = edges.shape[1] if edges is not None and edges.ndim == 2 and edges.shape[0] else int(numbins)
     nb = ne - 1
-    sum_w, sum_w2 = D.zeros((npts, nb)), D.zeros((npts, nb))
-    count = D.zeros((npts, nb), dtype=torch.int64)
-    _lib.check(_lib.lib.jmc_run_batch(arr, npts, n_local, key, first, prec, edges.ctypes.data_as(C.c_void_p), ne,
-                                      D.ptr(sum_w), D.ptr(sum_w2), D.ptr(count), None, D.stream()))
-    dist_utils.allreduce_histograms(sum_w, sum_w2, count, group)
     bc_kind, bc_value = _bc_args(first_bc, None if last_bc is None else list(last_bc))
-    edges_dev = D.to_device(edges)
-    areas = D.to_device(np.array([ig.area for ig in integrands], dtype=np.float64))
     dens, err = D.empty((npts, nb)), D.empty((npts, nb))
     integ, ierr = D.empty((npts, ne)), D.empty((npts, nb))
-    _lib.check(_lib.lib.jmc_finalize_batch(npts, D.ptr(sum_w), D.ptr(sum_w2), D.ptr(count), D.ptr(edges_dev), ne,
-                                           D.ptr(areas), num_samples, bc_kind, bc_value, D.ptr(dens), D.ptr(err),
-                                           D.ptr(integ), D.ptr(ierr), D.stream()))
-    return dict(bins=edges, density=D.to_host(dens), densityErr=D.to_host(err), integral=D.to_host(integ),
-                integralErr=D.to_host(ierr), count=D.to_host(count))
+    count = D.zeros((npts, nb), dtype=torch.int64)
+    edges_dev = D.to_device(edges if npts else np.zeros((0, ne)))
+    if npts:
+        arr = _as_struct_array(mine)
+        sum_w, sum_w2 = D.zeros((npts, nb)), D.zeros((npts, nb))
+        edges = np.ascontiguousarray(edges, dtype=np.float64)
+        _lib.check(_lib.lib.jmc_run_batch(arr, npts, num_samples, key, 0, prec, edges.ctypes.data_as(C.c_void_p), ne,
+                                          D.ptr(sum_w), D.ptr(sum_w2), D.ptr(count), None, D.stream()))
+        areas = D.to_device(np.array([ig.area for ig in mine], dtype=np.float64))
+        _lib.check(_lib.lib.jmc_finalize_batch(npts, D.ptr(sum_w), D.ptr(sum_w2), D.ptr(count), D.ptr(edges_dev), ne,
+                                               D.ptr(areas), num_samples, bc_kind, bc_value, D.ptr(dens), D.ptr(err),
+                                               D.ptr(integ), D.ptr(ierr), D.stream()))
+    out = dict(bins=edges_dev.reshape(npts, ne), density=dens, densityErr=err, integral=integ, integralErr=ierr,
+               count=count)
+    if world > 1:
+        out = {k: dist_utils.gather_rows(v, npts_all, world, group) for k, v in out.items()}
+    return {k: D.to_host(v) for k, v in out.items()}

@@ -32,9 +32,20 @@ edges = np.logspace(-11, np.log10(.5), 100)
 n = 20_000_001
 it = fused.integrate(ig, n, edges=edges, seed=3, precision='f32', last_bc=[1., 'minus'])
 it2 = fused.integrate(ig, n, numbins=50, binspacing='log', seed=3, precision='f64', last_bc=[1., 'minus'])
+# BASELINE config 5: the parameter GRID is sharded (rows gathered, nothing reduced)
+if backend == "gloo":
+    _ag = dist.all_gather_into_tensor
+    def all_gather_into_tensor(out, inp, group=None):
+        ho, hi = out.cpu(), inp.cpu(); _ag(ho, hi, group=group); out.copy_(ho)
+    dist.all_gather_into_tensor = all_gather_into_tensor
+grid = np.array([1e-3, 1e-2, .1, .3, 1.])
+igs = [Integrand.radiator('log', 1e-8, beta=2., jet_type='quark', fixedcoupling=True, theta_scale=float(t)) for t in grid]
+res = fused.integrate_batch(igs, 400_000, numbins=30, binspacing='log', min_log_bins=grid ** 2. * 1e-15, seed=4,
+                            precision='f32', last_bc=[0., 'plus'])
 if rank == 0:
     np.savez(%(out)r, count=it._count.cpu().numpy(), sum_w=it._sum_w.cpu().numpy(), integral=np.asarray(it.integral),
-             bins2=it2.bins, count2=it2._count.cpu().numpy(), backend=backend)
+             bins2=it2.bins, count2=it2._count.cpu().numpy(), backend=backend, grid_bins=res['bins'],
+             grid_count=res['count'], grid_integral=res['integral'])
 dist.barrier()
 dist.destroy_process_group()
 '''
@@ -68,3 +79,11 @@ def test_two_ranks_equal_one(cuda, tmp_path):
     one2 = fused.integrate(ig, n, numbins=50, binspacing='log', seed=3, precision='f64', last_bc=[1., 'minus'])
     np.testing.assert_array_equal(got['bins2'], one2.bins)          # data-dependent edges via the min/max all-reduce
     np.testing.assert_array_equal(got['count2'], one2._count.cpu().numpy())
+    # the sharded grid (rank 0: points 0-2, rank 1: points 3-4) equals the grid on one GPU
+    grid = np.array([1e-3, 1e-2, .1, .3, 1.])
+    igs = [Integrand.radiator('log', 1e-8, beta=2., jet_type='quark', fixedcoupling=True, theta_scale=float(t)) for t in grid]
+    res = fused.integrate_batch(igs, 400_000, numbins=30, binspacing='log', min_log_bins=grid ** 2. * 1e-15, seed=4,
+                                precision='f32', last_bc=[0., 'plus'])
+    np.testing.assert_array_equal(got['grid_bins'], res['bins'])
+    np.testing.assert_array_equal(got['grid_count'], res['count'])
+    np.testing.assert_allclose(got['grid_integral'], res['integral'], rtol=1e-9)

@@ -224,6 +224,12 @@ grid = torch.tensor([[1. + rank, 5. + rank], [2. - rank, 9. - rank], [float("nan
 du.allreduce_minmax(grid)
 assert grid[[0, 1, 3]].tolist() == [[1., 6.], [1., 9.], [-3., -2.]]
 assert torch.isnan(grid[2]).all()
+# a parameter grid sharded by rows: every rank contributes its block of finished rows, one all-gather, no reduction
+for n_total in (5, 4, 1):
+    p0, cnt = du.shard_bounds(n_total, rank, 2)
+    rows = (torch.arange(n_total, dtype=torch.float64)[:, None] * 10 + torch.arange(3, dtype=torch.float64)[None, :])[p0:p0 + cnt]
+    full = du.gather_rows(rows, n_total, 2)
+    assert full.shape == (n_total, 3) and torch.equal(full[:, 0], torch.arange(n_total, dtype=torch.float64) * 10)
 dist.barrier()
 dist.destroy_process_group()
 print("rank", rank, "ok")
