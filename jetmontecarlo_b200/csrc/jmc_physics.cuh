@@ -196,8 +196,8 @@ __device__ __forceinline__ double sub_hc2(double C, double beta, int jet, double
                       / ((1.0 + lam(JMC_MU_NP, alpha)) * beta);
     return colour_norm(hc, b_bar(C, jet), alpha);
 }
-// :119-148
-__device__ __forceinline__ double rad_sub_rc(double C, double beta, int jet, double max_radius) {
+// :119-148, every region evaluated and masked as the reference writes it
+static __device__ __noinline__ double rad_sub_rc_all_regions(double C, double beta, int jet, double max_radius) {
     C = C / np_pow(max_radius, beta);
     const double alpha = alpha_one_loop(np_max(JMC_PT * max_radius, 1.0));
     const double knee = pow(JMC_MU_NP, beta) * pow(2.0, beta - 1.0);
@@ -208,6 +208,27 @@ __device__ __forceinline__ double rad_sub_rc(double C, double beta, int jet, dou
                            + sub_sc3(C, beta, jet, alpha));
     const double hard = msk(C > knee) * sub_hc1(C, beta, jet, alpha)
                         + msk(C < knee) * (sub_hc1(knee, beta, jet, alpha) + sub_hc2(C, beta, jet, alpha));
+    return (soft + hard) * msk(C < 1.0 / 2.0);
+}
+
+// The same value from the ACTIVE region only.  The reference's sum  m1*X1 + m2*X2 + m3*X3  of masked regions equals the
+// one region whose mask is 1 exactly (0 * finite = +-0, and x + 0 = x) -- unless some region's expression is NaN, which
+// happens iff one of its logarithm arguments is negative.  Those arguments are, for every region,
+// 1 + Lambda(MU_NP), 1 + Lambda(C) and 2 - 2C (b_bar) or larger (for beta > 1; derivation in DESIGN.md 4.2), so: test
+// the three, take the all-regions form when one fails (it yields the reference's NaN), else evaluate one region
+// (5 logarithms instead of ~25).
+__device__ __forceinline__ double rad_sub_rc(double C_in, double beta, int jet, double max_radius) {
+    const double C = C_in / np_pow(max_radius, beta);
+    const double alpha = alpha_one_loop(np_max(JMC_PT * max_radius, 1.0));
+    if (!(beta > 1.0) || !(1.0 + lam(JMC_MU_NP, alpha) > 0.0) || !(1.0 + lam(C, alpha) > 0.0) || !(2.0 - 2.0 * C > 0.0))
+        return rad_sub_rc_all_regions(C_in, beta, jet, max_radius);
+    const double knee = pow(JMC_MU_NP, beta) * pow(2.0, beta - 1.0);
+    double soft = 0.0, hard = 0.0;
+    if (C > JMC_MU_NP) soft = sub_sc1(C, beta, jet, alpha);
+    else if ((knee < C) && (C < JMC_MU_NP)) soft = sub_sc1(JMC_MU_NP, beta, jet, alpha) + sub_sc2(C, beta, jet, alpha);
+    else if (C < knee) soft = sub_sc1(JMC_MU_NP, beta, jet, alpha) + sub_sc2(knee, beta, jet, alpha) + sub_sc3(C, beta, jet, alpha);
+    if (C > knee) hard = sub_hc1(C, beta, jet, alpha);
+    else if (C < knee) hard = sub_hc1(knee, beta, jet, alpha) + sub_hc2(C, beta, jet, alpha);
     return (soft + hard) * msk(C < 1.0 / 2.0);
 }
 
@@ -245,7 +266,7 @@ __device__ __forceinline__ double crit_hc2(double theta, double z_c, int jet, do
 }
 // :263-289.  The third soft region calls critSC2/critSC3 with the DEFAULT alpha
 // (:276-277); kept.
-__device__ __forceinline__ double rad_crit_rc(double theta, double z_c, int jet) {
+static __device__ __noinline__ double rad_crit_rc_all_regions(double theta, double z_c, int jet) {
     const double alpha = JMC_ALPHA_FIXED;
     const double soft =
         msk(theta > JMC_MU_NP / z_c) * crit_sc1(theta, z_c, jet, alpha)
@@ -257,6 +278,24 @@ __device__ __forceinline__ double rad_crit_rc(double theta, double z_c, int jet)
     const double hard = msk(theta > 2.0 * JMC_MU_NP) * crit_hc1(theta, z_c, jet, alpha)
                         + msk(theta < 2.0 * JMC_MU_NP)
                               * (crit_hc1(2.0 * JMC_MU_NP, z_c, jet, alpha) + crit_hc2(theta, z_c, jet, alpha));
+    return soft + hard;
+}
+// The active region only (see rad_sub_rc).  The smallest logarithm arguments of all regions are 1 + Lambda(z_c theta)
+// (z_c < 1/2) and the constants 1 + Lambda(z_c), 1 + Lambda(MU_NP).
+__device__ __forceinline__ double rad_crit_rc(double theta, double z_c, int jet) {
+    const double alpha = JMC_ALPHA_FIXED;
+    if (!(z_c < 0.5) || !(1.0 + lam(z_c * theta, alpha) > 0.0) || !(1.0 + lam(z_c, alpha) > 0.0)
+        || !(1.0 + lam(JMC_MU_NP, alpha) > 0.0))
+        return rad_crit_rc_all_regions(theta, z_c, jet);
+    double soft = 0.0, hard = 0.0;
+    if (theta > JMC_MU_NP / z_c) soft = crit_sc1(theta, z_c, jet, alpha);
+    else if ((2.0 * JMC_MU_NP < theta) && (theta < JMC_MU_NP / z_c))
+        soft = crit_sc1(JMC_MU_NP / z_c, z_c, jet, alpha) + crit_sc2(theta, z_c, jet, alpha);
+    else if (theta < 2.0 * JMC_MU_NP)
+        soft = crit_sc1(JMC_MU_NP / z_c, z_c, jet, alpha) + crit_sc2(2.0 * JMC_MU_NP, z_c, jet, JMC_ALPHA_FIXED)
+               + crit_sc3(theta, z_c, jet, JMC_ALPHA_FIXED);
+    if (theta > 2.0 * JMC_MU_NP) hard = crit_hc1(theta, z_c, jet, alpha);
+    else if (theta < 2.0 * JMC_MU_NP) hard = crit_hc1(2.0 * JMC_MU_NP, z_c, jet, alpha) + crit_hc2(theta, z_c, jet, alpha);
     return soft + hard;
 }
 // :326-347
