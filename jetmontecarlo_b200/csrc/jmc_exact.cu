@@ -36,7 +36,7 @@ __device__ __forceinline__ double fn_arg(const FnArgs& A, int k, uint64_t i) {
 // One instantiation per function id: the register allocation of the simple functions (products, observables,
 // fixed-coupling forms) is no longer that of the running-coupling radiators (the single switch kernel of round 1
 // needed 226 registers for all 23 of them), and the dead branches are gone.
-template <int FN>
+template <int FN, bool ACTIVE>
 __device__ __forceinline__ double eval_one(const jmc_fn_params& p, double x0, double x1, double x2, double x3) {
     switch (FN) {
         case JMC_FN_ALPHA_S: return alpha_running(x0, x1);
@@ -48,20 +48,20 @@ __device__ __forceinline__ double eval_one(const jmc_fn_params& p, double x0, do
         case JMC_FN_SUB_RADPRIME_FC: return radprime_sub_fc(x0, p.beta, p.jet, x1);
         case JMC_FN_SUB_PDF_FC: return pdf_sub_fc(x0, p.beta, p.jet, x1);
         case JMC_FN_PRE_RAD_FC: return rad_pre_fc(x0, x1, p.z_cut, p.jet, x2);
-        case JMC_FN_CRIT_RAD_RC: return rad_crit_rc(x0, p.z_cut, p.jet);
+        case JMC_FN_CRIT_RAD_RC: return rad_crit_rc<ACTIVE>(x0, p.z_cut, p.jet);
         case JMC_FN_CRIT_RADPRIME_RC: return radprime_crit_rc(x0, p.z_cut, p.jet);
         // (the *_surely_nan tests return early with the NaN the full evaluation would produce, see jmc_integrand.cuh)
-        case JMC_FN_CRIT_PDF_RC: return crit_rc_surely_nan(x1, p.z_cut) ? qnan() : pdf_crit_rc(x0, x1, p.z_cut, p.jet);
-        case JMC_FN_SUB_RAD_RC: return rad_sub_rc(x0, p.beta, p.jet, x1);
+        case JMC_FN_CRIT_PDF_RC: return crit_rc_surely_nan(x1, p.z_cut) ? qnan() : pdf_crit_rc<ACTIVE>(x0, x1, p.z_cut, p.jet);
+        case JMC_FN_SUB_RAD_RC: return rad_sub_rc<ACTIVE>(x0, p.beta, p.jet, x1);
         case JMC_FN_SUB_RADPRIME_RC: return radprime_sub_rc(x0, p.beta, p.jet, x1);
-        case JMC_FN_SUB_PDF_RC: return sub_rc_surely_nan(x0, p.beta, x1) ? qnan() : pdf_sub_rc(x0, p.beta, p.jet, x1);
+        case JMC_FN_SUB_PDF_RC: return sub_rc_surely_nan(x0, p.beta, x1) ? qnan() : pdf_sub_rc<ACTIVE>(x0, p.beta, p.jet, x1);
         case JMC_FN_PRE_WEIGHT: return weight_precritical(x0, x1, p.z_cut, p.jet);
         case JMC_FN_C_GROOMED: return ecf_groomed(x0, x1, p.z_cut, p.beta, x2, x3, p.acc);
         case JMC_FN_C_UNGROOMED: return ecf_ungroomed(x0, x1, p.beta, p.acc);
         case JMC_FN_TWO_EMISSION:
             return (!p.fixed_coupling && (crit_rc_surely_nan(x1, p.z_cut)
                                           || sub_rc_surely_nan(csub_verbatim(x2, x3, p.beta), p.beta, x1)))
-                       ? qnan() : weight_two_emission(x0, x1, x2, x3, p.z_cut, p.beta, p.jet, p.fixed_coupling);
+                       ? qnan() : weight_two_emission<ACTIVE>(x0, x1, x2, x3, p.z_cut, p.beta, p.jet, p.fixed_coupling);
         case JMC_FN_PRE_WEIGHT_ZEROBIN: return weight_precritical_zerobin(x0, x1, p.z_cut, p.jet, p.epsilon);
         case JMC_FN_ALPHA_SPLITTING:
             return (p.fixed_coupling ? JMC_ALPHA_FIXED : alpha_running(x0, x1)) * splitting(x0, p.jet, p.acc);
@@ -93,7 +93,7 @@ struct FnArity {
         : (FN == JMC_FN_C_GROOMED || FN == JMC_FN_TWO_EMISSION || FN == JMC_FN_EWOC_WEIGHT) ? 4 : 2;
 };
 
-template <int FN>
+template <int FN, bool ACTIVE>
 __global__ void __launch_bounds__(kThreads) eval_fn_kernel(jmc_fn_params p, FnArgs A, uint64_t n,
                                                             double* __restrict__ out) {
     constexpr int NA = FnArity<FN>::value;
@@ -101,15 +101,26 @@ __global__ void __launch_bounds__(kThreads) eval_fn_kernel(jmc_fn_params p, FnAr
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const double x0 = fn_arg(A, 0, i), x1 = NA > 1 ? fn_arg(A, 1, i) : 0.0, x2 = NA > 2 ? fn_arg(A, 2, i) : 0.0,
                      x3 = NA > 3 ? fn_arg(A, 3, i) : 0.0;
-        out[i] = eval_one<FN>(p, x0, x1, x2, x3);
+        out[i] = eval_one<FN, ACTIVE>(p, x0, x1, x2, x3);
     }
 }
 
 template <int FN>
 static void launch_eval_fn(int fn, const jmc_fn_params& p, const FnArgs& A, uint64_t n, double* out, int grid,
                            cudaStream_t st) {
-    if (fn == FN) eval_fn_kernel<FN><<<grid, kThreads, 0, st>>>(p, A, n, out);
-    else if constexpr (FN + 1 < JMC_FN_COUNT) launch_eval_fn<FN + 1>(fn, p, A, n, out, grid, st);
+    // the running-coupling functions evaluate the active region only where its derivation holds (beta > 1, z_c < 1/2);
+    // other parameters get the all-regions instantiation
+    constexpr bool RC = FN == JMC_FN_CRIT_RAD_RC || FN == JMC_FN_CRIT_PDF_RC || FN == JMC_FN_SUB_RAD_RC
+                        || FN == JMC_FN_SUB_PDF_RC || FN == JMC_FN_TWO_EMISSION;
+    const bool sub_fn = FN == JMC_FN_SUB_RAD_RC || FN == JMC_FN_SUB_PDF_RC || FN == JMC_FN_TWO_EMISSION;
+    const bool crit_fn = FN == JMC_FN_CRIT_RAD_RC || FN == JMC_FN_CRIT_PDF_RC || FN == JMC_FN_TWO_EMISSION;
+    const bool regular = (!sub_fn || p.beta > 1.0) && (!crit_fn || p.z_cut < 0.5);
+    if (fn == FN) {
+        if (RC && !regular) eval_fn_kernel<FN, !RC><<<grid, kThreads, 0, st>>>(p, A, n, out);
+        else eval_fn_kernel<FN, true><<<grid, kThreads, 0, st>>>(p, A, n, out);
+    } else if constexpr (FN + 1 < JMC_FN_COUNT) {
+        launch_eval_fn<FN + 1>(fn, p, A, n, out, grid, st);
+    }
 }
 
 static int grid_for(uint64_t n, int threads, int blocks_per_sm = 8) {
@@ -696,7 +707,7 @@ extern "C" int jmc_finalize2d(const double* d_sum_w, const double* d_sum_w2, con
 // ---------------------------------------------------------------------------
 namespace jmc {
 
-template <int KIND>
+template <int KIND, bool ACTIVE>
 __global__ void __launch_bounds__(kThreads)
 run_exact_kernel(RunParams p, uint64_t n, uint64_t seed, uint64_t first, const double* __restrict__ edges,
                  int n_edges, double* __restrict__ g_sum_w, double* __restrict__ g_sum_w2,
@@ -722,7 +733,7 @@ run_exact_kernel(RunParams p, uint64_t n, uint64_t seed, uint64_t first, const d
         s.zb_u = 2.0;
         draw_exact<KIND>(p, first + i, seed, s);
         double jac, obs, wj;
-        integrand_eval<KIND>(p, s, jac, obs, wj);
+        integrand_eval<KIND, ACTIVE>(p, s, jac, obs, wj);
         if (do_hist) hist_add(h, n_edges, obs, wj, true, &s_poison, G);
         if (d_minmax) {
             has_nan |= (obs != obs);
@@ -740,14 +751,18 @@ static int launch_run_exact(const RunParams& p, uint64_t n, uint64_t seed, uint6
                             double* d_minmax, size_t smem, cudaStream_t st) {
     const int shift = (d_edges && smem <= 64 * 1024) ? hist_spread_shift(n_edges, 64 * 1024) : 0;
     if (d_edges) smem = hist_smem_bytes(n_edges, shift);
-    JMC_CUDA(cudaFuncSetAttribute(run_exact_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // active-region evaluation of the running-coupling radiators where its derivation holds (jmc_physics.cuh)
+    constexpr bool HAS_RC = KIND == JMC_KIND_CRIT || KIND == JMC_KIND_CRIT_SUB;
+    const bool regular = !HAS_RC || p.g.fixed_coupling || (p.g.z_cut < 0.5 && (KIND != JMC_KIND_CRIT_SUB || p.g.beta > 1.0));
+    auto kern = regular ? run_exact_kernel<KIND, true> : run_exact_kernel<KIND, !HAS_RC>;
+    JMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    JMC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, run_exact_kernel<KIND>, kThreads, smem));
+    JMC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
     if (per_sm < 1) per_sm = 1;
     const int grid = grid_for(n, kThreads, per_sm);
     if (grid < 0) return JMC_ENODEV;
-    run_exact_kernel<KIND><<<grid, kThreads, smem, st>>>(p, n, seed, first, d_edges, n_edges, d_sum_w, d_sum_w2,
-                                                          (unsigned long long*)d_count, d_poison, d_minmax, shift);
+    kern<<<grid, kThreads, smem, st>>>(p, n, seed, first, d_edges, n_edges, d_sum_w, d_sum_w2,
+                                       (unsigned long long*)d_count, d_poison, d_minmax, shift);
     JMC_LAUNCHED("run_exact_kernel");
     return JMC_OK;
 }

@@ -197,7 +197,7 @@ __device__ __forceinline__ double sub_hc2(double C, double beta, int jet, double
     return colour_norm(hc, b_bar(C, jet), alpha);
 }
 // :119-148, every region evaluated and masked as the reference writes it
-static __device__ __noinline__ double rad_sub_rc_all_regions(double C, double beta, int jet, double max_radius) {
+__device__ __forceinline__ double rad_sub_rc_all_regions(double C, double beta, int jet, double max_radius) {
     C = C / np_pow(max_radius, beta);
     const double alpha = alpha_one_loop(np_max(JMC_PT * max_radius, 1.0));
     const double knee = pow(JMC_MU_NP, beta) * pow(2.0, beta - 1.0);
@@ -216,12 +216,15 @@ static __device__ __noinline__ double rad_sub_rc_all_regions(double C, double be
 // happens iff one of its logarithm arguments is negative.  Those arguments are, for every region,
 // 1 + Lambda(MU_NP), 1 + Lambda(C) and 2 - 2C (b_bar) or larger (for beta > 1; derivation in DESIGN.md 4.2), so: test
 // the three, take the all-regions form when one fails (it yields the reference's NaN), else evaluate one region
-// (5 logarithms instead of ~25).
+// (5 logarithms instead of ~25).  ACTIVE = false is the all-regions form, instantiated by the host for parameters
+// outside that derivation (beta <= 1, z_c >= 1/2): a launch-uniform choice, made where the kernel is picked.
+template <bool ACTIVE = true>
 __device__ __forceinline__ double rad_sub_rc(double C_in, double beta, int jet, double max_radius) {
+    if (!ACTIVE) return rad_sub_rc_all_regions(C_in, beta, jet, max_radius);
     const double C = C_in / np_pow(max_radius, beta);
     const double alpha = alpha_one_loop(np_max(JMC_PT * max_radius, 1.0));
-    if (!(beta > 1.0) || !(1.0 + lam(JMC_MU_NP, alpha) > 0.0) || !(1.0 + lam(C, alpha) > 0.0) || !(2.0 - 2.0 * C > 0.0))
-        return rad_sub_rc_all_regions(C_in, beta, jet, max_radius);
+    if (!(1.0 + lam(JMC_MU_NP, alpha) > 0.0) || !(1.0 + lam(C, alpha) > 0.0) || !(2.0 - 2.0 * C > 0.0))
+        return qnan();                                    // a negative logarithm argument in some region: NaN
     const double knee = pow(JMC_MU_NP, beta) * pow(2.0, beta - 1.0);
     double soft = 0.0, hard = 0.0;
     if (C > JMC_MU_NP) soft = sub_sc1(C, beta, jet, alpha);
@@ -266,7 +269,7 @@ __device__ __forceinline__ double crit_hc2(double theta, double z_c, int jet, do
 }
 // :263-289.  The third soft region calls critSC2/critSC3 with the DEFAULT alpha
 // (:276-277); kept.
-static __device__ __noinline__ double rad_crit_rc_all_regions(double theta, double z_c, int jet) {
+__device__ __forceinline__ double rad_crit_rc_all_regions(double theta, double z_c, int jet) {
     const double alpha = JMC_ALPHA_FIXED;
     const double soft =
         msk(theta > JMC_MU_NP / z_c) * crit_sc1(theta, z_c, jet, alpha)
@@ -282,11 +285,12 @@ static __device__ __noinline__ double rad_crit_rc_all_regions(double theta, doub
 }
 // The active region only (see rad_sub_rc).  The smallest logarithm arguments of all regions are 1 + Lambda(z_c theta)
 // (z_c < 1/2) and the constants 1 + Lambda(z_c), 1 + Lambda(MU_NP).
+template <bool ACTIVE = true>
 __device__ __forceinline__ double rad_crit_rc(double theta, double z_c, int jet) {
+    if (!ACTIVE) return rad_crit_rc_all_regions(theta, z_c, jet);
     const double alpha = JMC_ALPHA_FIXED;
-    if (!(z_c < 0.5) || !(1.0 + lam(z_c * theta, alpha) > 0.0) || !(1.0 + lam(z_c, alpha) > 0.0)
-        || !(1.0 + lam(JMC_MU_NP, alpha) > 0.0))
-        return rad_crit_rc_all_regions(theta, z_c, jet);
+    if (!(1.0 + lam(z_c * theta, alpha) > 0.0) || !(1.0 + lam(z_c, alpha) > 0.0) || !(1.0 + lam(JMC_MU_NP, alpha) > 0.0))
+        return qnan();
     double soft = 0.0, hard = 0.0;
     if (theta > JMC_MU_NP / z_c) soft = crit_sc1(theta, z_c, jet, alpha);
     else if ((2.0 * JMC_MU_NP < theta) && (theta < JMC_MU_NP / z_c))
@@ -325,13 +329,15 @@ __device__ __forceinline__ double radprime_sub_rc(double c, double beta, int jet
     return jac * alpha * (two_cr(jet) * sc + b_bar(c, jet) * hc) / (JMC_PI * beta * c);
 }
 // :386-404
+template <bool ACTIVE = true>
 __device__ __forceinline__ double pdf_crit_rc(double z, double theta, double z_c, int jet) {
-    return splitting(z, jet, JMC_ACC_MLL) * alpha_running(z, theta) * exp(-1.0 * rad_crit_rc(theta, z_c, jet))
+    return splitting(z, jet, JMC_ACC_MLL) * alpha_running(z, theta) * exp(-1.0 * rad_crit_rc<ACTIVE>(theta, z_c, jet))
            / (JMC_PI * theta);
 }
 // :409-422
+template <bool ACTIVE = true>
 __device__ __forceinline__ double pdf_sub_rc(double c, double beta, int jet, double max_radius) {
-    return radprime_sub_rc(c, beta, jet, max_radius) * exp(-rad_sub_rc(c, beta, jet, max_radius));
+    return radprime_sub_rc(c, beta, jet, max_radius) * exp(-rad_sub_rc<ACTIVE>(c, beta, jet, max_radius));
 }
 
 // ---- phase-space weights                          ref: numerics/weights.py
@@ -341,8 +347,9 @@ __device__ __forceinline__ double weight_radiator(double z, double theta, int je
     return splitting(z, jet, acc) * alpha / (theta * JMC_PI);
 }
 // :31-41
+template <bool ACTIVE = true>
 __device__ __forceinline__ double weight_critical(double z, double theta, double z_c, int jet, int fixed_coupling) {
-    return fixed_coupling ? pdf_crit_fc(z, theta, z_c, jet) : pdf_crit_rc(z, theta, z_c, jet);
+    return fixed_coupling ? pdf_crit_fc(z, theta, z_c, jet) : pdf_crit_rc<ACTIVE>(z, theta, z_c, jet);
 }
 // :43-58 (fixed coupling only; the host wrapper raises TypeError otherwise)
 __device__ __forceinline__ double weight_precritical(double z_pre, double theta_crit, double z_c, int jet) {
@@ -370,6 +377,7 @@ __device__ __forceinline__ double weight_precritical_zerobin(double z_pre, doubl
 __device__ __forceinline__ double csub_verbatim(double z_s, double th_s, double beta) {
     return z_s * np_pow(th_s, beta) * np_pow(th_s, beta);
 }
+template <bool ACTIVE = true>
 __device__ __forceinline__ double weight_two_emission(double z_c_em, double th_c, double z_s, double th_s,
                                                       double z_c, double beta, int jet, int fixed_coupling) {
     const double csub = csub_verbatim(z_s, th_s, beta);
@@ -378,8 +386,8 @@ __device__ __forceinline__ double weight_two_emission(double z_c_em, double th_c
         pc = pdf_crit_fc(z_c_em, th_c, z_c, jet);
         ps = pdf_sub_fc(csub, beta, jet, th_c);
     } else {
-        pc = pdf_crit_rc(z_c_em, th_c, z_c, jet);
-        ps = pdf_sub_rc(csub, beta, jet, th_c);
+        pc = pdf_crit_rc<ACTIVE>(z_c_em, th_c, z_c, jet);
+        ps = pdf_sub_rc<ACTIVE>(csub, beta, jet, th_c);
     }
     return pc * ps * (np_pow(th_s, beta) * np_pow(th_c, beta));
 }
