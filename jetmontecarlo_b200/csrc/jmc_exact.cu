@@ -37,7 +37,8 @@ __device__ __forceinline__ double fn_arg(const FnArgs& A, int k, uint64_t i) {
 // fixed-coupling forms) is no longer that of the running-coupling radiators (the single switch kernel of round 1
 // needed 226 registers for all 23 of them), and the dead branches are gone.
 template <int FN, bool ACTIVE>
-__device__ __forceinline__ double eval_one(const jmc_fn_params& p, double x0, double x1, double x2, double x3) {
+__device__ __forceinline__ double eval_one(const jmc_fn_params& p, double x0, double x1, double x2, double x3,
+                                           const CritConsts* cc) {
     switch (FN) {
         case JMC_FN_ALPHA_S: return alpha_running(x0, x1);
         case JMC_FN_SPLITTING: return splitting(x0, p.jet, p.acc);
@@ -48,10 +49,10 @@ __device__ __forceinline__ double eval_one(const jmc_fn_params& p, double x0, do
         case JMC_FN_SUB_RADPRIME_FC: return radprime_sub_fc(x0, p.beta, p.jet, x1);
         case JMC_FN_SUB_PDF_FC: return pdf_sub_fc(x0, p.beta, p.jet, x1);
         case JMC_FN_PRE_RAD_FC: return rad_pre_fc(x0, x1, p.z_cut, p.jet, x2);
-        case JMC_FN_CRIT_RAD_RC: return rad_crit_rc<ACTIVE>(x0, p.z_cut, p.jet);
+        case JMC_FN_CRIT_RAD_RC: return rad_crit_rc<ACTIVE>(x0, p.z_cut, p.jet, cc);
         case JMC_FN_CRIT_RADPRIME_RC: return radprime_crit_rc(x0, p.z_cut, p.jet);
         // (the *_surely_nan tests return early with the NaN the full evaluation would produce, see jmc_integrand.cuh)
-        case JMC_FN_CRIT_PDF_RC: return crit_rc_surely_nan(x1, p.z_cut) ? qnan() : pdf_crit_rc<ACTIVE>(x0, x1, p.z_cut, p.jet);
+        case JMC_FN_CRIT_PDF_RC: return crit_rc_surely_nan(x1, p.z_cut) ? qnan() : pdf_crit_rc<ACTIVE>(x0, x1, p.z_cut, p.jet, cc);
         case JMC_FN_SUB_RAD_RC: return rad_sub_rc<ACTIVE>(x0, p.beta, p.jet, x1);
         case JMC_FN_SUB_RADPRIME_RC: return radprime_sub_rc(x0, p.beta, p.jet, x1);
         case JMC_FN_SUB_PDF_RC: return sub_rc_surely_nan(x0, p.beta, x1) ? qnan() : pdf_sub_rc<ACTIVE>(x0, p.beta, p.jet, x1);
@@ -61,7 +62,7 @@ __device__ __forceinline__ double eval_one(const jmc_fn_params& p, double x0, do
         case JMC_FN_TWO_EMISSION:
             return (!p.fixed_coupling && (crit_rc_surely_nan(x1, p.z_cut)
                                           || sub_rc_surely_nan(csub_verbatim(x2, x3, p.beta), p.beta, x1)))
-                       ? qnan() : weight_two_emission<ACTIVE>(x0, x1, x2, x3, p.z_cut, p.beta, p.jet, p.fixed_coupling);
+                       ? qnan() : weight_two_emission<ACTIVE>(x0, x1, x2, x3, p.z_cut, p.beta, p.jet, p.fixed_coupling, cc);
         case JMC_FN_PRE_WEIGHT_ZEROBIN: return weight_precritical_zerobin(x0, x1, p.z_cut, p.jet, p.epsilon);
         case JMC_FN_ALPHA_SPLITTING:
             return (p.fixed_coupling ? JMC_ALPHA_FIXED : alpha_running(x0, x1)) * splitting(x0, p.jet, p.acc);
@@ -97,11 +98,16 @@ template <int FN, bool ACTIVE>
 __global__ void __launch_bounds__(kThreads) eval_fn_kernel(jmc_fn_params p, FnArgs A, uint64_t n,
                                                             double* __restrict__ out) {
     constexpr int NA = FnArity<FN>::value;
+    constexpr bool CRIT_RC = FN == JMC_FN_CRIT_RAD_RC || FN == JMC_FN_CRIT_PDF_RC || FN == JMC_FN_TWO_EMISSION;
+    // region-boundary values of the critical radiator: functions of (z_c, jet), once per thread
+    CritConsts consts{0.0, 0.0, 0.0};
+    if (CRIT_RC && ACTIVE && !p.fixed_coupling) consts = make_crit_consts(p.z_cut, p.jet);
+    const CritConsts* cc = (CRIT_RC && ACTIVE) ? &consts : nullptr;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const double x0 = fn_arg(A, 0, i), x1 = NA > 1 ? fn_arg(A, 1, i) : 0.0, x2 = NA > 2 ? fn_arg(A, 2, i) : 0.0,
                      x3 = NA > 3 ? fn_arg(A, 3, i) : 0.0;
-        out[i] = eval_one<FN, ACTIVE>(p, x0, x1, x2, x3);
+        out[i] = eval_one<FN, ACTIVE>(p, x0, x1, x2, x3, cc);
     }
 }
 
@@ -724,6 +730,10 @@ run_exact_kernel(RunParams p, uint64_t n, uint64_t seed, uint64_t first, const d
     } else {
         __syncthreads();
     }
+    constexpr bool CRIT_RC = KIND == JMC_KIND_CRIT || KIND == JMC_KIND_CRIT_SUB;
+    CritConsts consts{0.0, 0.0, 0.0};
+    if (CRIT_RC && ACTIVE && !p.g.fixed_coupling) consts = make_crit_consts(p.g.z_cut, p.g.jet);
+    const CritConsts* cc = (CRIT_RC && ACTIVE) ? &consts : nullptr;
     double mn = INFINITY, mx = -INFINITY;
     bool has_nan = false;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
@@ -733,7 +743,7 @@ run_exact_kernel(RunParams p, uint64_t n, uint64_t seed, uint64_t first, const d
         s.zb_u = 2.0;
         draw_exact<KIND>(p, first + i, seed, s);
         double jac, obs, wj;
-        integrand_eval<KIND, ACTIVE>(p, s, jac, obs, wj);
+        integrand_eval<KIND, ACTIVE>(p, s, jac, obs, wj, cc);
         if (do_hist) hist_add(h, n_edges, obs, wj, true, &s_poison, G);
         if (d_minmax) {
             has_nan |= (obs != obs);

@@ -95,7 +95,7 @@ __device__ __forceinline__ bool sub_rc_surely_nan(double csub, double beta, doub
 // weight first when g.nan_to_num is set.
 template <int KIND, bool ACTIVE = true>
 __device__ __forceinline__ void integrand_eval(const RunParams& p, const SampleSet& s, double& jac, double& obs,
-                                               double& wj) {
+                                               double& wj, const CritConsts* cc = nullptr) {
     const jmc_integrand& g = p.g;
     const bool is_log = g.method == JMC_LOG;
     if (KIND == JMC_KIND_RADIATOR) {
@@ -110,7 +110,7 @@ __device__ __forceinline__ void integrand_eval(const RunParams& p, const SampleS
         // ref: examples/tests/oneEmission_tests/test_fixedcoupcritsudakov.py:124-220
         obs = ecf_groomed(s.z_c, s.th_c, g.z_cut, g.beta, g.z_pre, g.f_soft, g.obs_acc);
         double w = (!g.fixed_coupling && crit_rc_surely_nan(s.th_c, g.z_cut))
-                       ? qnan() : weight_critical<ACTIVE>(s.z_c, s.th_c, g.z_cut, g.jet, g.fixed_coupling);
+                       ? qnan() : weight_critical<ACTIVE>(s.z_c, s.th_c, g.z_cut, g.jet, g.fixed_coupling, cc);
         if (g.nan_to_num) w = nan_to_num(w);
         jac = is_log ? (s.z_c - g.z_cut) * s.th_c : 1.0;
         wj = w * jac;
@@ -121,7 +121,7 @@ __device__ __forceinline__ void integrand_eval(const RunParams& p, const SampleS
         obs = np_max(ccrit, csub);
         double w = (!g.fixed_coupling && (crit_rc_surely_nan(s.th_c, g.z_cut) || sub_rc_surely_nan(csub, g.beta, s.th_c)))
                        ? qnan()
-                       : weight_two_emission<ACTIVE>(s.z_c, s.th_c, s.z_s, s.th_s, g.z_cut, g.beta, g.jet, g.fixed_coupling);
+                       : weight_two_emission<ACTIVE>(s.z_c, s.th_c, s.z_s, s.th_s, g.z_cut, g.beta, g.jet, g.fixed_coupling, cc);
         if (g.nan_to_num) w = nan_to_num(w);
         const double jc = is_log ? (s.z_c - g.z_cut) * s.th_c : 1.0;
         const double js = is_log ? s.z_s * s.th_s : 1.0;

@@ -285,21 +285,31 @@ __device__ __forceinline__ double rad_crit_rc_all_regions(double theta, double z
 }
 // The active region only (see rad_sub_rc).  The smallest logarithm arguments of all regions are 1 + Lambda(z_c theta)
 // (z_c < 1/2) and the constants 1 + Lambda(z_c), 1 + Lambda(MU_NP).
+// The values the lower regions carry over from the region boundaries depend on (z_c, jet) only: a kernel computes them
+// once per thread (CritConsts) instead of once per sample and region.
+struct CritConsts {
+    double s1, s2, h1;     // critSC1(MU_NP / z_c), critSC2(2 MU_NP), critHC1(2 MU_NP)
+};
+__device__ __forceinline__ CritConsts make_crit_consts(double z_c, int jet) {
+    CritConsts c;
+    c.s1 = crit_sc1(JMC_MU_NP / z_c, z_c, jet, JMC_ALPHA_FIXED);
+    c.s2 = crit_sc2(2.0 * JMC_MU_NP, z_c, jet, JMC_ALPHA_FIXED);
+    c.h1 = crit_hc1(2.0 * JMC_MU_NP, z_c, jet, JMC_ALPHA_FIXED);
+    return c;
+}
 template <bool ACTIVE = true>
-__device__ __forceinline__ double rad_crit_rc(double theta, double z_c, int jet) {
+__device__ __forceinline__ double rad_crit_rc(double theta, double z_c, int jet, const CritConsts* cc = nullptr) {
     if (!ACTIVE) return rad_crit_rc_all_regions(theta, z_c, jet);
     const double alpha = JMC_ALPHA_FIXED;
     if (!(1.0 + lam(z_c * theta, alpha) > 0.0) || !(1.0 + lam(z_c, alpha) > 0.0) || !(1.0 + lam(JMC_MU_NP, alpha) > 0.0))
         return qnan();
+    const CritConsts local = cc ? *cc : make_crit_consts(z_c, jet);
     double soft = 0.0, hard = 0.0;
     if (theta > JMC_MU_NP / z_c) soft = crit_sc1(theta, z_c, jet, alpha);
-    else if ((2.0 * JMC_MU_NP < theta) && (theta < JMC_MU_NP / z_c))
-        soft = crit_sc1(JMC_MU_NP / z_c, z_c, jet, alpha) + crit_sc2(theta, z_c, jet, alpha);
-    else if (theta < 2.0 * JMC_MU_NP)
-        soft = crit_sc1(JMC_MU_NP / z_c, z_c, jet, alpha) + crit_sc2(2.0 * JMC_MU_NP, z_c, jet, JMC_ALPHA_FIXED)
-               + crit_sc3(theta, z_c, jet, JMC_ALPHA_FIXED);
+    else if ((2.0 * JMC_MU_NP < theta) && (theta < JMC_MU_NP / z_c)) soft = local.s1 + crit_sc2(theta, z_c, jet, alpha);
+    else if (theta < 2.0 * JMC_MU_NP) soft = local.s1 + local.s2 + crit_sc3(theta, z_c, jet, JMC_ALPHA_FIXED);
     if (theta > 2.0 * JMC_MU_NP) hard = crit_hc1(theta, z_c, jet, alpha);
-    else if (theta < 2.0 * JMC_MU_NP) hard = crit_hc1(2.0 * JMC_MU_NP, z_c, jet, alpha) + crit_hc2(theta, z_c, jet, alpha);
+    else if (theta < 2.0 * JMC_MU_NP) hard = local.h1 + crit_hc2(theta, z_c, jet, alpha);
     return soft + hard;
 }
 // :326-347
@@ -330,8 +340,8 @@ __device__ __forceinline__ double radprime_sub_rc(double c, double beta, int jet
 }
 // :386-404
 template <bool ACTIVE = true>
-__device__ __forceinline__ double pdf_crit_rc(double z, double theta, double z_c, int jet) {
-    return splitting(z, jet, JMC_ACC_MLL) * alpha_running(z, theta) * exp(-1.0 * rad_crit_rc<ACTIVE>(theta, z_c, jet))
+__device__ __forceinline__ double pdf_crit_rc(double z, double theta, double z_c, int jet, const CritConsts* cc = nullptr) {
+    return splitting(z, jet, JMC_ACC_MLL) * alpha_running(z, theta) * exp(-1.0 * rad_crit_rc<ACTIVE>(theta, z_c, jet, cc))
            / (JMC_PI * theta);
 }
 // :409-422
@@ -348,8 +358,9 @@ __device__ __forceinline__ double weight_radiator(double z, double theta, int je
 }
 // :31-41
 template <bool ACTIVE = true>
-__device__ __forceinline__ double weight_critical(double z, double theta, double z_c, int jet, int fixed_coupling) {
-    return fixed_coupling ? pdf_crit_fc(z, theta, z_c, jet) : pdf_crit_rc<ACTIVE>(z, theta, z_c, jet);
+__device__ __forceinline__ double weight_critical(double z, double theta, double z_c, int jet, int fixed_coupling,
+                                                  const CritConsts* cc = nullptr) {
+    return fixed_coupling ? pdf_crit_fc(z, theta, z_c, jet) : pdf_crit_rc<ACTIVE>(z, theta, z_c, jet, cc);
 }
 // :43-58 (fixed coupling only; the host wrapper raises TypeError otherwise)
 __device__ __forceinline__ double weight_precritical(double z_pre, double theta_crit, double z_c, int jet) {
@@ -379,14 +390,15 @@ __device__ __forceinline__ double csub_verbatim(double z_s, double th_s, double 
 }
 template <bool ACTIVE = true>
 __device__ __forceinline__ double weight_two_emission(double z_c_em, double th_c, double z_s, double th_s,
-                                                      double z_c, double beta, int jet, int fixed_coupling) {
+                                                      double z_c, double beta, int jet, int fixed_coupling,
+                                                      const CritConsts* cc = nullptr) {
     const double csub = csub_verbatim(z_s, th_s, beta);
     double pc, ps;
     if (fixed_coupling) {
         pc = pdf_crit_fc(z_c_em, th_c, z_c, jet);
         ps = pdf_sub_fc(csub, beta, jet, th_c);
     } else {
-        pc = pdf_crit_rc<ACTIVE>(z_c_em, th_c, z_c, jet);
+        pc = pdf_crit_rc<ACTIVE>(z_c_em, th_c, z_c, jet, cc);
         ps = pdf_sub_rc<ACTIVE>(csub, beta, jet, th_c);
     }
     return pc * ps * (np_pow(th_s, beta) * np_pow(th_c, beta));

@@ -95,7 +95,7 @@ def test_device_sampling_is_the_reference_algorithm(cuda, method):
                                         lambda a, b: O.ee2h_differential_xsec(a, b, pre))
         ref_s.append(s[0]); ref_w.append(w[0]); rejected += r
     assert_allclose(p.samples, np.array(ref_s), rtol=4e-16, atol=0)            # exp(): 1 ulp
-    assert_allclose(p.jacobians, np.array(ref_w), rtol=2e-15, atol=0)
+    assert_allclose(p.jacobians, np.array(ref_w), rtol=1e-14, atol=0)      # exp() twice, a product, a quotient
     assert p.num_rejected_samples == rejected
     assert p.area == O.process_area(bounds, n, rejected)
     assert (rejected > .8 * n) == (method == 'lin')                             # half of the linear box is outside
