@@ -21,6 +21,8 @@ import torch
 from .. import _device as D
 from .. import _lib
 from .sampler import simpleSampler
+from ..utils.hist_utils import histDerivative, nan_info  # noqa: F401  (held by the reference's module as well)
+from ..utils.interpolation import get_1d_interpolation, get_2d_interpolation  # noqa: F401
 
 MIN_LOG_BIN = 1e-15
 

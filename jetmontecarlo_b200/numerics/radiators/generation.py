@@ -6,6 +6,12 @@ every grid point is a handful of kernel launches on device-resident arrays, noth
 """
 import numpy as np
 
+from ...montecarlo.integrator import *  # noqa: F401,F403  (re-exported as the reference's module does)
+from ..observables import *  # noqa: F401,F403  (re-exported as the reference's module does)
+from ..weights import *  # noqa: F401,F403  (re-exported as the reference's module does)
+from ...analytics.radiators.running_coupling import *  # noqa: F401,F403  (re-exported as the reference's module does)
+from ...analytics.radiators.fixedcoupling import *  # noqa: F401,F403  (re-exported as the reference's module does)
+from ...utils.interpolation import is_monotonic_arr, is_monotonic_func, monotonic_domain  # noqa: F401,F403  (re-exported as the reference's module does)
 from ... import _device as D
 from ...montecarlo.integrator import integrator, integrator_2d
 from ...utils.interpolation import get_2d_interpolation, lin_log_mixed_list

@@ -6,6 +6,7 @@ assertion messages; sampling itself is the jmc_sample CUDA kernel.
 import numpy as np
 
 from ... import _lib
+from ...utils.montecarlo_utils import *  # noqa: F401,F403  (re-exported as the reference's module does)
 from ...montecarlo.sampler import sampler
 
 

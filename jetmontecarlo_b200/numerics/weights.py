@@ -4,6 +4,8 @@ import numpy as np
 from .. import _lib
 from .._arrayfn import eval_fn
 from ..analytics.qcd_utils import *  # noqa: F401,F403  (re-exported as the reference's module does)
+from ..analytics.radiators.running_coupling import *  # noqa: F401,F403  (re-exported as the reference's module does)
+from ..analytics.radiators.fixedcoupling import *  # noqa: F401,F403  (re-exported as the reference's module does)
 from ..analytics.qcd_utils import _jet
 
 

@@ -14,7 +14,7 @@ import numpy as np
 
 from .. import _device as D
 from .. import _lib
-from ..montecarlo.sampler import next_key
+from .._seed import next_key
 
 
 def _uniforms(n, k=1):

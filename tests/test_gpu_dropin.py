@@ -1,0 +1,148 @@
+"""Drop-in on the GPU: scripts written against the REFERENCE's import paths (``from jetmontecarlo.... import *``) run on
+the device path after ``jetmontecarlo_b200.install_as('jetmontecarlo')``.  The flows below use the reference's API in
+the order its own tests do -- examples/tests/oneEmission_tests/test_fixedcoupcritsudakov.py:124-220 (one critical
+emission, log sampling, Sudakov factor against the closed form) and
+examples/tests/multipleEmissions_tests/LL/test_critsub_sudakov.py:151-258 (critical + subsequent) -- minus the
+plotting, and check the Monte Carlo cdfs against the closed forms those tests plot them against.  A third flow runs
+the production chain of examples/sudakov_comparisons: numerical radiator on a (z_pre, theta_crit) grid -> table ->
+per-event conditional inverse-transform samples (sudakov_utils.py:134-182, 568-607)."""
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+_PRELUDE = """
+import numpy as np
+from jetmontecarlo.montecarlo.integrator import *
+from jetmontecarlo.numerics.radiators.samplers import *
+from jetmontecarlo.numerics.observables import *
+from jetmontecarlo.numerics.radiators.generation import *
+from jetmontecarlo.analytics.sudakov_factors.fixedcoupling import *
+"""
+
+_ONE_EMISSION = _PRELUDE + """
+results = {}
+testInt = integrator()
+testInt.setLastBinBndCondition([1., 'minus'])
+for jet_type in ['quark', 'gluon']:
+    for beta in betas:
+        for zc in zcuts:
+            for eps in epsilons:
+                testSampler = criticalSampler('log', zc=zc, epsilon=eps)
+                testSampler.generateSamples(numSamples)
+                samples = testSampler.getSamples()
+                z = samples[:, 0]; theta = samples[:, 1]
+                obs = C_groomed(z, theta, zc, beta)
+                testInt.setBins(numBins, obs, 'log')
+                weights = criticalEmissionWeight(z, theta, zc, jet_type, fixedcoupling=True)
+                jacs = testSampler.jacobians
+                area = testSampler.area
+                testInt.setDensity(obs, weights * jacs, area)
+                testInt.integrate()
+                xs = testInt.bins[:-1]
+                analytic = np.array([float(a) for a in critSudakov_fc_LL(xs, zc, beta, jet_type=jet_type)])
+                results[(jet_type, beta, zc, eps)] = (np.array(testInt.integral[:-1]), np.array(testInt.integralErr), analytic)
+"""
+
+_CRIT_SUB = _PRELUDE + """
+results = {}
+test_int = integrator()
+test_int.setLastBinBndCondition([1., 'minus'])
+for jet_type in ['quark', 'gluon']:
+    for beta in betas:
+        for z_c in z_cuts:
+            for eps in epsilons:
+                crit_sampler = criticalSampler('log', zc=z_c, epsilon=eps)
+                crit_sampler.generateSamples(NUM_SAMPLES)
+                samples = crit_sampler.getSamples()
+                z_crit = samples[:, 0]
+                theta_crit = samples[:, 1]
+                sub_sampler = ungroomedSampler('log', epsilon=eps)
+                sub_sampler.generateSamples(NUM_SAMPLES)
+                samples = sub_sampler.getSamples()
+                c_sub = samples[:, 0]
+                obs = (C_groomed(z_crit, theta_crit, z_c, beta, z_pre=0., f=1., acc='LL') + c_sub)
+                test_int.setBins(NUM_BINS, obs, 'log')
+                weights = (criticalEmissionWeight(z_crit, theta_crit, z_c, jet_type, fixedcoupling=True)
+                           * subPDFAnalytic_fc_LL(c_sub, beta, jet_type=jet_type))
+                jacs = (np.array(crit_sampler.jacobians) * np.array(sub_sampler.jacobians))
+                area = (np.array(crit_sampler.area) * np.array(sub_sampler.area))
+                test_int.setDensity(obs, weights * jacs, area)
+                test_int.integrate()
+                results[(jet_type, beta, z_c, eps)] = (np.array(test_int.bins), np.array(test_int.integral),
+                                                       np.array(test_int.integralErr))
+"""
+
+
+@pytest.fixture()
+def as_jetmontecarlo():
+    import jetmontecarlo_b200
+    saved = {k: v for k, v in sys.modules.items() if k == "jetmontecarlo" or k.startswith("jetmontecarlo.")}
+    for k in saved:
+        del sys.modules[k]
+    jetmontecarlo_b200.install_as("jetmontecarlo")
+    yield
+    for k in [k for k in sys.modules if k == "jetmontecarlo" or k.startswith("jetmontecarlo.")]:
+        del sys.modules[k]
+    sys.modules.update(saved)
+
+
+def test_one_emission_flow_of_the_reference_tests(cuda, as_jetmontecarlo):
+    from jetmontecarlo_b200.montecarlo.sampler import set_seed
+    set_seed(20260101)
+    ns = dict(numSamples=400_000, numBins=60, betas=[2., 3.], zcuts=[.05, .1], epsilons=[1e-5, 1e-10])
+    exec(_ONE_EMISSION, ns)
+    assert ns['integrator'].__module__ == 'jetmontecarlo_b200.montecarlo.integrator'
+    assert len(ns['results']) == 16
+    for key, (integral, err, analytic) in ns['results'].items():
+        # the Sudakov factor of one critical emission against its closed form (what the reference plots): where the
+        # Monte Carlo has support (the closed form's power-law tail below the sampled range is cut by epsilon)
+        ok = (analytic > .05) & (err > 0)
+        pull = (integral[ok] - analytic[ok]) / err[ok]
+        assert ok.sum() > 15 and np.abs(pull).max() < 5. and np.abs(integral[ok] - analytic[ok]).max() < 2e-2, (key, np.abs(pull).max())
+
+
+def test_crit_sub_flow_of_the_reference_tests(cuda, as_jetmontecarlo):
+    """critical + subsequent emission with fixed coupling: the cdf of C_crit + C_sub ends at 1, is monotone, and lies
+    below the single-emission Sudakov factor (a second emission can only raise the observable)"""
+    from jetmontecarlo_b200.montecarlo.sampler import set_seed
+    from jetmontecarlo_b200.analytics.sudakov_factors.fixedcoupling import critSudakov_fc_LL
+    set_seed(7)
+    ns = dict(NUM_SAMPLES=400_000, NUM_BINS=60, betas=[2.], z_cuts=[.1], epsilons=[1e-5, 1e-10])
+    exec(_CRIT_SUB, ns)
+    for (jet_type, beta, z_c, eps), (bins, integral, err) in ns['results'].items():
+        assert integral[-1] == 1. and np.all(np.diff(integral) > -4 * np.r_[err, err[-1]][:-1] - 1e-9)
+        single = np.array([float(a) for a in critSudakov_fc_LL(bins[:-1], z_c, beta, jet_type=jet_type)])
+        ok = (single > .05) & (single < .999)
+        assert np.all(integral[:-1][ok] <= single[ok] + 4 * err[ok] + 2e-3), (jet_type, eps)
+        assert (integral[:-1][ok] < single[ok]).mean() > .8
+
+
+def test_production_chain_radiator_table_to_conditional_samples(cuda, as_jetmontecarlo):
+    """gen_pre_num_rad on the device (2-D integrator) -> TableRadiator -> one z_pre per critical angle by the
+    conditional inverse-transform kernel: the samples follow the cdf the table defines"""
+    from jetmontecarlo.numerics.radiators.samplers import criticalSampler, precriticalSampler
+    from jetmontecarlo.numerics.radiators.generation import gen_pre_num_rad
+    from jetmontecarlo_b200.montecarlo.sampler import set_seed
+    from jetmontecarlo_b200.numerics import sudakov_sampling as S
+    set_seed(3)
+    z_cut = .1
+    crit, pre = criticalSampler('log', zc=z_cut, epsilon=1e-8), precriticalSampler('log', zc=z_cut, epsilon=1e-8)
+    crit.generateSamples(2_000_000)
+    pre.generateSamples(2_000_000)
+    fn, d = gen_pre_num_rad(pre, crit, jet_type='quark', splitfn_accuracy='LL', bin_space='log', fixed_coupling=True,
+                            num_bins=40)
+    bins = np.array(d['bins'])
+    rad = S.TableRadiator(bins[0], bins[1], np.array(d['integral']))
+    theta = np.full(40_000, .3)
+    z_pre, w = S.generate_precritical_samples(rad, theta, z_cut, seed=5)
+    z_pre = z_pre.cpu().numpy()
+    assert np.all(w.cpu().numpy() == 1.) and np.all((z_pre >= 0) & (z_pre <= z_cut * 1.001))
+    # empirical cdf of the samples against exp(-R(z, theta)) of the same table
+    zs = np.sort(z_pre[z_pre > 1e-7])
+    probe = zs[::400]
+    emp = np.searchsorted(np.sort(z_pre), probe, side='right') / len(z_pre)
+    model = np.exp(-rad(probe, np.full_like(probe, .3)))
+    assert np.abs(emp - model).max() < .03, np.abs(emp - model).max()
