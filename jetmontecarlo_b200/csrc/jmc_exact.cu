@@ -101,8 +101,10 @@ __global__ void __launch_bounds__(kThreads) eval_fn_kernel(jmc_fn_params p, FnAr
     constexpr bool CRIT_RC = FN == JMC_FN_CRIT_RAD_RC || FN == JMC_FN_CRIT_PDF_RC || FN == JMC_FN_TWO_EMISSION;
     // region-boundary values of the critical radiator: functions of (z_c, jet), once per thread
     CritConsts consts{0.0, 0.0, 0.0};
-    if (CRIT_RC && ACTIVE && !p.fixed_coupling) consts = make_crit_consts(p.z_cut, p.jet);
-    const CritConsts* cc = (CRIT_RC && ACTIVE) ? &consts : nullptr;
+    // (fixed_coupling selects a branch of twoEmissionWeight only; the two radiator functions have no such argument)
+    const bool wanted = CRIT_RC && ACTIVE && (FN != JMC_FN_TWO_EMISSION || !p.fixed_coupling);
+    if (wanted) consts = make_crit_consts(p.z_cut, p.jet);
+    const CritConsts* cc = wanted ? &consts : nullptr;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const double x0 = fn_arg(A, 0, i), x1 = NA > 1 ? fn_arg(A, 1, i) : 0.0, x2 = NA > 2 ? fn_arg(A, 2, i) : 0.0,
