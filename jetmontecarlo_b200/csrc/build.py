@@ -30,7 +30,8 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
           "-I", os.path.join(ROOT, "include")]
 # compile-time experiment switches (scripts/try_variants.sh); unset = the defaults in the sources
 SWITCHES = ("JMC_FAST_MIN_BLOCKS", "JMC_FAST_PAIRS", "JMC_FAST_PAIRS_2W", "JMC_FAST_PIN_KEYS", "JMC_PHILOX_SPLIT", "JMC_ACC_MODE",
-            "JMC_HIST_MODE", "JMC_HIST_UNROLL", "JMC_SHOWER_MODE")
+            "JMC_HIST_MODE", "JMC_HIST_UNROLL", "JMC_SHOWER_GROUP", "JMC_SHOWER_BIN_GROUP", "JMC_SHOWER_CHUNK",
+            "JMC_SHOWER_MIN_BLOCKS")
 _DEFS = ["-D%s=%s" % (k, os.environ[k]) for k in SWITCHES if os.environ.get(k)]
 UNITS = {
     "jmc_exact.cu": ["--fmad=false"] + _DEFS,
@@ -76,9 +77,14 @@ def build(force=False, verbose=False):
     nvcc = _nvcc()
     units = {u: f for u, f in UNITS.items() if os.path.exists(os.path.join(HERE, u))}
 
+    # experiments that touch one translation unit: JMC_BUILD_ONLY=jmc_shower.cu reuses the other objects
+    only = [u for u in os.environ.get("JMC_BUILD_ONLY", "").split(",") if u]
+
     def compile_one(item):
         unit, flags = item
         obj = os.path.join(OBJ_DIR, unit.replace(".cu", ".o"))
+        if only and unit not in only and os.path.exists(obj):
+            return obj
         cmd = [nvcc, *ARCH, *COMMON, *flags, *(["-Xptxas", "-v"] if verbose else []),
                "-c", os.path.join(HERE, unit), "-o", obj]
         res = subprocess.run(cmd, capture_output=True, text=True)

@@ -11,16 +11,18 @@
 // that chain.  Nothing per jet is stored.
 //
 // Device design: one jet per lane, but lanes do not wait for each other: the
-// kernel loops over veto TRIALS, and a lane whose chain ends bins its
-// observable and immediately starts its next jet (persistent lanes with
-// refill).  Trial counts per jet are geometric (about 30 for quark, 57 for
-// gluon jets at the 1 GeV cutoff), so lock-step jets would idle most lanes.
+// kernels loop over veto TRIALS, and a lane whose chain ends starts its next
+// jet (persistent lanes with refill).  Trial counts per jet are geometric
+// (about 30 for quark, 57 for gluon jets at the 1 GeV cutoff), so lock-step
+// jets would idle most lanes.
 //
-// Two arithmetic modes:
-//   FP64: the reference's operation sequence on 53-bit Philox uniforms, jet by
-//         jet comparable with oracle/jmc_oracle.py: shower_emissions;
-//   FP32: ln(2 ang) carried instead of ang, one Philox block (r1, r2, r3) per
-//         trial, MUFU transcendentals.
+// Two kernels:
+//   shower_kernel (FP64): the reference's operation sequence on 53-bit Philox
+//         uniforms, jet by jet comparable with oracle/jmc_oracle.py:
+//         shower_emissions;
+//   shower_fast_kernel (FP32): log2(2 ang) carried instead of ang, one Philox
+//         block (r1, r2, r3) per trial, MUFU transcendentals, division-free
+//         veto, deferred observable work (see the kernel).
 // compiled with --fmad=false (shared flag of the NumPy-order translation units)
 #include <climits>
 #include <cmath>
@@ -38,8 +40,8 @@ static constexpr int kTopN = 4;              // n_emissions up to 4 (+ 'all')
 
 // lanes of a warp that have finished their jet wait until this many are ready, then bin their observables and
 // refill together (see shower_kernel)
-#ifndef JMC_SHOWER_GROUP
-#define JMC_SHOWER_GROUP 8
+#ifndef JMC_SHOWER_GROUP_EXACT
+#define JMC_SHOWER_GROUP_EXACT 8
 #endif
 
 struct ShowerParams {
@@ -219,9 +221,34 @@ __device__ __forceinline__ bool trial_exact(const ShowerParams& p, UStream& us, 
     return us.next() < cut;
 }
 
-// Launch-uniform choices are template parameters (shower accuracy, groomer, jet type, whether anything per jet is
-// written out): the veto loop runs ~30 times per jet and every uniform branch in it costs issue slots on all of them.
-template <bool EXACT, bool MLL, int GROOMER, bool QUARK, bool RECORD>
+// warp-reduced (min, max) of the observables into the two global slots
+__device__ __forceinline__ void block_minmax_to_global(double mn, double mx, double* __restrict__ d_minmax) {
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if ((threadIdx.x & 31) == 0 && mn <= mx) {
+        unsigned long long* a0 = (unsigned long long*)&d_minmax[0];
+        unsigned long long* a1 = (unsigned long long*)&d_minmax[1];
+        unsigned long long old = *a0;
+        while (mn < __longlong_as_double(old)) {
+            const unsigned long long as = old;
+            old = atomicCAS(a0, as, (unsigned long long)__double_as_longlong(mn));
+            if (old == as) break;
+        }
+        old = *a1;
+        while (mx > __longlong_as_double(old)) {
+            const unsigned long long as = old;
+            old = atomicCAS(a1, as, (unsigned long long)__double_as_longlong(mx));
+            if (old == as) break;
+        }
+    }
+}
+
+// The FP64 shower: the reference's operation order, jet by jet comparable with the oracle.  One jet per lane with
+// refill; launch-uniform choices are template parameters (shower accuracy, groomer, jet type, whether anything per
+// jet is written out).
+template <bool MLL, int GROOMER, bool QUARK, bool RECORD>
 __global__ void __launch_bounds__(kShowerThreads)
 shower_kernel(ShowerParams p, uint64_t n, uint64_t seed, uint64_t first, const double* __restrict__ edges,
               int n_edges, unsigned long long* __restrict__ g_count, double* __restrict__ d_minmax,
@@ -238,37 +265,21 @@ shower_kernel(ShowerParams p, uint64_t n, uint64_t seed, uint64_t first, const d
     uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     double mn = INFINITY, mx = -INFINITY;
 
-    // launch constants of the FP32 mode
-    const float kfac_f = (float)p.kfac, inv_beta_f = (float)(1.0 / p.beta), ln_cut_f = (float)log(p.cutoff);
-    const float beta_f = (float)p.beta, beta_sd_f = (float)p.beta_sd;
-    const float ln_zcut_f = p.z_cut > 0.0 ? (float)log(p.z_cut) : -INFINITY;
-    const float lnPT_f = (float)log(JMC_PT), lnMZ_f = (float)log(JMC_MZ), ca_f = (float)(2.0 * JMC_ALPHA_MZ * JMC_BETA0);
-    const float veto_norm_f = (float)(1.0 / (2.0 * p.cr * p.alpha));
-
     // per-lane jet state
     UStream us;
-    EcfAcc<typename std::conditional<EXACT, double, float>::type> acc;
+    EcfAcc<double> acc;
     double ang = 0.0, z = 0.0, theta = 0.0;
-    float zf = 0.5f, lnz = 0.0f, lnth = 0.0f;   // FP32 mode: the last trial's z, ln z, ln theta
-    const PhiloxKeys keys(seed);
-    float lf = 0.0f;                            // FP32 mode: ln(2 ang)
     int n_em = 0, n_trials = 0;
-    uint32_t blk32 = 0u;
     bool in_veto_loop = false;
     bool alive = j < n;
     auto start_jet = [&]() {
         us.reset(first + j, seed);
         acc.reset(GROOMER, p.z_cut);
         ang = p.ang_init;                       // ang_init = R^beta / 2, z_init = 1/2, theta_init = R (:316-321)
-        lf = p.lf_init;
         z = 0.5;
         theta = p.radius;
-        zf = 0.5f;
-        lnz = -0.69314718f;
-        lnth = lf * inv_beta_f;                 // ln R
         n_em = 0;
         n_trials = 0;
-        blk32 = 0u;
         in_veto_loop = false;
     };
     if (alive) start_jet();
@@ -277,74 +288,33 @@ shower_kernel(ShowerParams p, uint64_t n, uint64_t seed, uint64_t first, const d
         // does the chain continue?  (angularity_shower: recurse while z theta > cutoff, :262-279).  The cutoff is
         // tested on ACCEPTED emissions only: inside angularity_split the veto loop keeps trying without it (:188-209)
         bool finished = false;
-        if (alive && !in_veto_loop) {
-            if (EXACT) finished = !(z * theta > p.cutoff) || n_em >= kMaxEmissions;
-            else finished = !(lnz + lnth > ln_cut_f) || n_em >= kMaxEmissions;
-        }
+        if (alive && !in_veto_loop) finished = !(z * theta > p.cutoff) || n_em >= kMaxEmissions;
         // Finishing a jet (observable, bin, histogram atomic, refill) is ~100 instructions that only the finished
         // lanes execute; with ~30 trials per jet some lane of a warp finishes in two iterations out of three, and
-        // the other lanes would idle through it every time.  Finished lanes therefore wait until JMC_SHOWER_GROUP
+        // the other lanes would idle through it every time.  Finished lanes therefore wait until JMC_SHOWER_GROUP_EXACT
         // of them are ready (or until no lane of the warp has a trial left to do) and finish together.
         const unsigned alive_mask = __ballot_sync(0xffffffffu, alive);
         if (!alive_mask) break;
         const unsigned fin_mask = __ballot_sync(0xffffffffu, finished);
-        const bool flush = __popc(fin_mask) >= JMC_SHOWER_GROUP || fin_mask == alive_mask;
+        const bool flush = __popc(fin_mask) >= JMC_SHOWER_GROUP_EXACT || fin_mask == alive_mask;
         if (!alive || (finished && !flush)) continue;
         if (!finished) {
-            bool accepted;
             ++n_trials;
-            if (EXACT) {
-                accepted = trial_exact<MLL, QUARK>(p, us, ang, z, theta, error_flag);
-            } else {
-                // FP32: l' = -sqrt(l^2 - K ln r1); ln z = r2 l' - ln 2; ln theta = (1 - r2) l' / beta
-                uint32_t r[4];
-                philox4x32_10(first + j, blk32++, keys, r);
-                const float r1 = u32_to_unit_float(r[0]), r2 = u32_to_unit_float(r[1]), r3 = u32_to_unit_float(r[2]);
-                const float lp = -sqrtf(fmaf(lf, lf, -kfac_f * __logf(r1)));
-                lnz = fmaf(r2, lp, -0.69314718f);
-                lnth = (1.0f - r2) * lp * inv_beta_f;
-                lf = lp;
-                zf = __expf(lnz);
-                accepted = true;
-                if (MLL) {
-                    const float alpha = 0.118f / (1.0f + ca_f * (fmaxf(lnPT_f + lnz + lnth, 0.0f) - lnMZ_f));
-                    const float omz = 1.0f - zf;
-                    float zp;                    // z * (P(z) + P(1-z))
-                    if (QUARK) {
-                        zp = (float)JMC_CF * ((1.0f + omz * omz) + zf * (1.0f + zf * zf) / omz);
-                    } else {
-                        const float pz = (float)JMC_CA * (2.0f * omz + zf * zf * omz)
-                                         + (float)(JMC_TF * JMC_NF) * zf * (zf * zf + omz * omz);
-                        const float p1 = ((float)JMC_CA * (2.0f * zf + omz * omz * zf)
-                                          + (float)(JMC_TF * JMC_NF) * omz * (zf * zf + omz * omz)) / omz;
-                        zp = pz + zf * p1;
-                    }
-                    const float cut = alpha * zp * veto_norm_f;
-                    if (cut > 1.0f) atomicOr(error_flag, 1);
-                    accepted = r3 < cut;
-                }
-            }
+            const bool accepted = trial_exact<MLL, QUARK>(p, us, ang, z, theta, error_flag);
             in_veto_loop = !accepted;
             if (accepted) {
                 if (RECORD && dump_chain && n_em < chain_cap) {        // event record on request: (z, theta) of emission n_em
                     double* c = dump_chain + ((size_t)j * chain_cap + n_em) * 2;
-                    c[0] = EXACT ? z : (double)zf;
-                    c[1] = EXACT ? theta : (double)__expf(lnth);
+                    c[0] = z;
+                    c[1] = theta;
                 }
                 ++n_em;
                 if (n_em >= kMaxEmissions && error_flag) atomicOr(error_flag, 2);     // the record is cut here
-                if (GROOMER == 2) {
-                    if (EXACT) acc.add_rss(z, np_pow(theta, p.beta), p);
-                    else acc.add_rss(zf, __expf(beta_f * lnth), p);
-                } else if (EXACT) {
+                if (GROOMER == 2)
+                    acc.add_rss(z, np_pow(theta, p.beta), p);
+                else
                     acc.add(ecf_ungroomed(z, theta, p.beta, p.obs_mll ? JMC_ACC_MLL : JMC_ACC_LL),
                             z > p.z_cut * np_pow(theta, p.beta_sd), GROOMER);
-                } else {
-                    // C = z theta^beta [(1 - z)], grooming condition ln z > ln z_cut + beta_sd ln theta
-                    float c = __expf(fmaf(beta_f, lnth, lnz));
-                    if (p.obs_mll) c *= 1.0f - zf;
-                    acc.add(c, lnz > fmaf(beta_sd_f, lnth, ln_zcut_f), GROOMER);
-                }
             }
             continue;
         }
@@ -373,28 +343,256 @@ shower_kernel(ShowerParams p, uint64_t n, uint64_t seed, uint64_t first, const d
     __syncthreads();
     for (int k = threadIdx.x; k < nb; k += blockDim.x)
         if (s_count[k]) atomicAdd(&g_count[k], (unsigned long long)s_count[k]);
-    if (d_minmax) {
-        for (int o = 16; o > 0; o >>= 1) {
-            mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-            mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        }
-        if ((threadIdx.x & 31) == 0 && mn <= mx) {
-            unsigned long long* a0 = (unsigned long long*)&d_minmax[0];
-            unsigned long long* a1 = (unsigned long long*)&d_minmax[1];
-            unsigned long long old = *a0;
-            while (mn < __longlong_as_double(old)) {
-                const unsigned long long as = old;
-                old = atomicCAS(a0, as, (unsigned long long)__double_as_longlong(mn));
-                if (old == as) break;
+    if (d_minmax) block_minmax_to_global(mn, mx, d_minmax);
+}
+
+// ---- the FP32 shower ------------------------------------------------------------------------------------------------
+// Same algorithm, organised around what the hardware charges for: issue slots of instructions that run with few
+// lanes.  About one trial in ten is accepted and one in thirty ends a jet, so code that handles either "at once" runs
+// after nearly every trial of a warp with 1-3 of 32 lanes.  Three stages are therefore decoupled:
+//   * the PRODUCER of a lane draws veto trials -- one Philox block (r1, r2, r3) each -- and only carries
+//     (Philox index of the jet, block counter, log2(2 ang), emission count).  Everything is in base-2 logarithms, the
+//     MUFU units' native base; the veto test  r3 < alpha_s(kt) z P(z) / (2 C_R alpha_veto / z)  is multiplied through
+//     by its two denominators (both positive), so a trial has no division: LG2, SQRT, EX2 and ~35 FP32 operations.
+//     A lane whose jet ended takes the next jet index from the warp's range straight away; ranges come from one
+//     global counter (JMC_SHOWER_CHUNK jets per atomic), so lanes and blocks run dry together instead of each owning
+//     a fixed 1/grid share of geometrically distributed work;
+//   * an accepted emission is an EVENT (log2 z, log2 theta, "last of its jet") pushed on the lane's 4-deep ring in
+//     shared memory.  The ACCUMULATOR stage -- ECF top-N/sum, grooming -- pops one event per lane for all lanes
+//     together, when JMC_SHOWER_GROUP lanes have events, when a lane's ring is full, or when the warp has no trials
+//     left;
+//   * a jet's last event turns the accumulators into the observable, parked in a register; the BINNING stage
+//     (bin search, shared-memory counter, min/max) runs when JMC_SHOWER_BIN_GROUP lanes have one parked or a lane
+//     needs its slot again.
+// Jet j always uses Philox stream (first + j): the histogram does not depend on which lane ran which jet.
+#ifndef JMC_SHOWER_CHUNK
+#define JMC_SHOWER_CHUNK 128
+#endif
+#ifndef JMC_SHOWER_GROUP
+#define JMC_SHOWER_GROUP 24
+#endif
+#ifndef JMC_SHOWER_BIN_GROUP
+#define JMC_SHOWER_BIN_GROUP 24
+#endif
+#ifndef JMC_SHOWER_MIN_BLOCKS
+#define JMC_SHOWER_MIN_BLOCKS 1
+#endif
+static constexpr int kRing = 4;
+__device__ __forceinline__ float sh_ex2(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float sh_lg2(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float sh_sqrt(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
+static size_t shower_fast_smem(int n_edges) {
+    const size_t nb = n_edges > 0 ? (size_t)n_edges - 1 : 0;
+    const size_t bytes = sizeof(double) * ((size_t)(n_edges > 0 ? n_edges : 0) + (nb + 1) / 2);      // edges, counters
+    return bytes + sizeof(float2) * kRing * kShowerThreads;
+}
+
+template <bool MLL, int GROOMER, bool QUARK, bool RECORD>
+__global__ void __launch_bounds__(kShowerThreads, JMC_SHOWER_MIN_BLOCKS)
+shower_fast_kernel(ShowerParams p, uint64_t n, uint64_t seed, uint64_t first, const double* __restrict__ edges,
+                   int n_edges, unsigned long long* __restrict__ g_count, double* __restrict__ d_minmax,
+                   double* __restrict__ dump_obs, int* __restrict__ dump_n, int* __restrict__ dump_trials,
+                   double* __restrict__ dump_chain, int chain_cap, int* error_flag,
+                   unsigned long long* __restrict__ next_jet) {
+    extern __shared__ double s_raw[];
+    const int nb = n_edges > 0 ? n_edges - 1 : 0;
+    double* s_edges = s_raw;
+    unsigned int* s_count = (unsigned int*)(s_edges + (n_edges > 0 ? n_edges : 0));
+    float2* s_ring = (float2*)(s_raw + (n_edges > 0 ? n_edges : 0) + (nb + 1) / 2) + threadIdx.x;   // slot k: s_ring[k * 128]
+    for (int k = threadIdx.x; k < n_edges; k += blockDim.x) s_edges[k] = edges[k];
+    for (int k = threadIdx.x; k < nb; k += blockDim.x) s_count[k] = 0u;
+    __syncthreads();
+    const unsigned lane = threadIdx.x & 31u, lanes_below = (1u << lane) - 1u;
+    double mn = INFINITY, mx = -INFINITY;
+
+    // launch constants, base-2 logarithms
+    constexpr float kLn2 = 0.69314718055994531f, kLog2e = 1.4426950408889634f, k2m24 = 5.9604644775390625e-08f;
+    const float k2 = (float)(p.kfac / 0.69314718055994531);               // l'^2 = l^2 - (K / ln 2) log2 r1
+    const float inv_beta = (float)(1.0 / p.beta), beta_f = (float)p.beta, beta_sd_f = (float)p.beta_sd;
+    const float l2_init = p.lf_init * kLog2e;
+    const float l2_cut = (float)(log(p.cutoff) * 1.4426950408889634);
+    const float l2_zcut = p.z_cut > 0.0 ? (float)(log(p.z_cut) * 1.4426950408889634) : -INFINITY;
+    const float l2_pt = (float)(log(JMC_PT) * 1.4426950408889634);
+    // alpha_s(kt) = alpha_MZ / D,  D = 1 + 2 alpha_MZ beta_0 (max(ln(pT z theta), 0) - ln M_Z) = d0 + d1 max(log2 .., 0)
+    const float d1 = (float)(2.0 * JMC_ALPHA_MZ * JMC_BETA0) * kLn2;
+    const float d0 = (float)(1.0 - 2.0 * JMC_ALPHA_MZ * JMC_BETA0 * log(JMC_MZ));
+    // accept  <=>  (i3 + 1/2) D (1 - z) < 2^24 alpha_MZ / (2 C_R alpha_veto) * [z P(z) + z P(1 - z)] (1 - z)
+    const float veto_c = (float)(16777216.0 * JMC_ALPHA_MZ / (2.0 * p.cr * p.alpha));
+    // the jet's first splitting has z = 1/2, theta = R: a shower whose cutoff is above R / 2 has no emissions at all
+    const bool start_ok = -1.0f + l2_init * inv_beta > l2_cut;
+    const PhiloxKeys keys(seed);
+
+    // producer
+    uint64_t jx = 0;                                  // Philox index of the lane's jet: first + j
+    uint32_t blk = 0u;
+    float l2 = 0.0f;
+    int n_em = 0, n_trials = 0, err = 0;
+    bool run = false;
+    int q_n = 0, q_head = 0;                          // the lane's ring of events
+    uint64_t ev_j = 0;                                // RECORD: jet of the (single) queued event
+    // accumulator stage, and the parked observable (NaN = none)
+    EcfAcc<float> acc;
+    acc.reset(GROOMER, p.z_cut);
+    double done_obs = qnan();
+    // the warp's range of jet indices (warp-uniform): Philox indices w_base + [w_off, w_cnt)
+    uint64_t w_base = 0;
+    unsigned w_off = 0u, w_cnt = 0u;
+    bool dry = false;                                 // the global counter has reached n
+    unsigned want_mask = 0xffffffffu;                 // lanes that need a jet
+
+    while (true) {
+        // ---- hand out jets ----
+        if (want_mask != 0u && (w_off < w_cnt || !dry)) {
+            const unsigned need = __popc(want_mask), left = w_cnt - w_off;
+            const unsigned r = __popc(want_mask & lanes_below);
+            const bool mine = (want_mask >> lane) & 1u;
+            if (need <= left) {
+                if (mine) { jx = w_base + (w_off + r); run = true; }
+                w_off += need;
+            } else {                                  // one atomic for the warp; the old range's rest is used first
+                uint64_t fresh = 0;
+                if (!dry) {
+                    if (lane == 0) fresh = atomicAdd(next_jet, (unsigned long long)JMC_SHOWER_CHUNK);
+                    fresh = __shfl_sync(0xffffffffu, fresh, 0);
+                }
+                const unsigned cnt = (dry || fresh >= n) ? 0u
+                                     : (n - fresh < (uint64_t)JMC_SHOWER_CHUNK ? (unsigned)(n - fresh) : (unsigned)JMC_SHOWER_CHUNK);
+                if (mine) {
+                    if (r < left) { jx = w_base + (w_off + r); run = true; }
+                    else if (r - left < cnt) { jx = first + fresh + (r - left); run = true; }
+                }
+                w_base = first + fresh;
+                w_off = need - left < cnt ? need - left : cnt;
+                w_cnt = cnt;
+                if (cnt < (unsigned)JMC_SHOWER_CHUNK) dry = true;
             }
-            old = *a1;
-            while (mx > __longlong_as_double(old)) {
-                const unsigned long long as = old;
-                old = atomicCAS(a1, as, (unsigned long long)__double_as_longlong(mx));
-                if (old == as) break;
+            if (mine && run) { blk = 0u; l2 = l2_init; n_em = 0; n_trials = 0; }
+        }
+        const unsigned run_mask = __ballot_sync(0xffffffffu, run);
+        const unsigned ev_mask = __ballot_sync(0xffffffffu, q_n != 0);
+        const unsigned done_mask = __ballot_sync(0xffffffffu, done_obs == done_obs);
+        if (!(run_mask | ev_mask | done_mask)) break;
+
+        // ---- one veto trial ----
+        bool accepted = false, last = false;
+        float lz = __int_as_float(0x7fc00000), lth = 0.0f;
+        if (run) {
+            if (!start_ok) {
+                accepted = last = true;              // event without emission (log2 z = NaN)
+            } else {
+                uint32_t r[4];
+                philox4x32_10(jx, blk++, keys, r);
+                if (RECORD) ++n_trials;
+                const float i1 = (float)(r[0] >> 8) + 0.5f, i2 = (float)(r[1] >> 8) + 0.5f, i3 = (float)(r[2] >> 8) + 0.5f;
+                const float lp = -sh_sqrt(fmaf(-k2, sh_lg2(i1 * k2m24), l2 * l2));
+                const float a = (i2 * k2m24) * lp;                            // r2 l'
+                lz = a - 1.0f;                                                // log2 z = r2 l' - 1
+                lth = (lp - a) * inv_beta;                                    // log2 theta = (1 - r2) l' / beta
+                l2 = lp;
+                accepted = true;
+                if (MLL) {
+                    const float zf = sh_ex2(lz), omz = 1.0f - zf;
+                    const float D = fmaf(d1, fmaxf(l2_pt + lz + lth, 0.0f), d0);
+                    float num;                       // [z P(z) + z P(1 - z)] (1 - z)
+                    if (QUARK) {
+                        const float o2 = omz * omz, z2 = zf * zf;
+                        num = (float)JMC_CF * (fmaf(o2, omz, omz) + fmaf(z2, zf, zf));
+                    } else {
+                        const float s2 = fmaf(zf, zf, omz * omz);
+                        const float pz = (float)JMC_CA * (2.0f * omz + zf * zf * omz) + (float)(JMC_TF * JMC_NF) * zf * s2;
+                        const float p1 = (float)JMC_CA * (2.0f * zf + omz * omz * zf) + (float)(JMC_TF * JMC_NF) * omz * s2;
+                        num = fmaf(pz, omz, zf * p1);
+                    }
+                    const float rhs = veto_c * num, lhs = D * omz;
+                    if (rhs > 16777216.0f * lhs) err |= 1;    // the reference raises: acceptance probability above 1
+                    accepted = i3 * lhs < rhs;
+                }
+                if (accepted) {
+                    if (RECORD && dump_chain && n_em < chain_cap) {
+                        double* c = dump_chain + ((size_t)(jx - first) * chain_cap + n_em) * 2;
+                        c[0] = (double)sh_ex2(lz);
+                        c[1] = (double)sh_ex2(lth);
+                    }
+                    ++n_em;
+                    // the chain continues while z theta > cutoff (angularity_shower, :262-279); tested on accepted
+                    // emissions only -- the veto loop keeps trying without it (:188-209)
+                    last = !(lz + lth > l2_cut);
+                    if (n_em >= kMaxEmissions) { last = true; err |= 2; }
+                }
             }
         }
+        // ---- accumulator stage: one event of every lane that has one ----
+        const bool full = accepted && q_n == kRing;
+        const bool drain = RECORD || __popc(ev_mask) >= JMC_SHOWER_GROUP || run_mask == 0u || __any_sync(0xffffffffu, full);
+        if (drain) {
+            const bool have = q_n != 0;
+            float e_lz = 0.0f, e_lth = 0.0f;
+            if (have) {
+                const float2 e = s_ring[q_head * kShowerThreads];
+                e_lz = e.x;
+                e_lth = e.y;
+                q_head = (q_head + 1) & (kRing - 1);
+                --q_n;
+            }
+            const bool e_last = have && (__float_as_uint(e_lth) & 1u);
+            // binning stage, before a lane overwrites its parked observable
+            const bool parked = done_obs == done_obs;
+            const bool bin_now = RECORD || __popc(done_mask) >= JMC_SHOWER_BIN_GROUP || (run_mask | ev_mask) == 0u
+                                 || __any_sync(0xffffffffu, e_last && parked);
+            if (bin_now && parked) {
+                if (n_edges > 0) {
+                    int b;
+                    if (p.guess.mode == 0 || done_obs < s_edges[p.guess_offset]) {
+                        b = bin_index(done_obs, s_edges, n_edges);
+                    } else {
+                        b = bin_index_guided(done_obs, s_edges + p.guess_offset, n_edges - p.guess_offset, p.guess);
+                        if (b >= 0) b += p.guess_offset;
+                    }
+                    if (b >= 0) atomicAdd(&s_count[b], 1u);
+                }
+                mn = fmin(mn, done_obs);
+                mx = fmax(mx, done_obs);
+                done_obs = qnan();
+            }
+            if (have) {
+                if (e_lz == e_lz) {
+                    const float zf = sh_ex2(e_lz);
+                    if (GROOMER == 2) {
+                        acc.add_rss(zf, sh_ex2(beta_f * e_lth), p);
+                    } else {
+                        float c = sh_ex2(fmaf(beta_f, e_lth, e_lz));                  // C = z theta^beta [(1 - z)]
+                        if (p.obs_mll) c *= 1.0f - zf;
+                        acc.add(c, e_lz > fmaf(beta_sd_f, e_lth, l2_zcut), GROOMER);  // z > z_cut theta^beta_sd
+                    }
+                }
+                if (e_last) {
+                    done_obs = acc.template result<GROOMER>(p);
+                    if (RECORD && dump_obs) dump_obs[ev_j] = done_obs;
+                    acc.reset(GROOMER, p.z_cut);
+                }
+            }
+        }
+        // ---- push the new event; a lane whose jet ended asks for the next one ----
+        if (accepted) {
+            // "last" travels in the lowest mantissa bit of log2 theta
+            s_ring[((q_head + q_n) & (kRing - 1)) * kShowerThreads] =
+                make_float2(lz, __uint_as_float((__float_as_uint(lth) & ~1u) | (last ? 1u : 0u)));
+            ++q_n;
+            if (RECORD) ev_j = jx - first;
+            if (last) {
+                if (RECORD && dump_n) dump_n[jx - first] = n_em;
+                if (RECORD && dump_trials) dump_trials[jx - first] = n_trials;
+                run = false;
+            }
+        }
+        want_mask = __ballot_sync(0xffffffffu, accepted && last);
     }
+    if (err) atomicOr(error_flag, err);
+    __syncthreads();
+    for (int k = threadIdx.x; k < nb; k += blockDim.x)
+        if (s_count[k]) atomicAdd(&g_count[k], (unsigned long long)s_count[k]);
+    if (d_minmax) block_minmax_to_global(mn, mx, d_minmax);
 }
 
 // ECF of stored event records (replay form of the pickers): one jet per thread walks its (z, theta) chain through the
@@ -526,7 +724,8 @@ static int shower_launch(const jmc_integrand* g, uint64_t n, uint64_t seed, uint
         shower_bin_guess(e, &p);
     }
     const size_t nb = n_edges > 0 ? (size_t)n_edges - 1 : 0;
-    const size_t smem = sizeof(double) * (size_t)n_edges + sizeof(unsigned int) * nb;
+    const size_t smem = precision == JMC_F64 ? sizeof(double) * (size_t)n_edges + sizeof(unsigned int) * nb
+                                             : shower_fast_smem(n_edges);
     if (smem > (size_t)di.max_smem_optin)
         return set_error(JMC_ELIMIT, "jmc_run: %d edges exceed shared memory", n_edges);
     cudaStream_t st = (cudaStream_t)stream;
@@ -534,33 +733,41 @@ static int shower_launch(const jmc_integrand* g, uint64_t n, uint64_t seed, uint
     rc = scratch(256 + sizeof(unsigned long long) * nb, (void**)&scr, (void*)st);
     if (rc) return rc;
     int* d_err = (int*)scr;
+    unsigned long long* d_next = (unsigned long long*)(scr + 8);         // FP32 kernel: next unassigned jet
     unsigned long long* d_before = (unsigned long long*)(scr + 256);
-    JMC_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int), st));
+    JMC_CUDA(cudaMemsetAsync(scr, 0, 16, st));
     if (nb) JMC_CUDA(cudaMemcpyAsync(d_before, d_count, sizeof(unsigned long long) * nb, cudaMemcpyDeviceToDevice, st));
-    uint64_t want = (n + kShowerThreads - 1) / kShowerThreads;
-    const uint64_t cap = (uint64_t)di.sm_count * 8;
-    const int grid = (int)(want < cap ? want : cap);
+    const uint64_t want = (n + kShowerThreads - 1) / kShowerThreads;
     const bool record = d_obs || d_n_em || d_trials || d_chain;
-    // instantiation for (precision, shower accuracy, groomer, jet type, record)
-    auto launch = [&](auto kern) -> cudaError_t {
+    const bool exact = precision == JMC_F64;
+    // instantiation for (shower accuracy, groomer, jet type, record); the grid fills every SM with resident blocks
+    auto launch = [&](auto kern, auto... extra) -> cudaError_t {
+        static int per_sm = 0;                 // per instantiation (the lambda body is instantiated per kernel)
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
+        int blocks = per_sm;
+        if (blocks == 0 || smem > 8192) {
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, kern, kShowerThreads, smem);
+            if (e != cudaSuccess) return e;
+            if (blocks < 1) blocks = 1;
+            if (smem <= 8192) per_sm = blocks;
+        }
+        const uint64_t cap = (uint64_t)di.sm_count * blocks;
+        const int grid = (int)(want < cap ? want : cap);
         kern<<<grid, kShowerThreads, smem, st>>>(p, n, seed, first_index, d_edges, n_edges, (unsigned long long*)d_count,
-                                                 d_minmax, d_obs, d_n_em, d_trials, d_chain, chain_cap, d_err);
+                                                 d_minmax, d_obs, d_n_em, d_trials, d_chain, chain_cap, d_err, extra...);
         return cudaSuccess;
     };
-#define JMC_SH5(E, M, G, Q, R) launch(shower_kernel<E, M, G, Q, R>)
-#define JMC_SH4(E, M, G, Q) (record ? JMC_SH5(E, M, G, Q, true) : JMC_SH5(E, M, G, Q, false))
-#define JMC_SH3(E, M, G) (p.jet == JMC_QUARK ? JMC_SH4(E, M, G, true) : JMC_SH4(E, M, G, false))
-#define JMC_SH2(E, M) (p.groomer == 0 ? JMC_SH3(E, M, 0) : (p.groomer == 1 ? JMC_SH3(E, M, 1) : JMC_SH3(E, M, 2)))
-#define JMC_SH1(E) (p.mll_shower ? JMC_SH2(E, true) : JMC_SH2(E, false))
-    JMC_CUDA(precision == JMC_F64 ? JMC_SH1(true) : JMC_SH1(false));
-#undef JMC_SH1
+#define JMC_SH5(M, G, Q, R) (exact ? launch(shower_kernel<M, G, Q, R>) : launch(shower_fast_kernel<M, G, Q, R>, d_next))
+#define JMC_SH4(M, G, Q) (record ? JMC_SH5(M, G, Q, true) : JMC_SH5(M, G, Q, false))
+#define JMC_SH3(M, G) (p.jet == JMC_QUARK ? JMC_SH4(M, G, true) : JMC_SH4(M, G, false))
+#define JMC_SH2(M) (p.groomer == 0 ? JMC_SH3(M, 0) : (p.groomer == 1 ? JMC_SH3(M, 1) : JMC_SH3(M, 2)))
+    JMC_CUDA(p.mll_shower ? JMC_SH2(true) : JMC_SH2(false));
 #undef JMC_SH2
 #undef JMC_SH3
 #undef JMC_SH4
 #undef JMC_SH5
-    JMC_LAUNCHED("shower_kernel");
+    JMC_LAUNCHED(exact ? "shower_kernel" : "shower_fast_kernel");
     if (nb) {
         shower_sums_kernel<<<(int)((nb + 255) / 256), 256, 0, st>>>(d_before, (const unsigned long long*)d_count, (int)nb,
                                                                      d_sum_w, d_sum_w2);

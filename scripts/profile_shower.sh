@@ -15,6 +15,6 @@ for k in range(3):
 print("done")
 PY
 python gpurun_out/_shower_job.py > gpurun_out/${TAG}_plain.log 2>&1 || { echo "plain failed"; tail -3 gpurun_out/${TAG}_plain.log; exit 1; }
-ncu --set full --clock-control none --import-source on -k regex:shower_kernel -s 1 -c 1 -f -o gpurun_out/${TAG}_prof \
+ncu --set full --clock-control none --import-source on -k regex:shower_fast_kernel -s 1 -c 1 -f -o gpurun_out/${TAG}_prof \
     python gpurun_out/_shower_job.py > gpurun_out/${TAG}_ncu.log 2>&1
 echo "shower capture rc=$?"
