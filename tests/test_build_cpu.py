@@ -64,4 +64,5 @@ def test_bandwidth_and_shower_kernels_do_not_spill():
             seen += 1
     assert seen >= 8
     fp32_shower = [v for k, v in usage.items() if "shower_fast_kernelI" in k]
-    assert fp32_shower and max(v[0] for v in fp32_shower) <= 64          # FP32 shower: at least 8 blocks of 128 threads per SM
+    assert fp32_shower and max(v[0] for v in fp32_shower) <= 80          # FP32 shower: at least 6 blocks of 128 threads per SM
+    # (measured: forcing 10 or 12 resident blocks costs 7 %, profiles/r02h_shower_shootout.log)
