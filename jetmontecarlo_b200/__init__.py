@@ -13,6 +13,7 @@ raises ImportError and calling into it without a CUDA device raises
 RuntimeError.
 """
 import importlib
+import importlib.util
 import pkgutil
 import sys
 
@@ -24,8 +25,10 @@ __version__ = "0.2.0"
 def install_as(name="jetmontecarlo"):
     """Make ``import <name>.<module>`` resolve to this package's mirror of that module, so that a script written
     against the reference (``from jetmontecarlo.montecarlo.integrator import *`` ...) runs on the GPU path unchanged.
-    Modules of the reference that are not on the hot path (plotting, file catalog, ...) are not provided: importing
-    them fails as it would without the reference installed.  Returns the list of aliased module names."""
+    Modules of the reference that are not on the hot path (plotting, ...) are not provided: importing them fails as
+    it would without the reference installed.  The reference's second top-level package, ``file_management`` (the
+    catalog of stored samples / integrals), is registered too unless a package of that name is importable.
+    Returns the list of aliased module names."""
     me = sys.modules[__name__]
     aliased = []
     sys.modules[name] = me
@@ -35,4 +38,8 @@ def install_as(name="jetmontecarlo"):
             continue
         sys.modules[name + "." + short] = importlib.import_module(info.name)
         aliased.append(name + "." + short)
+    if name == "jetmontecarlo" and "file_management" not in sys.modules and importlib.util.find_spec("file_management") is None:
+        for short in ("file_management", "file_management.catalog_utils", "file_management.data_management"):
+            sys.modules[short] = importlib.import_module(__name__ + "." + short)
+            aliased.append(short)
     return aliased

@@ -773,3 +773,41 @@ def process_ewoc():
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "process":
     process_ewoc()
+
+
+def catalog_files():
+    """A file catalog written by the reference's own file_management package (catalog_utils.py:115-185,
+    data_management.py:43-69): one 1-D numerical integral and one 2-D one (.npz) plus a pickled sample dictionary.
+    The catalog's YAML and the data files are committed as they were written, paths relative to the catalog's root."""
+    import os, shutil, tempfile
+    sys.path.insert(0, "/root/reference")
+    here = os.path.dirname(os.path.abspath(__file__))
+    dest = os.path.join(here, "..", "tests", "golden", "catalog")
+    work = tempfile.mkdtemp()
+    cwd = os.getcwd()
+    try:
+        os.chdir(work)                                  # the reference's folders are relative to the working directory
+        os.makedirs("output/examples/current")
+        os.makedirs("output/examples/overwritten")
+        open("output/examples/file_catalog.yaml", "w").close()
+        from file_management.data_management import save_new_data
+        rng = np.random.RandomState(11)
+        edges = np.logspace(-6, 0, 21)
+        save_new_data({'bins': edges, 'integral': np.sort(rng.rand(21))[::-1].copy()}, 'numerical integral', 'critical radiator',
+                      {'z_cut': 0.1, 'jet type': 'quark', 'fixed coupling': True, 'number of samples': 1000}, '.npz')
+        xs, ys = np.logspace(-8, -1, 9), np.logspace(-8, 0, 7)
+        save_new_data({'bins': np.array([xs[:7], ys]), 'integral': rng.rand(7, 7)}, 'numerical integral', 'pre-critical radiator',
+                      {'z_cut': 0.1, 'jet type': 'gluon', 'fixed coupling': False, 'number of samples': 1000}, '.npz')
+        save_new_data({'samples': rng.rand(5), 'weights': np.ones(5)}, 'montecarlo samples', 'critical sudakov inverse transform',
+                      {'z_cut': 0.05, 'beta': 2, 'epsilon': 1e-10}, '.pkl')
+        if os.path.exists(dest):
+            shutil.rmtree(dest)
+        shutil.copytree("output", os.path.join(dest, "output"))
+    finally:
+        os.chdir(cwd)
+        shutil.rmtree(work)
+    print("wrote", dest)
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "catalog":
+    catalog_files()

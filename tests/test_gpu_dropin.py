@@ -123,9 +123,10 @@ def test_crit_sub_flow_of_the_reference_tests(cuda, as_jetmontecarlo):
         assert (integral[:-1][ok] < single[ok]).mean() > .8
 
 
-def test_production_chain_radiator_table_to_conditional_samples(cuda, as_jetmontecarlo):
-    """gen_pre_num_rad on the device (2-D integrator) -> TableRadiator -> one z_pre per critical angle by the
-    conditional inverse-transform kernel: the samples follow the cdf the table defines"""
+def test_production_chain_radiator_table_to_conditional_samples(cuda, as_jetmontecarlo, tmp_path):
+    """gen_pre_num_rad on the device (2-D integrator) -> stored in the file catalog as the reference's
+    phase_space_sampling.py stores it -> loaded as a TableRadiator -> one z_pre per critical angle by the conditional
+    inverse-transform kernel: the samples follow the cdf the table defines"""
     from jetmontecarlo.numerics.radiators.samplers import criticalSampler, precriticalSampler
     from jetmontecarlo.numerics.radiators.generation import gen_pre_num_rad
     from jetmontecarlo_b200.montecarlo.sampler import set_seed
@@ -137,8 +138,15 @@ def test_production_chain_radiator_table_to_conditional_samples(cuda, as_jetmont
     pre.generateSamples(2_000_000)
     fn, d = gen_pre_num_rad(pre, crit, jet_type='quark', splitfn_accuracy='LL', bin_space='log', fixed_coupling=True,
                             num_bins=40)
-    bins = np.array(d['bins'])
-    rad = S.TableRadiator(bins[0], bins[1], np.array(d['integral']))
+    from file_management.data_management import save_new_data
+    from file_management import catalog_utils
+    from jetmontecarlo_b200.file_management.data_management import load_and_tabulate
+    catalog_utils.set_output_root(tmp_path / "output")
+    params = {'z_cut': z_cut, 'jet type': 'quark', 'fixed coupling': True, 'number of samples': 2_000_000}
+    save_new_data({'bins': np.array(d['bins']), 'integral': np.array(d['integral'])}, 'numerical integral',
+                  'pre-critical radiator', params, '.npz')
+    rad = load_and_tabulate('pre-critical radiator', params)
+    assert isinstance(rad, S.TableRadiator) and rad.zs.shape == (40, 40)
     theta = np.full(40_000, .3)
     z_pre, w = S.generate_precritical_samples(rad, theta, z_cut, seed=5)
     z_pre = z_pre.cpu().numpy()
