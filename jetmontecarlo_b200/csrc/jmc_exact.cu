@@ -715,11 +715,21 @@ extern "C" int jmc_finalize2d(const double* d_sum_w, const double* d_sum_w2, con
 // ---------------------------------------------------------------------------
 namespace jmc {
 
-template <int KIND, bool ACTIVE>
+// COMPACT (running-coupling CRIT / CRIT_SUB): 65 % / 99.7 % of the samples lie below the Landau scale and have weight
+// NaN -> 0; the rest need the ~60 FP64 transcendentals of the radiators.  Evaluated in place, 9 % of the CRIT_SUB
+// warps would run that code with one or two live lanes -- 70 % of the kernel's time.  Instead a warp appends the
+// samples that passed the NaN test to its shared-memory queue (ballot + popc) and evaluates 32 of them at a time with
+// every lane busy; the others go straight to the count histogram.  Sums are order-independent up to FP64 rounding,
+// as they already are between blocks.
+static constexpr int kExactQueueFields = 5, kExactQueueSlots = 64;       // z_c, th_c, z_s, th_s, obs
+static constexpr size_t kExactQueueBytes = sizeof(double) * kExactQueueFields * kExactQueueSlots * (kThreads / 32);
+
+template <int KIND, bool ACTIVE, bool COMPACT>
 __global__ void __launch_bounds__(kThreads)
 run_exact_kernel(RunParams p, uint64_t n, uint64_t seed, uint64_t first, const double* __restrict__ edges,
                  int n_edges, double* __restrict__ g_sum_w, double* __restrict__ g_sum_w2,
-                 unsigned long long* __restrict__ g_count, int* g_poison, double* __restrict__ d_minmax, int shift) {
+                 unsigned long long* __restrict__ g_count, int* g_poison, double* __restrict__ d_minmax, int shift,
+                 int queue_offset) {
     extern __shared__ __align__(16) double s_raw[];
     __shared__ int s_poison;
     HistSmem h(s_raw, n_edges > 0 ? n_edges : 1, shift);
@@ -739,18 +749,72 @@ run_exact_kernel(RunParams p, uint64_t n, uint64_t seed, uint64_t first, const d
     double mn = INFINITY, mx = -INFINITY;
     bool has_nan = false;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        SampleSet s;
-        s.z_c = s.th_c = s.z_s = s.th_s = s.z_pre = 0.0;
-        s.zb_u = 2.0;
-        draw_exact<KIND>(p, first + i, seed, s);
-        double jac, obs, wj;
-        integrand_eval<KIND, ACTIVE>(p, s, jac, obs, wj, cc);
-        if (do_hist) hist_add(h, n_edges, obs, wj, true, &s_poison, G);
-        if (d_minmax) {
-            has_nan |= (obs != obs);
-            mn = fmin(mn, obs);
-            mx = fmax(mx, obs);
+    if (!COMPACT) {
+        for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+            SampleSet s;
+            s.z_c = s.th_c = s.z_s = s.th_s = s.z_pre = 0.0;
+            s.zb_u = 2.0;
+            draw_exact<KIND>(p, first + i, seed, s);
+            double jac, obs, wj;
+            integrand_eval<KIND, ACTIVE>(p, s, jac, obs, wj, cc, do_hist);
+            if (do_hist) hist_add(h, n_edges, obs, wj, true, &s_poison, G);
+            if (d_minmax) {
+                has_nan |= (obs != obs);
+                mn = fmin(mn, obs);
+                mx = fmax(mx, obs);
+            }
+        }
+    } else {
+        const unsigned lane = threadIdx.x & 31u;
+        double* q = s_raw + queue_offset + (threadIdx.x >> 5) * (kExactQueueFields * kExactQueueSlots);
+        int qn = 0;                                      // warp-uniform
+        auto drain = [&](int slot) {
+            const double wj = integrand_heavy_rc<KIND, ACTIVE>(p, q[slot], q[kExactQueueSlots + slot],
+                                                               q[2 * kExactQueueSlots + slot], q[3 * kExactQueueSlots + slot], cc);
+            hist_add(h, n_edges, q[4 * kExactQueueSlots + slot], wj, true, &s_poison, G);
+        };
+        // whole warps step together (the queue is warp-collective); lanes past n are idle in the last trip
+        for (uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); i0 < n; i0 += stride) {
+            const uint64_t i = i0 + lane;
+            const bool valid = i < n;
+            SampleSet s;
+            s.z_c = s.th_c = s.z_s = s.th_s = s.z_pre = 0.0;
+            s.zb_u = 2.0;
+            double obs = 0.0;
+            bool active = false;
+            if (valid) {
+                draw_exact<KIND>(p, first + i, seed, s);
+                active = integrand_light_rc<KIND>(p, s, obs);
+                if (d_minmax) {
+                    has_nan |= (obs != obs);
+                    mn = fmin(mn, obs);
+                    mx = fmax(mx, obs);
+                }
+                // certainly NaN: nan_to_num makes it a zero weight (count only), else it poisons like any NaN
+                if (do_hist && !active) hist_add(h, n_edges, obs, p.g.nan_to_num ? 0.0 : qnan(), true, &s_poison, G);
+            }
+            if (!do_hist) continue;
+            const unsigned m = __ballot_sync(0xffffffffu, active);
+            if (!m) continue;
+            if (active) {
+                const int slot = qn + __popc(m & ((1u << lane) - 1u));
+                q[slot] = s.z_c;
+                q[kExactQueueSlots + slot] = s.th_c;
+                q[2 * kExactQueueSlots + slot] = s.z_s;
+                q[3 * kExactQueueSlots + slot] = s.th_s;
+                q[4 * kExactQueueSlots + slot] = obs;
+            }
+            qn += __popc(m);
+            __syncwarp();
+            if (qn >= 32) {
+                qn -= 32;
+                drain(qn + (int)lane);
+                __syncwarp();
+            }
+        }
+        if (do_hist) {
+            __syncwarp();
+            if ((int)lane < qn) drain((int)lane);
         }
     }
     if (do_hist) hist_flush(h, n_edges, g_sum_w, g_sum_w2, g_count, &s_poison, g_poison);
@@ -761,12 +825,21 @@ template <int KIND>
 static int launch_run_exact(const RunParams& p, uint64_t n, uint64_t seed, uint64_t first, const double* d_edges,
                             int n_edges, double* d_sum_w, double* d_sum_w2, uint64_t* d_count, int* d_poison,
                             double* d_minmax, size_t smem, cudaStream_t st) {
-    const int shift = (d_edges && smem <= 64 * 1024) ? hist_spread_shift(n_edges, 64 * 1024) : 0;
-    if (d_edges) smem = hist_smem_bytes(n_edges, shift);
     // active-region evaluation of the running-coupling radiators where its derivation holds (jmc_physics.cuh)
     constexpr bool HAS_RC = KIND == JMC_KIND_CRIT || KIND == JMC_KIND_CRIT_SUB;
     const bool regular = !HAS_RC || p.g.fixed_coupling || (p.g.z_cut < 0.5 && (KIND != JMC_KIND_CRIT_SUB || p.g.beta > 1.0));
-    auto kern = regular ? run_exact_kernel<KIND, true> : run_exact_kernel<KIND, !HAS_RC>;
+    DeviceInfo di;
+    if (device_info(&di)) return JMC_ENODEV;
+    // (a block histogram close to the shared-memory limit leaves no room for the queues: evaluated in place then)
+    const bool compact = HAS_RC && !p.g.fixed_coupling && regular
+                         && smem + kExactQueueBytes + 16 <= (size_t)di.max_smem_optin;
+    const size_t queue = compact ? kExactQueueBytes : 0;
+    const int shift = (d_edges && smem + queue <= 64 * 1024) ? hist_spread_shift(n_edges, 64 * 1024 - queue) : 0;
+    if (d_edges) smem = hist_smem_bytes(n_edges, shift);
+    const int queue_offset = (int)((smem + 15) / 16 * 2);          // in doubles, 16-byte aligned
+    if (compact) smem = (size_t)queue_offset * sizeof(double) + queue;
+    auto kern = compact ? run_exact_kernel<KIND, true, HAS_RC>
+                        : (regular ? run_exact_kernel<KIND, true, false> : run_exact_kernel<KIND, !HAS_RC, false>);
     JMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     JMC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
@@ -774,7 +847,7 @@ static int launch_run_exact(const RunParams& p, uint64_t n, uint64_t seed, uint6
     const int grid = grid_for(n, kThreads, per_sm);
     if (grid < 0) return JMC_ENODEV;
     kern<<<grid, kThreads, smem, st>>>(p, n, seed, first, d_edges, n_edges, d_sum_w, d_sum_w2,
-                                       (unsigned long long*)d_count, d_poison, d_minmax, shift);
+                                       (unsigned long long*)d_count, d_poison, d_minmax, shift, queue_offset);
     JMC_LAUNCHED("run_exact_kernel");
     return JMC_OK;
 }

@@ -519,10 +519,16 @@ fast_body(const FastParams& P_in, uint64_t n, uint64_t seed, uint64_t first, con
     //  (dropped: both sums as two floats in one slot updated by an explicit 64-bit atomicCAS -- ATOMS.CAS.64 returns
     //   the old value and is served lane by lane, ~64 cycles per warp: 0.98e11 / 1.49e11 / 1.38e11)
     //  4 / 5: mode 3 with FP32 slots for both sums / for sum w^2 only (summed in FP64 at the flush)
+#if JMC_ACC_MODE == 9
+    float dbg_w = 0.0f, dbg_w2 = 0.0f;
+#endif
     auto accumulate = [&](float w, int bq) {
         if (bq >= 0 && fabsf(w) > 0.0f) {                // the common case first: one compare rejects 0 and NaN
             if (LAZY) atomicAdd(&s_count[(bq << sh) | (int)(lane & ((1u << sh) - 1u))], 1u);
-#if JMC_ACC_MODE == 2
+#if JMC_ACC_MODE == 9       // measurement only: no shared-memory atomics at all (upper bound of any back end)
+            dbg_w += w + (float)bq;
+            dbg_w2 += w * w;
+#elif JMC_ACC_MODE == 2
             const unsigned mask = __activemask();
             const unsigned peers = __match_any_sync(mask, bq);
             const int leader = __ffs(peers) - 1;
@@ -745,6 +751,9 @@ fast_body(const FastParams& P_in, uint64_t n, uint64_t seed, uint64_t first, con
         __syncwarp();
         if ((int)lane < qn) drain((int)lane);
     }
+#if JMC_ACC_MODE == 9
+    if (dbg_w == 1.2345f) atomicAdd(&s_sum_w[0], (acc_w_t)dbg_w2);
+#endif
     __syncthreads();
     if (do_hist) {
         for (int k = threadIdx.x; k < nb; k += blockDim.x) {

@@ -89,15 +89,71 @@ __device__ __forceinline__ bool sub_rc_surely_nan(double csub, double beta, doub
     return 2.0 - 2.0 * C < 0.0;                                      // log(2 - 2C) in b_bar(C) of subHC1
 }
 
+// ---- the observable alone ---------------------------------------------------
+// (the same expressions as in integrand_eval, for passes that need nothing else)
+template <int KIND>
+__device__ __forceinline__ double integrand_observable(const RunParams& p, const SampleSet& s) {
+    const jmc_integrand& g = p.g;
+    if (KIND == JMC_KIND_RADIATOR) return ecf_ungroomed(s.z_s, s.th_s * g.theta_scale, g.beta, g.obs_acc);
+    if (KIND == JMC_KIND_CRIT) return ecf_groomed(s.z_c, s.th_c, g.z_cut, g.beta, g.z_pre, g.f_soft, g.obs_acc);
+    if (KIND == JMC_KIND_CRIT_SUB)
+        return np_max(ecf_groomed(s.z_c, s.th_c, g.z_cut, g.beta, g.z_pre, g.f_soft, g.obs_acc),
+                      csub_verbatim(s.z_s, s.th_s, g.beta));
+    if (KIND == JMC_KIND_PRE_CRIT_SUB) {
+        const double cr = casimir(g.jet);
+        const double cdf_eps = exp(-2.0 * cr * JMC_ALPHA_FIXED / JMC_PI * log(JMC_R0 / s.th_c) * log(g.z_cut / g.epsilon));
+        const double zp = (g.method == JMC_LOG && s.zb_u < cdf_eps) ? 0.0 : s.z_pre;
+        return np_max(ecf_groomed(s.z_c, s.th_c, g.z_cut, g.beta, zp, g.f_soft, g.obs_acc), s.z_s * np_pow(s.th_c, g.beta));
+    }
+    return s.z_pre;
+}
+
+// ---- running-coupling CRIT / CRIT_SUB in two steps ---------------------------
+// light: observable and "is the weight certainly NaN"; heavy: the weight times the jacobians of a sample that
+// passed -- the same expressions and operation order as integrand_eval, so that a kernel may evaluate the heavy step
+// for a different lane than the one that drew the sample (run_exact_kernel's warp compaction).
+template <int KIND>
+__device__ __forceinline__ bool integrand_light_rc(const RunParams& p, const SampleSet& s, double& obs) {
+    const jmc_integrand& g = p.g;
+    if (KIND == JMC_KIND_CRIT) {
+        obs = ecf_groomed(s.z_c, s.th_c, g.z_cut, g.beta, g.z_pre, g.f_soft, g.obs_acc);
+        return !crit_rc_surely_nan(s.th_c, g.z_cut);
+    }
+    const double csub = csub_verbatim(s.z_s, s.th_s, g.beta);
+    obs = np_max(ecf_groomed(s.z_c, s.th_c, g.z_cut, g.beta, g.z_pre, g.f_soft, g.obs_acc), csub);
+    return !(crit_rc_surely_nan(s.th_c, g.z_cut) || sub_rc_surely_nan(csub, g.beta, s.th_c));
+}
+template <int KIND, bool ACTIVE>
+__device__ __forceinline__ double integrand_heavy_rc(const RunParams& p, double z_c, double th_c, double z_s, double th_s,
+                                                     const CritConsts* cc) {
+    const jmc_integrand& g = p.g;
+    const bool is_log = g.method == JMC_LOG;
+    if (KIND == JMC_KIND_CRIT) {
+        double w = weight_critical<ACTIVE>(z_c, th_c, g.z_cut, g.jet, 0, cc);
+        if (g.nan_to_num) w = nan_to_num(w);
+        return w * (is_log ? (z_c - g.z_cut) * th_c : 1.0);
+    }
+    double w = weight_two_emission<ACTIVE>(z_c, th_c, z_s, th_s, g.z_cut, g.beta, g.jet, 0, cc);
+    if (g.nan_to_num) w = nan_to_num(w);
+    const double jc = is_log ? (z_c - g.z_cut) * th_c : 1.0;
+    const double js = is_log ? z_s * th_s : 1.0;
+    return w * jc * js;
+}
+
 // ---- one sample of the integrand -------------------------------------------
 // jac: product of the sampler jacobians (incl. theta_scale for log RADIATOR);
 // obs: the binned observable; wj: weight * jac, nan_to_num applied to the
 // weight first when g.nan_to_num is set.
 template <int KIND, bool ACTIVE = true>
 __device__ __forceinline__ void integrand_eval(const RunParams& p, const SampleSet& s, double& jac, double& obs,
-                                               double& wj, const CritConsts* cc = nullptr) {
+                                               double& wj, const CritConsts* cc = nullptr, bool need_w = true) {
     const jmc_integrand& g = p.g;
     const bool is_log = g.method == JMC_LOG;
+    if (!need_w) {          // a pass that only looks at the observables (setBins' min/max): no weight, no jacobian
+        jac = wj = 0.0;
+        obs = integrand_observable<KIND>(p, s);
+        return;
+    }
     if (KIND == JMC_KIND_RADIATOR) {
         // ref: numerics/radiators/generation.py:303-335 (theta_scale = theta_crit), weights.py:15-26
         const double th_em = s.th_s * g.theta_scale;
