@@ -104,7 +104,9 @@ def test_one_emission_flow_of_the_reference_tests(cuda, as_jetmontecarlo):
         # the phase space below epsilon is an offset of the cdf (up to ~0.1 at 1e-5): invisible at 1e-10 only
         worst = np.abs(integral[ok] - analytic[ok]).max()
         assert ok.sum() > 15 and worst < (.15 if key[3] > 1e-8 else 3e-2), (key, worst)
-        assert key[3] > 1e-8 or np.abs(pull).max() < 5., (key, np.abs(pull).max())
+        # (away from the end point, where the boundary condition pins the integral and the error bar collapses)
+        body = analytic[ok] < .97
+        assert key[3] > 1e-8 or np.abs(pull[body]).max() < 5., (key, np.abs(pull[body]).max())
 
 
 def test_crit_sub_flow_of_the_reference_tests(cuda, as_jetmontecarlo):
