@@ -43,6 +43,7 @@ int device_info(DeviceInfo* out);
 
 // small device scratch per (host thread, device, stream): poison flags, FP32 edges, staged batch parameters
 int scratch(size_t bytes, void** ptr, void* stream);
+int pinned_scratch(size_t bytes, void** ptr);
 
 // Shared-memory accumulation of (sum w, sum w^2).  FP64 (and FP32) shared-memory atomic adds are compare-and-swap
 // loops on sm_100 (ATOMS.CAST.SPIN); only 32-bit integer ones are native.  Measured alternative: interleaving the

@@ -32,6 +32,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <vector>
+#include <thread>
+#include <atomic>
 #include "jmc_common.cuh"
 #include "jmc_philox.cuh"
 
@@ -1285,18 +1287,57 @@ int run_fast_batch(const jmc_integrand* g, int n_points, uint64_t n, uint64_t se
         n_edges = 0;
     }
     std::vector<FastParams> params(n_points);
-    std::vector<float> edges_all((size_t)n_points * n_edges), one;
-    bool hot = h_edges != nullptr && d_minmax == nullptr;
-    for (int i = 0; i < n_points; ++i) {
+    // FP32 edges of every point, staged in pinned memory (100 MB for the reference's 5000 x 5000 grid)
+    const size_t n_edges_all = (size_t)n_points * (size_t)n_edges;
+    float* edges_all = nullptr;
+    if (n_edges_all) {
+        int prc = pinned_scratch(sizeof(float) * n_edges_all, (void**)&edges_all);
+        if (prc) return prc;
+    }
+    for (int i = 0; i < n_points; ++i)
         JMC_REQUIRE(g[i].kind == g[0].kind && g[i].fixed_coupling == g[0].fixed_coupling && g[i].obs_acc == g[0].obs_acc,
                     "jmc_run_batch: all points must share kind, coupling and observable accuracy (point %d differs)", i);
-        int rc = make_fast_params(&g[i], h_edges ? h_edges + (size_t)i * n_edges : nullptr, n_edges, &params[i], &one);
-        if (rc) return rc;
-        if (h_edges) std::memcpy(&edges_all[(size_t)i * n_edges], one.data(), sizeof(float) * n_edges);
+    // Per point: kernel parameters and the FP32 compare-domain edges (a log2 per edge: 25 M of them for the
+    // reference's 5000 x 5000 grid -- 0.2 s on one core, which was two thirds of that histogram pass).  Points are
+    // independent: split over the host's cores.  A failing point is redone on the calling thread for its message.
+    std::atomic<int> first_bad(n_points);
+    auto plan_points = [&](int lo, int hi) {
+        std::vector<float> one;
+        for (int i = lo; i < hi && first_bad.load(std::memory_order_relaxed) > i; ++i) {
+            const int rc = make_fast_params(&g[i], h_edges ? h_edges + (size_t)i * n_edges : nullptr, n_edges, &params[i], &one);
+            if (rc) {
+                int seen = first_bad.load();
+                while (i < seen && !first_bad.compare_exchange_weak(seen, i)) {}
+                return;
+            }
+            if (h_edges) std::memcpy(&edges_all[(size_t)i * n_edges], one.data(), sizeof(float) * n_edges);
+            if (!h_edges) params[i].n_edges = 0;
+        }
+    };
+    const size_t work = (size_t)n_points * (size_t)(n_edges > 0 ? n_edges : 1);
+    unsigned workers = work < (1u << 18) ? 1u : std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+    if (workers > (unsigned)n_points) workers = (unsigned)n_points;
+    if (workers <= 1) {
+        plan_points(0, n_points);
+    } else {
+        std::vector<std::thread> pool;
+        const int per = (n_points + (int)workers - 1) / (int)workers;
+        for (unsigned t = 0; t < workers; ++t) {
+            const int lo = (int)t * per, hi = std::min(n_points, lo + per);
+            if (lo < hi) pool.emplace_back(plan_points, lo, hi);
+        }
+        for (auto& th : pool) th.join();
+    }
+    if (first_bad.load() < n_points) {
+        std::vector<float> one;
+        const int i = first_bad.load();
+        const int rc = make_fast_params(&g[i], h_edges ? h_edges + (size_t)i * n_edges : nullptr, n_edges, &params[i], &one);
+        return rc ? rc : set_error(JMC_EINVAL, "jmc_run_batch: point %d could not be planned", i);
+    }
+    bool hot = h_edges != nullptr && d_minmax == nullptr;
+    for (int i = 0; i < n_points; ++i)
         hot = hot && params[i].dom_log && params[i].uniform
               && (params[i].nan_to_num || g[0].fixed_coupling || g[0].kind == JMC_KIND_RADIATOR);
-        if (!h_edges) params[i].n_edges = 0;
-    }
     if (n == 0) return JMC_OK;
     const bool big = hot && fast_smem_bytes(n_edges) > kBigSmemThreshold;
     const int shift = h_edges ? fast_spread_shift(n_edges, big ? kFastThreadsBig : kFastThreads,
@@ -1304,7 +1345,7 @@ int run_fast_batch(const jmc_integrand* g, int n_points, uint64_t n, uint64_t se
     for (int i = 0; i < n_points; ++i) params[i].spread_shift = shift;
     const size_t bytes_params = sizeof(FastParams) * (size_t)n_points;
     const size_t off_edges = (bytes_params + 255) & ~(size_t)255;
-    const size_t bytes_edges = sizeof(float) * edges_all.size();
+    const size_t bytes_edges = sizeof(float) * n_edges_all;
     const size_t off_poison = (off_edges + bytes_edges + 255) & ~(size_t)255;
     char* scr;
     int rc = scratch(off_poison + sizeof(int) * (size_t)n_points, (void**)&scr, (void*)st);
@@ -1313,7 +1354,7 @@ int run_fast_batch(const jmc_integrand* g, int n_points, uint64_t n, uint64_t se
     float* d_edges_f = h_edges ? (float*)(scr + off_edges) : nullptr;
     int* d_poison = (int*)(scr + off_poison);
     JMC_CUDA(cudaMemcpyAsync(d_params, params.data(), bytes_params, cudaMemcpyHostToDevice, st));
-    if (h_edges) JMC_CUDA(cudaMemcpyAsync(d_edges_f, edges_all.data(), bytes_edges, cudaMemcpyHostToDevice, st));
+    if (h_edges) JMC_CUDA(cudaMemcpyAsync(d_edges_f, edges_all, bytes_edges, cudaMemcpyHostToDevice, st));
     JMC_CUDA(cudaMemsetAsync(d_poison, 0x7f, sizeof(int) * (size_t)n_points, st));
     JMC_CUDA(cudaStreamSynchronize(st));           // the staging vectors die at return
     const bool mll = g[0].obs_acc == JMC_ACC_MLL, fixed = g[0].fixed_coupling != 0;

@@ -73,6 +73,21 @@ int scratch(size_t bytes, void** ptr, void* stream) {
     return JMC_OK;
 }
 
+// Pinned host staging of the same kind (uploads of a parameter grid's edges): one block per host thread, grows on
+// demand.  The caller synchronises the stream that reads it before asking again.
+int pinned_scratch(size_t bytes, void** ptr) {
+    static thread_local void* block = nullptr;
+    static thread_local size_t cap = 0;
+    if (cap < bytes) {
+        if (block) JMC_CUDA(cudaFreeHost(block));
+        block = nullptr; cap = 0;
+        JMC_CUDA(cudaHostAlloc(&block, bytes, cudaHostAllocDefault));
+        cap = bytes;
+    }
+    *ptr = block;
+    return JMC_OK;
+}
+
 static bool valid_eps(double e) { return e > 0.0 && e < 1.0; }
 
 // Validation mirrors the reference's assertions; the Python layer raises
