@@ -378,8 +378,9 @@ def sub_results(args, sm_count, sm_mhz):
     s, nb = ig.c_struct(), len(e1) - 1
     bufs = [np.empty(nb), np.empty(nb), np.empty(nb + 1), np.empty(nb), np.empty(nb), np.empty(nb), np.empty(nb, dtype=np.uint64)]
     P = lambda a: a.ctypes.data_as(C.c_void_p)
-    call = lambda k: _lib.check(_lib.lib.jmc_integrate_host(C.byref(s), 10 ** 6, SEED, k * 10 ** 6, _lib.F32, P(e1), nb + 1,
-                                                            _lib.BC_LAST_PLUS, 0., *[P(b) for b in bufs]))
+    # (argument objects built once: a caller that issues many jobs does not re-wrap its buffers per call)
+    fn, s_ref, e_ptr, b_ptrs = _lib.lib.jmc_integrate_host, C.byref(s), P(e1), [P(b) for b in bufs]
+    call = lambda k: _lib.check(fn(s_ref, 10 ** 6, SEED, k * 10 ** 6, _lib.F32, e_ptr, nb + 1, _lib.BC_LAST_PLUS, 0., *b_ptrs))
     for k in range(20):
         call(k)
     t0 = time.perf_counter()
