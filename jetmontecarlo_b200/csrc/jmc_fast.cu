@@ -57,6 +57,9 @@ static constexpr int kQueueFields = 5, kQueueSlots = 64;   // per-warp compactio
 #ifndef JMC_FAST_PIN_KEYS
 #define JMC_FAST_PIN_KEYS 1      // keep the Philox round keys in registers across the loop
 #endif
+#ifndef JMC_FAST_CHUNK
+#define JMC_FAST_CHUNK 32        // units (warp trips) a warp takes per request from the global work counter
+#endif
 #ifndef JMC_ACC_MODE
 #define JMC_ACC_MODE 3           // shared-memory accumulation of (sum w, sum w^2), see fast_body::accumulate
 #endif
@@ -663,81 +666,91 @@ fast_body(const FastParams& P_in, uint64_t n, uint64_t seed, uint64_t first, con
     const uint64_t pa = (first + 1) >> 1, pb = end >> 1;
     const uint32_t np = pb > pa ? (uint32_t)(pb - pa) : 0u;
     const uint32_t p_hi = (uint32_t)(first >> 33);
-    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t stride = gridDim.x * blockDim.x;
-    const uint32_t mine = np > tid ? (np - tid + stride - 1) / stride : 0u;      // pairs of this thread
-    uint32_t idx = (uint32_t)pa + tid;
 
     // V pairs per trip: their Philox chains are independent, so the scheduler interleaves them (the generator
     // is a 10-deep dependent chain of IMAD.WIDE -> LOP3), and the warp-uniform work of a trip (constant loads, loop
     // control, and for the compacted kinds ONE vote on "any lane has an active sample") is paid once per 2V samples.
-    // The ballots need every lane of the warp in every trip, so all lanes run to the warp's longest trip count.
     PhiloxKeys keys(seed);
 #if JMC_FAST_PIN_KEYS
     keys.pin();
 #endif
     constexpr int V = PairWords<KIND>::FOUR ? JMC_FAST_PAIRS : JMC_FAST_PAIRS_2W;
-    const uint32_t strideV = (uint32_t)V * stride;
-    // Main loop: trips in which every lane of the warp has all V pairs (no validity tests); then at most two
-    // checked trips for the ragged end.  Lanes of a warp differ by at most one pair (consecutive tid).
-    // (small jobs take the checked loop only: every stretch of code a block runs through once is fetched cold, and
-    // below ~1e6 samples that fetch, not the arithmetic, is the kernel's duration)
-    const uint32_t full = P.checked_only ? 0u : __shfl_sync(0xffffffffu, mine, 31) / (uint32_t)V;
-    const uint32_t trips = (__shfl_sync(0xffffffffu, mine, 0) + (uint32_t)(V - 1)) / (uint32_t)V;
-    for (uint32_t j = 0; j < full; ++j, idx += strideV) {
-        PairWords<KIND> pw[V];
+    // Work is handed out, not pre-assigned.  A UNIT is 32 V consecutive pairs (one trip of one warp: lane l takes pairs
+    // l, l + 32, ...); warps take JMC_FAST_CHUNK units at a time from one global counter.  With a fixed 1/#warps share
+    // per warp the hardware scheduler lets some warps of an SM run ahead, they exit early, and the SM finishes its
+    // work with ever fewer warps to hide latencies (ncu: 23 of the 32 resident warps active on average over the
+    // kernel).  The next chunk is requested before the current one is processed, so the atomic's latency is hidden.
+    // g_poison[1] is the counter, g_poison[2] counts finished blocks: the last one re-arms both for the next launch.
+    const uint32_t n_units = np / (32u * (uint32_t)V);
+    const uint32_t n_chunks = (n_units + (uint32_t)JMC_FAST_CHUNK - 1u) / (uint32_t)JMC_FAST_CHUNK;
+    unsigned int* g_next = (unsigned int*)g_poison + 1;
+    unsigned int fetched = 0u;
+    if (lane == 0) fetched = atomicAdd(g_next, 1u);
+    while (true) {
+        const uint32_t chunk = __shfl_sync(0xffffffffu, fetched, 0);
+        if (chunk >= n_chunks) break;
+        if (lane == 0) fetched = atomicAdd(g_next, 1u);
+        const uint32_t u_end = min(n_units, (chunk + 1u) * (uint32_t)JMC_FAST_CHUNK);
+        uint32_t idx = (uint32_t)pa + chunk * (uint32_t)JMC_FAST_CHUNK * (32u * (uint32_t)V) + lane;
+        for (uint32_t u = chunk * (uint32_t)JMC_FAST_CHUNK; u < u_end; ++u, idx += 32u * (uint32_t)V) {
+            PairWords<KIND> pw[V];
 #pragma unroll
-        for (int v = 0; v < V; ++v) draw_pair<KIND>(idx + (uint32_t)v * stride, p_hi, keys, pw[v]);
-        if (COMPACT) {
-            bool act[2 * V];
-            bool any = false;
+            for (int v = 0; v < V; ++v) draw_pair<KIND>(idx + (uint32_t)v * 32u, p_hi, keys, pw[v]);
+            if (COMPACT) {
+                bool act[2 * V];
+                bool any = false;
 #pragma unroll
-            for (int k = 0; k < 2 * V; ++k) {
-                const Words w = sample_words<KIND>(pw[k >> 1], k & 1);
-                if (LAZY) {
-                    act[k] = active_from_words<KIND, FIXED>(P, w.r);
-                } else {
+                for (int k = 0; k < 2 * V; ++k) {
+                    const Words w = sample_words<KIND>(pw[k >> 1], k & 1);
+                    if (LAZY) {
+                        act[k] = active_from_words<KIND, FIXED>(P, w.r);
+                    } else {
+                        Draw d;
+                        float o;
+                        act[k] = light<KIND, FIXED, OBS_MLL>(P, w, d, o);
+                        tally(o, true);
+                        if (do_hist && !nan_to_num && !act[k]) accumulate(fnan(), weight_bin(o));
+                    }
+                    any |= act[k];
+                }
+                if (do_hist && __any_sync(0xffffffffu, any)) {
+#pragma unroll
+                    for (int k = 0; k < 2 * V; ++k) enqueue(sample_words<KIND>(pw[k >> 1], k & 1), act[k]);
+                }
+            } else {
+                // all arithmetic of the trip first (independent chains the scheduler can interleave), then its
+                // shared-memory atomics back to back: an atomic in the middle would order the samples' instruction
+                // streams
+                float o[2 * V], wt[2 * V];
+#pragma unroll
+                for (int k = 0; k < 2 * V; ++k) {
                     Draw d;
-                    float o;
-                    act[k] = light<KIND, FIXED, OBS_MLL>(P, w, d, o);
-                    tally(o, true);
-                    if (do_hist && !nan_to_num && !act[k]) accumulate(fnan(), weight_bin(o));
+                    const bool active = light<KIND, FIXED, OBS_MLL>(P, sample_words<KIND>(pw[k >> 1], k & 1), d, o[k]);
+                    wt[k] = 0.0f;
+                    if (do_hist) {
+                        if (active) wt[k] = heavy<KIND, FIXED>(P, d);
+                        else if (!FIXED && !nan_to_num) wt[k] = fnan();
+                    }
                 }
-                any |= act[k];
-            }
-            if (do_hist && __any_sync(0xffffffffu, any)) {
 #pragma unroll
-                for (int k = 0; k < 2 * V; ++k) enqueue(sample_words<KIND>(pw[k >> 1], k & 1), act[k]);
-            }
-        } else {
-            // all arithmetic of the trip first (independent chains the scheduler can interleave), then its shared-
-            // memory atomics back to back: an atomic in the middle would order the samples' instruction streams
-            float o[2 * V], wt[2 * V];
-#pragma unroll
-            for (int k = 0; k < 2 * V; ++k) {
-                Draw d;
-                const bool active = light<KIND, FIXED, OBS_MLL>(P, sample_words<KIND>(pw[k >> 1], k & 1), d, o[k]);
-                wt[k] = 0.0f;
-                if (do_hist) {
-                    if (active) wt[k] = heavy<KIND, FIXED>(P, d);
-                    else if (!FIXED && !nan_to_num) wt[k] = fnan();
+                for (int k = 0; k < 2 * V; ++k) {
+                    tally(o[k], true);
+                    if (do_hist) accumulate(wt[k], weight_bin(o[k]));
                 }
-            }
-#pragma unroll
-            for (int k = 0; k < 2 * V; ++k) {
-                tally(o[k], true);
-                if (do_hist) accumulate(wt[k], weight_bin(o[k]));
             }
         }
     }
-    for (uint32_t j = full; j < trips; ++j, idx += strideV) {
+    if (blockIdx.x == 0 && threadIdx.x < 32) {
+        // the pairs behind the last whole unit (fewer than 32 V), with every check
+        const uint32_t done = n_units * 32u * (uint32_t)V;
 #pragma unroll 1
         for (int v = 0; v < V; ++v) {
+            const uint32_t k = done + (uint32_t)v * 32u + lane;
+            if (!__any_sync(0xffffffffu, k < np)) break;
             PairWords<KIND> pw;
-            draw_pair<KIND>(idx + (uint32_t)v * stride, p_hi, keys, pw);
-            const bool valid = (uint32_t)V * j + (uint32_t)v < mine;
-            one(sample_words<KIND>(pw, 0), valid);
-            one(sample_words<KIND>(pw, 1), valid);
+            draw_pair<KIND>((uint32_t)pa + k, p_hi, keys, pw);
+            one(sample_words<KIND>(pw, 0), k < np);
+            one(sample_words<KIND>(pw, 1), k < np);
         }
     }
     if (blockIdx.x == 0 && threadIdx.x < 32) {
@@ -773,6 +786,14 @@ fast_body(const FastParams& P_in, uint64_t n, uint64_t seed, uint64_t first, con
             }
         }
         if (threadIdx.x == 0 && s_poison != INT_MAX) atomicMin(g_poison, s_poison);
+    }
+    // the last block to get here has seen every other block leave the loop: re-arm the work counter
+    if (threadIdx.x == 0) {
+        unsigned int* g_done = (unsigned int*)g_poison + 2;
+        if (atomicAdd(g_done, 1u) == gridDim.x - 1u) {
+            *g_next = 0u;
+            *g_done = 0u;
+        }
     }
     if (do_minmax) {
         for (int o = 16; o > 0; o >>= 1) {
@@ -833,7 +854,7 @@ run_fast_batch_kernel(const FastParams* __restrict__ params, uint64_t n, uint64_
     fast_body<KIND, FIXED, OBS_MLL, HOT, true>(
         sP, n, seed, first, edges_all ? edges_all + (size_t)point * n_edges : nullptr,
         sum_w_all ? sum_w_all + point * nb : nullptr, sum_w2_all ? sum_w2_all + point * nb : nullptr,
-        count_all ? count_all + point * nb : nullptr, poison_all + point,
+        count_all ? count_all + point * nb : nullptr, poison_all + 4 * point,
         minmax_all ? minmax_all + 2 * (size_t)point : nullptr, s_dyn);
 }
 
@@ -1095,7 +1116,11 @@ static int launch_fast_t(const FastParams& P, uint64_t n, uint64_t seed, uint64_
     // persistent: at most one wave of resident blocks; small jobs get fewer blocks (>= 8 sample pairs per thread),
     // so that zeroing and flushing the block histograms does not dominate them
     const uint64_t want = (n / 16 + threads) / threads;
-    const uint64_t cap = (uint64_t)di.sm_count * cfg.per_sm;
+    static const uint64_t waves = [] {                   // experiment switch: blocks per resident slot
+        const char* e = getenv("JMC_FAST_WAVES");
+        return e ? (uint64_t)std::max(1, atoi(e)) : (uint64_t)1;
+    }();
+    const uint64_t cap = (uint64_t)di.sm_count * cfg.per_sm * waves;
     const int grid = (int)(want < cap ? want : cap);
     static const uint64_t small_n = [] {                 // experiment switch: jobs below this take the checked loop only
         const char* e = getenv("JMC_FAST_SMALL_N");
@@ -1155,8 +1180,9 @@ int fast_plan_make(const jmc_integrand* g, const double* h_edges, int n_edges, F
 void fast_plan_free(FastPlan* p) { delete p; }
 const float* fast_plan_edges(const FastPlan* p) { return p->edges_f.data(); }
 
-// d_edges_f: the plan's FP32 edges on the device (NULL for a min/max-only pass); d_poison: one int preset to
-// 0x7f7f7f7f ("no poison"), left in that state.  Asynchronous on the stream, no host synchronisation.
+// d_edges_f: the plan's FP32 edges on the device (NULL for a min/max-only pass); d_poison: FOUR ints -- [0] preset to
+// 0x7f7f7f7f ("no poison"), [1] (work counter) and [2] (finished blocks) preset to 0 -- all left in that state.
+// Asynchronous on the stream, no host synchronisation.
 int fast_plan_run(const FastPlan* plan, const float* d_edges_f, int* d_poison, uint64_t n, uint64_t seed,
                   uint64_t first_index, double* d_sum_w, double* d_sum_w2, uint64_t* d_count, double* d_minmax,
                   void* stream, bool defer_poison) {
@@ -1222,7 +1248,8 @@ int run_fast(const jmc_integrand* g, uint64_t n, uint64_t seed, uint64_t first_i
     if (rc) { fast_plan_free(plan); return rc; }
     int* d_poison = (int*)scr;
     float* d_edges_f = nullptr;
-    cudaError_t e = cudaMemsetAsync(d_poison, 0x7f, sizeof(int), st);
+    cudaError_t e = cudaMemsetAsync(d_poison, 0x7f, sizeof(int), st);          // [0] poison flag: "none"
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_poison + 1, 0, 3 * sizeof(int), st);    // [1] work counter, [2] finished blocks
     if (e == cudaSuccess && d_edges) {
         d_edges_f = (float*)(scr + 256);
         e = cudaMemcpyAsync(d_edges_f, plan->edges_f.data(), sizeof(float) * n_edges, cudaMemcpyHostToDevice, st);
@@ -1236,7 +1263,7 @@ int run_fast(const jmc_integrand* g, uint64_t n, uint64_t seed, uint64_t first_i
 
 __global__ void poison_batch_kernel(const int* poison_all, int nb, double* sum_w_all, double* sum_w2_all) {
     const int point = blockIdx.x;
-    const int pb = poison_all[point];
+    const int pb = poison_all[4 * point];
     if (pb < 0 || pb >= nb) return;
     for (int k = pb + threadIdx.x; k < nb; k += blockDim.x) {
         sum_w_all[(size_t)point * nb + k] = __longlong_as_double(0x7ff8000000000000LL);
@@ -1348,14 +1375,16 @@ int run_fast_batch(const jmc_integrand* g, int n_points, uint64_t n, uint64_t se
     const size_t bytes_edges = sizeof(float) * n_edges_all;
     const size_t off_poison = (off_edges + bytes_edges + 255) & ~(size_t)255;
     char* scr;
-    int rc = scratch(off_poison + sizeof(int) * (size_t)n_points, (void**)&scr, (void*)st);
+    int rc = scratch(off_poison + 4 * sizeof(int) * (size_t)n_points, (void**)&scr, (void*)st);
     if (rc) return rc;
     FastParams* d_params = (FastParams*)scr;
     float* d_edges_f = h_edges ? (float*)(scr + off_edges) : nullptr;
     int* d_poison = (int*)(scr + off_poison);
     JMC_CUDA(cudaMemcpyAsync(d_params, params.data(), bytes_params, cudaMemcpyHostToDevice, st));
     if (h_edges) JMC_CUDA(cudaMemcpyAsync(d_edges_f, edges_all, bytes_edges, cudaMemcpyHostToDevice, st));
-    JMC_CUDA(cudaMemsetAsync(d_poison, 0x7f, sizeof(int) * (size_t)n_points, st));
+    // per point: [poison flag = "none", work counter = 0, finished blocks = 0, unused]
+    JMC_CUDA(cudaMemsetAsync(d_poison, 0, 4 * sizeof(int) * (size_t)n_points, st));
+    JMC_CUDA(cudaMemset2DAsync(d_poison, 4 * sizeof(int), 0x7f, sizeof(int), (size_t)n_points, st));
     JMC_CUDA(cudaStreamSynchronize(st));           // the staging vectors die at return
     const bool mll = g[0].obs_acc == JMC_ACC_MLL, fixed = g[0].fixed_coupling != 0;
 #define JMC_B(K, F, M, H)                                                                                              \

@@ -423,7 +423,8 @@ int handle_reserve(jmc_handle* h, int n_edges) {
         h->d_ws = nullptr; h->ws_cap = 0;
         JMC_CUDA(cudaMalloc((void**)&h->d_ws, L.total));
         h->ws_cap = L.total;
-        JMC_CUDA(cudaMemset(h->d_ws, 0x7f, 256));           // poison flag: "none"; the poison kernels re-arm it
+        JMC_CUDA(cudaMemset(h->d_ws, 0, 256));              // work counter / finished blocks of the fused kernels: 0
+        JMC_CUDA(cudaMemset(h->d_ws, 0x7f, sizeof(int)));   // poison flag: "none"; the kernels re-arm all three
         h->has_job = false;
     }
     if (h->pin_cap < L.total) {

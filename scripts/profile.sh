@@ -10,6 +10,6 @@ tail -1 gpurun_out/${TAG}_plain.log | cut -c1-300
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv \
     python bench.py $ARGS > gpurun_out/${TAG}_ncu_list.log 2>&1
 echo "launch list rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:run_fast_kernel -s 3 -c 2 -f -o gpurun_out/${TAG}_prof \
+ncu --set full --clock-control none --import-source on -k regex:run_fast_kernel -s 3 -c 1 -f -o gpurun_out/${TAG}_prof \
     python bench.py $ARGS > gpurun_out/${TAG}_ncu_full.log 2>&1
 echo "full capture rc=$?"
