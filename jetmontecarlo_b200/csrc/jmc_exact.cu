@@ -844,7 +844,11 @@ static int launch_run_exact(const RunParams& p, uint64_t n, uint64_t seed, uint6
     int per_sm = 0;
     JMC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
     if (per_sm < 1) per_sm = 1;
-    const int grid = grid_for(n, kThreads, per_sm);
+    static const int waves = [] {                         // experiment switch: blocks per resident slot
+        const char* e = getenv("JMC_EXACT_WAVES");
+        return e ? std::max(1, atoi(e)) : 1;
+    }();
+    const int grid = grid_for(n, kThreads, per_sm * waves);
     if (grid < 0) return JMC_ENODEV;
     kern<<<grid, kThreads, smem, st>>>(p, n, seed, first, d_edges, n_edges, d_sum_w, d_sum_w2,
                                        (unsigned long long*)d_count, d_poison, d_minmax, shift, queue_offset);
