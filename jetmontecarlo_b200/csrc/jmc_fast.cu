@@ -51,6 +51,9 @@ static constexpr int kQueueFields = 5, kQueueSlots = 64;   // per-warp compactio
 #ifndef JMC_FAST_PAIRS
 #define JMC_FAST_PAIRS 1         // sample pairs per loop trip, kinds with >= 4 uniforms per sample
 #endif
+#ifndef JMC_FAST_PAIRS_COMPACT
+#define JMC_FAST_PAIRS_COMPACT 2 // the same for the warp-compacted kinds (running-coupling critical x subsequent)
+#endif
 #ifndef JMC_FAST_PAIRS_2W
 #define JMC_FAST_PAIRS_2W 2      // sample pairs per loop trip, kinds with 2 uniforms per sample (one Philox block per pair)
 #endif
@@ -674,7 +677,9 @@ fast_body(const FastParams& P_in, uint64_t n, uint64_t seed, uint64_t first, con
 #if JMC_FAST_PIN_KEYS
     keys.pin();
 #endif
-    constexpr int V = PairWords<KIND>::FOUR ? JMC_FAST_PAIRS : JMC_FAST_PAIRS_2W;
+    // (measured with chunked work, profiles/r02q_pairs.log: the compacted 4-word kinds gain 3-6 % from two pairs per
+    // trip -- one vote per four samples --, the others lose 1 %)
+    constexpr int V = PairWords<KIND>::FOUR ? (COMPACT ? JMC_FAST_PAIRS_COMPACT : JMC_FAST_PAIRS) : JMC_FAST_PAIRS_2W;
     // Work is handed out, not pre-assigned.  A UNIT is 32 V consecutive pairs (one trip of one warp: lane l takes pairs
     // l, l + 32, ...); warps take JMC_FAST_CHUNK units at a time from one global counter.  With a fixed 1/#warps share
     // per warp the hardware scheduler lets some warps of an SM run ahead, they exit early, and the SM finishes its
