@@ -687,17 +687,23 @@ fast_body(const FastParams& P_in, uint64_t n, uint64_t seed, uint64_t first, con
     // kernel).  The next chunk is requested before the current one is processed, so the atomic's latency is hidden.
     // g_poison[1] is the counter, g_poison[2] counts finished blocks: the last one re-arms both for the next launch.
     const uint32_t n_units = np / (32u * (uint32_t)V);
-    const uint32_t n_chunks = (n_units + (uint32_t)JMC_FAST_CHUNK - 1u) / (uint32_t)JMC_FAST_CHUNK;
+    // Large jobs only (>= 16 units per warp): a small job is launch- and latency-bound, there every warp takes its
+    // fixed share (unit w, w + #warps, ...) without touching the counter.
+    const uint32_t n_warps = gridDim.x * (blockDim.x >> 5);
+    const bool dynamic = n_units >= 16u * n_warps;
+    const uint32_t chunk_units = dynamic ? min((uint32_t)JMC_FAST_CHUNK, n_units / (4u * n_warps)) : 1u;
+    const uint32_t n_chunks = (n_units + chunk_units - 1u) / chunk_units;
     unsigned int* g_next = (unsigned int*)g_poison + 1;
-    unsigned int fetched = 0u;
-    if (lane == 0) fetched = atomicAdd(g_next, 1u);
+    unsigned int fetched = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);        // static: the warp's number
+    if (dynamic && lane == 0) fetched = atomicAdd(g_next, 1u);
     while (true) {
         const uint32_t chunk = __shfl_sync(0xffffffffu, fetched, 0);
         if (chunk >= n_chunks) break;
-        if (lane == 0) fetched = atomicAdd(g_next, 1u);
-        const uint32_t u_end = min(n_units, (chunk + 1u) * (uint32_t)JMC_FAST_CHUNK);
-        uint32_t idx = (uint32_t)pa + chunk * (uint32_t)JMC_FAST_CHUNK * (32u * (uint32_t)V) + lane;
-        for (uint32_t u = chunk * (uint32_t)JMC_FAST_CHUNK; u < u_end; ++u, idx += 32u * (uint32_t)V) {
+        if (!dynamic) fetched += n_warps;
+        else if (lane == 0) fetched = atomicAdd(g_next, 1u);
+        const uint32_t u_end = min(n_units, (chunk + 1u) * chunk_units);
+        uint32_t idx = (uint32_t)pa + chunk * chunk_units * (32u * (uint32_t)V) + lane;
+        for (uint32_t u = chunk * chunk_units; u < u_end; ++u, idx += 32u * (uint32_t)V) {
             PairWords<KIND> pw[V];
 #pragma unroll
             for (int v = 0; v < V; ++v) draw_pair<KIND>(idx + (uint32_t)v * 32u, p_hi, keys, pw[v]);
@@ -793,7 +799,7 @@ fast_body(const FastParams& P_in, uint64_t n, uint64_t seed, uint64_t first, con
         if (threadIdx.x == 0 && s_poison != INT_MAX) atomicMin(g_poison, s_poison);
     }
     // the last block to get here has seen every other block leave the loop: re-arm the work counter
-    if (threadIdx.x == 0) {
+    if (dynamic && threadIdx.x == 0) {
         unsigned int* g_done = (unsigned int*)g_poison + 2;
         if (atomicAdd(g_done, 1u) == gridDim.x - 1u) {
             *g_next = 0u;
