@@ -474,7 +474,8 @@ __device__ __forceinline__ int bin_fast(const FastParams& P, float l2obs, const 
 // anyway, so density, error and integral are the same -- but the kinds whose weight is NaN -> 0 for most samples (the
 // running-coupling Landau region: 99.7 % of CRIT_SUB samples) then need neither observable nor bin nor count atomic
 // for those samples: the random words decide (active_from_words) and the rest is evaluated only for the survivors.
-template <int KIND, bool FIXED, bool OBS_MLL, bool HOT, bool COUNT_ALL>
+// SLIM: the 1024-thread instantiations (block histograms above 72 KB) have 64 registers per thread
+template <int KIND, bool FIXED, bool OBS_MLL, bool HOT, bool COUNT_ALL, bool SLIM = false>
 __device__ __forceinline__ void
 fast_body(const FastParams& P_in, uint64_t n, uint64_t seed, uint64_t first, const float* __restrict__ g_edges,
           double* __restrict__ g_sum_w, double* __restrict__ g_sum_w2, unsigned long long* __restrict__ g_count,
@@ -679,7 +680,7 @@ fast_body(const FastParams& P_in, uint64_t n, uint64_t seed, uint64_t first, con
 #endif
     // (measured with chunked work, profiles/r02q_pairs.log: the compacted 4-word kinds gain 3-6 % from two pairs per
     // trip -- one vote per four samples --, the others lose 1 %)
-    constexpr int V = PairWords<KIND>::FOUR ? (COMPACT ? JMC_FAST_PAIRS_COMPACT : JMC_FAST_PAIRS) : JMC_FAST_PAIRS_2W;
+    constexpr int V = PairWords<KIND>::FOUR ? ((COMPACT && !SLIM) ? JMC_FAST_PAIRS_COMPACT : JMC_FAST_PAIRS) : JMC_FAST_PAIRS_2W;
     // Work is handed out, not pre-assigned.  A UNIT is 32 V consecutive pairs (one trip of one warp: lane l takes pairs
     // l, l + 32, ...); warps take JMC_FAST_CHUNK units at a time from one global counter.  With a fixed 1/#warps share
     // per warp the hardware scheduler lets some warps of an SM run ahead, they exit early, and the SM finishes its
@@ -841,7 +842,7 @@ run_fast_kernel(FastParams P, uint64_t n, uint64_t seed, uint64_t first, const f
                 double* __restrict__ g_sum_w, double* __restrict__ g_sum_w2,
                 unsigned long long* __restrict__ g_count, int* g_poison, double* __restrict__ d_minmax) {
     extern __shared__ __align__(16) double s_dyn[];
-    fast_body<KIND, FIXED, OBS_MLL, HOT, COUNT_ALL>(P, n, seed, first, g_edges, g_sum_w, g_sum_w2, g_count, g_poison,
+    fast_body<KIND, FIXED, OBS_MLL, HOT, COUNT_ALL, BIG>(P, n, seed, first, g_edges, g_sum_w, g_sum_w2, g_count, g_poison,
                                                     d_minmax, s_dyn);
 }
 
@@ -862,7 +863,7 @@ run_fast_batch_kernel(const FastParams* __restrict__ params, uint64_t n, uint64_
     for (int k = threadIdx.x; k < words; k += blockDim.x) ((int*)&sP)[k] = ((const int*)&params[point])[k];
     __syncthreads();
     const size_t nb = n_edges > 0 ? (size_t)n_edges - 1 : 0;
-    fast_body<KIND, FIXED, OBS_MLL, HOT, true>(
+    fast_body<KIND, FIXED, OBS_MLL, HOT, true, BIG>(
         sP, n, seed, first, edges_all ? edges_all + (size_t)point * n_edges : nullptr,
         sum_w_all ? sum_w_all + point * nb : nullptr, sum_w2_all ? sum_w2_all + point * nb : nullptr,
         count_all ? count_all + point * nb : nullptr, poison_all + 4 * point,
