@@ -365,6 +365,32 @@ def test_full_size_properties(cuda):
     assert integ[-1] == 1. and np.all(np.diff(integ) >= 0)
 
 
+@pytest.mark.parametrize("kind,jet,fc,acc", [CASES[0], CASES[4], CASES[6], CASES[8], CASES[10],
+                                             ('crit_sub_counts_on_request', 'quark', False, 'MLL')])
+def test_fast_chunked_work_covers_every_sample_once(cuda, kind, jet, fc, acc):
+    """Large jobs hand work out in chunks from a global counter (re-armed by the last block), small ones give every
+    warp a fixed share: one job over an odd index range equals the sum of a large, a small and a tiny job over the
+    same range, counts exactly -- every sample is drawn once whichever path took it, launch after launch."""
+    import gpu_helpers as H
+    from jetmontecarlo_b200.fused import Integrand
+    ig = (_integrand(kind, jet, fc, acc) if kind != 'crit_sub_counts_on_request' else
+          Integrand.crit_sub('log', ZC, EPS, beta=BETA, jet_type=jet, fixedcoupling=fc, obs_acc=acc, counts='weighted'))
+    edges = np.logspace(-11, np.log10(.5), 100)
+    first, n = 1, 33_333_337
+    whole = H.run(ig, n, 9, edges, 'f32', first=first)
+    again = H.run(ig, n, 9, edges, 'f32', first=first)
+    assert_array_equal(whole['count'].cpu().numpy(), again['count'].cpu().numpy())
+    acc_bufs, at = None, first
+    for piece in (30_000_001, 3_333_000, 336):
+        rr = H.run(ig, piece, 9, edges, 'f32', first=at, accumulate_into=acc_bufs)
+        acc_bufs = (rr['sum_w'], rr['sum_w2'], rr['count'])
+        at += piece
+    assert at == first + n
+    assert_array_equal(acc_bufs[2].cpu().numpy(), whole['count'].cpu().numpy())
+    assert_allclose(acc_bufs[0].cpu().numpy(), whole['sum_w'].cpu().numpy(), rtol=1e-6, atol=1e-12)
+    assert int(whole['count'].sum().item()) > 0
+
+
 def test_batched_grid_equals_point_by_point(cuda):
     """jmc_run_batch: a theta_crit grid in one launch == one jmc_run per point (same streams: counts exact), with
     given edges and with the reference's data-dependent log bins; and gen_crit_sub_num_rad_fused reproduces the
