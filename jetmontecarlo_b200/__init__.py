@@ -39,7 +39,8 @@ def install_as(name="jetmontecarlo"):
         sys.modules[name + "." + short] = importlib.import_module(info.name)
         aliased.append(name + "." + short)
     if name == "jetmontecarlo" and "file_management" not in sys.modules and importlib.util.find_spec("file_management") is None:
-        for short in ("file_management", "file_management.catalog_utils", "file_management.data_management"):
+        for short in ("file_management", "file_management.catalog_utils", "file_management.data_management",
+                      "file_management.load_data"):
             sys.modules[short] = importlib.import_module(__name__ + "." + short)
             aliased.append(short)
     return aliased

@@ -4,4 +4,4 @@ file_management/data_management.py) with the same file formats -- a YAML catalog
 dictionary and one .npz / .npy / .pkl file per entry -- so that files written by either side load on the other.
 ``jetmontecarlo_b200.install_as`` also registers this package as top-level ``file_management`` when no such package
 is importable."""
-from . import catalog_utils, data_management      # noqa: F401
+from . import catalog_utils, data_management, load_data      # noqa: F401

@@ -90,11 +90,36 @@ def load_and_interpolate(data_source, params, **interp_kwargs):
     raise ValueError('Dimensionality of data must be 1 or 2.')
 
 
-def load_and_tabulate(data_source, params, method="RectangularGrid"):
-    """The stored 2-D numerical radiator as a ``TableRadiator`` for the device's conditional sampler"""
+def load_and_tabulate(data_source, params, method="RectangularGrid", num_x=None):
+    """The stored 2-D numerical radiator as a ``TableRadiator`` for the device's conditional sampler.
+    Binned data (pre-critical radiator: ``bins`` = two axes) is the table itself.  The subsequent radiator is stored
+    as scattered points -- one row of observable bins per theta_crit, every row with its own bins
+    (numerics/radiators/generation.py:253-400) -- and interpolated by nearest neighbour; it is re-tabulated here:
+    its own theta_crit values form one axis, ``num_x`` (default 4 x the row length) log-spaced observable values
+    over the rows' common range the other, and every node takes the value of the nearest stored point of its OWN row
+    (the row's cumulative integral is a step function of the observable on that row's bins)."""
     from ..numerics.sudakov_sampling import TableRadiator
     data = load_data('numerical integral', data_source, params)
     dim, axes, integral = _grid_of(data, data_source)
     if dim != 2:
         raise ValueError('A radiator table is two-dimensional.')
-    return TableRadiator(np.asarray(axes[0]), np.asarray(axes[1]), np.asarray(integral), method)
+    xs, ys, zs = np.asarray(axes[0], dtype=float), np.asarray(axes[1], dtype=float), np.asarray(integral, dtype=float)
+    if zs.ndim == 2 and xs.ndim == 1 and zs.shape == (len(xs), len(ys)):
+        return TableRadiator(xs, ys, zs, method)
+    # scattered rows: ys is constant along a row
+    thetas, first = np.unique(ys, return_index=True)
+    row_len = len(ys) // len(thetas)
+    if row_len * len(thetas) != len(ys) or not np.all(np.diff(np.sort(first)) == row_len):
+        raise ValueError('scattered radiator data must be whole rows of constant theta')
+    by_theta = np.argsort(ys.reshape(len(thetas), row_len)[:, 0])          # storage order -> increasing theta
+    rows_x = xs.reshape(len(thetas), row_len)[by_theta]
+    rows_z = zs.reshape(len(thetas), row_len)[by_theta]
+    positive = rows_x[rows_x > 0]
+    grid_x = np.logspace(np.log10(positive.min()), np.log10(rows_x.max()), int(num_x or 4 * row_len))
+    table = np.empty((len(grid_x), len(thetas)))
+    for j in range(len(thetas)):
+        x_row = rows_x[j]
+        right = np.clip(np.searchsorted(x_row, grid_x), 1, row_len - 1)
+        nearest = np.where(np.abs(grid_x - x_row[right - 1]) <= np.abs(x_row[right] - grid_x), right - 1, right)
+        table[:, j] = rows_z[j][nearest]
+    return TableRadiator(grid_x, thetas, table, "Nearest")

@@ -57,6 +57,16 @@ class sampler(ABC):
     def _next_key():
         return next_key()
 
+    def __getstate__(self):
+        """Pickled as the reference's samplers are (file_management.save_new_data(sampler, ..., '.pkl'),
+        examples/event_generation/phase_space_sampling.py:145-148): the host arrays carry the data, the device copies
+        are dropped and re-uploaded on demand."""
+        state = dict(self.__dict__)
+        for key in ('device_samples', 'device_jacobians'):
+            if key in state:
+                state[key] = None
+        return state
+
     def addSample(self):
         """Adds a single sample (and its jacobian) to the lists."""
         samples, jac = self._draw(1, next_key())
