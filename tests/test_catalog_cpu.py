@@ -108,3 +108,42 @@ def test_install_as_registers_file_management():
         for k in [k for k in sys.modules if k.split('.')[0] in ("jetmontecarlo", "file_management")]:
             del sys.modules[k]
         sys.modules.update(saved)
+
+
+def test_loaders_and_scattered_radiator_rows(tmp_path, monkeypatch):
+    """file_management/load_data.py:114-195 with the parameter dictionaries as arguments: 1-D radiator -> monotone
+    interpolant, binned 2-D radiator -> grid, the subsequent radiator's scattered rows (one row of bins per
+    theta_crit) -> a table whose nodes carry the nearest stored value of their own row; pickled functions come back."""
+    monkeypatch.chdir(tmp_path)
+    from jetmontecarlo_b200.file_management import catalog_utils as CU
+    from jetmontecarlo_b200.file_management.data_management import save_new_data, load_and_tabulate
+    from jetmontecarlo_b200.file_management.load_data import load_radiators, load_splittingfns
+    CU.set_output_root("output")
+    rp = {'jet type': 'quark', 'epsilon': 1e-10}
+    edges = np.logspace(-10, 0, 30)
+    save_new_data({'bins': edges, 'integral': np.linspace(5, 0, 30)}, 'numerical integral', 'critical radiator',
+                  dict(rp, z_cut=.1), '.npz')
+    xs, ys = np.logspace(-9, -1, 12), np.logspace(-8, 0, 9)
+    save_new_data({'bins': np.array([xs[:9], ys]), 'integral': np.outer(np.linspace(3, 0, 9), np.linspace(2, 1, 9))},
+                  'numerical integral', 'pre-critical radiator', dict(rp, z_cut=.1), '.npz')
+    thetas = np.array([1., 1e-3, .1, 1e-2])                     # rows stored out of order
+    rows_x = np.array([np.logspace(-12, 0, 30) * t ** 2 for t in thetas])
+    rows_z = np.array([np.linspace(5, 0, 30) * (1 + j) for j in range(4)])
+    save_new_data({'xs': rows_x.flatten(), 'ys': np.repeat(thetas, 30), 'integral': rows_z.flatten()},
+                  'numerical integral', 'subsequent radiator', dict(rp, beta=2.), '.npz')
+    save_new_data(np.sqrt, 'serialized function', 'splitting function', dict(rp, z_cut=.1), '.pkl')
+    rads = load_radiators(rp, [.1], [2.], as_tables=True)
+    np.testing.assert_allclose(rads['critical'][.1](edges[5:-5]), np.linspace(5, 0, 30)[5:-5], rtol=1e-12)
+    assert rads['pre-critical'][.1].zs.shape == (9, 9) and rads['pre-critical'][.1].method == "RectangularGrid"
+    table = rads['subsequent'][2.]
+    assert table.method == "Nearest" and np.array_equal(table.ys, np.sort(thetas)) and table.zs.shape == (120, 4)
+    for j, t in enumerate(np.sort(thetas)):
+        row = list(thetas).index(t)
+        for k in (0, 17, 60, 119):
+            nearest = np.abs(rows_x[row] - table.xs[k]).argmin()
+            assert table.zs[k, j] == rows_z[row][nearest]
+    host = load_radiators(rp, [.1], [2.])                       # the reference's form: host interpolants
+    assert callable(host['subsequent'][2.]) and callable(host['pre-critical'][.1])
+    assert load_splittingfns(rp, [.1])[.1](4.) == 2.
+    with pytest.raises(ValueError):
+        load_and_tabulate('critical radiator', dict(rp, z_cut=.1))
