@@ -8,24 +8,22 @@ from pathlib import Path
 
 import yaml
 
-# ---- folders (ref :15-22) ----
-fig_folder = Path('output/figures/current/')
-example_output_folder = Path('output/examples')
-example_storage = Path('output/examples/current')
-example_trashbin = Path('output/examples/overwritten')
-example_catalog = example_output_folder / 'file_catalog.yaml'
+# ---- folders (ref :15-22): module attributes, as in the reference, but all derived from one root ----
+def _layout(root):
+    """(figures, output folder, storage, trash bin, catalog file) below ``root``"""
+    root = Path(root)
+    out = root / 'examples'
+    return root / 'figures' / 'current', out, out / 'current', out / 'overwritten', out / 'file_catalog.yaml'
+
+
+fig_folder, example_output_folder, example_storage, example_trashbin, example_catalog = _layout('output')
 
 
 def set_output_root(root, create=True):
     """Point the catalog, its storage and its trash bin below ``root`` (the reference hard-codes ``output/`` relative
     to the working directory); creates the folders and an empty catalog file on request."""
     global fig_folder, example_output_folder, example_storage, example_trashbin, example_catalog
-    root = Path(root)
-    fig_folder = root / 'figures' / 'current'
-    example_output_folder = root / 'examples'
-    example_storage = example_output_folder / 'current'
-    example_trashbin = example_output_folder / 'overwritten'
-    example_catalog = example_output_folder / 'file_catalog.yaml'
+    fig_folder, example_output_folder, example_storage, example_trashbin, example_catalog = _layout(root)
     if create:
         for folder in (fig_folder, example_storage, example_trashbin):
             folder.mkdir(parents=True, exist_ok=True)
