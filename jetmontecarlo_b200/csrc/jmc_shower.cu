@@ -374,6 +374,9 @@ shower_kernel(ShowerParams p, uint64_t n, uint64_t seed, uint64_t first, const d
 #ifndef JMC_SHOWER_BIN_GROUP
 #define JMC_SHOWER_BIN_GROUP 24
 #endif
+#ifndef JMC_SHOWER_TRIALS
+#define JMC_SHOWER_TRIALS 3
+#endif
 #ifndef JMC_SHOWER_MIN_BLOCKS
 #define JMC_SHOWER_MIN_BLOCKS 1
 #endif
@@ -474,52 +477,59 @@ shower_fast_kernel(ShowerParams p, uint64_t n, uint64_t seed, uint64_t first, co
         const unsigned done_mask = __ballot_sync(0xffffffffu, done_obs == done_obs);
         if (!(run_mask | ev_mask | done_mask)) break;
 
-        // ---- one veto trial ----
+        // ---- veto trials: JMC_SHOWER_TRIALS per iteration (a lane stops at its first accepted one), so that the
+        // warp-level work around them -- hand-out, votes, queue decisions, the push -- is paid once per that many ----
         bool accepted = false, last = false;
         float lz = __int_as_float(0x7fc00000), lth = 0.0f;
+        auto trial = [&]() {
+            uint32_t r[4];
+            philox4x32_10(jx, blk++, keys, r);
+            if (RECORD) ++n_trials;
+            const float i1 = (float)(r[0] >> 8) + 0.5f, i2 = (float)(r[1] >> 8) + 0.5f, i3 = (float)(r[2] >> 8) + 0.5f;
+            const float lp = -sh_sqrt(fmaf(-k2, sh_lg2(i1 * k2m24), l2 * l2));
+            const float a = (i2 * k2m24) * lp;                            // r2 l'
+            lz = a - 1.0f;                                                // log2 z = r2 l' - 1
+            lth = (lp - a) * inv_beta;                                    // log2 theta = (1 - r2) l' / beta
+            l2 = lp;
+            bool ok = true;
+            if (MLL) {
+                const float zf = sh_ex2(lz), omz = 1.0f - zf;
+                const float D = fmaf(d1, fmaxf(l2_pt + lz + lth, 0.0f), d0);
+                float num;                       // [z P(z) + z P(1 - z)] (1 - z)
+                if (QUARK) {
+                    const float o2 = omz * omz, z2 = zf * zf;
+                    num = (float)JMC_CF * (fmaf(o2, omz, omz) + fmaf(z2, zf, zf));
+                } else {
+                    const float s2 = fmaf(zf, zf, omz * omz);
+                    const float pz = (float)JMC_CA * (2.0f * omz + zf * zf * omz) + (float)(JMC_TF * JMC_NF) * zf * s2;
+                    const float p1 = (float)JMC_CA * (2.0f * zf + omz * omz * zf) + (float)(JMC_TF * JMC_NF) * omz * s2;
+                    num = fmaf(pz, omz, zf * p1);
+                }
+                const float rhs = veto_c * num, lhs = D * omz;
+                if (rhs > 16777216.0f * lhs) err |= 1;    // the reference raises: acceptance probability above 1
+                ok = i3 * lhs < rhs;
+            }
+            if (ok) {
+                if (RECORD && dump_chain && n_em < chain_cap) {
+                    double* c = dump_chain + ((size_t)(jx - first) * chain_cap + n_em) * 2;
+                    c[0] = (double)sh_ex2(lz);
+                    c[1] = (double)sh_ex2(lth);
+                }
+                ++n_em;
+                // the chain continues while z theta > cutoff (angularity_shower, :262-279); tested on accepted
+                // emissions only -- the veto loop keeps trying without it (:188-209)
+                last = !(lz + lth > l2_cut);
+                if (n_em >= kMaxEmissions) { last = true; err |= 2; }
+            }
+            return ok;
+        };
         if (run) {
             if (!start_ok) {
                 accepted = last = true;              // event without emission (log2 z = NaN)
             } else {
-                uint32_t r[4];
-                philox4x32_10(jx, blk++, keys, r);
-                if (RECORD) ++n_trials;
-                const float i1 = (float)(r[0] >> 8) + 0.5f, i2 = (float)(r[1] >> 8) + 0.5f, i3 = (float)(r[2] >> 8) + 0.5f;
-                const float lp = -sh_sqrt(fmaf(-k2, sh_lg2(i1 * k2m24), l2 * l2));
-                const float a = (i2 * k2m24) * lp;                            // r2 l'
-                lz = a - 1.0f;                                                // log2 z = r2 l' - 1
-                lth = (lp - a) * inv_beta;                                    // log2 theta = (1 - r2) l' / beta
-                l2 = lp;
-                accepted = true;
-                if (MLL) {
-                    const float zf = sh_ex2(lz), omz = 1.0f - zf;
-                    const float D = fmaf(d1, fmaxf(l2_pt + lz + lth, 0.0f), d0);
-                    float num;                       // [z P(z) + z P(1 - z)] (1 - z)
-                    if (QUARK) {
-                        const float o2 = omz * omz, z2 = zf * zf;
-                        num = (float)JMC_CF * (fmaf(o2, omz, omz) + fmaf(z2, zf, zf));
-                    } else {
-                        const float s2 = fmaf(zf, zf, omz * omz);
-                        const float pz = (float)JMC_CA * (2.0f * omz + zf * zf * omz) + (float)(JMC_TF * JMC_NF) * zf * s2;
-                        const float p1 = (float)JMC_CA * (2.0f * zf + omz * omz * zf) + (float)(JMC_TF * JMC_NF) * omz * s2;
-                        num = fmaf(pz, omz, zf * p1);
-                    }
-                    const float rhs = veto_c * num, lhs = D * omz;
-                    if (rhs > 16777216.0f * lhs) err |= 1;    // the reference raises: acceptance probability above 1
-                    accepted = i3 * lhs < rhs;
-                }
-                if (accepted) {
-                    if (RECORD && dump_chain && n_em < chain_cap) {
-                        double* c = dump_chain + ((size_t)(jx - first) * chain_cap + n_em) * 2;
-                        c[0] = (double)sh_ex2(lz);
-                        c[1] = (double)sh_ex2(lth);
-                    }
-                    ++n_em;
-                    // the chain continues while z theta > cutoff (angularity_shower, :262-279); tested on accepted
-                    // emissions only -- the veto loop keeps trying without it (:188-209)
-                    last = !(lz + lth > l2_cut);
-                    if (n_em >= kMaxEmissions) { last = true; err |= 2; }
-                }
+#pragma unroll
+                for (int t = 0; t < JMC_SHOWER_TRIALS; ++t)
+                    if (!accepted) accepted = trial();
             }
         }
         // ---- accumulator stage: one event of every lane that has one ----
