@@ -63,6 +63,9 @@ def test_bandwidth_and_shower_kernels_do_not_spill():
             assert stack == 0, "%s spills %d B" % (name, stack)
             seen += 1
     assert seen >= 8
-    fp32_shower = [v for k, v in usage.items() if "shower_fast_kernelI" in k]
-    assert fp32_shower and max(v[0] for v in fp32_shower) <= 80          # FP32 shower: at least 6 blocks of 128 threads per SM
-    # (measured: forcing 10 or 12 resident blocks costs 7 %, profiles/r02h_shower_shootout.log)
+    fp32_shower = {k: v for k, v in usage.items() if "shower_fast_kernelI" in k}
+    # FP32 shower: at least 5 blocks of 128 threads per SM for every instantiation (the RSS ones are the largest), 7 for
+    # the benchmarked Soft Drop one (measured: forcing 10 or 12 resident blocks costs 7 %,
+    # profiles/r02h_shower_shootout.log)
+    assert fp32_shower and max(v[0] for v in fp32_shower.values()) <= 96
+    assert [v for k, v in fp32_shower.items() if "shower_fast_kernelILb1ELi1ELb1ELb0E" in k][0][0] <= 72
