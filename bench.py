@@ -312,6 +312,67 @@ def time_kind(name, ig, edges, bc, precision, n, sm_count, sm_mhz, contract=None
     return rec
 
 
+def next_row_results(hbm_gbs):    # noqa: C901
+    """SURVEY 8 "next" rows on the device, one short measurement each (CUDA events around the library call):
+    f1 per-event Sudakov sampling, f3 RSS shower + replay of a stored event record, f4 fused EWOC."""
+    import torch
+    from jetmontecarlo_b200 import _device as D
+    from jetmontecarlo_b200.fused import Integrand
+    from jetmontecarlo_b200 import fused
+    from jetmontecarlo_b200.numerics import sudakov_sampling as S
+    from jetmontecarlo_b200.analytics.radiators.fixedcoupling import preRadAnalytic_fc_LL
+    from jetmontecarlo_b200.utils import partonshower_utils as PS
+    from jetmontecarlo_b200.montecarlo.ewoc import fused_ewoc
+    from jetmontecarlo_b200.processes import ee2hadrons_LO as EE
+    out = []
+
+    def timed(fn, reps=3):
+        best = None
+        for _ in range(reps):
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            ev[0].record(); r = fn(); ev[1].record(); torch.cuda.synchronize()
+            ms = ev[0].elapsed_time(ev[1])
+            best = ms if best is None else min(best, ms)
+        return best, r
+
+    # f1: one z_pre per event from exp(-R_pre(z, theta_crit)) on [0, z_cut], R_pre a 100 x 100 table
+    gz, gt = np.logspace(-10, np.log10(Z_CUT), 100), np.logspace(-8, 0, 100)
+    table = np.asarray(preRadAnalytic_fc_LL(gz[:, None] * np.ones((1, 100)), np.ones((100, 1)) * gt[None, :], Z_CUT, 'quark'))
+    rad = S.TableRadiator(gz, gt, np.nan_to_num(table))
+    n1 = 1_000_000
+    theta = torch.exp(torch.rand(n1, dtype=torch.float64, device="cuda") * np.log(1e-6))
+    ms, _ = timed(lambda: S.generate_precritical_samples(rad, theta, Z_CUT, seed=3))
+    out.append({"name": "f1: per-event inverse-transform Sudakov samples (pre-critical, 100 x 100 radiator table, one event "
+                        "per thread block, 1e6 events)", "kernel_ms": ms, "value": n1 / (ms * 1e-3), "unit": "events/s",
+                "reference_note": "the reference loops over events in Python, one samples_from_cdf call each "
+                                  "(~1e3 probe evaluations of a scipy interpolant): O(1e2) events/s"})
+    # f3: RSS-groomed shower (grooming in the kernel's accumulator) and the replay of a stored event record
+    edges = np.insert(np.logspace(-10, np.log10(.5), 100), 0, 1e-100)
+    ig = Integrand.shower(beta=2., jet_type='quark', acc='MLL', groomer='rss', z_cut=Z_CUT, f=1., obs_acc='MLL', n_emissions=2)
+    rec = time_kind("f3: veto shower with RSS grooming (f = 1, two-emission ECF), quark MLL, jets", ig, edges, 0., 'f32',
+                    50_000_000, 0, 0.)
+    rec["unit"] = "jets/s"
+    out.append(rec)
+    jets = PS.gen_jets(10_000_000, beta=2., jet_type='quark', acc='MLL', verbose=0, seed=5)
+    lens, chains = jets.chains_device(max_emissions=32, precision='f32')
+    ms, _ = timed(lambda: PS.ecfs_from_chains(lens, chains, beta=2., obs_acc='MLL', n_emissions=2, groomer='rss',
+                                              z_cut=Z_CUT, f=1.))
+    nbytes = chains.numel() * 8 + lens.numel() * 4 + lens.numel() * 8
+    out.append({"name": "f3: getECFs_rss on a stored event record (1e7 jets x 32 emission slots), replay kernel", "kernel_ms": ms,
+                "value": lens.numel() / (ms * 1e-3), "unit": "jets/s",
+                "roofline": {"bound": "hbm", "achieved": nbytes / ms / 1e6, "peak": hbm_gbs, "unit": "GB/s",
+                             "frac": nbytes / ms / 1e6 / hbm_gbs, "bytes_per_jet": nbytes / lens.numel()}})
+    del chains, lens
+    # f4: energy-weighted correlator of e+e- -> hadrons at LO, fused (nothing stored per event)
+    proc = EE.ee2hadrons_LO(energy=1000., num_samples=8, sampleMethod='lin', seed=1)
+    n4 = 100_000_000
+    ms, _ = timed(lambda: fused_ewoc(proc, n4, EE.costheta_ij, energy_weights=(1, 1),
+                                     edges=np.linspace(-1., 1., 101), seed=9))
+    out.append({"name": "f4: fused EWOC of ee -> hadrons (hit-or-miss events -> 3 pairs -> energy-weighted histogram), "
+                        "1e8 accepted events", "kernel_ms": ms, "value": n4 / (ms * 1e-3), "unit": "events/s"})
+    return out
+
+
 def sub_results(args, sm_count, sm_mhz):
     """the other BASELINE configurations, briefly, one GPU (driver-measured numbers for C1, C2, C4, C5,
     FP64 and the fixed-coupling control)"""
@@ -427,6 +488,10 @@ def sub_results(args, sm_count, sm_mhz):
                 "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
                              "bytes_per_sample": 16,
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "recipe fallback 6550"}})
+    try:
+        out.extend(next_row_results(hbm))
+    except Exception as exc:          # the SURVEY 8(f) rows must never take the C1-C5 records down
+        out.append({"name": "next rows (SURVEY 8 f1-f4)", "error": repr(exc)})
     return out
 
 
