@@ -228,6 +228,19 @@ int jmc_conditional_inverse_transform(const double* d_grid_x, int nx, const doub
                                       uint64_t n, int catch_turnpoint, int force_monotone, double* d_samples,
                                       void* stream);
 
+/* generate_precritical_samples / generate_subsequent_samples of the production workflow, complete in one kernel
+ * (examples/sudakov_comparisons/sudakov_utils.py:134-182, 185-238): one sample per critical angle from the forced-
+ * monotone cdf exp(-R(x, theta_crit_i)) of the tabulated radiator, on [0, param] (JMC_SUDAKOV_PRECRITICAL, param =
+ * z_cut) or on [0, theta_crit_i^param / 2] (JMC_SUDAKOV_SUBSEQUENT, param = beta; events whose upper end is below
+ * 1e-10 take the underflow value 1e-100).  Uniform of event i: d_uniforms[i], or (d_uniforms NULL) the first uniform
+ * of Philox stream (seed, i) -- what jmc_uniforms(n, seed, 0, 1, ...) returns.  An infinite sample is returned as 0
+ * with weight 0 (:117-120), every other weight is 1. */
+enum { JMC_SUDAKOV_PRECRITICAL = 1, JMC_SUDAKOV_SUBSEQUENT = 2 };
+int jmc_sudakov_generate(int emission, const double* d_grid_x, int nx, const double* d_grid_y, int ny,
+                         const double* d_table, int interpolation, const double* d_theta_crit, double param,
+                         const double* d_uniforms, uint64_t seed, uint64_t n, double* d_samples, double* d_weights,
+                         void* stream);
+
 /* ---- replay path: arrays in, arrays out -------------------------------- */
 int jmc_eval_fn(int fn, const jmc_fn_params* p, uint64_t n,
                 const double* d_a0, int64_t stride0, const double* d_a1, int64_t stride1,
@@ -436,6 +449,15 @@ int jmc_handle_integrate_host(jmc_handle* h, const jmc_integrand* g, uint64_t n,
                               double* h_density, double* h_density_err,
                               double* h_integral, double* h_integral_err,
                               double* h_sum_w, double* h_sum_w2, uint64_t* h_count);
+
+/* Device plumbing for hosts without an array library of their own: d_out[0..n) = value (FP64), and a byte fill
+ * (cudaMemsetAsync).  Asynchronous on `stream`. */
+int jmc_fill(double* d_out, uint64_t n, double value, void* stream);
+int jmc_memset(void* d_ptr, int byte_value, uint64_t n_bytes, void* stream);
+/* np.tile(d_in, reps) into d_out [reps * n] (the event weights of the three parton pairs, ewoc.py:11-57) */
+int jmc_tile(const double* d_in, uint64_t n, int reps, double* d_out, void* stream);
+/* number of finite entries (vals_to_pdf's "no finite values" test, utils/hist_utils.py:105-112); synchronises */
+int jmc_count_finite(const double* d_in, uint64_t n, uint64_t* h_count, void* stream);
 
 /* sampler.generateSamples into host arrays */
 int jmc_sample_host(const jmc_sampler* s, uint64_t n, uint64_t seed, uint64_t first_index,

@@ -50,8 +50,12 @@ def eval_fn(fn, args, jet=_lib.QUARK, acc=_lib.ACC_LL, fixed_coupling=True, z_cu
         shapes = [tuple(a.shape) for a in arrays.values()]
         shape = np.broadcast_shapes(*shapes)
         n = int(np.prod(shape, dtype=np.int64))
-    dev = {}
+    dev, stride_of = {}, {}
     for k, a in arrays.items():
+        if (isinstance(a, torch.Tensor) and a.is_cuda and a.dtype == torch.float64 and a.dim() == 1
+                and tuple(a.shape) == shape and a.stride(0) >= 1):
+            dev[k], stride_of[k] = a, a.stride(0)      # a column of an (N, 2) sample array is read in place
+            continue
         if tuple(a.shape) != shape:
             a = torch.broadcast_to(a, shape) if isinstance(a, torch.Tensor) else np.broadcast_to(a, shape)
         dev[k] = D.to_device(a).reshape(-1)
@@ -60,7 +64,7 @@ def eval_fn(fn, args, jet=_lib.QUARK, acc=_lib.ACC_LL, fixed_coupling=True, z_cu
     for k in range(4):
         t = dev.get(k)
         ptrs.append(D.ptr(t))
-        strides.append(C.c_int64(1))
+        strides.append(C.c_int64(stride_of.get(k, 1)))
     _lib.check(_lib.lib.jmc_eval_fn(fn, C.byref(params), n, ptrs[0], strides[0], ptrs[1], strides[1],
                                     ptrs[2], strides[2], ptrs[3], strides[3], D.ptr(out), D.stream()))
     if on_device:

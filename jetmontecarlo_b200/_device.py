@@ -44,9 +44,22 @@ def to_device(x):
     if isinstance(x, torch.Tensor):
         if not x.is_cuda:
             x = x.to(device())
+        if x.dtype == _F64 and x.dim() == 1 and not x.is_contiguous() and x.stride(0) > 0:
+            return _gather_strided(x)
         return x.to(_F64).contiguous()
     a = np.ascontiguousarray(x, dtype=np.float64)
     return torch.from_numpy(a).to(device(), non_blocking=False)
+
+
+def _gather_strided(x):
+    """contiguous copy of a strided 1-D FP64 device view (a column of an (N, 2) sample array) by the library's own
+    strided-read kernel: x * 1.0 through jmc_eval_fn, which takes an element stride per argument"""
+    out = torch.empty((x.numel(),), dtype=_F64, device=x.device)
+    params = _lib.FnParams(s1=1.)
+    null, one = C.c_void_p(0), C.c_int64(1)
+    _lib.check(_lib.lib.jmc_eval_fn(_lib.FN_MUL, C.byref(params), x.numel(), ptr(x), C.c_int64(x.stride(0)), null, one,
+                                    null, one, null, one, ptr(out), stream()))
+    return out
 
 
 def empty(shape, dtype=_F64):
@@ -54,7 +67,24 @@ def empty(shape, dtype=_F64):
 
 
 def zeros(shape, dtype=_F64):
-    return torch.zeros(shape, dtype=dtype, device=device())
+    """zero-filled device tensor: allocation by torch, the fill by cudaMemsetAsync on torch's stream (jmc_memset)"""
+    t = torch.empty(shape, dtype=dtype, device=device())
+    zero_(t)
+    return t
+
+
+def zero_(t):
+    """t[...] = 0 for a contiguous device tensor"""
+    assert t.is_contiguous()
+    _lib.check(_lib.lib.jmc_memset(ptr(t), 0, t.numel() * t.element_size(), stream()))
+    return t
+
+
+def full(shape, value):
+    """FP64 device tensor filled with ``value`` (jmc_fill)"""
+    t = torch.empty(shape, dtype=_F64, device=device())
+    _lib.check(_lib.lib.jmc_fill(ptr(t), t.numel(), float(value), stream()))
+    return t
 
 
 _STAGE_BYTES = 32 << 20        # per pinned staging buffer

@@ -28,6 +28,7 @@ SAMPLER_SIMPLE, SAMPLER_CRITICAL, SAMPLER_PRECRITICAL, SAMPLER_UNGROOMED = 0, 1,
  FN_CRIT_HC1, FN_CRIT_HC2) = range(34)
 KIND_RADIATOR, KIND_CRIT, KIND_CRIT_SUB, KIND_PRE_CRIT_SUB, KIND_SIMPLE, KIND_SHOWER = range(6)
 
+SUDAKOV_PRECRITICAL, SUDAKOV_SUBSEQUENT = 1, 2
 METHODS = {'lin': LIN, 'log': LOG}
 JETS = {'quark': QUARK, 'gluon': GLUON}
 ACCS = {'LL': ACC_LL, 'LL_nonsing': ACC_LL_NONSING, 'MLL': ACC_MLL}
@@ -39,7 +40,7 @@ EXPORTS = (
     "jmc_finalize", "jmc_cumulative", "jmc_set_density_host", "jmc_integrate_host", "jmc_sample_host",
     "jmc_eval_fn_host", "jmc_launch_count", "jmc_create", "jmc_destroy", "jmc_handle_run", "jmc_handle_integrate_host",
     "jmc_chain_ecf", "jmc_process_sample", "jmc_process_pairs", "jmc_process_ewoc",
-    "jmc_conditional_inverse_transform",
+    "jmc_conditional_inverse_transform", "jmc_sudakov_generate", "jmc_fill", "jmc_memset", "jmc_tile", "jmc_count_finite",
 )
 
 
@@ -127,6 +128,11 @@ def _load():
         "jmc_process_pairs": (i32, [P(Process), vp, u64, i32, dbl, vp, vp]),
         "jmc_process_ewoc": (i32, [P(Process), u64, u64, u64, i32, dbl, dbl, dbl, vp, i32, vp, vp, vp, vp, vp, vp]),
         "jmc_conditional_inverse_transform": (i32, [vp, i32, vp, i32, vp, i32, vp, vp, vp, vp, u64, i32, i32, vp, vp]),
+        "jmc_sudakov_generate": (i32, [i32, vp, i32, vp, i32, vp, i32, vp, dbl, vp, u64, u64, vp, vp, vp]),
+        "jmc_fill": (i32, [vp, u64, dbl, vp]),
+        "jmc_memset": (i32, [vp, i32, u64, vp]),
+        "jmc_tile": (i32, [vp, u64, i32, vp, vp]),
+        "jmc_count_finite": (i32, [vp, u64, P(u64), vp]),
         "jmc_create": (i32, [P(vp)]),
         "jmc_destroy": (i32, [vp]),
         "jmc_handle_run": (i32, [vp, P(Integrand), u64, u64, u64, i32, vp, i32, vp, vp, vp, vp, vp]),

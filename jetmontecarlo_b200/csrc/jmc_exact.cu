@@ -173,6 +173,32 @@ extern "C" int jmc_eval_fn(int fn, const jmc_fn_params* p, uint64_t n, const dou
 // ---------------------------------------------------------------------------
 namespace jmc {
 
+// plumbing the Python mirror would otherwise ask an array library for: a constant into an FP64 array
+__global__ void __launch_bounds__(kThreads) fill_kernel(double* __restrict__ out, uint64_t n, double value) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = value;
+}
+
+// out[r * n + i] = in[i]: np.tile(in, reps)
+__global__ void __launch_bounds__(kThreads) tile_kernel(const double* __restrict__ in, uint64_t n, int reps,
+                                                         double* __restrict__ out) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double v = in[i];
+        for (int r = 0; r < reps; ++r) out[(uint64_t)r * n + i] = v;
+    }
+}
+
+// number of finite entries
+__global__ void __launch_bounds__(kThreads) count_finite_kernel(const double* __restrict__ in, uint64_t n,
+                                                                 unsigned long long* __restrict__ count) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    unsigned long long c = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) c += isfinite(in[i]) ? 1u : 0u;
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(count, c);
+}
+
 __global__ void __launch_bounds__(kThreads) uniforms_kernel(uint64_t n, uint64_t seed, uint64_t first, int n_uniform,
                                                              double* __restrict__ out) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
@@ -230,6 +256,59 @@ extern "C" int jmc_uniforms(uint64_t n, uint64_t seed, uint64_t first_index, int
     if (grid < 0) return JMC_ENODEV;
     uniforms_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(n, seed, first_index, n_uniform, d_out);
     JMC_LAUNCHED("uniforms_kernel");
+    return JMC_OK;
+}
+
+extern "C" int jmc_fill(double* d_out, uint64_t n, double value, void* stream) {
+    if (n == 0) return JMC_OK;
+    JMC_REQUIRE(d_out != nullptr, "jmc_fill: out is NULL");
+    if (value == 0.0) {                                  // +0.0 is all-zero bytes: no kernel needed
+        JMC_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double) * n, (cudaStream_t)stream));
+        return JMC_OK;
+    }
+    const int grid = grid_for(n, kThreads);
+    if (grid < 0) return JMC_ENODEV;
+    fill_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(d_out, n, value);
+    JMC_LAUNCHED("fill_kernel");
+    return JMC_OK;
+}
+
+extern "C" int jmc_tile(const double* d_in, uint64_t n, int reps, double* d_out, void* stream) {
+    JMC_REQUIRE(reps >= 1, "jmc_tile: reps must be positive");
+    if (n == 0) return JMC_OK;
+    JMC_REQUIRE(d_in && d_out, "jmc_tile: NULL array");
+    const int grid = grid_for(n, kThreads);
+    if (grid < 0) return JMC_ENODEV;
+    tile_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(d_in, n, reps, d_out);
+    JMC_LAUNCHED("tile_kernel");
+    return JMC_OK;
+}
+
+extern "C" int jmc_count_finite(const double* d_in, uint64_t n, uint64_t* h_count, void* stream) {
+    JMC_REQUIRE(h_count != nullptr, "jmc_count_finite: count is NULL");
+    *h_count = 0;
+    if (n == 0) return JMC_OK;
+    JMC_REQUIRE(d_in != nullptr, "jmc_count_finite: NULL array");
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned long long* d_count;
+    int rc = scratch(sizeof(unsigned long long), (void**)&d_count, stream);
+    if (rc) return rc;
+    JMC_CUDA(cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), st));
+    const int grid = grid_for(n, kThreads);
+    if (grid < 0) return JMC_ENODEV;
+    count_finite_kernel<<<grid, kThreads, 0, st>>>(d_in, n, d_count);
+    JMC_LAUNCHED("count_finite_kernel");
+    unsigned long long h = 0;
+    JMC_CUDA(cudaMemcpyAsync(&h, d_count, sizeof(h), cudaMemcpyDeviceToHost, st));
+    JMC_CUDA(cudaStreamSynchronize(st));
+    *h_count = h;
+    return JMC_OK;
+}
+
+extern "C" int jmc_memset(void* d_ptr, int byte_value, uint64_t n_bytes, void* stream) {
+    if (n_bytes == 0) return JMC_OK;
+    JMC_REQUIRE(d_ptr != nullptr, "jmc_memset: pointer is NULL");
+    JMC_CUDA(cudaMemsetAsync(d_ptr, byte_value, n_bytes, (cudaStream_t)stream));
     return JMC_OK;
 }
 

@@ -611,7 +611,7 @@ shower_fast_kernel(ShowerParams p, uint64_t n, uint64_t seed, uint64_t first, co
 // record are 128-byte rows rather than one 16-byte element per lane.
 __global__ void __launch_bounds__(kShowerThreads)
 chain_ecf_kernel(ShowerParams p, const int* __restrict__ lens, const double* __restrict__ chains, uint64_t n, int cap,
-                 double* __restrict__ out) {
+                 double* __restrict__ out, int* __restrict__ truncated) {
     __shared__ double2 s_tile[kShowerThreads / 32][32][9];      // [warp][jet][emission], padded against bank conflicts
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
@@ -619,7 +619,9 @@ chain_ecf_kernel(ShowerParams p, const int* __restrict__ lens, const double* __r
     for (uint64_t r = 0; r < rounds; ++r) {
         const uint64_t base = r * stride + (uint64_t)blockIdx.x * blockDim.x + warp * 32;   // first jet of this warp
         const uint64_t j = base + lane;
-        const int len = j < n ? min(lens[j], cap) : 0;
+        const int stored = j < n ? lens[j] : 0;
+        if (stored > cap) *truncated = 1;                     // a record longer than its slots (any writer wins)
+        const int len = min(stored, cap);
         int longest = len;
         for (int o = 16; o > 0; o >>= 1) longest = max(longest, __shfl_xor_sync(0xffffffffu, longest, o));
         EcfAcc<double> acc;
@@ -827,9 +829,19 @@ extern "C" int jmc_chain_ecf(const jmc_integrand* g, const int32_t* d_n_emission
     jmc::DeviceInfo di;
     if (jmc::device_info(&di)) return JMC_ENODEV;
     const uint64_t want = (n + jmc::kShowerThreads - 1) / jmc::kShowerThreads, cap = (uint64_t)di.sm_count * 8;
+    int* d_flag;
+    rc = jmc::scratch(sizeof(int), (void**)&d_flag, stream);
+    if (rc) return rc;
+    JMC_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), (cudaStream_t)stream));
     jmc::chain_ecf_kernel<<<(int)(want < cap ? want : cap), jmc::kShowerThreads, 0, (cudaStream_t)stream>>>(
-        p, d_n_emissions, d_chains, n, max_emissions, d_obs);
+        p, d_n_emissions, d_chains, n, max_emissions, d_obs, d_flag);
     JMC_LAUNCHED("chain_ecf_kernel");
+    int h_flag = 0;
+    JMC_CUDA(cudaMemcpyAsync(&h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    JMC_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    if (h_flag)
+        return jmc::set_error(JMC_ELIMIT, "emission chains were truncated: raise max_emissions (a record is longer than "
+                                          "its %d slots)", max_emissions);
     return JMC_OK;
 }
 

@@ -13,6 +13,8 @@
 #include <cfloat>
 #include <cmath>
 #include "jmc_common.cuh"
+#include "jmc_philox.cuh"
+#include "jmc_physics.cuh"
 
 namespace jmc {
 
@@ -78,22 +80,47 @@ __device__ __forceinline__ int block_min_index(int v, int* s_red) {
 
 enum { SUD_OK = 0, SUD_NOT_MONOTONE = 1, SUD_ROUNDS = 2, SUD_SHORT_TABLE = 3 };
 
+// What an event's domain, uniform and result formatting are.  kind 0: all given by the caller's arrays (the general
+// entry point).  kinds 1 / 2: the generators of the production workflow, complete in the kernel --
+//   1 pre-critical: domain [0, param] (param = z_cut);
+//   2 subsequent:   domain [0, cond^param / 2] (param = beta); an event whose upper end is below 1e-10 takes the
+//                   underflow value 1e-100 without sampling (sudakov_utils.py:203-211);
+// the uniform of event e is uniforms[e] if given, else the first 53-bit Philox uniform of stream (seed, e); an
+// infinite sample becomes 0 with weight 0 (sudakov_utils.py:117-120), every other weight is 1.
+struct SudGen {
+    int kind;
+    double param;
+    uint64_t seed;
+    double* weights;
+};
+
 __global__ void __launch_bounds__(kSudThreads)
 conditional_inverse_kernel(SudTable T, const double* __restrict__ cond, const double* __restrict__ dom_lo,
                            const double* __restrict__ dom_hi, const double* __restrict__ uniforms, uint64_t n,
                            int catch_turnpoint, int force_monotone, int max_rounds, double* __restrict__ samples,
-                           int* __restrict__ status) {
+                           int* __restrict__ status, SudGen gen) {
     __shared__ double s_x[kSudPoints], s_c[kSudPoints];      // probe points / cdf values (then: the sorted table)
     __shared__ double s_aux[kSudPoints];                      // merge scratch: the two halves of the mixed grid
     __shared__ int s_key[kSudPoints];                         // original position (stable tie-break)
     __shared__ int s_red[kSudThreads / 32];
     const int tid = threadIdx.x;
     for (uint64_t ev = blockIdx.x; ev < n; ev += gridDim.x) {
-        double lo = dom_lo[ev], hi = dom_hi[ev];
-        const double c = cond[ev], r = uniforms[ev];
+        const double c = cond[ev];
+        double lo = gen.kind == 0 ? dom_lo[ev] : 0.0;
+        double hi = gen.kind == 0 ? dom_hi[ev] : (gen.kind == 1 ? gen.param : np_pow(c, gen.param) / 2.);
+        double r;
+        if (uniforms) {
+            r = uniforms[ev];
+        } else {
+            double unused;
+            philox_uniform53x2(ev, 0u, gen.seed, r, unused);
+        }
         int result_status = SUD_ROUNDS;
         double result = nan("");
-        for (int round = 0; round < max_rounds; ++round) {
+        // (NumPy's `upper < 1e-10` is false for NaN: such an event is sampled, as in the reference)
+        const bool underflow = gen.kind == 2 && hi < 1e-10;
+        if (underflow) { result = 1e-100; result_status = SUD_OK; }
+        for (int round = 0; round < max_rounds && !underflow; ++round) {
             // ---- probe points (utils/montecarlo_utils.py:147-154, utils/interpolation.py:18-41)
             int M;
             __syncthreads();
@@ -237,7 +264,14 @@ conditional_inverse_kernel(SudTable T, const double* __restrict__ cond, const do
             break;
         }
         if (tid == 0) {
-            samples[ev] = result;
+            if (gen.kind != 0) {
+                const bool lost = isinf(result);
+                samples[ev] = lost ? 0.0 : result;
+                if (gen.weights) gen.weights[ev] = lost ? 0.0 : 1.0;
+            } else {
+                samples[ev] = result;
+                if (gen.weights) gen.weights[ev] = 1.0;
+            }
             if (result_status != SUD_OK) atomicMax(status, result_status);
         }
         __syncthreads();
@@ -248,17 +282,10 @@ conditional_inverse_kernel(SudTable T, const double* __restrict__ cond, const do
 
 using namespace jmc;
 
-extern "C" int jmc_conditional_inverse_transform(const double* d_grid_x, int nx, const double* d_grid_y, int ny,
-                                                 const double* d_table, int interpolation, const double* d_cond,
-                                                 const double* d_dom_lo, const double* d_dom_hi,
-                                                 const double* d_uniforms, uint64_t n, int catch_turnpoint,
-                                                 int force_monotone, double* d_samples, void* stream) {
-    JMC_REQUIRE(nx >= 2 && ny >= 2, "jmc_conditional_inverse_transform: the radiator grid needs at least 2 x 2 points");
-    JMC_REQUIRE(interpolation == 0 || interpolation == 1, "jmc_conditional_inverse_transform: interpolation must be 0 "
-                                                          "(RectangularGrid) or 1 (Nearest)");
-    JMC_REQUIRE(d_grid_x && d_grid_y && d_table, "jmc_conditional_inverse_transform: NULL radiator table");
-    if (n == 0) return JMC_OK;
-    JMC_REQUIRE(d_cond && d_dom_lo && d_dom_hi && d_uniforms && d_samples, "jmc_conditional_inverse_transform: NULL array");
+static int launch_conditional(const double* d_grid_x, int nx, const double* d_grid_y, int ny, const double* d_table,
+                              int interpolation, const double* d_cond, const double* d_dom_lo, const double* d_dom_hi,
+                              const double* d_uniforms, uint64_t n, int catch_turnpoint, int force_monotone,
+                              double* d_samples, SudGen gen, void* stream) {
     DeviceInfo di;
     if (device_info(&di)) return JMC_ENODEV;
     cudaStream_t st = (cudaStream_t)stream;
@@ -270,7 +297,7 @@ extern "C" int jmc_conditional_inverse_transform(const double* d_grid_x, int nx,
     const uint64_t cap = (uint64_t)di.sm_count * 8;
     const int grid = (int)(n < cap ? n : cap);
     conditional_inverse_kernel<<<grid, kSudThreads, 0, st>>>(T, d_cond, d_dom_lo, d_dom_hi, d_uniforms, n, catch_turnpoint,
-                                                             force_monotone, 64, d_samples, d_status);
+                                                             force_monotone, 64, d_samples, d_status, gen);
     JMC_LAUNCHED("conditional_inverse_kernel");
     int h_status = 0;
     JMC_CUDA(cudaMemcpyAsync(&h_status, d_status, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -283,4 +310,39 @@ extern "C" int jmc_conditional_inverse_transform(const double* d_grid_x, int nx,
     if (h_status == SUD_SHORT_TABLE)
         return set_error(JMC_EDOMAIN, "conditional_samples_from_cdf: a cdf table needs at least two points");
     return JMC_OK;
+}
+
+static int check_table(const char* who, const double* d_grid_x, int nx, const double* d_grid_y, int ny,
+                       const double* d_table, int interpolation) {
+    JMC_REQUIRE(nx >= 2 && ny >= 2, "%s: the radiator grid needs at least 2 x 2 points", who);
+    JMC_REQUIRE(interpolation == 0 || interpolation == 1, "%s: interpolation must be 0 (RectangularGrid) or 1 (Nearest)", who);
+    JMC_REQUIRE(d_grid_x && d_grid_y && d_table, "%s: NULL radiator table", who);
+    return JMC_OK;
+}
+
+extern "C" int jmc_conditional_inverse_transform(const double* d_grid_x, int nx, const double* d_grid_y, int ny,
+                                                 const double* d_table, int interpolation, const double* d_cond,
+                                                 const double* d_dom_lo, const double* d_dom_hi,
+                                                 const double* d_uniforms, uint64_t n, int catch_turnpoint,
+                                                 int force_monotone, double* d_samples, void* stream) {
+    int rc = check_table("jmc_conditional_inverse_transform", d_grid_x, nx, d_grid_y, ny, d_table, interpolation);
+    if (rc) return rc;
+    if (n == 0) return JMC_OK;
+    JMC_REQUIRE(d_cond && d_dom_lo && d_dom_hi && d_uniforms && d_samples, "jmc_conditional_inverse_transform: NULL array");
+    return launch_conditional(d_grid_x, nx, d_grid_y, ny, d_table, interpolation, d_cond, d_dom_lo, d_dom_hi, d_uniforms, n,
+                              catch_turnpoint, force_monotone, d_samples, SudGen{0, 0.0, 0ull, nullptr}, stream);
+}
+
+extern "C" int jmc_sudakov_generate(int emission, const double* d_grid_x, int nx, const double* d_grid_y, int ny,
+                                    const double* d_table, int interpolation, const double* d_theta_crit, double param,
+                                    const double* d_uniforms, uint64_t seed, uint64_t n, double* d_samples,
+                                    double* d_weights, void* stream) {
+    int rc = check_table("jmc_sudakov_generate", d_grid_x, nx, d_grid_y, ny, d_table, interpolation);
+    if (rc) return rc;
+    JMC_REQUIRE(emission == JMC_SUDAKOV_PRECRITICAL || emission == JMC_SUDAKOV_SUBSEQUENT,
+                "jmc_sudakov_generate: emission must be JMC_SUDAKOV_PRECRITICAL or JMC_SUDAKOV_SUBSEQUENT");
+    if (n == 0) return JMC_OK;
+    JMC_REQUIRE(d_theta_crit && d_samples && d_weights, "jmc_sudakov_generate: NULL array");
+    return launch_conditional(d_grid_x, nx, d_grid_y, ny, d_table, interpolation, d_theta_crit, nullptr, nullptr, d_uniforms,
+                              n, 0, 1, d_samples, SudGen{emission, param, seed, d_weights}, stream);
 }

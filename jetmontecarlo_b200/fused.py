@@ -283,8 +283,7 @@ def integrate_batch(integrands, num_samples, *, edges=None, numbins=None, binspa
         edges = np.ascontiguousarray(edges, dtype=np.float64)[p0:p0 + p_count]
     elif npts:
         arr = _as_struct_array(mine)
-        mm = torch.empty((npts, 2), dtype=torch.float64, device=D.device())
-        mm[:, 0], mm[:, 1] = float('inf'), float('-inf')
+        mm = D.to_device(np.tile(np.array([np.inf, -np.inf]), (npts, 1)))      # per point: [min, max] to be merged
         _lib.check(_lib.lib.jmc_run_batch(arr, npts, num_samples, key, 0, prec, None, 0, None, None, None, D.ptr(mm),
                                           D.stream()))
         mm = D.to_host(mm)

@@ -128,7 +128,7 @@ def fused_ewoc(process, num_samples, pair_function, energy_weights=(1, 1), numbi
         if maxval is not None:
             hi = max(maxval, hi)
         it._edges_from_range(numbins, lo, hi, binspacing, 1e-15)
-        rejected.zero_()
+        D.zero_(rejected)
     else:
         it.bins, it.binspacing, it.hasBins = np.asarray(edges, dtype=np.float64), binspacing, True
         it.bin_midpoints = ((it.bins[1:] + it.bins[:-1]) / 2. if binspacing == 'lin'

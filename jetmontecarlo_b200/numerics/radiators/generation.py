@@ -33,7 +33,7 @@ def _device_columns(sampler_obj):
     jac = getattr(sampler_obj, 'device_jacobians', None)
     if jac is None or jac.shape[0] != len(samples):
         jac = D.to_device(np.asarray(sampler_obj.jacobians, dtype=np.float64)[-len(samples):])
-    return dev[:, 0].contiguous(), dev[:, 1].contiguous(), jac
+    return dev[:, 0], dev[:, 1], jac          # column views: the kernels read them with their stride
 
 
 def gen_numerical_radiator(rad_sampler, emission_type, jet_type='quark', obs_accuracy='LL', splitfn_accuracy='LL',

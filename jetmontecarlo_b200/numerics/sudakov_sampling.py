@@ -79,55 +79,44 @@ def conditional_samples_from_table(radiator, conds, domain_lo, domain_hi, unifor
     if rc == -5:        # JMC_EDOMAIN: what the reference raises as ValueError
         raise ValueError(_lib.lib.jmc_last_error().decode("utf-8", "replace"))
     _lib.check(rc)
-    return out, torch.ones_like(out)
+    return out, D.full((n,), 1.)
 
 
 # ---- the three generators of the production workflow ---------------------------------------------------------------
-def _device_uniforms(n, seed):
-    """n uniforms of the counter RNG (sample index = event index) on the device"""
+def _generate(emission, radiator, theta_crits, param, seed, uniforms):
+    """jmc_sudakov_generate: domains, uniforms, sampling, inf -> (0, weight 0) formatting and weights in ONE kernel"""
     D.require_cuda()
+    assert isinstance(radiator, TableRadiator), "the conditional sampler needs the radiator's table (TableRadiator)"
     from ..montecarlo.sampler import next_key
-    out = D.empty((n, 1))
-    _lib.check(_lib.lib.jmc_uniforms(n, next_key() if seed is None else int(seed), 0, 1, D.ptr(out), D.stream()))
-    return out[:, 0].contiguous()
-
-
-def _format(samples, weights):
-    """inf -> 0 with zero weight.  ref: sudakov_utils.py:117-120"""
-    bad = torch.isinf(samples)
-    zero = torch.zeros_like(samples)
-    return torch.where(bad, zero, samples), torch.where(bad, zero, weights)
+    theta_crits = D.to_device(theta_crits).reshape(-1)
+    n = theta_crits.numel()
+    r = None if uniforms is None else D.to_device(uniforms).reshape(-1)
+    assert r is None or r.numel() == n
+    key = 0 if r is not None else (next_key() if seed is None else int(seed) & 0xFFFFFFFFFFFFFFFF)
+    gx, gy, table = radiator.device()
+    samples, weights = D.empty((n,)), D.empty((n,))
+    rc = _lib.lib.jmc_sudakov_generate(emission, D.ptr(gx), gx.numel(), D.ptr(gy), gy.numel(), D.ptr(table),
+                                       int(radiator.method == "Nearest"), D.ptr(theta_crits), float(param), D.ptr(r), key,
+                                       n, D.ptr(samples), D.ptr(weights), D.stream())
+    if rc == -5:        # JMC_EDOMAIN: what the reference raises as ValueError
+        raise ValueError(_lib.lib.jmc_last_error().decode("utf-8", "replace"))
+    _lib.check(rc)
+    return samples, weights
 
 
 def generate_precritical_samples(pre_radiator, theta_crits, z_cut, seed=None, uniforms=None):
-    """z_pre for every critical angle, from the cdf exp(-R_pre(z_pre, theta_crit)) on [0, z_cut] forced monotone.
-    ``pre_radiator``: ``TableRadiator`` of a gen_pre_num_rad result; ``theta_crits``: array / CUDA tensor.
-    Returns (samples, weights) CUDA tensors.  ref: examples/sudakov_comparisons/sudakov_utils.py:134-182"""
-    theta_crits = D.to_device(theta_crits).reshape(-1)
-    n = theta_crits.numel()
-    r = _device_uniforms(n, seed) if uniforms is None else uniforms
-    zeros = torch.zeros_like(theta_crits)
-    samples, weights = conditional_samples_from_table(pre_radiator, theta_crits, zeros, zeros + float(z_cut), r,
-                                                      force_monotone=True)
-    return _format(samples, weights)
+    """z_pre for every critical angle, from the cdf exp(-R_pre(z_pre, theta_crit)) on [0, z_cut] forced monotone;
+    an infinite sample comes back as 0 with weight 0.  ``pre_radiator``: ``TableRadiator`` of a gen_pre_num_rad
+    result; ``theta_crits``: array / CUDA tensor.  Returns (samples, weights) CUDA tensors.
+    ref: examples/sudakov_comparisons/sudakov_utils.py:134-182, 117-120"""
+    return _generate(_lib.SUDAKOV_PRECRITICAL, pre_radiator, theta_crits, z_cut, seed, uniforms)
 
 
 def generate_subsequent_samples(sub_radiator, theta_crits, beta, seed=None, uniforms=None):
     """C_sub for every critical angle, from exp(-R_sub(C, theta_crit)) on [0, theta_crit^beta / 2] forced monotone;
     events with theta_crit^beta / 2 < 1e-10 go to the underflow value 1e-100.
     ref: examples/sudakov_comparisons/sudakov_utils.py:185-238"""
-    theta_crits = D.to_device(theta_crits).reshape(-1)
-    n = theta_crits.numel()
-    r = _device_uniforms(n, seed) if uniforms is None else D.to_device(uniforms).reshape(-1)
-    upper = theta_crits ** beta / 2.
-    live = ~(upper < 1e-10)
-    samples = torch.full_like(theta_crits, 1e-100)
-    weights = torch.ones_like(theta_crits)
-    if bool(live.any()):
-        s, w = conditional_samples_from_table(sub_radiator, theta_crits[live], torch.zeros_like(upper[live]),
-                                              upper[live], r[live], force_monotone=True)
-        samples[live], weights[live] = s, w
-    return _format(samples, weights)
+    return _generate(_lib.SUDAKOV_SUBSEQUENT, sub_radiator, theta_crits, beta, seed, uniforms)
 
 
 def generate_critical_samples(crit_radiator, num_samples, seed=None):

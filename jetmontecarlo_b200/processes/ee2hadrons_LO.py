@@ -81,7 +81,8 @@ class ee2hLO_PairwiseObservable(MonteCarloObservable):
                                                   float(getattr(self.kinematic_function, 'kappa', 0.)), D.ptr(out),
                                                   D.stream()))
             self.device_observables = out
-            self.device_weights = p.device_jacobians.repeat(3)
+            self.device_weights = D.empty((3 * n,))
+            _lib.check(_lib.lib.jmc_tile(D.ptr(p.device_jacobians), n, 3, D.ptr(self.device_weights), D.stream()))
             self.observables = D.to_host(out)
             self.weights = np.tile(np.asarray(p.jacobians, dtype=float), 3)
             return

@@ -5,6 +5,8 @@ histogram) runs on the GPU (JMC_FN_MASK_FINITE, jmc_hist); the O(bins) normalisa
 """
 from warnings import warn
 
+import ctypes as C
+
 import numpy as np
 import torch
 
@@ -20,7 +22,9 @@ def vals_to_pdf(vals, num_bins, weights=None, bin_space='log', log_cutoff=None, 
     if make_finite:
         # a removed sample == a sample of weight 0 (the pdf is normalised by the histogram's own sum)
         w = eval_fn(_lib.FN_MASK_FINITE, [w, v])
-        if not bool(torch.isfinite(v).any()):
+        n_finite = C.c_uint64(0)
+        _lib.check(_lib.lib.jmc_count_finite(D.ptr(v), v.numel(), C.byref(n_finite), D.stream()))
+        if n_finite.value == 0:
             warn("No finite values in `vals`, the values given to "
                  "vals_to_pdf. Returning empty arrays.")
             return np.array([]), np.array([])

@@ -198,7 +198,7 @@ class JetList:
         beyond a jet's length)."""
         D.require_cuda()
         n = self.num_events
-        chains = torch.full((n, int(max_emissions), 2), float('nan'), dtype=torch.float64, device=D.device())
+        chains = D.full((n, int(max_emissions), 2), float('nan'))
         lens = D.empty((n,), dtype=torch.int32)
         s = self._integrand().c_struct()
         _lib.check(_lib.lib.jmc_shower_chains(C.byref(s), n, self.seed, 0, PRECISIONS[precision], int(max_emissions),
@@ -308,12 +308,13 @@ def ecfs_from_chains(lens, chains, beta=2., obs_acc='LL', n_emissions=1, groomer
     lens = lens.to(device=D.device(), dtype=torch.int32).contiguous()
     chains = chains.to(device=D.device(), dtype=torch.float64).contiguous()
     assert chains.dim() == 3 and chains.shape[0] == lens.numel() and chains.shape[2] == 2
-    assert lens.numel() == 0 or int(lens.max().item()) <= chains.shape[1], \
-        "emission chains were truncated: raise max_emissions"
     out = D.empty((lens.numel(),))
     s = ig.c_struct()
-    _lib.check(_lib.lib.jmc_chain_ecf(C.byref(s), D.ptr(lens), D.ptr(chains), lens.numel(), int(chains.shape[1]),
-                                      D.ptr(out), D.stream()))
+    rc = _lib.lib.jmc_chain_ecf(C.byref(s), D.ptr(lens), D.ptr(chains), lens.numel(), int(chains.shape[1]),
+                                D.ptr(out), D.stream())
+    # (the kernel checks every record's length against its slots: no separate reduction over ``lens``)
+    assert rc != -4, "emission chains were truncated: raise max_emissions"
+    _lib.check(rc)
     return out
 
 
