@@ -265,7 +265,7 @@ class Job:
 
     def run(self, n, first):
         D, L = self.D, self.L
-        self.sum_w.zero_(); self.sum_w2.zero_(); self.count.zero_()
+        D.zero_(self.sum_w); D.zero_(self.sum_w2); D.zero_(self.count)     # cudaMemsetAsync (jmc_memset)
         L.check(L.lib.jmc_handle_run(self.handle.ptr, C.byref(self.s), n, SEED, first, self.prec,
                                      self.h_edges.ctypes.data_as(C.c_void_p), self.ne, D.ptr(self.sum_w),
                                      D.ptr(self.sum_w2), D.ptr(self.count), None, D.stream()))
@@ -567,11 +567,11 @@ def main():
     barrier()
     t_wall0 = time.perf_counter()
     for k in range(args.steps):
-        flush.zero_()
+        job.D.zero_(flush)
         ev[k][0].record()
         base = (args.warmup + k) * J
         # the first job of the step carries the kernel-only events
-        job.sum_w.zero_(); job.sum_w2.zero_(); job.count.zero_()
+        job.D.zero_(job.sum_w); job.D.zero_(job.sum_w2); job.D.zero_(job.count)
         kev0, kev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         kev0.record()
         _lib.check(_lib.lib.jmc_handle_run(job.handle.ptr, C.byref(job.s), n, SEED, (base * world + rank) * n, job.prec,

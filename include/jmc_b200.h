@@ -454,6 +454,13 @@ int jmc_handle_integrate_host(jmc_handle* h, const jmc_integrand* g, uint64_t n,
  * (cudaMemsetAsync).  Asynchronous on `stream`. */
 int jmc_fill(double* d_out, uint64_t n, double value, void* stream);
 int jmc_memset(void* d_ptr, int byte_value, uint64_t n_bytes, void* stream);
+/* Buffers of the two collectives of a sharded job.  Histograms: d_buf [3, nb] FP64 = (sum w, sum w^2, count as FP64,
+ * exact up to 2^53), unpack != 0 writes the reduced buffer back; one SUM all-reduce in between.  Min/max: d_buf
+ * [n_pairs, 3] = (-min, max, has-NaN) with NaN -> -inf, so that ONE MAX all-reduce merges minima, maxima and the NaN
+ * flags (a NaN on any rank makes the pair NaN, as np.min / np.max of the whole sample set would). */
+int jmc_pack_histograms(double* d_sum_w, double* d_sum_w2, uint64_t* d_count, uint64_t nb, double* d_buf, int unpack,
+                        void* stream);
+int jmc_pack_minmax(double* d_minmax, uint64_t n_pairs, double* d_buf, int unpack, void* stream);
 /* np.tile(d_in, reps) into d_out [reps * n] (the event weights of the three parton pairs, ewoc.py:11-57) */
 int jmc_tile(const double* d_in, uint64_t n, int reps, double* d_out, void* stream);
 /* number of finite entries (vals_to_pdf's "no finite values" test, utils/hist_utils.py:105-112); synchronises */

@@ -40,7 +40,7 @@ EXPORTS = (
     "jmc_finalize", "jmc_cumulative", "jmc_set_density_host", "jmc_integrate_host", "jmc_sample_host",
     "jmc_eval_fn_host", "jmc_launch_count", "jmc_create", "jmc_destroy", "jmc_handle_run", "jmc_handle_integrate_host",
     "jmc_chain_ecf", "jmc_process_sample", "jmc_process_pairs", "jmc_process_ewoc",
-    "jmc_conditional_inverse_transform", "jmc_sudakov_generate", "jmc_fill", "jmc_memset", "jmc_tile", "jmc_count_finite",
+    "jmc_conditional_inverse_transform", "jmc_sudakov_generate", "jmc_fill", "jmc_memset", "jmc_tile", "jmc_count_finite", "jmc_pack_histograms", "jmc_pack_minmax",
 )
 
 
@@ -133,6 +133,8 @@ def _load():
         "jmc_memset": (i32, [vp, i32, u64, vp]),
         "jmc_tile": (i32, [vp, u64, i32, vp, vp]),
         "jmc_count_finite": (i32, [vp, u64, P(u64), vp]),
+        "jmc_pack_histograms": (i32, [vp, vp, vp, u64, vp, i32, vp]),
+        "jmc_pack_minmax": (i32, [vp, u64, vp, i32, vp]),
         "jmc_create": (i32, [P(vp)]),
         "jmc_destroy": (i32, [vp]),
         "jmc_handle_run": (i32, [vp, P(Integrand), u64, u64, u64, i32, vp, i32, vp, vp, vp, vp, vp]),

@@ -189,6 +189,45 @@ __global__ void __launch_bounds__(kThreads) tile_kernel(const double* __restrict
     }
 }
 
+// ---- packing for the collectives of a sharded job (jetmontecarlo_b200/distributed.py) ----
+// [sum w | sum w^2 | count as FP64] <-> the three histograms; counts are exact in FP64 up to 2^53
+__global__ void __launch_bounds__(kThreads) pack_hist_kernel(const double* __restrict__ sum_w, const double* __restrict__ sum_w2,
+                                                              const unsigned long long* __restrict__ count, uint64_t nb,
+                                                              double* __restrict__ buf, int unpack,
+                                                              double* __restrict__ o_sum_w, double* __restrict__ o_sum_w2,
+                                                              unsigned long long* __restrict__ o_count) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nb; k += stride) {
+        if (!unpack) {
+            buf[k] = sum_w[k];
+            buf[nb + k] = sum_w2[k];
+            buf[2 * nb + k] = (double)count[k];
+        } else {
+            o_sum_w[k] = buf[k];
+            o_sum_w2[k] = buf[nb + k];
+            o_count[k] = (unsigned long long)llrint(buf[2 * nb + k]);
+        }
+    }
+}
+// rows (min, max) <-> rows (-min, max, has-NaN) with NaN -> -inf: ONE MAX all-reduce merges minima, maxima and NaN flags
+__global__ void __launch_bounds__(kThreads) pack_minmax_kernel(double* __restrict__ mm, uint64_t n, double* __restrict__ buf,
+                                                                int unpack) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
+        if (!unpack) {
+            const double lo = mm[2 * k], hi = mm[2 * k + 1];
+            const bool bad = lo != lo || hi != hi;
+            buf[3 * k] = lo != lo ? -INFINITY : -lo;
+            buf[3 * k + 1] = hi != hi ? -INFINITY : hi;
+            buf[3 * k + 2] = bad ? 1.0 : 0.0;
+        } else {
+            const bool bad = buf[3 * k + 2] > 0.0;
+            mm[2 * k] = bad ? qnan() : -buf[3 * k];
+            mm[2 * k + 1] = bad ? qnan() : buf[3 * k + 1];
+        }
+    }
+}
+
 // number of finite entries
 __global__ void __launch_bounds__(kThreads) count_finite_kernel(const double* __restrict__ in, uint64_t n,
                                                                  unsigned long long* __restrict__ count) {
@@ -302,6 +341,29 @@ extern "C" int jmc_count_finite(const double* d_in, uint64_t n, uint64_t* h_coun
     JMC_CUDA(cudaMemcpyAsync(&h, d_count, sizeof(h), cudaMemcpyDeviceToHost, st));
     JMC_CUDA(cudaStreamSynchronize(st));
     *h_count = h;
+    return JMC_OK;
+}
+
+extern "C" int jmc_pack_histograms(double* d_sum_w, double* d_sum_w2, uint64_t* d_count, uint64_t nb, double* d_buf,
+                                   int unpack, void* stream) {
+    if (nb == 0) return JMC_OK;
+    JMC_REQUIRE(d_sum_w && d_sum_w2 && d_count && d_buf, "jmc_pack_histograms: NULL array");
+    const int grid = grid_for(nb, kThreads);
+    if (grid < 0) return JMC_ENODEV;
+    pack_hist_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(d_sum_w, d_sum_w2, (const unsigned long long*)d_count, nb,
+                                                                  d_buf, unpack, d_sum_w, d_sum_w2,
+                                                                  (unsigned long long*)d_count);
+    JMC_LAUNCHED("pack_hist_kernel");
+    return JMC_OK;
+}
+
+extern "C" int jmc_pack_minmax(double* d_minmax, uint64_t n_pairs, double* d_buf, int unpack, void* stream) {
+    if (n_pairs == 0) return JMC_OK;
+    JMC_REQUIRE(d_minmax && d_buf, "jmc_pack_minmax: NULL array");
+    const int grid = grid_for(n_pairs, kThreads);
+    if (grid < 0) return JMC_ENODEV;
+    pack_minmax_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(d_minmax, n_pairs, d_buf, unpack);
+    JMC_LAUNCHED("pack_minmax_kernel");
     return JMC_OK;
 }
 
