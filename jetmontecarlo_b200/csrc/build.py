@@ -28,7 +28,7 @@ LIB = os.path.join(LIB_DIR, "libjmc_b200.so")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
           "-I", os.path.join(ROOT, "include")]
-# compile-time experiment switches (scripts/try_variants.sh); unset = the defaults in the sources
+# compile-time experiment switches (scripts/fast_shootout.sh, scripts/shower_shootout.sh); unset = the defaults in the sources
 SWITCHES = ("JMC_FAST_CHUNK", "JMC_FAST_MIN_BLOCKS", "JMC_FAST_PAIRS", "JMC_FAST_PAIRS_2W", "JMC_FAST_PIN_KEYS", "JMC_PHILOX_SPLIT", "JMC_ACC_MODE",
             "JMC_HIST_MODE", "JMC_HIST_UNROLL", "JMC_SHOWER_GROUP", "JMC_SHOWER_BIN_GROUP", "JMC_SHOWER_CHUNK",
             "JMC_SHOWER_MIN_BLOCKS", "JMC_SHOWER_TRIALS")

@@ -43,7 +43,7 @@ static constexpr int kFastThreads = 256, kFastThreadsBig = 1024;
 static constexpr size_t kBigSmemThreshold = 72 * 1024;     // block histograms above this use the 1024-thread kernels
 static constexpr int kQueueFields = 5, kQueueSlots = 64;   // per-warp compaction queue (see run_fast_kernel)
 // resident blocks per SM the register allocation must allow (3 x 256 threads: <= 85 registers) and sample pairs per
-// loop trip; swept with scripts/try_variants.sh.
+// loop trip; swept with scripts/fast_shootout.sh.
 // The rarely executed running-coupling radiator code may spill; the per-sample light path must not.
 #ifndef JMC_FAST_MIN_BLOCKS
 #define JMC_FAST_MIN_BLOCKS 3
