@@ -13,6 +13,7 @@ import numpy as np
 from jetmontecarlo.montecarlo.integrator import *
 from jetmontecarlo.numerics.radiators.samplers import *
 from jetmontecarlo.numerics.observables import *
+from jetmontecarlo.numerics.radiators.generation import *
 from jetmontecarlo.analytics.radiators.fixedcoupling import *
 from file_management.data_management import save_new_data, load_data
 from file_management import catalog_utils
