@@ -48,7 +48,41 @@ def to_device(x):
             return _gather_strided(x)
         return x.to(_F64).contiguous()
     a = np.ascontiguousarray(x, dtype=np.float64)
+    if a.nbytes >= 2 * _STAGE_BYTES:
+        return _upload_staged(a)
     return torch.from_numpy(a).to(device(), non_blocking=False)
+
+
+def _staging(dev):
+    if dev not in _stage:
+        _stage[dev] = ([torch.empty(_STAGE_BYTES, dtype=torch.uint8, pin_memory=True) for _ in range(2)],
+                       torch.cuda.Stream(device=torch.device("cuda", dev)), [torch.cuda.Event() for _ in range(2)])
+    return _stage[dev]
+
+
+def _upload_staged(a):
+    """Large host array -> device tensor through the two pinned staging buffers: the host copy of chunk k + 1 into
+    its buffer (four threads) overlaps the host-to-device copy of chunk k (the reference's API hands over host
+    arrays, so for large N these copies are what its drop-in calls cost)."""
+    dev = device()
+    bufs, side, events = _staging(dev.index)
+    out = torch.empty(a.shape, dtype=_F64, device=dev)
+    flat_out = out.reshape(-1).view(torch.uint8)
+    flat_in = a.reshape(-1).view(np.uint8)
+    total = flat_in.size
+    side.wait_stream(torch.cuda.current_stream(dev))
+    for k, o in enumerate(range(0, total, _STAGE_BYTES)):
+        nbytes = min(_STAGE_BYTES, total - o)
+        events[k & 1].synchronize()                 # the copy that last read this buffer has finished
+        dst = bufs[k & 1][:nbytes].numpy()
+        quarter = -(-nbytes // 4)
+        list(_copy_pool().map(lambda j: dst[j:j + quarter].__setitem__(slice(None), flat_in[o + j:o + min(nbytes, j + quarter)]),
+                              range(0, nbytes, quarter)))
+        with torch.cuda.stream(side):
+            flat_out[o:o + nbytes].copy_(bufs[k & 1][:nbytes], non_blocking=True)
+            events[k & 1].record(side)
+    torch.cuda.current_stream(dev).wait_stream(side)
+    return out
 
 
 def _gather_strided(x):
@@ -98,11 +132,7 @@ def to_host(t):
     if not t.is_cuda or t.numel() * t.element_size() < 2 * _STAGE_BYTES:
         return t.cpu().numpy()
     t = t.contiguous()
-    dev = t.device.index
-    if dev not in _stage:
-        _stage[dev] = ([torch.empty(_STAGE_BYTES, dtype=torch.uint8, pin_memory=True) for _ in range(2)],
-                       torch.cuda.Stream(device=t.device), [torch.cuda.Event() for _ in range(2)])
-    bufs, side, events = _stage[dev]
+    bufs, side, events = _staging(t.device.index)
     out = np.empty(tuple(t.shape), dtype=torch.empty(0, dtype=t.dtype).numpy().dtype)
     flat_out = out.reshape(-1).view(np.uint8)
     flat_in = t.reshape(-1).view(torch.uint8)
