@@ -89,9 +89,10 @@ __device__ __forceinline__ void hist_add_weight(HistSmem& h, int b, double w) {
 
 // One sample into the block histogram.  A NaN weight is not added; it lowers
 // the poison bin instead (NumPy: NaN in a cumsum reaches every later bin).
+template <int MODE = -1>
 __device__ __forceinline__ void hist_add(HistSmem& h, int n_edges, double obs, double w, bool has_w,
                                          int* s_poison, const BinGuess& G = BinGuess{0, 0.f, 0.f, 0.f}) {
-    const int b = bin_index_guided(obs, h.edges, n_edges, G);
+    const int b = bin_index_guided<MODE>(obs, h.edges, n_edges, G);
     if (has_w && w != w) {
         // obs below the first edge sorts before every bin -> poisons them all;
         // obs above the last edge or NaN sorts after the last bin -> harmless.

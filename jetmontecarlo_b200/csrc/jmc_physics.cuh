@@ -435,12 +435,16 @@ struct BinGuess {
     float eps;             // > 0: the guess is CERTAIN when the fractional part of the mapped value lies in
                            // (eps, 1 - eps) -- eps bounds every rounding error of the FP32 map (derive_bin_guess)
 };
+// MODE >= 0: the guess's mode as a compile-time constant (a streaming kernel branches on it once per block, not once
+// per sample); MODE < 0: read it from G
+template <int MODE = -1>
 __device__ __forceinline__ int bin_index_guided(double x, const double* __restrict__ edges, int n_edges,
                                                 const BinGuess& G) {
-    if (G.mode == 0) return bin_index(x, edges, n_edges);
+    const int mode = MODE < 0 ? G.mode : MODE;
+    if (mode == 0) return bin_index(x, edges, n_edges);
     if (!(x >= edges[0]) || !(x <= edges[n_edges - 1])) return -1;
     const float xf = (float)x;
-    const float g = G.mode == 1 ? xf : __log2f(xf);
+    const float g = mode == 1 ? xf : __log2f(xf);
     const float f = (g - G.b0) * G.inv_d;
     const float fl = floorf(f);
     int idx = (int)fl;
