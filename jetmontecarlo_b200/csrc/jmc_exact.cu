@@ -94,7 +94,25 @@ struct FnArity {
         : (FN == JMC_FN_C_GROOMED || FN == JMC_FN_TWO_EMISSION || FN == JMC_FN_EWOC_WEIGHT) ? 4 : 2;
 };
 
-template <int FN, bool ACTIVE>
+// "the reference's value is certainly NaN" for the running-coupling functions (the tests of jmc_integrand.cuh): the
+// cheap part of eval_one, used by the compacting form of the kernel to decide which elements need the radiators
+template <int FN>
+__device__ __forceinline__ bool eval_surely_nan(const jmc_fn_params& p, double x0, double x1, double x2, double x3) {
+    if (FN == JMC_FN_CRIT_PDF_RC) return crit_rc_surely_nan(x1, p.z_cut);
+    if (FN == JMC_FN_SUB_PDF_RC) return sub_rc_surely_nan(x0, p.beta, x1);
+    if (FN == JMC_FN_TWO_EMISSION)
+        return !p.fixed_coupling && (crit_rc_surely_nan(x1, p.z_cut) || sub_rc_surely_nan(csub_verbatim(x2, x3, p.beta), p.beta, x1));
+    return false;
+}
+
+// COMPACT (running-coupling pdfs and twoEmissionWeight): most elements of a C3 sample set lie below the Landau scale
+// (99.7 %) and are NaN after a few operations; the others need ~60 FP64 transcendentals.  Evaluated in place, one
+// warp in eleven runs the radiator code with one or two live lanes and the kernel is an order of magnitude off its
+// 40 B / element HBM roofline.  A warp writes the NaNs at once, appends the arguments and index of the other
+// elements to its shared-memory queue and evaluates 32 of them at a time with every lane busy.
+static constexpr int kFnQueueSlots = 64;
+
+template <int FN, bool ACTIVE, bool COMPACT>
 __global__ void __launch_bounds__(kThreads) eval_fn_kernel(jmc_fn_params p, FnArgs A, uint64_t n,
                                                             double* __restrict__ out) {
     constexpr int NA = FnArity<FN>::value;
@@ -106,11 +124,55 @@ __global__ void __launch_bounds__(kThreads) eval_fn_kernel(jmc_fn_params p, FnAr
     if (wanted) consts = make_crit_consts(p.z_cut, p.jet);
     const CritConsts* cc = wanted ? &consts : nullptr;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const double x0 = fn_arg(A, 0, i), x1 = NA > 1 ? fn_arg(A, 1, i) : 0.0, x2 = NA > 2 ? fn_arg(A, 2, i) : 0.0,
-                     x3 = NA > 3 ? fn_arg(A, 3, i) : 0.0;
-        out[i] = eval_one<FN, ACTIVE>(p, x0, x1, x2, x3, cc);
+    if (!COMPACT) {
+        for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+            const double x0 = fn_arg(A, 0, i), x1 = NA > 1 ? fn_arg(A, 1, i) : 0.0, x2 = NA > 2 ? fn_arg(A, 2, i) : 0.0,
+                         x3 = NA > 3 ? fn_arg(A, 3, i) : 0.0;
+            out[i] = eval_one<FN, ACTIVE>(p, x0, x1, x2, x3, cc);
+        }
+        return;
     }
+    __shared__ double s_q[kThreads / 32][4][kFnQueueSlots];
+    __shared__ unsigned long long s_qi[kThreads / 32][kFnQueueSlots];
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    int qn = 0;                                          // warp-uniform
+    auto drain = [&](int slot) {
+        out[s_qi[warp][slot]] = eval_one<FN, ACTIVE>(p, s_q[warp][0][slot], s_q[warp][1][slot], s_q[warp][2][slot],
+                                                     s_q[warp][3][slot], cc);
+    };
+    for (uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); i0 < n; i0 += stride) {
+        const uint64_t i = i0 + lane;
+        const bool valid = i < n;
+        double x0 = 0.0, x1 = 0.0, x2 = 0.0, x3 = 0.0;
+        bool active = false;
+        if (valid) {
+            x0 = fn_arg(A, 0, i);
+            x1 = NA > 1 ? fn_arg(A, 1, i) : 0.0;
+            x2 = NA > 2 ? fn_arg(A, 2, i) : 0.0;
+            x3 = NA > 3 ? fn_arg(A, 3, i) : 0.0;
+            active = !eval_surely_nan<FN>(p, x0, x1, x2, x3);
+            if (!active) out[i] = qnan();
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, active);
+        if (!m) continue;
+        if (active) {
+            const int slot = qn + __popc(m & ((1u << lane) - 1u));
+            s_q[warp][0][slot] = x0;
+            s_q[warp][1][slot] = x1;
+            s_q[warp][2][slot] = x2;
+            s_q[warp][3][slot] = x3;
+            s_qi[warp][slot] = i;
+        }
+        qn += __popc(m);
+        __syncwarp();
+        if (qn >= 32) {
+            qn -= 32;
+            drain(qn + (int)lane);
+            __syncwarp();
+        }
+    }
+    __syncwarp();
+    if ((int)lane < qn) drain((int)lane);
 }
 
 template <int FN>
@@ -120,12 +182,15 @@ static void launch_eval_fn(int fn, const jmc_fn_params& p, const FnArgs& A, uint
     // other parameters get the all-regions instantiation
     constexpr bool RC = FN == JMC_FN_CRIT_RAD_RC || FN == JMC_FN_CRIT_PDF_RC || FN == JMC_FN_SUB_RAD_RC
                         || FN == JMC_FN_SUB_PDF_RC || FN == JMC_FN_TWO_EMISSION;
+    constexpr bool CAN_COMPACT = FN == JMC_FN_CRIT_PDF_RC || FN == JMC_FN_SUB_PDF_RC || FN == JMC_FN_TWO_EMISSION;
     const bool sub_fn = FN == JMC_FN_SUB_RAD_RC || FN == JMC_FN_SUB_PDF_RC || FN == JMC_FN_TWO_EMISSION;
     const bool crit_fn = FN == JMC_FN_CRIT_RAD_RC || FN == JMC_FN_CRIT_PDF_RC || FN == JMC_FN_TWO_EMISSION;
     const bool regular = (!sub_fn || p.beta > 1.0) && (!crit_fn || p.z_cut < 0.5);
     if (fn == FN) {
-        if (RC && !regular) eval_fn_kernel<FN, !RC><<<grid, kThreads, 0, st>>>(p, A, n, out);
-        else eval_fn_kernel<FN, true><<<grid, kThreads, 0, st>>>(p, A, n, out);
+        if (RC && !regular) eval_fn_kernel<FN, !RC, false><<<grid, kThreads, 0, st>>>(p, A, n, out);
+        else if (CAN_COMPACT && !(FN == JMC_FN_TWO_EMISSION && p.fixed_coupling))
+            eval_fn_kernel<FN, true, CAN_COMPACT><<<grid, kThreads, 0, st>>>(p, A, n, out);
+        else eval_fn_kernel<FN, true, false><<<grid, kThreads, 0, st>>>(p, A, n, out);
     } else if constexpr (FN + 1 < JMC_FN_COUNT) {
         launch_eval_fn<FN + 1>(fn, p, A, n, out, grid, st);
     }
