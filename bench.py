@@ -18,8 +18,10 @@ lasts seconds and the GPU reaches its steady clocks and power).  Weak scaling:
 S per GPU is fixed.
 
 Besides the headline, rank 0 of a single-GPU run times the other BASELINE
-configurations briefly and reports them under "sub_results" (each with its
-kernel time and roofline fractions).  Prints ONE JSON line (rank 0).
+configurations and the SURVEY 8(f) rows (per-event Sudakov sampling, RSS shower
+and record replay, fused EWOC) briefly and reports them under "sub_results"
+(each with its kernel time and, where one applies, roofline fractions).
+Prints ONE JSON line (rank 0).
 """
 import argparse
 import ctypes as C
