@@ -199,3 +199,41 @@ def test_large_event_counts_and_counter_rng(cuda):
     sub = slice(0, 300)
     ref = _loop(_table_cdf(zs, ths, R), theta[sub], np.zeros(300), np.full(300, z_cut), r[sub], force_monotone=True)
     assert np.isclose(got[sub], ref, rtol=1e-9, atol=1e-300).mean() > .97
+
+
+def test_generators_edge_cases(cuda):
+    """empty input, the underflow rule, a zero critical angle, NULL arguments: jmc_sudakov_generate itself"""
+    import ctypes as C
+    import torch
+    from jetmontecarlo_b200 import _device as D, _lib
+    from jetmontecarlo_b200.numerics import sudakov_sampling as S
+    gx, gy = np.logspace(-10, -1, 30), np.logspace(-8, 0, 25)
+    table = np.outer(np.linspace(4., 0., 30), np.linspace(2., .5, 25))
+    rad = S.TableRadiator(gx, gy, table)
+    s, w = S.generate_precritical_samples(rad, np.array([]), .1, seed=1)
+    assert s.numel() == 0 and w.numel() == 0
+    # subsequent: theta^beta / 2 < 1e-10 -> 1e-100 with weight 1, without sampling
+    theta = np.array([1e-6, 1e-5 * .9, .3, 0.])
+    s, w = S.generate_subsequent_samples(S.TableRadiator(gx, gy, table, "Nearest"), theta, 2., uniforms=np.full(4, .5))
+    s, w = s.cpu().numpy(), w.cpu().numpy()
+    assert s[0] == 1e-100 and s[1] == 1e-100 and s[3] == 1e-100 and np.all(w == 1.)
+    assert 0. <= s[2] <= .3 ** 2 / 2.
+    # the same uniforms give the same samples whether passed in or drawn from the event's Philox stream
+    th = np.full(1000, .2)
+    u = np.empty((1000, 1))
+    ud = D.empty((1000, 1))
+    _lib.check(_lib.lib.jmc_uniforms(1000, 77, 0, 1, D.ptr(ud), D.stream()))
+    a, _ = S.generate_precritical_samples(rad, th, .1, seed=77)
+    b, _ = S.generate_precritical_samples(rad, th, .1, uniforms=ud[:, 0].contiguous())
+    np.testing.assert_array_equal(a.cpu().numpy(), b.cpu().numpy())
+    L, null = _lib.lib, C.c_void_p(0)
+    dx, dy, dt = rad.device()
+    out = D.empty((4,))
+    assert L.jmc_sudakov_generate(3, D.ptr(dx), 30, D.ptr(dy), 25, D.ptr(dt), 0, D.ptr(out), .1, null, 1, 4, D.ptr(out),
+                                  D.ptr(out), D.stream()) == -1                  # unknown emission
+    assert L.jmc_sudakov_generate(1, D.ptr(dx), 30, D.ptr(dy), 25, D.ptr(dt), 0, null, .1, null, 1, 4, D.ptr(out),
+                                  D.ptr(out), D.stream()) == -1                  # NULL critical angles
+    assert L.jmc_sudakov_generate(1, D.ptr(dx), 1, D.ptr(dy), 25, D.ptr(dt), 0, D.ptr(out), .1, null, 1, 4, D.ptr(out),
+                                  D.ptr(out), D.stream()) == -1                  # a 1-point grid axis
+    assert L.jmc_sudakov_generate(1, D.ptr(dx), 30, D.ptr(dy), 25, D.ptr(dt), 0, null, .1, null, 1, 0, null, null,
+                                  D.stream()) == 0                               # nothing to do
