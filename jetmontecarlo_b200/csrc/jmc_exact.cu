@@ -662,9 +662,11 @@ hist_kernel(const double* __restrict__ obs, const double* __restrict__ w, uint64
     if (threadIdx.x == 0) s_poison = INT_MAX;
     hist_init(h, edges, n_edges);
     const BinGuess G = derive_bin_guess(h.edges, n_edges);
-    // np.logspace edges (mode 2) are what every large job has: their loop carries no per-sample look at the mode
+    // np.logspace (mode 2) / np.linspace (mode 1) edges are what every large job has: their loops carry no per-sample
+    // look at the mode
     if (G.mode == 2) hist_stream<VEC, 2, HAS_W>(h, obs, w, n, n_edges, &s_poison, G);
-    else hist_stream<VEC, -1, HAS_W>(h, obs, w, n, n_edges, &s_poison, G);
+    else if (G.mode == 1) hist_stream<VEC, 1, HAS_W>(h, obs, w, n, n_edges, &s_poison, G);
+    else hist_stream<VEC, 0, HAS_W>(h, obs, w, n, n_edges, &s_poison, G);
     hist_flush(h, n_edges, g_sum_w, g_sum_w2, g_count, &s_poison, g_poison);
 }
 
