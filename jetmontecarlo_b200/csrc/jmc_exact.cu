@@ -666,6 +666,7 @@ hist_kernel(const double* __restrict__ obs, const double* __restrict__ w, uint64
     // look at the mode
     if (G.mode == 2) hist_stream<VEC, 2, HAS_W>(h, obs, w, n, n_edges, &s_poison, G);
     else if (G.mode == 1) hist_stream<VEC, 1, HAS_W>(h, obs, w, n, n_edges, &s_poison, G);
+    else if (G.mode == 3) hist_stream<VEC, 3, HAS_W>(h, obs, w, n, n_edges, &s_poison, G);
     else hist_stream<VEC, 0, HAS_W>(h, obs, w, n, n_edges, &s_poison, G);
     hist_flush(h, n_edges, g_sum_w, g_sum_w2, g_count, &s_poison, g_poison);
 }

@@ -155,12 +155,16 @@ __device__ __forceinline__ BinGuess derive_bin_guess(const double* s_edges, int 
             return BinGuess{1, (float)e0, (float)(1.0 / d), (all_tight && eps < 0.2) ? (float)eps : 0.f};
         }
     }
-    {
-        bool ok = e0 > 1e-30 && e1 < 1e30, tight = true;      // the FP32 log2 guess must not underflow
-        const double l0 = ok ? log2(e0) : 0.0, d = ok ? (log2(e1) - l0) / nb : 0.0;
+    // log-uniform edges, or (first = 1) log-uniform edges behind one zero-bin edge
+    for (int first = 0; first <= 1; ++first) {
+        const int m = n_edges - first;
+        if (m < 8) break;
+        const double ea = s_edges[first], mb = (double)(m - 1);
+        bool ok = ea > 1e-30 && e1 < 1e30, tight = true;      // the FP32 log2 guess must not underflow
+        const double l0 = ok ? log2(ea) : 0.0, d = ok ? (log2(e1) - l0) / mb : 0.0;
         ok = ok && d > 0.0 && isfinite(d);
-        for (int k = threadIdx.x; ok && k < n_edges; k += blockDim.x) {
-            const double dev = fabs(log2(s_edges[k]) - (l0 + k * d));
+        for (int k = threadIdx.x; ok && k < m; k += blockDim.x) {
+            const double dev = fabs(log2(s_edges[first + k]) - (l0 + k * d));
             ok = dev < 0.25 * d;
             tight = tight && dev < 1e-6 * d;
         }
@@ -169,8 +173,8 @@ __device__ __forceinline__ BinGuess derive_bin_guess(const double* s_edges, int 
             // __log2f: 2 ulp of the result outside [0.5, 2] (CUDA math API) -> 2 * 2^-23 * |log2 x|, at least 2^-21.4;
             // (float)x: 2^-24 / ln 2; (float)l0: 2^-24 |l0|; the product: 2^-24 relative of a value below nb
             const double span = fmax(fmax(fabs(l0), fabs(log2(e1))), 1.0);
-            const double eps = 2.0 * ((2.4e-7 * span + 4e-7 + 1e-7 + 6e-8 * span) / d + 1.2e-7 * nb + 1e-6);
-            return BinGuess{2, (float)l0, (float)(1.0 / d), (all_tight && eps < 0.2) ? (float)eps : 0.f};
+            const double eps = 2.0 * ((2.4e-7 * span + 4e-7 + 1e-7 + 6e-8 * span) / d + 1.2e-7 * mb + 1e-6);
+            return BinGuess{first ? 3 : 2, (float)l0, (float)(1.0 / d), (all_tight && eps < 0.2) ? (float)eps : 0.f};
         }
     }
     return G;

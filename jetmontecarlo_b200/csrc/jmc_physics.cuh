@@ -430,7 +430,7 @@ __device__ __forceinline__ int bin_index(double x, const double* __restrict__ ed
 // guess of the bin, then a walk against the stored FP64 edges -- which decides, so the result is the exact
 // searchsorted one whatever the guess.  mode: 0 binary search, 1 linear guess, 2 log2 guess.
 struct BinGuess {
-    int mode;
+    int mode;              // 0 none (binary search), 1 linear, 2 log-uniform, 3 log-uniform behind a zero-bin edge
     float b0, inv_d;       // guess = floor((g(x) - b0) * inv_d), g = identity or log2
     float eps;             // > 0: the guess is CERTAIN when the fractional part of the mapped value lies in
                            // (eps, 1 - eps) -- eps bounds every rounding error of the FP32 map (derive_bin_guess)
@@ -443,6 +443,14 @@ __device__ __forceinline__ int bin_index_guided(double x, const double* __restri
     const int mode = MODE < 0 ? G.mode : MODE;
     if (mode == 0) return bin_index(x, edges, n_edges);
     if (!(x >= edges[0]) || !(x <= edges[n_edges - 1])) return -1;
+    // mode 3: a zero bin [edges[0], edges[1]) in front of log-uniform edges (np.insert(np.logspace(...), 0, 1e-100):
+    // vals_to_pdf, utils/hist_utils.py:128-131; the shower histograms); the guess describes edges[1:]
+    const int off = mode == 3 ? 1 : 0;
+    if (off) {
+        if (x < edges[1]) return 0;
+        edges += 1;
+        n_edges -= 1;
+    }
     const float xf = (float)x;
     const float g = mode == 1 ? xf : __log2f(xf);
     const float f = (g - G.b0) * G.inv_d;
@@ -450,11 +458,11 @@ __device__ __forceinline__ int bin_index_guided(double x, const double* __restri
     int idx = (int)fl;
     // Away from the edges the FP32 map cannot be off by a bin: no look at the stored edges at all (two shared-memory
     // loads with scattered addresses less per sample).  Within eps of an edge the exact walk below decides.
-    if (G.eps > 0.0f && f - fl > G.eps && f - fl < 1.0f - G.eps && idx >= 0 && idx <= n_edges - 2) return idx;
+    if (G.eps > 0.0f && f - fl > G.eps && f - fl < 1.0f - G.eps && idx >= 0 && idx <= n_edges - 2) return idx + off;
     idx = max(0, min(idx, n_edges - 2));
     while (idx > 0 && x < edges[idx]) --idx;
     while (idx < n_edges - 2 && x >= edges[idx + 1]) ++idx;
-    return idx;
+    return idx + off;
 }
 
 }  // namespace jmc

@@ -15,7 +15,8 @@ for label, w in (("all weights non-zero", torch.rand(n, dtype=torch.float64, dev
         w[torch.rand(n, device="cuda", generator=g) < .997] = 0.
     for ne, edges in ((100, np.logspace(-11, np.log10(.5), 100)), (5000, np.logspace(-11, np.log10(.5), 5000)),
                       (100, np.sort(np.exp(np.random.RandomState(0).uniform(np.log(1e-11), 0, 100)))),
-                      (100, np.linspace(0., 1., 100))):
+                      (100, np.linspace(0., 1., 100)),
+                      (101, np.insert(np.logspace(-10, 0, 100), 0, 1e-100))):
         e = D.to_device(edges); nb = len(edges) - 1
         lin = bool(np.allclose(np.diff(edges), np.diff(edges)[0]))
         if lin and 'obs_lin' not in globals():
@@ -30,7 +31,8 @@ for label, w in (("all weights non-zero", torch.rand(n, dtype=torch.float64, dev
         ms = ev[0].elapsed_time(ev[1])
         with np.errstate(all='ignore'):
             uni = ("uniform-lin" if np.allclose(np.diff(edges), np.diff(edges)[0]) else
-                   "uniform-log" if np.allclose(np.diff(np.log(edges)), np.diff(np.log(edges))[0]) else "irregular")
+                   "uniform-log" if np.allclose(np.diff(np.log(edges)), np.diff(np.log(edges))[0]) else
+                   "zerobin+log" if np.allclose(np.diff(np.log(edges[1:])), np.diff(np.log(edges[1:]))[0]) else "irregular")
         print(f"jmc_hist  {label:28s} {ne:5d} {uni:11s} edges: {ms:7.3f} ms  {16*n/ms/1e6:7.0f} GB/s = {16*n/ms/1e6/peak:.2f} of measured HBM peak  ({n/ms*1e3:.3e} samples/s)")
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
 for rep in range(3):
