@@ -213,8 +213,7 @@ def integrate(integrand, num_samples, *, edges=None, numbins=None, binspacing='l
         # same arithmetic mode for both passes: the min/max pass must see the samples the histogram pass bins
         it.setBinsFused(numbins, integrand, num_samples, binspacing, seed, min_log_bin=min_log_bin,
                         precision=precision, group=group)
-    it.setDensityFused(integrand, num_samples, seed, precision=precision, group=group)
-    it.integrate()
+    it.integrateFused(integrand, num_samples, seed, precision=precision, group=group)
     return it
 
 

@@ -178,6 +178,33 @@ class integrator():
                          self._sum_w, self._sum_w2, self._count, group, edges_host=self.bins)
         self._density_from_hist(integrand.area, int(num_samples))
 
+    def integrateFused(self, integrand, num_samples, seed, precision='f32', group=None):
+        """setDensityFused + integrate in one pass over the device: the histograms go through ONE jmc_finalize
+        (density, its error, cumulative integral, its error) into one buffer and come back in ONE copy, instead of
+        density down / density up / integral down."""
+        from .. import fused
+        assert self.hasBins, "Need bins to produce density histogram."
+        bc_kind, bc_value = _bc_args(self.firstBinBndCond, self.lastBinBndCond)
+        nb = self._alloc_hist()
+        fused.accumulate(integrand, num_samples, seed, precision, self._edges_dev,
+                         self._sum_w, self._sum_w2, self._count, group, edges_host=self.bins)
+        out = D.empty((4 * nb + 1,))
+        base, step = out.data_ptr(), 8
+        _lib.check(_lib.lib.jmc_finalize(
+            D.ptr(self._sum_w), D.ptr(self._sum_w2), D.ptr(self._count), D.ptr(self._edges_dev), nb + 1,
+            float(integrand.area), int(num_samples), bc_kind, bc_value, C.c_void_p(base), C.c_void_p(base + step * nb),
+            C.c_void_p(base + step * 2 * nb), C.c_void_p(base + step * (3 * nb + 1)), D.stream()))
+        host = D.to_host(out)
+        self.density, self.densityErr = host[:nb].copy(), host[nb:2 * nb].copy()
+        self.integral, self.integralErr = list(host[2 * nb:3 * nb + 1]), host[3 * nb + 1:].copy()
+        self.useLastBinBndCond = bc_kind != _lib.BC_FIRST
+        self.useFirstBinBndCond = bc_kind == _lib.BC_FIRST
+        self.hasMCDensity = self.hasMCIntegral = True
+        if self.monotone:
+            arr = np.asarray(self.integral)
+            assert ((arr[1:] <= arr[:-1]).all() or (arr[1:] >= arr[:-1]).all()), \
+                "User asked for a monotone integral, but the integral is not monotone!"
+
     # ------------------
     # Saved data         (keys of the reference: integrator.py:204-224)
     # ------------------
