@@ -31,7 +31,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
 # compile-time experiment switches (scripts/fast_shootout.sh, scripts/shower_shootout.sh); unset = the defaults in the sources
 SWITCHES = ("JMC_FAST_CHUNK", "JMC_FAST_MIN_BLOCKS", "JMC_FAST_PAIRS", "JMC_FAST_PAIRS_2W", "JMC_FAST_PIN_KEYS", "JMC_PHILOX_SPLIT", "JMC_ACC_MODE",
             "JMC_HIST_MODE", "JMC_HIST_UNROLL", "JMC_SHOWER_GROUP", "JMC_SHOWER_BIN_GROUP", "JMC_SHOWER_CHUNK",
-            "JMC_SHOWER_MIN_BLOCKS", "JMC_SHOWER_TRIALS")
+            "JMC_SHOWER_MIN_BLOCKS", "JMC_SHOWER_TRIALS", "JMC_SHOWER_SHARE")
 _DEFS = ["-D%s=%s" % (k, os.environ[k]) for k in SWITCHES if os.environ.get(k)]
 UNITS = {
     "jmc_exact.cu": ["--fmad=false"] + _DEFS,

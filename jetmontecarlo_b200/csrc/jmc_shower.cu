@@ -377,6 +377,9 @@ shower_kernel(ShowerParams p, uint64_t n, uint64_t seed, uint64_t first, const d
 #ifndef JMC_SHOWER_TRIALS
 #define JMC_SHOWER_TRIALS 3
 #endif
+#ifndef JMC_SHOWER_SHARE
+#define JMC_SHOWER_SHARE 1      // three trials per iteration from two Philox blocks (0: JMC_SHOWER_TRIALS trials, a block each)
+#endif
 #ifndef JMC_SHOWER_MIN_BLOCKS
 #define JMC_SHOWER_MIN_BLOCKS 1
 #endif
@@ -481,11 +484,10 @@ shower_fast_kernel(ShowerParams p, uint64_t n, uint64_t seed, uint64_t first, co
         // warp-level work around them -- hand-out, votes, queue decisions, the push -- is paid once per that many ----
         bool accepted = false, last = false;
         float lz = __int_as_float(0x7fc00000), lth = 0.0f;
-        auto trial = [&]() {
-            uint32_t r[4];
-            philox4x32_10(jx, blk++, keys, r);
+        // one trial from two 24-bit uniforms (r1, r2) and the acceptance uniform i3 in units of 2^-24
+        auto trial = [&](uint32_t w1, uint32_t w2, float i3) {
             if (RECORD) ++n_trials;
-            const float i1 = (float)(r[0] >> 8) + 0.5f, i2 = (float)(r[1] >> 8) + 0.5f, i3 = (float)(r[2] >> 8) + 0.5f;
+            const float i1 = (float)(w1 >> 8) + 0.5f, i2 = (float)(w2 >> 8) + 0.5f;
             const float lp = -sh_sqrt(fmaf(-k2, sh_lg2(i1 * k2m24), l2 * l2));
             const float a = (i2 * k2m24) * lp;                            // r2 l'
             lz = a - 1.0f;                                                // log2 z = r2 l' - 1
@@ -527,9 +529,33 @@ shower_fast_kernel(ShowerParams p, uint64_t n, uint64_t seed, uint64_t first, co
             if (!start_ok) {
                 accepted = last = true;              // event without emission (log2 z = NaN)
             } else {
+#if JMC_SHOWER_SHARE
+                // Three trials from TWO Philox blocks: r1 and r2 take a word each (24 bits used), the acceptance
+                // uniform 21 bits -- the top 21 of a third word for trials 1 and 2, the 11 + 10 bits those left over
+                // for trial 3.  (The veto compares r3 with a probability of order 0.1: 2^-21 is 5e-6 of it.)
+                uint32_t a[4], b[4];
+                philox4x32_10(jx, blk, keys, a);
+                if (!MLL) {                      // LL: no veto, the first trial is the emission -- one block is enough
+                    ++blk;
+                    accepted = trial(a[0], a[1], 0.0f);
+                } else {
+                philox4x32_10(jx, blk + 1u, keys, b);
+                blk += 2u;
+                accepted = trial(a[0], a[1], fmaf((float)(a[2] >> 11), 8.0f, 4.0f));
+                if (!accepted) accepted = trial(a[3], b[0], fmaf((float)(b[1] >> 11), 8.0f, 4.0f));
+                if (!accepted)
+                    accepted = trial(b[2], b[3], fmaf((float)(((a[2] & 0x7ffu) << 10) | ((b[1] & 0x7ffu) >> 1)), 8.0f, 4.0f));
+                }
+#else
 #pragma unroll
-                for (int t = 0; t < JMC_SHOWER_TRIALS; ++t)
-                    if (!accepted) accepted = trial();
+                for (int t = 0; t < JMC_SHOWER_TRIALS; ++t) {
+                    if (!accepted) {
+                        uint32_t r[4];
+                        philox4x32_10(jx, blk++, keys, r);
+                        accepted = trial(r[0], r[1], (float)(r[2] >> 8) + 0.5f);
+                    }
+                }
+#endif
             }
         }
         // ---- accumulator stage: one event of every lane that has one ----
